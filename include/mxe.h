@@ -1,0 +1,141 @@
+/*
+ * mxe.h -- C ABI of the B200 minimizer sketch-and-filter engine (libmxe.so).
+ *
+ * This is the drop-in boundary for ntJoin's step-1/2/3 hot path.  The reference has no FFI of
+ * its own for this path; it crosses a process seam and three Python functions.  Each entry
+ * point below names the reference interface it replaces (paths relative to the ntJoin repo):
+ *
+ *   mxe_sketch_file / mxe_sketch_buffers / mxe_write_tsv
+ *        replace the `indexlr --seq --long --pos -k K -w W -t T FASTA > FASTA.kK.wW.tsv`
+ *        subprocess (ntJoin:204-205, bin/ntjoin_utils.py:195-202) and btllib.Indexlr
+ *        (bin/ntjoin_assemble.py:478-481).
+ *   mxe_filter_and_edges
+ *        replaces read_minimizers' uniqueness filter (bin/ntjoin_utils.py:167-193),
+ *        filter_minimizers (bin/ntjoin_utils.py:152-165) and the edge stage of build_graph
+ *        (bin/ntjoin_utils.py:94-115) with calc_total_weight (:54-56).
+ *
+ * Conventions: plain C, every call returns 0 on success or a negative code; the message is in
+ * mxe_last_error() (thread local).  Objects returned by the engine are owned by the engine and
+ * released with the matching *_free.  Calls on one engine handle are not re-entrant.  There is
+ * no CPU fallback: without a CUDA device mxe_create fails.
+ */
+#ifndef MXE_H
+#define MXE_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mxe_engine mxe_t;
+typedef struct mxe_sketch mxe_sketch_t;
+typedef struct mxe_result mxe_result_t;
+
+enum {
+    MXE_OK = 0,
+    MXE_ERR_ARG = -1,      /* bad argument                         */
+    MXE_ERR_IO = -2,       /* file could not be read / written     */
+    MXE_ERR_CUDA = -3,     /* CUDA runtime error                   */
+    MXE_ERR_NOMEM = -4,
+    MXE_ERR_INTERNAL = -5
+};
+
+/* flags for the sketch calls */
+enum {
+    MXE_CANON_SUM = 0,     /* hash0 = fwd + rev   (current btllib / ntHash2; default)           */
+    MXE_CANON_MIN = 1,     /* hash0 = min(fwd,rev) (legacy ntHash1; matches the shipped goldens) */
+    MXE_KEEP_DEVICE = 2    /* keep the minimizer arrays resident on the device for              */
+                           /* mxe_filter_and_edges / mxe_sketch_device_view                     */
+};
+
+const char* mxe_version(void);
+const char* mxe_last_error(void);
+
+/* One engine per process and device.  device = CUDA ordinal. */
+int  mxe_create(int device, mxe_t** out);
+void mxe_destroy(mxe_t* e);
+
+/* Tunables (name = "tau" candidate threshold multiplier, "chunk" positions per thread, ...). */
+int  mxe_set_option(mxe_t* e, const char* name, double value);
+
+/* ---- step 1: ordered minimizer sketch --------------------------------------------------- */
+
+/* FASTA file (multi-line records, '>' headers; id = header up to first whitespace).
+ * Replaces: indexlr subprocess, ntJoin:204-205. */
+int mxe_sketch_file(mxe_t* e, const char* fasta_path, int k, int w, int flags, mxe_sketch_t** out);
+
+/* Host buffers: `seq` = all records concatenated (ASCII, either case, no separators),
+ * `offsets` = n_contigs+1 starts, `names` may be NULL.  Host->device copy is inside the call. */
+int mxe_sketch_buffers(mxe_t* e, const uint8_t* seq, const uint64_t* offsets, uint32_t n_contigs,
+                       const char* const* names, int k, int w, int flags, mxe_sketch_t** out);
+
+/* Same, with `d_seq` already resident in device memory of this engine's device (16-byte aligned).
+ * `offsets` stays a host array.  `stream` = cudaStream_t as an integer (0 = engine stream). */
+int mxe_sketch_device(mxe_t* e, const void* d_seq, const uint64_t* offsets, uint32_t n_contigs,
+                      const char* const* names, int k, int w, int flags, mxe_sketch_t** out);
+
+/* Host view (SoA, sorted by (contig, pos); contigs in input order).  Pointers stay valid until
+ * mxe_sketch_free.  Any output pointer may be NULL. */
+int mxe_sketch_view(mxe_sketch_t* s, uint64_t* n,
+                    const uint64_t** out_hash,   /* hash1: the minimizer's identity in ntJoin   */
+                    const uint64_t** min_hash,   /* hash0: window selection key                 */
+                    const uint32_t** pos,        /* 0-based offset in the record                */
+                    const uint32_t** contig,     /* record index                                */
+                    const uint8_t**  forward);   /* fwd <= rev                                  */
+
+/* Device view (valid only with MXE_KEEP_DEVICE): raw device pointers of the same SoA. */
+int mxe_sketch_device_view(mxe_sketch_t* s, uint64_t* n, const void** d_out_hash,
+                           const void** d_pos, const void** d_contig);
+
+/* Record name (header up to the first whitespace) of record `idx`; valid until mxe_sketch_free. */
+int mxe_sketch_contig_name(mxe_sketch_t* s, uint32_t idx, const char** name);
+
+int mxe_sketch_counts(mxe_sketch_t* s, uint64_t* n_bases, uint64_t* n_valid_kmers,
+                      uint64_t* n_candidates, uint64_t* n_gap_windows, uint32_t* n_contigs);
+
+/* `indexlr` text output: id \t hash[:pos][:strand][:seq] ...   path "-" = stdout.
+ * with_seq needs the sequence: available after mxe_sketch_file / mxe_sketch_buffers only. */
+int mxe_write_tsv(mxe_sketch_t* s, const char* path, int with_pos, int with_strand, int with_seq);
+
+void mxe_sketch_free(mxe_sketch_t* s);
+
+/* ---- steps 2-3: uniqueness, found-in-all intersection, adjacent-pair edge list ----------- */
+
+/* Sketches in assembly order (references in CLI order, target LAST: bin/ntjoin.py:181-185,
+ * bin/ntjoin_assemble.py:804-807).  weights[a] as passed to build_graph. n_asm <= 32. */
+int mxe_filter_and_edges(mxe_t* e, mxe_sketch_t* const* sketches, int n_asm, const double* weights,
+                         mxe_result_t** out);
+
+/* Same on raw device arrays (used by the multi-GPU path after the NCCL all-gather):
+ * d_hash[a] -> n[a] uint64 out_hash in (contig,pos) order; d_contig[a] -> n[a] uint32. */
+int mxe_filter_and_edges_device(mxe_t* e, const void* const* d_hash, const void* const* d_contig,
+                                const uint64_t* n, int n_asm, const double* weights,
+                                mxe_result_t** out);
+
+/* Per assembly: flags over its minimizers in sketch order.
+ * uniq[i]=1: out_hash occurs once in the assembly (survives read_minimizers);
+ * keep[i]=1: additionally found (unique) in every assembly (survives filter_minimizers). */
+int mxe_result_flags(mxe_result_t* r, int asm_idx, uint64_t* n, const uint8_t** uniq, const uint8_t** keep);
+
+/* Graph: vertices = surviving out_hash values (ascending); edges in the order
+ * bin/ntjoin_utils.py:115 lists them, (u,v) in first-seen orientation, support_mask bit a =
+ * assembly a, weight = sum of weights in assembly order (IEEE double, bit-identical to Python). */
+int mxe_result_graph(mxe_result_t* r, uint64_t* n_vertices, const uint64_t** vertices,
+                     uint64_t* n_edges, const uint64_t** edge_u, const uint64_t** edge_v,
+                     const uint32_t** support_mask, const double** weight);
+
+void mxe_result_free(mxe_result_t* r);
+
+/* ---- measurement hooks (bench.py) -------------------------------------------------------- */
+
+/* Device time in milliseconds and launch count of the engine's kernels since the last reset,
+ * measured with CUDA events on the engine stream.  name = "cand" (dominant sketch kernel),
+ * "pack", "sketch" (whole step 1), "filter" (steps 2-3), "all". */
+int mxe_timing(mxe_t* e, const char* name, double* ms, uint64_t* launches);
+int mxe_timing_reset(mxe_t* e);
+uint64_t mxe_kernel_launches(mxe_t* e);   /* total kernels launched by this engine */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

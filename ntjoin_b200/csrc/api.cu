@@ -1,0 +1,450 @@
+// api.cu -- the C ABI declared in include/mxe.h, plus host-side FASTA ingest and TSV output.
+#include "engine.cuh"
+
+#include <errno.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+
+namespace mxe {
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+cudaEvent_t Engine::get_event()
+{
+    if (!event_pool.empty()) { cudaEvent_t ev = event_pool.back(); event_pool.pop_back(); return ev; }
+    cudaEvent_t ev = nullptr;
+    cudaEventCreate(&ev);
+    return ev;
+}
+void Engine::span_begin(const char*, cudaEvent_t* a)
+{
+    *a = get_event();
+    cudaEventRecord(*a, stream);
+}
+void Engine::span_end(const char* name, cudaEvent_t a, uint64_t n_launch)
+{
+    cudaEvent_t b = get_event();
+    cudaEventRecord(b, stream);
+    PhaseTimer& t = timers[name];
+    t.spans.push_back({a, b});
+    t.launches += n_launch;
+}
+}  // namespace mxe
+
+using namespace mxe;
+
+void* mxe_engine::pinned_alloc(size_t bytes)
+{
+    if (bytes == 0) bytes = 1;
+    for (size_t i = 0; i < pinned_free.size(); i++) {
+        if (pinned_free[i].bytes >= bytes && pinned_free[i].bytes <= 2 * bytes + 4096) {
+            void* p = pinned_free[i].p;
+            pinned_free.erase(pinned_free.begin() + i);
+            return p;
+        }
+    }
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+    return p;
+}
+void mxe_engine::pinned_release(void* p, size_t bytes)
+{
+    if (!p) return;
+    if (pinned_free.size() >= 16) { cudaFreeHost(pinned_free[0].p); pinned_free.erase(pinned_free.begin()); }
+    pinned_free.push_back({p, bytes});
+}
+
+extern "C" {
+
+const char* mxe_version(void) { return "ntjoin_b200 mxe 0.1 (sm_100a)"; }
+const char* mxe_last_error(void) { return g_err; }
+
+int mxe_create(int device, mxe_t** out)
+{
+    if (!out) { set_error("out is NULL"); return MXE_ERR_ARG; }
+    *out = nullptr;
+    int count = 0;
+    cudaError_t err = cudaGetDeviceCount(&count);
+    if (err != cudaSuccess || count == 0) {
+        set_error("no CUDA device available (%s); this engine has no CPU fallback", cudaGetErrorString(err));
+        return MXE_ERR_CUDA;
+    }
+    if (device < 0 || device >= count) { set_error("device %d out of range (have %d)", device, count); return MXE_ERR_ARG; }
+    MXE_CUDA(cudaSetDevice(device));
+    mxe_engine* e = new mxe_engine();
+    e->device = device;
+    MXE_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    cudaDeviceProp prop;
+    MXE_CUDA(cudaGetDeviceProperties(&prop, device));
+    e->sm_count = prop.multiProcessorCount;
+    cudaMemPool_t pool;
+    MXE_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thresh = ~0ULL;   // keep freed blocks cached in the pool across steps
+    MXE_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    if (const char* s = getenv("MXE_TAU")) e->tau = atof(s);
+    if (const char* s = getenv("MXE_CHUNK")) e->chunk = atoi(s);
+    if (const char* s = getenv("MXE_CAND_VARIANT")) e->cand_variant = atoi(s);
+    *out = e;
+    return MXE_OK;
+}
+
+void mxe_destroy(mxe_t* e)
+{
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    for (auto& kv : e->timers)
+        for (auto& sp : kv.second.spans) { cudaEventDestroy(sp.first); cudaEventDestroy(sp.second); }
+    for (auto ev : e->event_pool) cudaEventDestroy(ev);
+    for (auto& p : e->pinned_free) cudaFreeHost(p.p);
+    cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int mxe_set_option(mxe_t* e, const char* name, double value)
+{
+    if (!e || !name) { set_error("null argument"); return MXE_ERR_ARG; }
+    if (!strcmp(name, "tau")) { if (value <= 0) { set_error("tau must be > 0"); return MXE_ERR_ARG; } e->tau = value; }
+    else if (!strcmp(name, "chunk")) { if (value < 32) { set_error("chunk must be >= 32"); return MXE_ERR_ARG; } e->chunk = (int)value; }
+    else if (!strcmp(name, "cand_variant")) e->cand_variant = (int)value;
+    else if (!strcmp(name, "timing")) e->timing = value != 0;
+    else { set_error("unknown option %s", name); return MXE_ERR_ARG; }
+    return MXE_OK;
+}
+
+// ------------------------------------------------------------------ sketch entry points
+static int sketch_from_host(mxe_t* e, const uint8_t* seq, uint64_t n, const uint64_t* offsets, uint32_t n_contigs,
+                            int k, int w, int flags, mxe_sketch* S)
+{
+    DBuf<uint8_t> d_seq;
+    MXE_TRY(d_seq.alloc(n + 64, e->stream));
+    if (n) MXE_CUDA(cudaMemcpyAsync(d_seq.p, seq, n, cudaMemcpyHostToDevice, e->stream));
+    return sketch_device_impl(e, d_seq.p, n, offsets, n_contigs, k, w, flags, S);
+}
+
+static void set_names(mxe_sketch* S, const char* const* names, uint32_t n_contigs)
+{
+    S->names.resize(n_contigs);
+    for (uint32_t c = 0; c < n_contigs; c++) S->names[c] = names ? names[c] : std::to_string(c);
+}
+
+int mxe_sketch_buffers(mxe_t* e, const uint8_t* seq, const uint64_t* offsets, uint32_t n_contigs,
+                       const char* const* names, int k, int w, int flags, mxe_sketch_t** out)
+{
+    if (!e || !out || !offsets || (!seq && n_contigs && offsets[n_contigs])) { set_error("null argument"); return MXE_ERR_ARG; }
+    MXE_CUDA(cudaSetDevice(e->device));
+    mxe_sketch* S = new mxe_sketch();
+    set_names(S, names, n_contigs);
+    S->seq_borrowed = seq;
+    int rc = sketch_from_host(e, seq, n_contigs ? offsets[n_contigs] : 0, offsets, n_contigs, k, w, flags, S);
+    if (rc != MXE_OK) { mxe_sketch_free(S); return rc; }
+    *out = S;
+    return MXE_OK;
+}
+
+int mxe_sketch_device(mxe_t* e, const void* d_seq, const uint64_t* offsets, uint32_t n_contigs,
+                      const char* const* names, int k, int w, int flags, mxe_sketch_t** out)
+{
+    if (!e || !out || !offsets || !d_seq) { set_error("null argument"); return MXE_ERR_ARG; }
+    MXE_CUDA(cudaSetDevice(e->device));
+    mxe_sketch* S = new mxe_sketch();
+    set_names(S, names, n_contigs);
+    int rc = sketch_device_impl(e, (const uint8_t*)d_seq, n_contigs ? offsets[n_contigs] : 0, offsets, n_contigs, k, w, flags, S);
+    if (rc != MXE_OK) { mxe_sketch_free(S); return rc; }
+    *out = S;
+    return MXE_OK;
+}
+
+// FASTA / FASTQ ingest (reference: btllib SeqReader behind indexlr): id = header up to the
+// first whitespace, multi-line sequences concatenated, input order kept, sequence upper-cased.
+static int read_fasta(const char* path, std::vector<char>& seq, std::vector<uint64_t>& offsets, std::vector<std::string>& names)
+{
+    FILE* f = fopen(path, "rb");
+    if (!f) { set_error("cannot open %s: %s", path, strerror(errno)); return MXE_ERR_IO; }
+    fseek(f, 0, SEEK_END);
+    long long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    std::vector<char> buf((size_t)sz + 1);
+    if (sz && fread(buf.data(), 1, (size_t)sz, f) != (size_t)sz) { fclose(f); set_error("short read on %s", path); return MXE_ERR_IO; }
+    fclose(f);
+    buf[sz] = '\n';
+    seq.resize((size_t)sz + 64);
+    offsets.clear(); names.clear();
+    size_t at = 0;
+    const char* p = buf.data();
+    const char* end = p + sz;
+    if (p < end && *p == '@') {   // FASTQ: 4-line records
+        while (p < end) {
+            const char* nl = (const char*)memchr(p, '\n', end - p); if (!nl) nl = end;
+            const char* s = p + 1; const char* q = s;
+            while (q < nl && *q != ' ' && *q != '\t' && *q != '\r') q++;
+            names.emplace_back(s, q - s);
+            offsets.push_back(at);
+            p = nl + 1;
+            nl = (const char*)memchr(p, '\n', end > p ? end - p : 0); if (!nl) nl = end;
+            size_t len = nl - p; if (len && p[len - 1] == '\r') len--;
+            memcpy(&seq[at], p, len); at += len;
+            p = nl + 1;
+            for (int i = 0; i < 2 && p < end; i++) { nl = (const char*)memchr(p, '\n', end - p); p = nl ? nl + 1 : end; }
+        }
+    } else {
+        bool have = false;
+        while (p < end) {
+            const char* nl = (const char*)memchr(p, '\n', end - p + 1);
+            if (*p == '>') {
+                const char* s = p + 1; const char* q = s;
+                while (q < nl && *q != ' ' && *q != '\t' && *q != '\r') q++;
+                names.emplace_back(s, q - s);
+                offsets.push_back(at);
+                have = true;
+            } else if (have) {
+                size_t len = nl - p; if (len && p[len - 1] == '\r') len--;
+                memcpy(&seq[at], p, len); at += len;
+            }
+            p = nl + 1;
+        }
+    }
+    offsets.push_back(at);
+    for (size_t i = 0; i < at; i++) { char c = seq[i]; if (c >= 'a' && c <= 'z') seq[i] = (char)(c - 32); }
+    memset(&seq[at], 0, 64);
+    seq.resize(at + 64);
+    return MXE_OK;
+}
+
+int mxe_sketch_file(mxe_t* e, const char* fasta_path, int k, int w, int flags, mxe_sketch_t** out)
+{
+    if (!e || !out || !fasta_path) { set_error("null argument"); return MXE_ERR_ARG; }
+    MXE_CUDA(cudaSetDevice(e->device));
+    mxe_sketch* S = new mxe_sketch();
+    std::vector<uint64_t> offsets;
+    int rc = read_fasta(fasta_path, S->seq_text, offsets, S->names);
+    if (rc == MXE_OK)
+        rc = sketch_from_host(e, (const uint8_t*)S->seq_text.data(), offsets.back(), offsets.data(), (uint32_t)S->names.size(), k, w, flags, S);
+    if (rc != MXE_OK) { mxe_sketch_free(S); return rc; }
+    *out = S;
+    return MXE_OK;
+}
+
+static int ensure_host(mxe_sketch* S)
+{
+    if (S->h_block || S->n == 0) return MXE_OK;
+    mxe_engine* e = S->eng;
+    MXE_CUDA(cudaSetDevice(e->device));
+    size_t n = S->n;
+    size_t bytes = n * (8 + 8 + 4 + 4 + 1) + 64;
+    char* blk = (char*)e->pinned_alloc(bytes);
+    if (!blk) { set_error("pinned host allocation of %zu bytes failed", bytes); return MXE_ERR_NOMEM; }
+    S->h_block = blk; S->h_bytes = bytes;
+    S->h_out_hash = (uint64_t*)blk;
+    S->h_min_hash = (uint64_t*)(blk + 8 * n);
+    S->h_pos = (uint32_t*)(blk + 16 * n);
+    S->h_contig = (uint32_t*)(blk + 20 * n);
+    S->h_forward = (uint8_t*)(blk + 24 * n);
+    cudaStream_t st = e->stream;
+    MXE_CUDA(cudaMemcpyAsync(S->h_out_hash, S->d_out_hash, 8 * n, cudaMemcpyDeviceToHost, st));
+    MXE_CUDA(cudaMemcpyAsync(S->h_min_hash, S->d_min_hash, 8 * n, cudaMemcpyDeviceToHost, st));
+    MXE_CUDA(cudaMemcpyAsync(S->h_pos, S->d_pos, 4 * n, cudaMemcpyDeviceToHost, st));
+    MXE_CUDA(cudaMemcpyAsync(S->h_contig, S->d_contig, 4 * n, cudaMemcpyDeviceToHost, st));
+    MXE_CUDA(cudaMemcpyAsync(S->h_forward, S->d_forward, n, cudaMemcpyDeviceToHost, st));
+    MXE_CUDA(cudaStreamSynchronize(st));
+    return MXE_OK;
+}
+
+int mxe_sketch_view(mxe_sketch_t* S, uint64_t* n, const uint64_t** out_hash, const uint64_t** min_hash,
+                    const uint32_t** pos, const uint32_t** contig, const uint8_t** forward)
+{
+    if (!S) { set_error("null sketch"); return MXE_ERR_ARG; }
+    MXE_TRY(ensure_host(S));
+    if (n) *n = S->n;
+    if (out_hash) *out_hash = S->h_out_hash;
+    if (min_hash) *min_hash = S->h_min_hash;
+    if (pos) *pos = S->h_pos;
+    if (contig) *contig = S->h_contig;
+    if (forward) *forward = S->h_forward;
+    return MXE_OK;
+}
+
+int mxe_sketch_device_view(mxe_sketch_t* S, uint64_t* n, const void** d_out_hash, const void** d_pos, const void** d_contig)
+{
+    if (!S) { set_error("null sketch"); return MXE_ERR_ARG; }
+    if (n) *n = S->n;
+    if (d_out_hash) *d_out_hash = S->d_out_hash;
+    if (d_pos) *d_pos = S->d_pos;
+    if (d_contig) *d_contig = S->d_contig;
+    return MXE_OK;
+}
+
+int mxe_sketch_contig_name(mxe_sketch_t* S, uint32_t idx, const char** name)
+{
+    if (!S || !name || idx >= S->names.size()) { set_error("bad record index"); return MXE_ERR_ARG; }
+    *name = S->names[idx].c_str();
+    return MXE_OK;
+}
+
+int mxe_sketch_counts(mxe_sketch_t* S, uint64_t* n_bases, uint64_t* n_valid_kmers, uint64_t* n_candidates,
+                      uint64_t* n_gap_windows, uint32_t* n_contigs)
+{
+    if (!S) { set_error("null sketch"); return MXE_ERR_ARG; }
+    if (n_bases) *n_bases = S->n_bases;
+    if (n_valid_kmers) *n_valid_kmers = S->n_valid;
+    if (n_candidates) *n_candidates = S->n_cand;
+    if (n_gap_windows) *n_gap_windows = S->n_gap_windows;
+    if (n_contigs) *n_contigs = S->n_contigs;
+    return MXE_OK;
+}
+
+static inline char* put_u64(char* p, uint64_t v)
+{
+    char tmp[24];
+    int n = 0;
+    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (n) *p++ = tmp[--n];
+    return p;
+}
+
+int mxe_write_tsv(mxe_sketch_t* S, const char* path, int with_pos, int with_strand, int with_seq)
+{
+    if (!S || !path) { set_error("null argument"); return MXE_ERR_ARG; }
+    MXE_TRY(ensure_host(S));
+    const char* text = !S->seq_text.empty() ? S->seq_text.data() : (const char*)S->seq_borrowed;
+    if (with_seq && !text && S->n) { set_error("sequence text not available for --seq output"); return MXE_ERR_ARG; }
+    FILE* f = (path[0] == '-' && !path[1]) ? stdout : fopen(path, "wb");
+    if (!f) { set_error("cannot open %s: %s", path, strerror(errno)); return MXE_ERR_IO; }
+    std::vector<char> buf(1 << 22);
+    char* p = buf.data();
+    char* lim = buf.data() + buf.size() - (64 + (size_t)S->k + 8);
+    size_t i = 0;
+    bool ok = true;
+    for (uint32_t c = 0; c < S->n_contigs && ok; c++) {
+        const std::string& nm = S->names[c];
+        if ((size_t)(lim - p) < nm.size() + 2) { ok = fwrite(buf.data(), 1, p - buf.data(), f) == (size_t)(p - buf.data()); p = buf.data(); }
+        if (nm.size() + 2 > buf.size() / 2) { ok = ok && fwrite(nm.data(), 1, nm.size(), f) == nm.size(); }
+        else { memcpy(p, nm.data(), nm.size()); p += nm.size(); }
+        *p++ = '\t';
+        bool first = true;
+        while (i < S->n && S->h_contig[i] == c) {
+            if (p > lim) { ok = ok && fwrite(buf.data(), 1, p - buf.data(), f) == (size_t)(p - buf.data()); p = buf.data(); }
+            if (!first) *p++ = ' ';
+            first = false;
+            p = put_u64(p, S->h_out_hash[i]);
+            if (with_pos) { *p++ = ':'; p = put_u64(p, S->h_pos[i]); }
+            if (with_strand) { *p++ = ':'; *p++ = S->h_forward[i] ? '+' : '-'; }
+            if (with_seq) {
+                *p++ = ':';
+                const char* km = text + S->offsets[c] + S->h_pos[i];
+                for (int j = 0; j < S->k; j++) { char ch = km[j]; *p++ = (ch >= 'a' && ch <= 'z') ? (char)(ch - 32) : ch; }
+            }
+            i++;
+        }
+        *p++ = '\n';
+    }
+    ok = ok && fwrite(buf.data(), 1, p - buf.data(), f) == (size_t)(p - buf.data());
+    if (f != stdout) ok = (fclose(f) == 0) && ok; else fflush(f);
+    if (!ok) { set_error("write to %s failed", path); return MXE_ERR_IO; }
+    return MXE_OK;
+}
+
+void mxe_sketch_free(mxe_sketch_t* S)
+{
+    if (!S) return;
+    if (S->eng) {
+        cudaSetDevice(S->eng->device);
+        cudaStream_t st = S->eng->stream;
+        if (S->d_out_hash) cudaFreeAsync(S->d_out_hash, st);
+        if (S->d_min_hash) cudaFreeAsync(S->d_min_hash, st);
+        if (S->d_pos) cudaFreeAsync(S->d_pos, st);
+        if (S->d_contig) cudaFreeAsync(S->d_contig, st);
+        if (S->d_forward) cudaFreeAsync(S->d_forward, st);
+        S->eng->pinned_release(S->h_block, S->h_bytes);
+    }
+    delete S;
+}
+
+// ------------------------------------------------------------------ steps 2-3
+int mxe_filter_and_edges_device(mxe_t* e, const void* const* d_hash, const void* const* d_contig,
+                                const uint64_t* n, int n_asm, const double* weights, mxe_result_t** out)
+{
+    if (!e || !d_hash || !d_contig || !n || !weights || !out) { set_error("null argument"); return MXE_ERR_ARG; }
+    MXE_CUDA(cudaSetDevice(e->device));
+    mxe_result* R = new mxe_result();
+    int rc = filter_and_edges_impl(e, (const uint64_t* const*)d_hash, (const uint32_t* const*)d_contig, n, n_asm, weights, R);
+    if (rc != MXE_OK) { delete R; return rc; }
+    *out = R;
+    return MXE_OK;
+}
+
+int mxe_filter_and_edges(mxe_t* e, mxe_sketch_t* const* sketches, int n_asm, const double* weights, mxe_result_t** out)
+{
+    if (!e || !sketches || !weights || !out) { set_error("null argument"); return MXE_ERR_ARG; }
+    if (n_asm < 1 || n_asm > 32) { set_error("n_asm must be 1..32"); return MXE_ERR_ARG; }
+    const void* dh[32]; const void* dc[32]; uint64_t n[32];
+    for (int a = 0; a < n_asm; a++) {
+        if (!sketches[a] || sketches[a]->eng != e) { set_error("sketch %d does not belong to this engine", a); return MXE_ERR_ARG; }
+        dh[a] = sketches[a]->d_out_hash; dc[a] = sketches[a]->d_contig; n[a] = sketches[a]->n;
+    }
+    return mxe_filter_and_edges_device(e, dh, dc, n, n_asm, weights, out);
+}
+
+int mxe_result_flags(mxe_result_t* r, int a, uint64_t* n, const uint8_t** uniq, const uint8_t** keep)
+{
+    if (!r || a < 0 || a >= r->n_asm) { set_error("bad assembly index"); return MXE_ERR_ARG; }
+    if (n) *n = r->uniq[a].size();
+    if (uniq) *uniq = r->uniq[a].data();
+    if (keep) *keep = r->keep[a].data();
+    return MXE_OK;
+}
+
+int mxe_result_graph(mxe_result_t* r, uint64_t* n_vertices, const uint64_t** vertices, uint64_t* n_edges,
+                     const uint64_t** edge_u, const uint64_t** edge_v, const uint32_t** support_mask, const double** weight)
+{
+    if (!r) { set_error("null result"); return MXE_ERR_ARG; }
+    if (n_vertices) *n_vertices = r->vertices.size();
+    if (vertices) *vertices = r->vertices.data();
+    if (n_edges) *n_edges = r->edge_u.size();
+    if (edge_u) *edge_u = r->edge_u.data();
+    if (edge_v) *edge_v = r->edge_v.data();
+    if (support_mask) *support_mask = r->support.data();
+    if (weight) *weight = r->weight.data();
+    return MXE_OK;
+}
+
+void mxe_result_free(mxe_result_t* r) { delete r; }
+
+// ------------------------------------------------------------------ measurement
+int mxe_timing(mxe_t* e, const char* name, double* ms, uint64_t* launches)
+{
+    if (!e || !name) { set_error("null argument"); return MXE_ERR_ARG; }
+    MXE_CUDA(cudaSetDevice(e->device));
+    MXE_CUDA(cudaStreamSynchronize(e->stream));
+    double total = 0; uint64_t nl = 0;
+    auto it = e->timers.find(name);
+    if (it != e->timers.end()) {
+        for (auto& sp : it->second.spans) { float t = 0; cudaEventElapsedTime(&t, sp.first, sp.second); total += t; }
+        nl = it->second.launches;
+    }
+    if (ms) *ms = total;
+    if (launches) *launches = nl;
+    return MXE_OK;
+}
+
+int mxe_timing_reset(mxe_t* e)
+{
+    if (!e) { set_error("null engine"); return MXE_ERR_ARG; }
+    cudaStreamSynchronize(e->stream);
+    for (auto& kv : e->timers)
+        for (auto& sp : kv.second.spans) { e->event_pool.push_back(sp.first); e->event_pool.push_back(sp.second); }
+    e->timers.clear();
+    return MXE_OK;
+}
+
+uint64_t mxe_kernel_launches(mxe_t* e) { return e ? e->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,114 @@
+// common.cuh -- shared declarations of the B200 minimizer engine (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include <map>
+
+#include "../../include/mxe.h"
+
+namespace mxe {
+
+// ---------------------------------------------------------------- errors
+void set_error(const char* fmt, ...);
+
+#define MXE_CUDA(call)                                                                       \
+    do {                                                                                     \
+        cudaError_t _e = (call);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            ::mxe::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+            return MXE_ERR_CUDA;                                                             \
+        }                                                                                    \
+    } while (0)
+
+#define MXE_TRY(call)                \
+    do {                             \
+        int _r = (call);             \
+        if (_r != MXE_OK) return _r; \
+    } while (0)
+
+// ---------------------------------------------------------------- ntHash constants
+// Base codes used on the device: bits (2,1) of the ASCII byte -> A=0 C=1 T=2 G=3 ; complement = code^2.
+constexpr uint64_t SEED_A = 0x3c8bfbb395c60474ULL;
+constexpr uint64_t SEED_C = 0x3193c18562a02b4cULL;
+constexpr uint64_t SEED_G = 0x20323ed082572324ULL;
+constexpr uint64_t SEED_T = 0x295549f54be24456ULL;
+constexpr uint64_t MULTISEED = 0x90b45d39fb6da1faULL;
+constexpr int MULTISHIFT = 27;
+
+// ---------------------------------------------------------------- engine
+struct PhaseTimer {
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spans;
+    uint64_t launches = 0;
+};
+
+struct Engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    // tunables
+    double tau = 10.0;       // candidate threshold: hash0>>33 <= tau * 2^31 / w
+    int chunk = 256;         // positions per thread in the candidate kernel (multiple of 32)
+    int cand_variant = 1;    // 0 = generic 64-bit, 1 = 31-bit lane prefilter
+    bool timing = false;
+    // accounting
+    uint64_t launches = 0;
+    std::map<std::string, PhaseTimer> timers;
+    std::vector<cudaEvent_t> event_pool;
+
+    cudaEvent_t get_event();
+    void span_begin(const char* name, cudaEvent_t* a);
+    void span_end(const char* name, cudaEvent_t a, uint64_t n_launch);
+};
+
+// RAII span: records CUDA events on the engine stream around a group of launches when timing is on.
+struct Span {
+    Engine* e; const char* name; cudaEvent_t a = nullptr; uint64_t l0;
+    Span(Engine* e_, const char* n) : e(e_), name(n), l0(e_->launches) { if (e->timing) e->span_begin(name, &a); }
+    ~Span() { if (a) e->span_end(name, a, e->launches - l0); }
+};
+
+// stream-ordered device buffer
+template <typename T>
+struct DBuf {
+    T* p = nullptr; size_t n = 0; cudaStream_t s = nullptr;
+    DBuf() {}
+    DBuf(const DBuf&) = delete;
+    DBuf& operator=(const DBuf&) = delete;
+    int alloc(size_t count, cudaStream_t st) {
+        release();
+        s = st; n = count;
+        if (count == 0) count = 1;
+        cudaError_t err = cudaMallocAsync((void**)&p, count * sizeof(T), st);
+        if (err != cudaSuccess) { p = nullptr; set_error("cudaMallocAsync(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(err)); return MXE_ERR_NOMEM; }
+        return MXE_OK;
+    }
+    void release() { if (p) { cudaFreeAsync(p, s); p = nullptr; n = 0; } }
+    T* detach() { T* q = p; p = nullptr; n = 0; return q; }
+    ~DBuf() { release(); }
+};
+
+#define MXE_LAUNCH(eng, kernel, grid, block, smem, ...)                         \
+    do {                                                                        \
+        kernel<<<(grid), (block), (smem), (eng)->stream>>>(__VA_ARGS__);        \
+        (eng)->launches++;                                                      \
+    } while (0)
+
+// ---------------------------------------------------------------- primitives (sort_scan.cu)
+// Exclusive scan of n uint32 counts into uint64 prefixes (out[n] = total).  In-stream.
+int exclusive_scan_u32_u64(Engine* e, const uint32_t* d_in, uint64_t* d_out, size_t n);
+// Stable LSD radix sort of (key u64, value u32) pairs on bits [begin_bit, end_bit).
+// Result lands in d_keys/d_vals; the *_alt buffers are scratch of the same size.
+int radix_sort_pairs(Engine* e, uint64_t* d_keys, uint32_t* d_vals, uint64_t* d_keys_alt, uint32_t* d_vals_alt,
+                     size_t n, int begin_bit, int end_bit);
+
+// Bitmap rank directory: counts per 1024-bit block -> exclusive prefix (n_blocks+1 entries).
+constexpr int RANK_BLOCK_BITS = 1024;
+constexpr int RANK_BLOCK_WORDS = RANK_BLOCK_BITS / 32;
+int bitmap_rank_build(Engine* e, const uint32_t* d_bits, size_t n_words, uint64_t* d_prefix /* n_blocks+1 */);
+// Sorted positions of the set bits (d_out sized from prefix total).
+int bitmap_extract(Engine* e, const uint32_t* d_bits, size_t n_words, const uint64_t* d_prefix, uint64_t* d_out);
+
+}  // namespace mxe

@@ -1,0 +1,295 @@
+// filter.cu -- steps 2-3 on the device.
+//
+// Replaces (reference, Python):
+//   bin/ntjoin_utils.py:182-192  per-assembly uniqueness of out_hash           (read_minimizers)
+//   bin/ntjoin_utils.py:155-162  found-in-all intersection + ordered filtering  (filter_minimizers)
+//   bin/ntjoin_utils.py:94-115   adjacent-pair edge dictionary, support lists   (build_graph)
+//   bin/ntjoin_utils.py:54-56    edge weight = sum of assembly weights          (calc_total_weight)
+//
+// Method: one stable radix sort of all assemblies' out_hash (input concatenated in assembly
+// order, so equal hashes stay grouped by assembly) -> run analysis gives `uniq`, `keep` and a
+// dense vertex id per surviving hash; ordered compaction of survivors -> adjacent pairs ->
+// stable sort by (min id, max id) -> run reduction gives support masks and the first sighting;
+// a last sort by (first sighting of the source, first sighting of the edge) reproduces the
+// insertion order of the reference's dict-of-dicts (formatted_edges, :115).
+#include "engine.cuh"
+
+#include <algorithm>
+
+namespace mxe {
+
+struct AsmOffsets { uint64_t off[33]; int n; double weight[32]; };
+
+__device__ __forceinline__ int asm_of(const AsmOffsets& A, uint64_t idx)
+{
+    int a = 0;
+    while (a + 1 < A.n && idx >= A.off[a + 1]) a++;
+    return a;
+}
+
+__global__ void __launch_bounds__(256) concat_kernel(const uint64_t* __restrict__ src, uint64_t n, uint64_t base,
+                                                      uint64_t* __restrict__ keys, uint32_t* __restrict__ vals)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    keys[base + i] = src[i];
+    vals[base + i] = (uint32_t)(base + i);
+}
+
+__global__ void __launch_bounds__(256) copy_contig_kernel(const uint32_t* __restrict__ src, uint64_t n, uint64_t base, uint32_t* __restrict__ dst)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[base + i] = src[i];
+}
+
+// per sorted element: uniqueness inside its assembly, membership in a found-in-all run, run head
+__global__ void __launch_bounds__(256) mark_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t N,
+                                                    AsmOffsets A, uint8_t* __restrict__ uniq, uint8_t* __restrict__ keep,
+                                                    uint32_t* __restrict__ head)
+{
+    uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= N) return;
+    const uint64_t K = keys[s];
+    const uint32_t idx = vals[s];
+    const int a = asm_of(A, idx);
+    bool prev_same = s > 0 && keys[s - 1] == K && asm_of(A, vals[s - 1]) == a;
+    bool next_same = s + 1 < N && keys[s + 1] == K && asm_of(A, vals[s + 1]) == a;
+    uniq[idx] = !(prev_same || next_same);
+    bool in_all = false;
+    if ((uint64_t)a <= s && s - a + A.n <= N) {
+        uint64_t s0 = s - a;
+        in_all = (s0 == 0 || keys[s0 - 1] != K) && (s0 + A.n == N || keys[s0 + A.n] != K);
+        for (int j = 0; in_all && j < A.n; j++)
+            in_all = keys[s0 + j] == K && asm_of(A, vals[s0 + j]) == j;
+    }
+    keep[idx] = in_all;
+    head[s] = in_all && a == 0;
+}
+
+// vertex ids: heads get consecutive ids in ascending hash order; every member of the run shares it
+__global__ void __launch_bounds__(256) vertex_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t N,
+                                                      AsmOffsets A, const uint8_t* __restrict__ keep, const uint64_t* __restrict__ hprefix,
+                                                      uint32_t* __restrict__ vid, uint64_t* __restrict__ vertices)
+{
+    uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= N) return;
+    const uint32_t idx = vals[s];
+    if (!keep[idx]) return;
+    const int a = asm_of(A, idx);
+    uint32_t id = (uint32_t)hprefix[s - a];
+    vid[idx] = id;
+    if (a == 0) vertices[id] = keys[s];
+}
+
+__global__ void __launch_bounds__(256) widen_flags_kernel(const uint8_t* __restrict__ f, uint64_t N, uint32_t* __restrict__ out)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) out[i] = f[i];
+}
+
+// ordered compaction of survivors
+__global__ void __launch_bounds__(256) compact_kernel(const uint8_t* __restrict__ keep, const uint64_t* __restrict__ kprefix, uint64_t N,
+                                                       const uint32_t* __restrict__ vid, uint32_t* __restrict__ cvid, uint32_t* __restrict__ cidx)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N || !keep[i]) return;
+    uint64_t j = kprefix[i];
+    cvid[j] = vid[i];
+    cidx[j] = (uint32_t)i;
+}
+
+// adjacent survivors of the same record and assembly form an edge sighting
+__global__ void __launch_bounds__(256) pair_flag_kernel(const uint32_t* __restrict__ cidx, uint64_t n_keep, AsmOffsets A,
+                                                         const uint32_t* __restrict__ contig, uint32_t* __restrict__ eflag)
+{
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_keep) return;
+    uint32_t f = 0;
+    if (j + 1 < n_keep) {
+        uint32_t i1 = cidx[j], i2 = cidx[j + 1];
+        f = asm_of(A, i1) == asm_of(A, i2) && contig[i1] == contig[i2];
+    }
+    eflag[j] = f;
+}
+
+__global__ void __launch_bounds__(256) pair_emit_kernel(const uint32_t* __restrict__ cvid, const uint32_t* __restrict__ eflag,
+                                                         const uint64_t* __restrict__ eprefix, uint64_t n_keep,
+                                                         uint64_t* __restrict__ ekey, uint32_t* __restrict__ eval)
+{
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_keep || !eflag[j]) return;
+    uint32_t a = cvid[j], b = cvid[j + 1];
+    uint32_t lo = a < b ? a : b, hi = a < b ? b : a;
+    uint64_t q = eprefix[j];
+    ekey[q] = ((uint64_t)lo << 32) | hi;
+    eval[q] = (uint32_t)j;
+}
+
+__global__ void __launch_bounds__(256) edge_head_kernel(const uint64_t* __restrict__ ekey, uint64_t n_pairs, uint32_t* __restrict__ ehead)
+{
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n_pairs) ehead[r] = r == 0 || ekey[r] != ekey[r - 1];
+}
+
+// one thread per distinct edge: support mask over its run, first sighting, source's first appearance
+__global__ void __launch_bounds__(256) edge_reduce_kernel(const uint64_t* __restrict__ ekey, const uint32_t* __restrict__ eval,
+                                                           const uint32_t* __restrict__ ehead, const uint64_t* __restrict__ uprefix,
+                                                           uint64_t n_pairs, const uint32_t* __restrict__ cidx, const uint32_t* __restrict__ cvid,
+                                                           AsmOffsets A, uint32_t* __restrict__ ue_q0, uint32_t* __restrict__ ue_mask,
+                                                           uint32_t* __restrict__ srcmin)
+{
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_pairs || !ehead[r]) return;
+    const uint64_t K = ekey[r];
+    uint32_t mask = 0;
+    for (uint64_t x = r; x < n_pairs && ekey[x] == K; x++) mask |= 1u << asm_of(A, cidx[eval[x]]);
+    uint32_t q0 = eval[r];               // stable sort => smallest sighting index first
+    uint64_t t = uprefix[r];
+    ue_q0[t] = q0;
+    ue_mask[t] = mask;
+    atomicMin(&srcmin[cvid[q0]], q0);
+}
+
+__global__ void __launch_bounds__(256) edge_order_key_kernel(const uint32_t* __restrict__ ue_q0, uint64_t n_edges, const uint32_t* __restrict__ cvid,
+                                                              const uint32_t* __restrict__ srcmin, uint64_t* __restrict__ okey, uint32_t* __restrict__ oval)
+{
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_edges) return;
+    uint32_t q0 = ue_q0[t];
+    okey[t] = ((uint64_t)srcmin[cvid[q0]] << 32) | q0;
+    oval[t] = (uint32_t)t;
+}
+
+__global__ void __launch_bounds__(256) edge_gather_kernel(const uint32_t* __restrict__ oval, uint64_t n_edges, const uint32_t* __restrict__ ue_q0,
+                                                           const uint32_t* __restrict__ ue_mask, const uint32_t* __restrict__ cvid,
+                                                           const uint64_t* __restrict__ vertices, AsmOffsets A,
+                                                           uint64_t* __restrict__ eu, uint64_t* __restrict__ ev, uint32_t* __restrict__ emask,
+                                                           double* __restrict__ ew)
+{
+    uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n_edges) return;
+    uint32_t t = oval[o];
+    uint32_t q0 = ue_q0[t], mask = ue_mask[t];
+    eu[o] = vertices[cvid[q0]];
+    ev[o] = vertices[cvid[q0 + 1]];
+    emask[o] = mask;
+    double wsum = 0.0;   // Python: sum() starts at int 0 and adds in support-list (= assembly) order
+    for (int a = 0; a < A.n; a++)
+        if (mask & (1u << a)) wsum += A.weight[a];
+    ew[o] = wsum;
+}
+
+static inline unsigned gridf(uint64_t n) { return (unsigned)((n + 255) / 256); }
+static inline int bits_for(uint64_t v) { int b = 1; while (b < 32 && (1ULL << b) <= v) b++; return ((b + 7) / 8) * 8; }
+
+template <typename T>
+static int d2h(std::vector<T>& dst, const T* src, size_t n, cudaStream_t st)
+{
+    dst.resize(n);
+    if (n) MXE_CUDA(cudaMemcpyAsync(dst.data(), src, n * sizeof(T), cudaMemcpyDeviceToHost, st));
+    return MXE_OK;
+}
+
+int filter_and_edges_impl(mxe_engine* e, const uint64_t* const* d_hash, const uint32_t* const* d_contig,
+                          const uint64_t* n, int n_asm, const double* weights, mxe_result* R)
+{
+    if (n_asm < 1 || n_asm > 32) { set_error("n_asm must be 1..32"); return MXE_ERR_ARG; }
+    cudaStream_t st = e->stream;
+    Span whole(e, "filter");
+    AsmOffsets A;
+    A.n = n_asm;
+    A.off[0] = 0;
+    for (int a = 0; a < n_asm; a++) { A.off[a + 1] = A.off[a] + n[a]; A.weight[a] = weights[a]; }
+    const uint64_t N = A.off[n_asm];
+    if (N >= (1ULL << 32)) { set_error("too many minimizers (%llu)", (unsigned long long)N); return MXE_ERR_ARG; }
+    R->eng = e; R->n_asm = n_asm;
+    R->uniq.assign(n_asm, {}); R->keep.assign(n_asm, {});
+    if (N == 0) return MXE_OK;
+
+    DBuf<uint64_t> keys, keys2, hprefix, kprefix, vertices;
+    DBuf<uint32_t> vals, vals2, contig, head, vid, kflag;
+    DBuf<uint8_t> uniq, keep;
+    MXE_TRY(keys.alloc(N, st)); MXE_TRY(keys2.alloc(N, st));
+    MXE_TRY(vals.alloc(N, st)); MXE_TRY(vals2.alloc(N, st));
+    MXE_TRY(contig.alloc(N, st)); MXE_TRY(head.alloc(N, st)); MXE_TRY(vid.alloc(N, st)); MXE_TRY(kflag.alloc(N, st));
+    MXE_TRY(uniq.alloc(N, st)); MXE_TRY(keep.alloc(N, st));
+    MXE_TRY(hprefix.alloc(N + 1, st)); MXE_TRY(kprefix.alloc(N + 1, st));
+    for (int a = 0; a < n_asm; a++) {
+        if (!n[a]) continue;
+        MXE_LAUNCH(e, concat_kernel, gridf(n[a]), 256, 0, d_hash[a], n[a], A.off[a], keys.p, vals.p);
+        MXE_LAUNCH(e, copy_contig_kernel, gridf(n[a]), 256, 0, d_contig[a], n[a], A.off[a], contig.p);
+    }
+    MXE_TRY(radix_sort_pairs(e, keys.p, vals.p, keys2.p, vals2.p, N, 0, 64));
+    MXE_LAUNCH(e, mark_kernel, gridf(N), 256, 0, keys.p, vals.p, N, A, uniq.p, keep.p, head.p);
+    MXE_TRY(exclusive_scan_u32_u64(e, head.p, hprefix.p, N));
+    MXE_LAUNCH(e, widen_flags_kernel, gridf(N), 256, 0, keep.p, N, kflag.p);
+    MXE_TRY(exclusive_scan_u32_u64(e, kflag.p, kprefix.p, N));
+    uint64_t tot[2];
+    MXE_CUDA(cudaMemcpyAsync(&tot[0], hprefix.p + N, 8, cudaMemcpyDeviceToHost, st));
+    MXE_CUDA(cudaMemcpyAsync(&tot[1], kprefix.p + N, 8, cudaMemcpyDeviceToHost, st));
+    MXE_CUDA(cudaStreamSynchronize(st));
+    const uint64_t nV = tot[0], n_keep = tot[1];
+
+    // flags back to the host, split per assembly
+    for (int a = 0; a < n_asm; a++) {
+        MXE_TRY(d2h(R->uniq[a], uniq.p + A.off[a], n[a], st));
+        MXE_TRY(d2h(R->keep[a], keep.p + A.off[a], n[a], st));
+    }
+    if (nV == 0) { MXE_CUDA(cudaStreamSynchronize(st)); return MXE_OK; }
+
+    MXE_TRY(vertices.alloc(nV, st));
+    MXE_LAUNCH(e, vertex_kernel, gridf(N), 256, 0, keys.p, vals.p, N, A, keep.p, hprefix.p, vid.p, vertices.p);
+    MXE_TRY(d2h(R->vertices, vertices.p, nV, st));
+
+    DBuf<uint32_t> cvid, cidx, eflag;
+    DBuf<uint64_t> eprefix;
+    MXE_TRY(cvid.alloc(n_keep + 1, st)); MXE_TRY(cidx.alloc(n_keep + 1, st)); MXE_TRY(eflag.alloc(n_keep, st));
+    MXE_TRY(eprefix.alloc(n_keep + 1, st));
+    MXE_LAUNCH(e, compact_kernel, gridf(N), 256, 0, keep.p, kprefix.p, N, vid.p, cvid.p, cidx.p);
+    MXE_LAUNCH(e, pair_flag_kernel, gridf(n_keep), 256, 0, cidx.p, n_keep, A, contig.p, eflag.p);
+    MXE_TRY(exclusive_scan_u32_u64(e, eflag.p, eprefix.p, n_keep));
+    uint64_t n_pairs = 0;
+    MXE_CUDA(cudaMemcpyAsync(&n_pairs, eprefix.p + n_keep, 8, cudaMemcpyDeviceToHost, st));
+    MXE_CUDA(cudaStreamSynchronize(st));
+    if (n_pairs == 0) return MXE_OK;
+
+    DBuf<uint64_t> ekey, ekey2, uprefix;
+    DBuf<uint32_t> eval, eval2, ehead, srcmin;
+    MXE_TRY(ekey.alloc(n_pairs, st)); MXE_TRY(ekey2.alloc(n_pairs, st));
+    MXE_TRY(eval.alloc(n_pairs, st)); MXE_TRY(eval2.alloc(n_pairs, st));
+    MXE_TRY(ehead.alloc(n_pairs, st)); MXE_TRY(uprefix.alloc(n_pairs + 1, st));
+    MXE_TRY(srcmin.alloc(nV, st));
+    MXE_LAUNCH(e, pair_emit_kernel, gridf(n_keep), 256, 0, cvid.p, eflag.p, eprefix.p, n_keep, ekey.p, eval.p);
+    const int vb = bits_for(nV);
+    MXE_TRY(radix_sort_pairs(e, ekey.p, eval.p, ekey2.p, eval2.p, n_pairs, 0, vb));
+    MXE_TRY(radix_sort_pairs(e, ekey.p, eval.p, ekey2.p, eval2.p, n_pairs, 32, 32 + vb));
+    MXE_LAUNCH(e, edge_head_kernel, gridf(n_pairs), 256, 0, ekey.p, n_pairs, ehead.p);
+    MXE_TRY(exclusive_scan_u32_u64(e, ehead.p, uprefix.p, n_pairs));
+    uint64_t nE = 0;
+    MXE_CUDA(cudaMemcpyAsync(&nE, uprefix.p + n_pairs, 8, cudaMemcpyDeviceToHost, st));
+    MXE_CUDA(cudaMemsetAsync(srcmin.p, 0xFF, nV * sizeof(uint32_t), st));
+    MXE_CUDA(cudaStreamSynchronize(st));
+
+    DBuf<uint32_t> ue_q0, ue_mask, oval, oval2, emask;
+    DBuf<uint64_t> okey, okey2, eu, ev;
+    DBuf<double> ew;
+    MXE_TRY(ue_q0.alloc(nE, st)); MXE_TRY(ue_mask.alloc(nE, st)); MXE_TRY(oval.alloc(nE, st)); MXE_TRY(oval2.alloc(nE, st));
+    MXE_TRY(okey.alloc(nE, st)); MXE_TRY(okey2.alloc(nE, st));
+    MXE_TRY(eu.alloc(nE, st)); MXE_TRY(ev.alloc(nE, st)); MXE_TRY(emask.alloc(nE, st)); MXE_TRY(ew.alloc(nE, st));
+    MXE_LAUNCH(e, edge_reduce_kernel, gridf(n_pairs), 256, 0, ekey.p, eval.p, ehead.p, uprefix.p, n_pairs, cidx.p, cvid.p, A,
+               ue_q0.p, ue_mask.p, srcmin.p);
+    MXE_LAUNCH(e, edge_order_key_kernel, gridf(nE), 256, 0, ue_q0.p, nE, cvid.p, srcmin.p, okey.p, oval.p);
+    const int kb = bits_for(n_keep);
+    MXE_TRY(radix_sort_pairs(e, okey.p, oval.p, okey2.p, oval2.p, nE, 0, kb));
+    MXE_TRY(radix_sort_pairs(e, okey.p, oval.p, okey2.p, oval2.p, nE, 32, 32 + kb));
+    MXE_LAUNCH(e, edge_gather_kernel, gridf(nE), 256, 0, oval.p, nE, ue_q0.p, ue_mask.p, cvid.p, vertices.p, A, eu.p, ev.p, emask.p, ew.p);
+    MXE_TRY(d2h(R->edge_u, eu.p, nE, st));
+    MXE_TRY(d2h(R->edge_v, ev.p, nE, st));
+    MXE_TRY(d2h(R->support, emask.p, nE, st));
+    MXE_TRY(d2h(R->weight, ew.p, nE, st));
+    MXE_CUDA(cudaStreamSynchronize(st));
+    MXE_CUDA(cudaGetLastError());
+    return MXE_OK;
+}
+
+}  // namespace mxe

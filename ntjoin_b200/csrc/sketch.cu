@@ -1,0 +1,184 @@
+// sketch.cu -- host orchestration of step 1 (see sketch_kernels.cuh for the algorithm).
+#include "engine.cuh"
+#include "sketch_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+
+namespace mxe {
+
+static void build_tables(int k, SketchTables* T)
+{
+    const uint64_t seed[4] = {SEED_A, SEED_C, SEED_T, SEED_G};   // device code order A C T G
+    uint32_t shi_rolk[4];
+    for (int c = 0; c < 4; c++) {
+        T->seed[c] = seed[c];
+        uint64_t x = seed[c];
+        for (int i = 0; i < k; i++) x = srol1(x);
+        T->seed_rolk[c] = x;
+        T->shi[c] = (uint32_t)(seed[c] >> 33);
+        shi_rolk[c] = (uint32_t)(x >> 33);
+    }
+    for (int o = 0; o < 4; o++)
+        for (int in = 0; in < 4; in++) {
+            uint2 e;
+            e.x = shi_rolk[o] ^ T->shi[in];             // fwd' = rol(fwd) ^ rol^k(seed[out]) ^ seed[in]
+            e.y = shi_rolk[in ^ 2] ^ T->shi[o ^ 2];     // rev' = ror(rev ^ rol^k(seed[~in]) ^ seed[~out])
+            T->t16[(o << 2) | in] = e;
+        }
+}
+
+static inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
+
+int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const uint64_t* offsets, uint32_t n_contigs,
+                       int k, int w, int flags, mxe_sketch* S)
+{
+    if (k < 1 || k > 1024 || w < 1) { set_error("bad k/w (k=%d w=%d)", k, w); return MXE_ERR_ARG; }
+    if (n_contigs && offsets[0] != 0) { set_error("offsets[0] must be 0"); return MXE_ERR_ARG; }
+    for (uint32_t c = 0; c < n_contigs; c++) {
+        if (offsets[c + 1] < offsets[c]) { set_error("offsets not monotone at %u", c); return MXE_ERR_ARG; }
+        if (offsets[c + 1] - offsets[c] >= (1ULL << 32)) { set_error("record %u longer than 2^32-1 bases", c); return MXE_ERR_ARG; }
+    }
+    if (n_contigs && offsets[n_contigs] != n) { set_error("offsets[n_contigs] != n"); return MXE_ERR_ARG; }
+    if (((uintptr_t)d_seq & 15) != 0) { set_error("device sequence pointer must be 16-byte aligned"); return MXE_ERR_ARG; }
+
+    cudaStream_t st = e->stream;
+    S->eng = e; S->k = k; S->w = w; S->flags = flags;
+    S->n_bases = n; S->n_contigs = n_contigs;
+    S->offsets.assign(offsets, offsets + n_contigs + 1);
+    S->n = 0;
+    if (n == 0 || n_contigs == 0 || n < (uint64_t)k) return MXE_OK;
+
+    Span whole(e, "sketch");
+
+    SketchParams P;
+    P.n = n; P.n_words = (n + 31) / 32; P.k = k; P.w = w;
+    P.canon_min = (flags & MXE_CANON_MIN) ? 1 : 0;
+    {
+        double t = e->tau * 2147483648.0 / (double)w;
+        P.T = t >= 2147483646.0 ? 2147483646u : (uint32_t)t;
+    }
+    P.chunk = std::max(32, (e->chunk / 32) * 32);
+    SketchTables Tb;
+    build_tables(k, &Tb);
+
+    const uint64_t nW = P.n_words;
+    const uint64_t n_vblocks = (nW + RANK_BLOCK_WORDS - 1) / RANK_BLOCK_WORDS;
+    const uint64_t pk_words = 2 * nW + (uint64_t)(k / 16) + 16;
+
+    DBuf<uint32_t> pk, B, V, C, M;
+    DBuf<uint64_t> vprefix, cprefix, mprefix, d_offsets, ostart;
+    MXE_TRY(pk.alloc(pk_words, st));
+    MXE_TRY(B.alloc(nW, st));
+    MXE_TRY(V.alloc(nW, st));
+    MXE_TRY(C.alloc(nW, st));
+    MXE_TRY(M.alloc(nW, st));
+    MXE_TRY(vprefix.alloc(n_vblocks + 1, st));
+    MXE_TRY(cprefix.alloc(n_vblocks + 1, st));
+    MXE_TRY(mprefix.alloc(n_vblocks + 1, st));
+    MXE_TRY(d_offsets.alloc(n_contigs + 1, st));
+    MXE_TRY(ostart.alloc(n_contigs + 1, st));
+    MXE_CUDA(cudaMemcpyAsync(d_offsets.p, offsets, (n_contigs + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    MXE_CUDA(cudaMemsetAsync(pk.p + 2 * nW, 0, (pk_words - 2 * nW) * sizeof(uint32_t), st));
+    MXE_CUDA(cudaMemsetAsync(C.p, 0, nW * sizeof(uint32_t), st));
+    MXE_CUDA(cudaMemsetAsync(M.p, 0, nW * sizeof(uint32_t), st));
+
+    // ---- pack + validity
+    {
+        Span sp(e, "pack");
+        MXE_LAUNCH(e, pack_kernel, grid_for(nW, 256), 256, 0, d_seq, P, pk.p, B.p);
+        MXE_LAUNCH(e, vmask_kernel, grid_for(nW, 256), 256, 0, B.p, P, V.p);
+        if (n_contigs > 1) MXE_LAUNCH(e, boundary_kernel, grid_for(n_contigs - 1, 128), 128, 0, d_offsets.p, n_contigs, P, V.p);
+        MXE_TRY(bitmap_rank_build(e, V.p, nW, vprefix.p));
+        MXE_LAUNCH(e, contig_bounds_kernel, grid_for(n_contigs + 1, 128), 128, 0, d_offsets.p, n_contigs, P, V.p, vprefix.p, ostart.p);
+    }
+
+    // ---- candidates
+    {
+        Span sp(e, "cand");
+        uint64_t n_threads = (n + P.chunk - 1) / P.chunk;
+        bool fast = e->cand_variant >= 1 && (k % 4 == 0) && k >= 4;
+        if (fast) {
+            if (P.canon_min) MXE_LAUNCH(e, cand31_kernel<1>, grid_for(n_threads, 128), 128, 0, pk.p, V.p, P, Tb, C.p);
+            else MXE_LAUNCH(e, cand31_kernel<0>, grid_for(n_threads, 128), 128, 0, pk.p, V.p, P, Tb, C.p);
+        } else {
+            MXE_LAUNCH(e, cand_generic_kernel, grid_for(n_threads, 128), 128, 0, pk.p, V.p, P, Tb, C.p);
+        }
+    }
+    MXE_TRY(bitmap_rank_build(e, C.p, nW, cprefix.p));
+
+    uint64_t totals[2] = {0, 0};
+    MXE_CUDA(cudaMemcpyAsync(&totals[0], vprefix.p + n_vblocks, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    MXE_CUDA(cudaMemcpyAsync(&totals[1], cprefix.p + n_vblocks, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    MXE_CUDA(cudaStreamSynchronize(st));
+    const uint64_t n_valid = totals[0], n_cand = totals[1];
+    S->n_valid = n_valid; S->n_cand = n_cand;
+
+    // ---- candidate evaluation + sparse window selection
+    DBuf<uint64_t> cpos, ch0, cord;
+    DBuf<uint32_t> cctg;
+    DBuf<Gap> gaps;
+    DBuf<unsigned long long> gcount;
+    MXE_TRY(cpos.alloc(n_cand, st));
+    MXE_TRY(ch0.alloc(n_cand, st));
+    MXE_TRY(cord.alloc(n_cand, st));
+    MXE_TRY(cctg.alloc(n_cand, st));
+    MXE_TRY(gcount.alloc(2, st));
+    uint64_t gap_cap = std::max<uint64_t>(65536, n_cand / 8 + n_contigs);
+    unsigned long long gc[2] = {0, 0};
+    {
+        Span sp(e, "select");
+        MXE_TRY(bitmap_extract(e, C.p, nW, cprefix.p, cpos.p));
+        if (n_cand)
+            MXE_LAUNCH(e, cand_eval_kernel, grid_for(n_cand, 256), 256, 0, cpos.p, n_cand, pk.p, V.p, vprefix.p,
+                       d_offsets.p, n_contigs, P, Tb, ch0.p, cord.p, cctg.p);
+        for (int attempt = 0; attempt < 2; attempt++) {
+            MXE_TRY(gaps.alloc(gap_cap, st));
+            MXE_CUDA(cudaMemsetAsync(gcount.p, 0, 2 * sizeof(unsigned long long), st));
+            GapList G{gaps.p, gcount.p, gcount.p + 1, gap_cap};
+            if (n_cand)
+                MXE_LAUNCH(e, select_kernel, grid_for(n_cand, 256), 256, 0, cpos.p, ch0.p, cord.p, cctg.p, n_cand, ostart.p, P, M.p, G);
+            MXE_LAUNCH(e, empty_contig_gap_kernel, grid_for(n_contigs, 128), 128, 0, cpos.p, n_cand, d_offsets.p, n_contigs, ostart.p, P, G);
+            MXE_CUDA(cudaMemcpyAsync(gc, gcount.p, sizeof(gc), cudaMemcpyDeviceToHost, st));
+            MXE_CUDA(cudaStreamSynchronize(st));
+            if (gc[0] <= gap_cap) break;
+            gap_cap = gc[0];   // rerun with exact capacity (M updates are idempotent)
+        }
+    }
+    S->n_gaps = gc[0]; S->n_gap_windows = gc[1];
+
+    // ---- dense gap windows
+    if (gc[0]) {
+        Span sp(e, "gap");
+        unsigned grid = (unsigned)std::min<uint64_t>(gc[0], (uint64_t)e->sm_count * 4);
+        DBuf<uint64_t> sh, sq;
+        uint64_t stride = (uint64_t)GAP_CHUNK + (uint64_t)w;
+        MXE_TRY(sh.alloc(stride * grid, st));
+        MXE_TRY(sq.alloc(stride * grid, st));
+        MXE_LAUNCH(e, gap_kernel, grid, 256, 0, gaps.p, (uint64_t)gc[0], pk.p, V.p, vprefix.p, n_vblocks, P, Tb, sh.p, sq.p, M.p);
+    }
+
+    // ---- ordered emission
+    MXE_TRY(bitmap_rank_build(e, M.p, nW, mprefix.p));
+    uint64_t n_mx = 0;
+    MXE_CUDA(cudaMemcpyAsync(&n_mx, mprefix.p + n_vblocks, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    MXE_CUDA(cudaStreamSynchronize(st));
+    S->n = n_mx;
+    if (n_mx) {
+        Span sp(e, "emit");
+        DBuf<uint64_t> mpos;
+        MXE_TRY(mpos.alloc(n_mx, st));
+        MXE_TRY(bitmap_extract(e, M.p, nW, mprefix.p, mpos.p));
+        MXE_CUDA(cudaMallocAsync((void**)&S->d_out_hash, n_mx * sizeof(uint64_t), st));
+        MXE_CUDA(cudaMallocAsync((void**)&S->d_min_hash, n_mx * sizeof(uint64_t), st));
+        MXE_CUDA(cudaMallocAsync((void**)&S->d_pos, n_mx * sizeof(uint32_t), st));
+        MXE_CUDA(cudaMallocAsync((void**)&S->d_contig, n_mx * sizeof(uint32_t), st));
+        MXE_CUDA(cudaMallocAsync((void**)&S->d_forward, n_mx * sizeof(uint8_t), st));
+        MXE_LAUNCH(e, final_eval_kernel, grid_for(n_mx, 256), 256, 0, mpos.p, n_mx, pk.p, d_offsets.p, n_contigs, P, Tb,
+                   S->d_out_hash, S->d_min_hash, S->d_pos, S->d_contig, S->d_forward);
+    }
+    MXE_CUDA(cudaGetLastError());
+    return MXE_OK;
+}
+
+}  // namespace mxe

@@ -1,0 +1,509 @@
+// sketch_kernels.cuh -- step 1 on the device: ordered ntHash minimizer sketch.
+//
+// Replaces btllib indexlr as invoked at ntJoin:204-205 (algorithm: SURVEY.md Appendix A).
+//
+// Pipeline (all position-indexed bitmaps are 1 bit per base of the concatenated assembly):
+//   pack        ASCII -> 2-bit codes (pk) + bad-byte bitmap B                 [HBM-bound stream]
+//   vmask       V = positions where a valid k-mer starts (no bad byte, no contig boundary inside)
+//   rank(V)     valid-k-mer ordinals (windows are over ordinals)
+//   cand        C = V & { top 31 bits of hash0 <= T }      windowless prefilter [the hot kernel]
+//   extract(C), cand_eval (exact 64-bit hash0, ordinal, contig)
+//   select      sparse sliding-window arg-min over candidates -> minimizer bitmap M ; windows whose
+//               minimum cannot be decided from candidates become "gaps"
+//   gap         dense exact evaluation of gap windows -> M
+//   extract(M), final_eval -> (out_hash, min_hash, pos, contig, forward) sorted by position
+//
+// Why the prefilter is exact: let t(p) = hash0(p) >> 33.  Every window whose candidate arg-min has
+// t <= T has its true arg-min among the candidates (all k-mers with t <= T are candidates); every
+// other window is re-evaluated densely.  Ties on hash0 resolve to the rightmost k-mer (btllib `<=`).
+#pragma once
+#include "common.cuh"
+
+namespace mxe {
+
+struct SketchTables {
+    uint64_t seed[4];      // by device code (A C T G)
+    uint64_t seed_rolk[4]; // srol^k(seed)
+    uint2 t16[16];         // 31-bit lane roll table: idx = out<<2|in -> {fwd term, rev term}
+    uint32_t shi[4];       // seed >> 33 by code
+};
+
+struct SketchParams {
+    uint64_t n;            // bases
+    uint64_t n_words;      // ceil(n/32)
+    int k, w;
+    int canon_min;         // 0 sum, 1 min
+    uint32_t T;            // candidate threshold on hash0>>33
+    int chunk;             // positions per thread in cand kernels
+};
+
+// ---------------------------------------------------------------- bit helpers
+__host__ __device__ __forceinline__ uint64_t srol1(uint64_t x)
+{
+    uint64_t m = ((x & 0x8000000000000000ULL) >> 30) | ((x & 0x100000000ULL) >> 32);
+    return ((x << 1) & 0xFFFFFFFDFFFFFFFFULL) | m;
+}
+__host__ __device__ __forceinline__ uint64_t sror1(uint64_t x)
+{
+    uint64_t m = ((x & 0x200000000ULL) << 30) | ((x & 1ULL) << 32);
+    return ((x >> 1) & 0xFFFFFFFEFFFFFFFFULL) | m;
+}
+__host__ __device__ __forceinline__ uint32_t rol31(uint32_t v) { return ((v << 1) | (v >> 30)) & 0x7FFFFFFFu; }
+__host__ __device__ __forceinline__ uint32_t ror31(uint32_t v) { return (v >> 1) | ((v & 1u) << 30); }
+
+__host__ __device__ __forceinline__ uint64_t mix_out_hash(uint64_t h0, int k)
+{
+    uint64_t t = h0 * (1ULL ^ ((uint64_t)k * MULTISEED));
+    return t ^ (t >> MULTISHIFT);
+}
+
+// pk layout: word q holds positions 16q..16q+15; position i = 4*j + b sits at bit 8*b + 2*j
+// (byte-interleaved so that packing four ASCII words costs two ops per word).
+__device__ __forceinline__ uint32_t pk_code(const uint32_t* __restrict__ pk, uint64_t p)
+{
+    uint32_t wv = pk[p >> 4];
+    uint32_t i = (uint32_t)p & 15u;
+    uint32_t sh = ((i & 3u) << 3) | ((i >> 2) << 1);
+    return (wv >> sh) & 3u;
+}
+
+__device__ __forceinline__ uint64_t sel4(uint32_t c, const uint64_t* s)
+{
+    uint64_t lo = (c & 1u) ? s[1] : s[0];
+    uint64_t hi = (c & 1u) ? s[3] : s[2];
+    return (c & 2u) ? hi : lo;
+}
+
+// exact base hashes of the k-mer at p (all bases assumed valid)
+__device__ __forceinline__ void kmer_hash64(const uint32_t* __restrict__ pk, uint64_t p, int k, const uint64_t* seed,
+                                            uint64_t& fwd, uint64_t& rev)
+{
+    uint64_t f = 0, r = 0;
+    for (int i = 0; i < k; i++) {
+        f = srol1(f) ^ sel4(pk_code(pk, p + i), seed);
+        r = srol1(r) ^ sel4(pk_code(pk, p + k - 1 - i) ^ 2u, seed);
+    }
+    fwd = f;
+    rev = r;
+}
+
+__device__ __forceinline__ uint64_t canon(uint64_t f, uint64_t r, int canon_min)
+{
+    return canon_min ? (r < f ? r : f) : f + r;
+}
+
+// rank of position p in bitmap V (number of set bits strictly before p)
+__device__ __forceinline__ uint64_t bitmap_rank(const uint32_t* __restrict__ bits, const uint64_t* __restrict__ prefix, uint64_t p)
+{
+    uint64_t wi = p >> 5;
+    uint64_t blk = wi / RANK_BLOCK_WORDS;
+    uint64_t r = prefix[blk];
+    for (uint64_t j = blk * RANK_BLOCK_WORDS; j < wi; j++) r += __popc(bits[j]);
+    uint32_t b = (uint32_t)p & 31u;
+    if (b) r += __popc(bits[wi] & ((1u << b) - 1u));
+    return r;
+}
+
+// position of the set bit with rank o (o < total)
+__device__ __forceinline__ uint64_t bitmap_select(const uint32_t* __restrict__ bits, const uint64_t* __restrict__ prefix,
+                                                  uint64_t n_blocks, uint64_t o)
+{
+    uint64_t lo = 0, hi = n_blocks;   // find last blk with prefix[blk] <= o
+    while (hi - lo > 1) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (prefix[mid] <= o) lo = mid; else hi = mid;
+    }
+    uint64_t r = o - prefix[lo];
+    uint64_t wi = lo * RANK_BLOCK_WORDS;
+    for (;;) {
+        uint32_t wv = bits[wi];
+        uint32_t c = __popc(wv);
+        if (r < c) return (wi << 5) + __fns(wv, 0, (int)r + 1);
+        r -= c;
+        wi++;
+    }
+}
+
+// last c with offsets[c] <= p   (offsets has n_contigs+1 entries, offsets[0] == 0)
+__device__ __forceinline__ uint32_t contig_of(const uint64_t* __restrict__ offsets, uint32_t n_contigs, uint64_t p)
+{
+    uint32_t lo = 0, hi = n_contigs;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (offsets[mid] <= p) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// ---------------------------------------------------------------- pack: ASCII -> pk, B
+// One thread per 32 bases.  Valid bytes are ACGTacgt; everything else sets its bit in B.
+// Byte-SIMD validity: x = (byte & 0xDF) ^ 0x41 is one of 00 02 06 15 for A C G T.
+__device__ __forceinline__ uint32_t bad_bytes(uint32_t x)
+{
+    uint32_t m = x & ~(x << 1) & 0x04040404u;          // T pattern: bit2 set, bit1 clear
+    return (x & 0xF9F9F9F9u) ^ (m >> 2) ^ (m << 2);    // non-zero byte <=> invalid base
+}
+
+__global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ seq, SketchParams P,
+                                                   uint32_t* __restrict__ pk, uint32_t* __restrict__ B)
+{
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P.n_words) return;
+    uint64_t p0 = t << 5;
+    uint32_t pkw[2] = {0, 0};
+    uint32_t bad = 0;
+    if (p0 + 32 <= P.n) {
+        const uint4* src = reinterpret_cast<const uint4*>(seq + p0);
+        uint4 a = __ldg(src), b = __ldg(src + 1);
+        uint32_t wv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t anybad = 0;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            uint32_t x0 = (wv[4 * h + 0] & 0xDFDFDFDFu) ^ 0x41414141u;
+            uint32_t x1 = (wv[4 * h + 1] & 0xDFDFDFDFu) ^ 0x41414141u;
+            uint32_t x2 = (wv[4 * h + 2] & 0xDFDFDFDFu) ^ 0x41414141u;
+            uint32_t x3 = (wv[4 * h + 3] & 0xDFDFDFDFu) ^ 0x41414141u;
+            anybad |= bad_bytes(x0) | bad_bytes(x1) | bad_bytes(x2) | bad_bytes(x3);
+            pkw[h] = ((x0 >> 1) & 0x03030303u) | ((x1 << 1) & 0x0C0C0C0Cu) | ((x2 << 3) & 0x30303030u) | ((x3 << 5) & 0xC0C0C0C0u);
+        }
+        if (anybad) {   // rare: exact per-byte mask
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                uint32_t bb = bad_bytes((wv[j] & 0xDFDFDFDFu) ^ 0x41414141u);
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if ((bb >> (8 * q)) & 0xFFu) bad |= 1u << (4 * j + q);
+            }
+        }
+    } else {
+        for (int i = 0; i < 32; i++) {
+            uint64_t p = p0 + i;
+            uint32_t code = 0;
+            bool ok = false;
+            if (p < P.n) {
+                uint32_t x = ((uint32_t)seq[p] & 0xDFu) ^ 0x41u;
+                ok = (x == 0x00u) | (x == 0x02u) | (x == 0x06u) | (x == 0x15u);
+                code = (x >> 1) & 3u;
+            }
+            if (!ok) { bad |= 1u << i; code = 0; }
+            uint32_t ii = i & 15;
+            pkw[i >> 4] |= code << (((ii & 3u) << 3) | ((ii >> 2) << 1));
+        }
+    }
+    reinterpret_cast<uint2*>(pk)[t] = make_uint2(pkw[0], pkw[1]);
+    B[t] = bad;
+}
+
+// ---------------------------------------------------------------- vmask: V = valid k-mer starts
+__global__ void __launch_bounds__(256) vmask_kernel(const uint32_t* __restrict__ B, SketchParams P, uint32_t* __restrict__ V)
+{
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P.n_words) return;
+    const int reach = (31 + P.k - 1) / 32;     // last word touched = t + reach
+    uint32_t any = 0;
+    for (int j = 0; j <= reach; j++) any |= (t + j < P.n_words) ? B[t + j] : 0xFFFFFFFFu;
+    uint32_t v = 0xFFFFFFFFu;
+    if (any) {
+        v = 0;
+        // distance from bit position to the next bad position, scanning right to left
+        long long next_bad = -1;   // absolute bit index (relative to word t) of nearest bad at or after current
+        for (int j = reach; j >= 0; j--) {
+            uint32_t bw = (t + j < P.n_words) ? B[t + j] : 0xFFFFFFFFu;
+            for (int b = 31; b >= 0; b--) {
+                int idx = j * 32 + b;
+                if ((bw >> b) & 1u) next_bad = idx;
+                if (j == 0 && (next_bad < 0 || next_bad >= idx + P.k)) v |= 1u << b;
+            }
+        }
+    }
+    V[t] = v;
+}
+
+// contig boundaries: a k-mer may not straddle two records
+__global__ void boundary_kernel(const uint64_t* __restrict__ offsets, uint32_t n_contigs, SketchParams P, uint32_t* __restrict__ V)
+{
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (c >= n_contigs) return;
+    uint64_t q = offsets[c];
+    if (q == 0 || q >= P.n) return;
+    uint64_t lo = q >= (uint64_t)(P.k - 1) ? q - (P.k - 1) : 0;
+    for (uint64_t p = lo; p < q; p++) atomicAnd(&V[p >> 5], ~(1u << (p & 31)));
+}
+
+// ostart[c] = ordinal of the first valid k-mer at or after offsets[c]  (n_contigs+1 entries)
+__global__ void contig_bounds_kernel(const uint64_t* __restrict__ offsets, uint32_t n_contigs, SketchParams P,
+                                     const uint32_t* __restrict__ V, const uint64_t* __restrict__ vprefix,
+                                     uint64_t* __restrict__ ostart)
+{
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > n_contigs) return;
+    uint64_t q = offsets[c];
+    ostart[c] = q >= P.n ? vprefix[(P.n_words + RANK_BLOCK_WORDS - 1) / RANK_BLOCK_WORDS] : bitmap_rank(V, vprefix, q);
+}
+
+// ---------------------------------------------------------------- cand (generic): exact 64-bit test, any k
+__global__ void __launch_bounds__(128) cand_generic_kernel(const uint32_t* __restrict__ pk, const uint32_t* __restrict__ V,
+                                                            SketchParams P, SketchTables Tb, uint32_t* __restrict__ C)
+{
+    uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t p0 = tid * (uint64_t)P.chunk;
+    if (p0 >= P.n) return;
+    const int k = P.k;
+    uint64_t f, r;
+    kmer_hash64(pk, p0, k, Tb.seed, f, r);
+    const int n_w = P.chunk / 32;
+    for (int wi = 0; wi < n_w; wi++) {
+        uint64_t pw = p0 + (uint64_t)wi * 32;
+        if (pw >= P.n) break;
+        uint32_t bits = 0;
+        for (int b = 0; b < 32; b++) {
+            uint64_t p = pw + b;
+            uint64_t h0 = canon(f, r, P.canon_min);
+            if ((uint32_t)(h0 >> 33) <= P.T) bits |= 1u << b;
+            uint32_t o = pk_code(pk, p), in = pk_code(pk, p + k);
+            f = srol1(f) ^ sel4(o, Tb.seed_rolk) ^ sel4(in, Tb.seed);
+            r = sror1(r ^ sel4(in ^ 2u, Tb.seed_rolk) ^ sel4(o ^ 2u, Tb.seed));
+        }
+        C[pw >> 5] = bits & V[pw >> 5];
+    }
+}
+
+// ---------------------------------------------------------------- cand31: 31-bit lane prefilter, k % 4 == 0
+// Only the upper rotation group (bits 63:33) of fwd and rev is rolled, in 32-bit registers.
+//   sum mode: t = (f31 + r31 + carry) mod 2^31, carry in {0,1}  =>  superset test (f31+r31+1) mod 2^31 <= T+1
+//   min mode: t = min(f31, r31)
+template <int CANON_MIN>
+__global__ void __launch_bounds__(128) cand31_kernel(const uint32_t* __restrict__ pk, const uint32_t* __restrict__ V,
+                                                      SketchParams P, SketchTables Tb, uint32_t* __restrict__ C)
+{
+    __shared__ uint2 tab[16];
+    if (threadIdx.x < 16) tab[threadIdx.x] = Tb.t16[threadIdx.x];
+    __syncthreads();
+    uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t p0 = tid * (uint64_t)P.chunk;
+    if (p0 >= P.n) return;
+    const int k = P.k;
+    // direct 31-bit hash of the first k-mer
+    uint32_t F = 0, R = 0;
+    for (int i = 0; i < k; i++) {
+        uint32_t cf = pk_code(pk, p0 + i), cr = pk_code(pk, p0 + k - 1 - i) ^ 2u;
+        F = rol31(F) ^ Tb.shi[cf];
+        R = rol31(R) ^ Tb.shi[cr];
+    }
+    const uint64_t q0 = p0 >> 4;
+    const int kq = k >> 4, ks = (k & 15) >> 2;
+    const uint32_t lowmask = ks == 1 ? 0x3F3F3F3Fu : ks == 2 ? 0x0F0F0F0Fu : 0x03030303u;
+    const char* tb = reinterpret_cast<const char*>(tab);
+    const uint32_t T1 = CANON_MIN ? P.T : P.T + 1u;
+    const int n_g = P.chunk / 16;
+    uint32_t bits = 0;
+    for (int g = 0; g < n_g; g++) {
+        if (p0 + (uint64_t)g * 16 >= P.n) { if (g & 1) C[(p0 >> 5) + (g >> 1)] = bits & V[(p0 >> 5) + (g >> 1)]; break; }
+        uint32_t o = pk[q0 + g];
+        uint32_t a = pk[q0 + g + kq];
+        uint32_t in = a;
+        if (ks) {
+            uint32_t b2 = pk[q0 + g + kq + 1];
+            in = ((a >> (2 * ks)) & lowmask) | ((b2 << (8 - 2 * ks)) & ~lowmask);
+        }
+        // nibble words: z1 = idx for j=0 (low nibbles) and j=2 (high nibbles); z2 = j=1, j=3
+        uint32_t z1 = ((o << 2) & 0xCCCCCCCCu) | (in & 0x33333333u);
+        uint32_t z2 = (o & 0xCCCCCCCCu) | ((in >> 2) & 0x33333333u);
+        uint32_t gb = 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            uint32_t key;
+            if (CANON_MIN) key = min(F, R);
+            else key = (F + R + 1u) & 0x7FFFFFFFu;
+            if (key <= T1) gb |= 1u << i;
+            const int j = i >> 2, b = i & 3;
+            const uint32_t z = (j & 1) ? z2 : z1;
+            const int off = 8 * b + ((j & 2) ? 4 : 0);
+            uint32_t addr = off >= 3 ? ((z >> (off - 3)) & 0x78u) : ((z << (3 - off)) & 0x78u);
+            uint2 e = *reinterpret_cast<const uint2*>(tb + addr);
+            F = rol31(F) ^ e.x;
+            R = ror31(R ^ e.y);
+        }
+        if (g & 1) {
+            bits |= gb << 16;
+            uint64_t wi = (p0 >> 5) + (g >> 1);
+            C[wi] = bits & V[wi];
+        } else {
+            bits = gb;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- cand_eval
+__global__ void __launch_bounds__(256) cand_eval_kernel(const uint64_t* __restrict__ cpos, uint64_t n_cand,
+                                                         const uint32_t* __restrict__ pk, const uint32_t* __restrict__ V,
+                                                         const uint64_t* __restrict__ vprefix,
+                                                         const uint64_t* __restrict__ offsets, uint32_t n_contigs,
+                                                         SketchParams P, SketchTables Tb,
+                                                         uint64_t* __restrict__ h0, uint64_t* __restrict__ gord, uint32_t* __restrict__ ctg)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cand) return;
+    uint64_t p = cpos[i];
+    uint64_t f, r;
+    kmer_hash64(pk, p, P.k, Tb.seed, f, r);
+    h0[i] = canon(f, r, P.canon_min);
+    gord[i] = bitmap_rank(V, vprefix, p);
+    ctg[i] = contig_of(offsets, n_contigs, p);
+}
+
+// ---------------------------------------------------------------- select
+struct Gap { uint64_t ja, jb; };
+
+struct GapList {
+    Gap* items;
+    unsigned long long* count;      // attempted pushes
+    unsigned long long* windows;    // sum of gap lengths
+    uint64_t capacity;
+};
+
+__device__ __forceinline__ void push_gap(const GapList& G, uint64_t ja, uint64_t jb)
+{
+    unsigned long long slot = atomicAdd(G.count, 1ULL);
+    atomicAdd(G.windows, (unsigned long long)(jb - ja + 1));
+    if (slot < G.capacity) G.items[slot] = Gap{ja, jb};
+}
+
+__global__ void __launch_bounds__(256) select_kernel(const uint64_t* __restrict__ cpos, const uint64_t* __restrict__ h0,
+                                                      const uint64_t* __restrict__ gord, const uint32_t* __restrict__ ctg,
+                                                      uint64_t n_cand, const uint64_t* __restrict__ ostart,
+                                                      SketchParams P, uint32_t* __restrict__ M, GapList G)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cand) return;
+    const uint32_t c = ctg[i];
+    const uint64_t os = ostart[c], oe = ostart[c + 1];
+    const uint64_t w = (uint64_t)P.w;
+    if (oe - os < w) return;                      // record has fewer than w valid k-mers: no window
+    const uint64_t o = gord[i], h = h0[i];
+    const uint64_t jmin = os + w - 1, jmax = oe - 1;
+
+    uint64_t jlo = o > jmin ? o : jmin;
+    uint64_t jhi = o + w - 1 < jmax ? o + w - 1 : jmax;
+    // nearest strictly smaller to the left within the window span
+    for (uint64_t j = i; j-- > 0;) {
+        if (ctg[j] != c || gord[j] + w <= o) break;
+        if (h0[j] < h) { uint64_t b = gord[j] + w; if (b > jlo) jlo = b; break; }
+    }
+    // nearest smaller-or-equal to the right (rightmost wins ties)
+    for (uint64_t j = i + 1; j < n_cand; j++) {
+        if (ctg[j] != c || gord[j] >= o + w) break;
+        if (h0[j] <= h) { uint64_t b = gord[j] - 1; if (b < jhi) jhi = b; break; }
+    }
+    if (jlo <= jhi) {
+        if ((uint32_t)(h >> 33) <= P.T && h != ~0ULL) {
+            uint64_t p = cpos[i];
+            atomicOr(&M[p >> 5], 1u << (p & 31));
+        } else {
+            push_gap(G, jlo, jhi);
+        }
+    }
+    // candidate-free windows to the right of this candidate
+    {
+        bool has_next = (i + 1 < n_cand) && ctg[i + 1] == c;
+        uint64_t ga = o + w > jmin ? o + w : jmin;
+        uint64_t gb = has_next ? gord[i + 1] - 1 : jmax;
+        if (gb > jmax) gb = jmax;
+        if (ga <= gb) push_gap(G, ga, gb);
+    }
+    // ... and to the left of the first candidate of the record
+    if (i == 0 || ctg[i - 1] != c) {
+        if (o > jmin) push_gap(G, jmin, (o - 1 < jmax) ? o - 1 : jmax);
+    }
+}
+
+// records that have windows but no candidate at all
+__global__ void empty_contig_gap_kernel(const uint64_t* __restrict__ cpos, uint64_t n_cand,
+                                        const uint64_t* __restrict__ offsets, uint32_t n_contigs,
+                                        const uint64_t* __restrict__ ostart, SketchParams P, GapList G)
+{
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_contigs) return;
+    uint64_t os = ostart[c], oe = ostart[c + 1];
+    if (oe - os < (uint64_t)P.w) return;
+    uint64_t a = offsets[c], b = offsets[c + 1];
+    uint64_t lo = 0, hi = n_cand;      // lower_bound(cpos, a)
+    while (lo < hi) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (cpos[mid] < a) lo = mid + 1; else hi = mid;
+    }
+    if (lo == n_cand || cpos[lo] >= b) push_gap(G, os + P.w - 1, oe - 1);
+}
+
+// ---------------------------------------------------------------- gap: dense exact windows
+constexpr int GAP_CHUNK = 1024;   // window ends per chunk
+
+__global__ void __launch_bounds__(256) gap_kernel(const Gap* __restrict__ gaps, uint64_t n_gaps,
+                                                   const uint32_t* __restrict__ pk, const uint32_t* __restrict__ V,
+                                                   const uint64_t* __restrict__ vprefix, uint64_t n_vblocks,
+                                                   SketchParams P, SketchTables Tb,
+                                                   uint64_t* __restrict__ scratch_h, uint64_t* __restrict__ scratch_p,
+                                                   uint32_t* __restrict__ M)
+{
+    const uint64_t w = (uint64_t)P.w;
+    const uint64_t stride = (uint64_t)GAP_CHUNK + w;
+    uint64_t* H = scratch_h + (uint64_t)blockIdx.x * stride;
+    uint64_t* Q = scratch_p + (uint64_t)blockIdx.x * stride;
+    for (uint64_t g = blockIdx.x; g < n_gaps; g += gridDim.x) {
+        const uint64_t ja = gaps[g].ja, jb = gaps[g].jb;
+        for (uint64_t ca = ja; ca <= jb; ca += GAP_CHUNK) {
+            uint64_t cb = ca + GAP_CHUNK - 1 < jb ? ca + GAP_CHUNK - 1 : jb;
+            uint64_t o0 = ca - (w - 1);
+            uint64_t m = cb - o0 + 1;
+            __syncthreads();
+            for (uint64_t e = threadIdx.x; e < m; e += blockDim.x) {
+                uint64_t p = bitmap_select(V, vprefix, n_vblocks, o0 + e);
+                uint64_t f, r;
+                kmer_hash64(pk, p, P.k, Tb.seed, f, r);
+                H[e] = canon(f, r, P.canon_min);
+                Q[e] = p;
+            }
+            __syncthreads();
+            for (uint64_t e = threadIdx.x; e < m; e += blockDim.x) {
+                const uint64_t h = H[e];
+                if (h == ~0ULL) continue;
+                uint64_t jlo = e > w - 1 ? e : w - 1;
+                uint64_t jhi = e + w - 1 < m - 1 ? e + w - 1 : m - 1;
+                for (uint64_t d = 1; d < w && d <= e; d++)
+                    if (H[e - d] < h) { uint64_t b = e - d + w; if (b > jlo) jlo = b; break; }
+                if (jlo > jhi) continue;
+                for (uint64_t d = 1; d < w && e + d < m; d++)
+                    if (H[e + d] <= h) { uint64_t b = e + d - 1; if (b < jhi) jhi = b; break; }
+                if (jlo <= jhi) {
+                    uint64_t p = Q[e];
+                    atomicOr(&M[p >> 5], 1u << (p & 31));
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- final_eval
+__global__ void __launch_bounds__(256) final_eval_kernel(const uint64_t* __restrict__ mpos, uint64_t n_mx,
+                                                          const uint32_t* __restrict__ pk,
+                                                          const uint64_t* __restrict__ offsets, uint32_t n_contigs,
+                                                          SketchParams P, SketchTables Tb,
+                                                          uint64_t* __restrict__ out_hash, uint64_t* __restrict__ min_hash,
+                                                          uint32_t* __restrict__ pos, uint32_t* __restrict__ contig,
+                                                          uint8_t* __restrict__ forward)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_mx) return;
+    uint64_t p = mpos[i];
+    uint64_t f, r;
+    kmer_hash64(pk, p, P.k, Tb.seed, f, r);
+    uint64_t h0 = canon(f, r, P.canon_min);
+    uint32_t c = contig_of(offsets, n_contigs, p);
+    out_hash[i] = mix_out_hash(h0, P.k);
+    min_hash[i] = h0;
+    pos[i] = (uint32_t)(p - offsets[c]);
+    contig[i] = c;
+    forward[i] = f <= r;
+}
+
+}  // namespace mxe

@@ -1,0 +1,226 @@
+"""Python face of the engine: thin objects over the C ABI (include/mxe.h).
+
+Reference interfaces mirrored here:
+  Engine.sketch_file      <-> `indexlr --seq --long --pos -k K -w W -t T FASTA` (ntJoin:204-205)
+                              and btllib.Indexlr(path, k, w, ...) (bin/ntjoin_assemble.py:478-481)
+  Engine.filter_and_edges <-> read_minimizers uniqueness + filter_minimizers + build_graph edge stage
+                              (bin/ntjoin_utils.py:167-193, :152-165, :94-115)
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import check, load_library
+
+CANON = {"sum": 0, "min": 1}
+
+
+def _np_view(ptr, n, dtype):
+    if n == 0 or not ptr:
+        return np.empty(0, dtype=dtype)
+    ct = np.ctypeslib.as_ctypes_type(dtype)
+    arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(n,))
+    return arr
+
+
+class Sketch:
+    """Ordered minimizers of one assembly: SoA sorted by (contig, pos), contigs in input order."""
+
+    def __init__(self, engine, handle, names, keepalive=None):
+        self._e, self._h, self.names = engine, handle, list(names)
+        self._keep = keepalive
+        self._views = None
+
+    def _view(self):
+        if self._views is None:
+            lib = self._e._lib
+            n = C.c_uint64()
+            p = [C.c_void_p() for _ in range(5)]
+            check(lib, lib.mxe_sketch_view(self._h, C.byref(n), *[C.byref(x) for x in p]))
+            n = n.value
+            dt = [np.uint64, np.uint64, np.uint32, np.uint32, np.uint8]
+            self._views = tuple(_np_view(x.value, n, d) for x, d in zip(p, dt))
+        return self._views
+
+    out_hash = property(lambda s: s._view()[0])
+    min_hash = property(lambda s: s._view()[1])
+    pos = property(lambda s: s._view()[2])
+    contig = property(lambda s: s._view()[3])
+    forward = property(lambda s: s._view()[4])
+
+    @property
+    def n(self):
+        lib = self._e._lib
+        n = C.c_uint64()
+        check(lib, lib.mxe_sketch_device_view(self._h, C.byref(n), None, None, None))
+        return n.value
+
+    def device_pointers(self):
+        """(n, d_out_hash, d_pos, d_contig) raw device addresses (uint64 / uint32 / uint32 arrays)."""
+        lib = self._e._lib
+        n = C.c_uint64()
+        p = [C.c_void_p() for _ in range(3)]
+        check(lib, lib.mxe_sketch_device_view(self._h, C.byref(n), *[C.byref(x) for x in p]))
+        return (n.value,) + tuple(x.value or 0 for x in p)
+
+    def counts_raw(self):
+        lib = self._e._lib
+        a = [C.c_uint64() for _ in range(4)]
+        c = C.c_uint32()
+        check(lib, lib.mxe_sketch_counts(self._h, *[C.byref(x) for x in a], C.byref(c)))
+        return a[0].value, a[1].value, a[2].value, a[3].value, c.value
+
+    def counts(self):
+        b, v, cd, g, c = self.counts_raw()
+        return {"bases": b, "valid_kmers": v, "candidates": cd, "gap_windows": g, "contigs": c, "minimizers": self.n}
+
+    def write_tsv(self, path, pos=True, strand=False, seq=True):
+        """Write the `indexlr` text format (id \\t hash:pos:seq ...; bin/ntjoin_utils.py:173-185 reads it)."""
+        lib = self._e._lib
+        check(lib, lib.mxe_write_tsv(self._h, str(path).encode(), int(pos), int(strand), int(seq)))
+
+    def per_contig(self):
+        """[(name, out_hash[], pos[]) ...] for every record, in input order (empty arrays allowed)."""
+        oh, ps, cg = self.out_hash, self.pos, self.contig
+        bounds = np.searchsorted(cg, np.arange(len(self.names) + 1))
+        return [(self.names[c], oh[bounds[c]:bounds[c + 1]], ps[bounds[c]:bounds[c + 1]]) for c in range(len(self.names))]
+
+    def close(self):
+        if self._h:
+            self._e._lib.mxe_sketch_free(self._h)
+            self._h = None
+            self._views = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class FilterResult:
+    """Outcome of steps 2-3: per-assembly flags + the weighted edge list (copied to numpy)."""
+
+    def __init__(self, engine, handle, n_asm):
+        lib = engine._lib
+        self.uniq, self.keep = [], []
+        for a in range(n_asm):
+            n = C.c_uint64()
+            u, k = C.c_void_p(), C.c_void_p()
+            check(lib, lib.mxe_result_flags(handle, a, C.byref(n), C.byref(u), C.byref(k)))
+            self.uniq.append(_np_view(u.value, n.value, np.uint8).astype(bool))
+            self.keep.append(_np_view(k.value, n.value, np.uint8).astype(bool))
+        nv, ne = C.c_uint64(), C.c_uint64()
+        p = [C.c_void_p() for _ in range(5)]
+        check(lib, lib.mxe_result_graph(handle, C.byref(nv), C.byref(p[0]), C.byref(ne), *[C.byref(x) for x in p[1:]]))
+        self.vertices = _np_view(p[0].value, nv.value, np.uint64).copy()
+        self.edge_u = _np_view(p[1].value, ne.value, np.uint64).copy()
+        self.edge_v = _np_view(p[2].value, ne.value, np.uint64).copy()
+        self.support = _np_view(p[3].value, ne.value, np.uint32).copy()
+        self.weight = _np_view(p[4].value, ne.value, np.float64).copy()
+        lib.mxe_result_free(handle)
+
+
+class Engine:
+    """One engine per process and GPU (mxe_create)."""
+
+    def __init__(self, device=0, timing=False):
+        self._lib = load_library()
+        h = C.c_void_p()
+        check(self._lib, self._lib.mxe_create(int(device), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+        if timing:
+            self.set_option("timing", 1)
+
+    def set_option(self, name, value):
+        check(self._lib, self._lib.mxe_set_option(self._h, name.encode(), float(value)))
+
+    @staticmethod
+    def _flags(canonical):
+        return CANON[canonical]
+
+    @staticmethod
+    def _names(names, n):
+        if names is None:
+            return None, [str(i) for i in range(n)]
+        arr = (C.c_char_p * n)(*[str(x).encode() for x in names])
+        return arr, [str(x) for x in names]
+
+    def sketch_file(self, path, k, w, canonical="sum"):
+        out = C.c_void_p()
+        check(self._lib, self._lib.mxe_sketch_file(self._h, str(path).encode(), int(k), int(w), self._flags(canonical), C.byref(out)))
+        sk = Sketch(self, out, [])
+        nm = C.c_char_p()
+        n_contigs = sk.counts_raw()[4]
+        for i in range(n_contigs):
+            check(self._lib, self._lib.mxe_sketch_contig_name(out, i, C.byref(nm)))
+            sk.names.append(nm.value.decode("utf-8", "replace"))
+        return sk
+
+    def sketch_buffers(self, seq, offsets, k, w, names=None, canonical="sum"):
+        """seq: host bytes / numpy uint8 / CPU torch uint8 tensor (pinned memory is copied fastest)."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        if hasattr(seq, "data_ptr"):
+            ptr, keep = seq.data_ptr(), seq
+        else:
+            a = np.frombuffer(seq, dtype=np.uint8) if isinstance(seq, (bytes, bytearray, memoryview)) else np.ascontiguousarray(seq, dtype=np.uint8)
+            ptr, keep = a.ctypes.data, a
+        carr, pynames = self._names(names, n)
+        out = C.c_void_p()
+        check(self._lib, self._lib.mxe_sketch_buffers(self._h, C.c_void_p(ptr), offsets.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                                     n, carr, int(k), int(w), self._flags(canonical), C.byref(out)))
+        return Sketch(self, out, pynames, keepalive=keep)
+
+    def sketch_device(self, dptr, offsets, k, w, names=None, canonical="sum"):
+        """dptr: raw device address (e.g. torch_tensor.data_ptr()) of the concatenated ASCII sequence."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        carr, pynames = self._names(names, n)
+        out = C.c_void_p()
+        check(self._lib, self._lib.mxe_sketch_device(self._h, C.c_void_p(int(dptr)), offsets.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                                    n, carr, int(k), int(w), self._flags(canonical), C.byref(out)))
+        return Sketch(self, out, pynames)
+
+    def filter_and_edges(self, sketches, weights):
+        """sketches in assembly order: references (CLI order) then target (bin/ntjoin.py:181-185)."""
+        n = len(sketches)
+        hs = (C.c_void_p * n)(*[s._h for s in sketches])
+        ws = (C.c_double * n)(*[float(x) for x in weights])
+        out = C.c_void_p()
+        check(self._lib, self._lib.mxe_filter_and_edges(self._h, hs, n, ws, C.byref(out)))
+        return FilterResult(self, out, n)
+
+    def filter_and_edges_device(self, d_hash, d_contig, counts, weights):
+        """Raw device arrays per assembly (after a multi-GPU gather): uint64 hashes, uint32 record ids."""
+        n = len(counts)
+        dh = (C.c_void_p * n)(*[int(x) for x in d_hash])
+        dc = (C.c_void_p * n)(*[int(x) for x in d_contig])
+        cn = (C.c_uint64 * n)(*[int(x) for x in counts])
+        ws = (C.c_double * n)(*[float(x) for x in weights])
+        out = C.c_void_p()
+        check(self._lib, self._lib.mxe_filter_and_edges_device(self._h, dh, dc, cn, n, ws, C.byref(out)))
+        return FilterResult(self, out, n)
+
+    def timing(self, name):
+        ms, nl = C.c_double(), C.c_uint64()
+        check(self._lib, self._lib.mxe_timing(self._h, name.encode(), C.byref(ms), C.byref(nl)))
+        return ms.value, nl.value
+
+    def timing_reset(self):
+        check(self._lib, self._lib.mxe_timing_reset(self._h))
+
+    def kernel_launches(self):
+        return int(self._lib.mxe_kernel_launches(self._h))
+
+    def close(self):
+        if self._h:
+            self._lib.mxe_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

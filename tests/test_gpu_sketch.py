@@ -1,0 +1,130 @@
+"""GPU parity: CUDA sketch (through the C ABI) vs the CPU oracle and the reference's golden TSVs."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib
+from ntjoin_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+FIXTURES = ["ref.fa", "ref.multiple.fa", "scaf.f-f.fa", "scaf.f-f.termN.unassigned.fa", "scaf.multiple.fa",
+            "scaf.more_seqs.fa", "scaf.f-f.overlapping.fa", "scaf.r-r.fa"]
+KW = [(32, 1000), (32, 500), (32, 250), (15, 10), (24, 100), (40, 50), (21, 33), (32, 5000), (4, 3)]
+
+
+def assert_same(sk, ref):
+    assert sk.n == len(ref), f"minimizer count {sk.n} != oracle {len(ref)}"
+    np.testing.assert_array_equal(sk.contig, ref["contig"])
+    np.testing.assert_array_equal(sk.pos.astype(np.uint64), ref["pos"])
+    np.testing.assert_array_equal(sk.min_hash, ref["min_hash"])
+    np.testing.assert_array_equal(sk.out_hash, ref["out_hash"])
+    np.testing.assert_array_equal(sk.forward.astype(np.uint32), ref["forward"])
+
+
+@pytest.mark.parametrize("fname", ["ref.fa", "scaf.f-f.fa"])
+def test_golden_tsv_bytes(engine, golden_dir, tmp_path, fname):
+    """tests/expected_outputs/*.k32.w1000.tsv of the reference: byte-equal under canonical=min, --pos."""
+    sk = engine.sketch_file(os.path.join(golden_dir, "inputs", fname), 32, 1000, canonical="min")
+    out = tmp_path / "o.tsv"
+    sk.write_tsv(out, pos=True, strand=False, seq=False)
+    want = open(os.path.join(golden_dir, "expected", fname + ".k32.w1000.tsv"), "rb").read()
+    assert out.read_bytes() == want
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("canonical", ["sum", "min"])
+@pytest.mark.parametrize("fname", FIXTURES)
+def test_fixture_vs_oracle(engine, oracle, golden_dir, fname, canonical, variant):
+    names, seq, offs = oracle_lib.read_fasta(os.path.join(golden_dir, "inputs", fname))
+    engine.set_option("cand_variant", variant)
+    for k, w in KW:
+        ref = oracle.sketch(seq, offs, k, w, canonical=canonical)
+        sk = engine.sketch_buffers(seq, offs, k, w, names=names, canonical=canonical)
+        assert_same(sk, ref)
+    engine.set_option("cand_variant", 1)
+
+
+def _messy(n, seed):
+    """random sequence with N runs, lower-case stretches, IUPAC codes, low-complexity blocks, tiny records"""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    seq = synth.random_bases(n, rng)
+    for _ in range(20):
+        s = int(rng.integers(0, n - 5000)); ln = int(rng.integers(1, 4000))
+        seq[s:s + ln] = ord("N")
+    for _ in range(200):
+        s = int(rng.integers(0, n - 1)); seq[s] = rng.choice(np.frombuffer(b"NnRYKMSWBDHVU-*", dtype=np.uint8))
+    for _ in range(20):
+        s = int(rng.integers(0, n - 5000)); ln = int(rng.integers(1, 4000))
+        seq[s:s + ln] |= 0x20
+    for unit in (b"A", b"AT", b"ACG", b"AAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAC"):
+        s = int(rng.integers(0, n - 20000)); ln = int(rng.integers(3000, 12000))
+        seq[s:s + ln] = np.resize(np.frombuffer(unit, dtype=np.uint8), ln)
+    cuts = np.sort(rng.integers(0, n, size=40))
+    offs = np.unique(np.concatenate([[0], cuts, cuts[:5] + 3, cuts[5:8] + 40, [n]])).astype(np.uint64)
+    offs = offs[offs <= n]
+    offs = np.concatenate([offs[:3], offs[2:3], offs[3:]])   # one empty record
+    return seq, offs
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("canonical", ["sum", "min"])
+def test_messy_synthetic(engine, oracle, canonical, variant):
+    seq, offs = _messy(1_500_000, 7)
+    engine.set_option("cand_variant", variant)
+    for k, w in [(32, 1000), (32, 100), (16, 50), (20, 10), (40, 250), (15, 10), (32, 5000)]:
+        ref = oracle.sketch(seq, offs, k, w, canonical=canonical)
+        sk = engine.sketch_buffers(seq, offs, k, w, canonical=canonical)
+        assert_same(sk, ref)
+    engine.set_option("cand_variant", 1)
+
+
+@pytest.mark.parametrize("tau", [0.5, 3.0, 10.0, 1e9])
+def test_threshold_independence(engine, oracle, tau):
+    """the candidate threshold is a performance knob only: any tau gives the same sketch"""
+    seq, offs = _messy(600_000, 11)
+    ref = oracle.sketch(seq, offs, 32, 500)
+    engine.set_option("tau", tau)
+    try:
+        sk = engine.sketch_buffers(seq, offs, 32, 500)
+        assert_same(sk, ref)
+    finally:
+        engine.set_option("tau", 10.0)
+
+
+def test_config2_scale_down(engine, oracle):
+    """BASELINE config 2 generator at 1/10 scale: reference + derived target, k=32 w=1000"""
+    rseq, roffs, rnames = synth.make_reference(10_000_000, n_chrom=10)
+    tseq, toffs, tnames = synth.derive_target(rseq, roffs)
+    for seq, offs in ((rseq, roffs), (tseq, toffs)):
+        ref = oracle.sketch(seq, offs, 32, 1000, threads=8)
+        sk = engine.sketch_buffers(seq, offs, 32, 1000)
+        assert_same(sk, ref)
+        c = sk.counts()
+        assert c["bases"] == len(seq) and c["minimizers"] == len(ref)
+
+
+def test_edge_cases(engine, oracle):
+    for seq in (b"", b"ACGT", b"A" * 31, b"ACGT" * 8, b"N" * 100, b"ACGT" * 300):
+        offs = np.array([0, len(seq)], dtype=np.uint64)
+        for k, w in [(32, 1000), (32, 1), (4, 2), (8, 1169)]:
+            ref = oracle.sketch(seq, offs, k, w)
+            sk = engine.sketch_buffers(seq, offs, k, w)
+            assert_same(sk, ref)
+    # several empty / short records in a row
+    seq = b"ACGTTGCA" * 50
+    offs = np.array([0, 0, 10, 10, 45, 400, 400], dtype=np.uint64)
+    ref = oracle.sketch(seq, offs, 8, 5)
+    assert_same(engine.sketch_buffers(seq, offs, 8, 5), ref)
+
+
+def test_tsv_with_seq_matches_oracle_cli(engine, golden_dir, tmp_path):
+    """`indexlr --seq --long --pos` text (what bin/ntjoin_utils.py:173-185 parses)"""
+    import subprocess
+    fa = os.path.join(golden_dir, "inputs", "scaf.more_seqs.fa")
+    want = subprocess.check_output([oracle_lib.CLI, "--seq", "--long", "--pos", "-k", "32", "-w", "100", fa])
+    sk = engine.sketch_file(fa, 32, 100)
+    out = tmp_path / "o.tsv"
+    sk.write_tsv(out, pos=True, strand=False, seq=True)
+    assert out.read_bytes() == want
