@@ -1,0 +1,412 @@
+#!/usr/bin/env python3
+"""bench.py -- Gbases/s sketched+filtered at k=32 w=1000 (BASELINE.json metric).
+
+A "step" = one pass of the hot path over the whole workload: ordered minimizer sketch of every
+assembly (reference + target), per-assembly uniqueness, found-in-all intersection and the weighted
+adjacent-minimizer edge list, with the result (flags, vertices, edges) delivered to host memory.
+
+  value  : device-resident inputs (ASCII bases already in HBM), whole-job bases / step time
+  e2e    : same step through the public host API (Engine.sketch_buffers: pinned host buffers,
+           host->device copy inside the timed region, results read back)
+  roofline / cpu_baseline : see DESIGN.md "Measurement"
+
+N>1 (torchrun, one rank per GPU): records are sharded over ranks in contiguous ranges (strong
+scaling, total work fixed); one NCCL all-gather per assembly moves the per-rank minimizer lists
+(full multiset: uniqueness is per assembly, not per GPU) before steps 2-3.
+
+`--impl reference` times the CPU restatement of the reference path (oracle/, all host threads) on
+a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K, W = 32, 1000
+WEIGHTS = [2.0, 1.0]          # reference_weights='2', target_weight=1 (tests/ntjoin_test.py:22)
+GRCH38_MBP = [248, 242, 198, 190, 182, 171, 159, 145, 138, 134, 135, 133, 114, 107, 102, 90, 83, 80, 59, 64, 47, 51, 156, 57]
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=["c2", "c3"],
+                    help="c3: BASELINE configs[2] 3 Gbp target + 3 Gbp reference (default); c2: configs[1] 100 Mbp + 100 Mbp")
+    ap.add_argument("--bases", type=float, default=0, help="override bases per assembly")
+    ap.add_argument("--with-n", action="store_true", help="put 0.5%% of the reference in N runs (default: N-free headline variant)")
+    ap.add_argument("--cpu-sample", type=float, default=0, help="bases per assembly for the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_spec(args):
+    if args.workload == "c2":
+        g, nchr, prop, lo, hi, dup = 100e6, 10, None, 20_000, 2_000_000, 0.0
+        name = "configs[1]: synthetic 100 Mbp target + 100 Mbp reference"
+    else:
+        g, nchr, prop, lo, hi, dup = 3e9, 24, GRCH38_MBP, 50_000, 20_000_000, 0.02
+        name = "configs[2]: synthetic 3 Gbp human-scale target + 1 reference"
+    if args.bases:
+        g = args.bases
+        name += f" (scaled to {g:.3g} bp per assembly)"
+    return dict(G=int(g), n_chrom=nchr, prop=prop, lo=lo, hi=hi, dup=dup, name=name)
+
+
+# ------------------------------------------------------------------------------------ data (GPU)
+def gen_assemblies_gpu(spec, with_n, device):
+    """Reference (i.i.d. ACGT, duplicated 5 kb segments) and a target derived from it (cut into contigs
+    with log-uniform lengths, half reverse-complemented, 0.1 % substitutions, shuffled).  Generated on
+    the device with a fixed seed; identical on every rank."""
+    import torch
+    G = spec["G"]
+    g = torch.Generator(device=device)
+    g.manual_seed(20251017)
+    rng = np.random.Generator(np.random.PCG64(20251017))
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)
+    comp = torch.zeros(256, dtype=torch.uint8, device=device)
+    for a, b in zip(b"ACGTN", b"TGCAN"):
+        comp[a] = b
+    ref = torch.empty(G, dtype=torch.uint8, device=device)
+    step = 1 << 28
+    for s in range(0, G, step):
+        e = min(G, s + step)
+        ref[s:e] = lut[torch.randint(0, 4, (e - s,), dtype=torch.uint8, device=device, generator=g).long()]
+    prop = np.asarray(spec["prop"] or [1.0] * spec["n_chrom"], dtype=np.float64)[:spec["n_chrom"]]
+    lens = np.maximum(1, (prop / prop.sum() * G).astype(np.int64))
+    lens[-1] += G - lens.sum()
+    roffs = np.zeros(len(lens) + 1, dtype=np.uint64)
+    roffs[1:] = np.cumsum(lens)
+    if spec["dup"] > 0:
+        seg = 5000
+        for _ in range(max(1, int(G * spec["dup"] / seg / 6))):
+            s = int(rng.integers(0, G - seg))
+            for _c in range(int(rng.integers(1, 10))):
+                d = int(rng.integers(0, G - seg))
+                ref[d:d + seg] = ref[s:s + seg].clone()
+    if with_n:
+        done, target = 0, int(G * 0.005)
+        while done < target:
+            ln = int(min(target - done + 100, np.exp(rng.uniform(np.log(100), np.log(50000)))))
+            s = int(rng.integers(0, G - ln))
+            ref[s:s + ln] = ord("N")
+            done += ln
+    pieces = []
+    for c in range(len(lens)):
+        at, e = int(roffs[c]), int(roffs[c + 1])
+        while at < e:
+            ln = min(int(np.exp(rng.uniform(np.log(spec["lo"]), np.log(spec["hi"])))), e - at)
+            pieces.append((at, at + ln))
+            at += ln
+    order = rng.permutation(len(pieces))
+    tgt = torch.empty(G, dtype=torch.uint8, device=device)
+    toffs = np.zeros(len(pieces) + 1, dtype=np.uint64)
+    at = 0
+    for i, pi in enumerate(order):
+        a, b = pieces[pi]
+        chunk = ref[a:b]
+        if rng.random() < 0.5:
+            chunk = comp[chunk.flip(0).long()]
+        tgt[at:at + (b - a)] = chunk
+        at += b - a
+        toffs[i + 1] = at
+    n_sub = int(G * 0.001)
+    idx = torch.randint(0, G, (n_sub,), device=device, generator=g)
+    sub = lut[torch.randint(0, 4, (n_sub,), dtype=torch.uint8, device=device, generator=g).long()]
+    keep = tgt[idx] != ord("N")
+    tgt[idx[keep]] = sub[keep]
+    return [(ref, roffs), (tgt, toffs)]     # assembly order: reference(s) first, target last
+
+
+def shard_ranges(assemblies, world):
+    """Contiguous record ranges per rank over the pooled record list (reference records, then target
+    records), balanced by cumulative length.  Returns per rank: [(c0, c1) per assembly]."""
+    lens = np.concatenate([np.diff(o.astype(np.int64)) for _, o in assemblies])
+    cum = np.concatenate([[0], np.cumsum(lens)])
+    total = cum[-1]
+    cuts = [0]
+    for r in range(1, world):
+        cuts.append(int(np.argmin(np.abs(cum - total * r / world))))
+    cuts.append(len(lens))
+    cuts = np.maximum.accumulate(cuts)
+    starts = np.cumsum([0] + [len(o) - 1 for _, o in assemblies])
+    out = []
+    for r in range(world):
+        a0, a1 = cuts[r], cuts[r + 1]
+        per = []
+        for i in range(len(assemblies)):
+            lo, hi = max(a0, starts[i]), min(a1, starts[i + 1])
+            per.append((int(lo - starts[i]), int(max(lo, hi) - starts[i])))
+        out.append(per)
+    return out
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower() == "active"})
+        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_run(spec, args, steps, warmup, sample_bases=None):
+    """The reference path on host cores: oracle sketch (one record per worker thread, like indexlr -t)
+    + oracle steps 2-3, on a bounded sample of the same workload (same generator, smaller G)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    from ntjoin_b200 import synth
+    orc = oracle_lib.Oracle()
+    cores = os.cpu_count() or 1
+    if sample_bases is None:
+        sample_bases = args.cpu_sample or min(spec["G"], 25e6 * cores)   # ~1 s per core-step at ~30 Mbases/s/thread
+    sample_bases = int(sample_bases)
+    n_chrom = max(spec["n_chrom"], cores)         # enough records to keep every thread busy
+    rseq, roffs, _ = synth.make_reference(sample_bases, n_chrom=n_chrom, dup_frac=spec["dup"])
+    tseq, toffs, _ = synth.derive_target(rseq, roffs, min_len=spec["lo"], max_len=min(spec["hi"], max(spec["lo"] * 2, sample_bases // cores)))
+    asms = [(rseq, roffs), (tseq, toffs)]
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        sks = [orc.sketch(s, o, K, W, threads=cores) for s, o in asms]
+        orc.filter_and_edges([m["out_hash"] for m in sks], [m["contig"] for m in sks], WEIGHTS)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    total = 2 * sample_bases
+    sec = float(np.mean(times))
+    return {"value": total / sec / 1e9, "unit": "Gbases/s", "cores": cores, "kind": "port",
+            "sample": f"{sample_bases} bp reference + derived target (same generator as the workload), k={K} w={W}, "
+                      f"{steps} step(s) after {warmup} warm-up, oracle/mxo.c with {cores} threads"}, sec
+
+
+def run_reference_arm(args, spec):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    warm = max(1, min(args.warmup, 1))
+    steps = max(1, min(args.steps, 3))
+    cb, sec = cpu_reference_run(spec, args, steps, warm)
+    line = {"metric": "Gbases/s sketched+filtered at k=32 w=1000", "value": cb["value"], "unit": "Gbases/s", "impl": "reference",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": spec["name"], "k": K, "w": W, "note": "bounded sample on host cores"},
+            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+class _DevArray:
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def main():
+    args = parse_args()
+    spec = workload_spec(args)
+    if args.impl == "reference":
+        run_reference_arm(args, spec)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import ntjoin_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    eng = ntjoin_b200.Engine(local, timing=True)
+    eng.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    assemblies = gen_assemblies_gpu(spec, args.with_n, dev)
+    my = shard_ranges(assemblies, world)[rank]
+    shards = []            # per assembly: (device tensor, local offsets, first global record id)
+    for (seq, offs), (c0, c1) in zip(assemblies, my):
+        lo, hi = int(offs[c0]), int(offs[c1])
+        local_seq = seq[lo:hi].clone() if world > 1 else seq
+        shards.append((local_seq, (offs[c0:c1 + 1] - offs[c0]).astype(np.uint64), c0))
+    del assemblies
+    if world > 1:
+        torch.cuda.empty_cache()
+    my_bases = sum(int(o[-1]) for _, o, _ in shards)
+    total_bases = spec["G"] * 2
+    host = [torch.empty(s.numel(), dtype=torch.uint8).pin_memory() for s, _, _ in shards]
+    for h, (s, _, _) in zip(host, shards):
+        h.copy_(s)
+    torch.cuda.synchronize()
+
+    n_asm = len(shards)
+    stats = {}
+
+    def gather_and_filter(sks):
+        if world == 1:
+            res = eng.filter_and_edges(sks, WEIGHTS)
+            return res
+        d_hash, d_contig, counts, keep = [], [], [], []
+        for sk, (_, _, c0) in zip(sks, shards):
+            n, ph, _pp, pc = sk.device_pointers()
+            cnt = torch.tensor([n], dtype=torch.int64, device=dev)
+            allc = torch.empty(world, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(allc, cnt)
+            allc = allc.cpu().numpy()
+            mx = int(allc.max())
+            hbuf = torch.zeros(mx, dtype=torch.int64, device=dev)
+            cbuf = torch.zeros(mx, dtype=torch.int32, device=dev)
+            if n:
+                hbuf[:n] = torch.as_tensor(_DevArray(ph, n, "<i8"), device=dev)
+                cbuf[:n] = torch.as_tensor(_DevArray(pc, n, "<i4"), device=dev) + c0
+            gh = torch.empty(world * mx, dtype=torch.int64, device=dev)
+            gc = torch.empty(world * mx, dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(gh, hbuf)       # full multiset: uniqueness is per assembly, not per GPU
+            dist.all_gather_into_tensor(gc, cbuf)
+            hh = torch.cat([gh[r * mx:r * mx + int(allc[r])] for r in range(world)])
+            cc = torch.cat([gc[r * mx:r * mx + int(allc[r])] for r in range(world)])
+            keep += [hh, cc]
+            d_hash.append(hh.data_ptr()); d_contig.append(cc.data_ptr()); counts.append(hh.numel())
+        torch.cuda.current_stream().synchronize()
+        return eng.filter_and_edges_device(d_hash, d_contig, counts, WEIGHTS)
+
+    def step_device():
+        sks = [eng.sketch_device(s.data_ptr(), o, K, W) for s, o, _ in shards]
+        res = gather_and_filter(sks)
+        stats["n_mx"] = [sk.n for sk in sks]
+        stats["edges"] = len(res.edge_u)
+        stats["vertices"] = len(res.vertices)
+        stats["d2h"] = sum(len(u) * 2 for u in res.uniq) + len(res.vertices) * 8 + len(res.edge_u) * 28
+        for sk in sks:
+            sk.close()
+        return res
+
+    def step_e2e():
+        sks = [eng.sketch_buffers(h, o, K, W) for h, (_, o, _) in zip(host, shards)]
+        res = gather_and_filter(sks)
+        for sk in sks:
+            sk.close()
+        return res
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        dev_ms = ev0.elapsed_time(ev1)
+        t = torch.tensor([max(wall, dev_ms / 1e3)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(args.warmup):
+        step_device()
+    eng.timing_reset()
+    l0 = eng.kernel_launches()
+    sampler = ClockSampler(local)
+    sampler.start()
+    sec = timed(step_device, args.steps)
+    clocks = sampler.stop()
+    launches = eng.kernel_launches() - l0
+    t_cand, n_cand = eng.timing("cand")
+    t_pack, n_pack = eng.timing("pack")
+    t_sketch, _ = eng.timing("sketch")
+    t_filter, _ = eng.timing("filter")
+
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    sec_e2e = timed(step_e2e, args.steps)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak = peaks.get("hbm_gbs", 6650.0)
+        # algorithmic bytes of the sketch: 1 B per base read + 16 B per emitted minimizer
+        n_mx_local = sum(stats["n_mx"])
+        algo_bytes_per_launch = (my_bases + 16.0 * n_mx_local) / n_asm
+        cand_ms = t_cand / max(1, n_cand)
+        achieved = algo_bytes_per_launch / (cand_ms * 1e-3) / 1e9 if cand_ms > 0 else 0.0
+        value = total_bases * args.steps / sec / 1e9
+        line = {
+            "metric": "Gbases/s sketched+filtered at k=32 w=1000", "value": value, "unit": "Gbases/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": spec["name"], "k": K, "w": W, "bases_per_step": total_bases, "n_free": not args.with_n,
+                       "l2": "inputs larger than L2 (>= 200 MB per assembly)", "sharding": f"contiguous record ranges over {world} rank(s)",
+                       "minimizers": stats["n_mx"], "vertices": stats["vertices"], "edges": stats["edges"]},
+            "e2e": {"value": total_bases * args.steps / sec_e2e / 1e9, "unit": "Gbases/s", "ms_per_step": sec_e2e / args.steps * 1e3,
+                    "h2d_bytes_per_step": my_bases, "d2h_bytes_per_step": stats["d2h"]},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "cand31_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak if peak else None, "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                         "launch_ms": cand_ms, "algorithmic_bytes_per_launch": algo_bytes_per_launch,
+                         "phase_ms_per_step": {"pack": t_pack / args.steps, "cand": t_cand / args.steps,
+                                               "sketch_total": t_sketch / args.steps, "filter": t_filter / args.steps}},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline:
+            cb, _ = cpu_reference_run(spec, args, 1, 1)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -55,6 +55,10 @@ const char* mxe_last_error(void);
 int  mxe_create(int device, mxe_t** out);
 void mxe_destroy(mxe_t* e);
 
+/* Run all engine work on a caller-owned stream (cudaStream_t passed as a pointer-sized integer),
+ * e.g. torch.cuda.current_stream().cuda_stream.  NULL restores the engine's own stream. */
+int  mxe_set_stream(mxe_t* e, void* cuda_stream);
+
 /* Tunables (name = "tau" candidate threshold multiplier, "chunk" positions per thread, ...). */
 int  mxe_set_option(mxe_t* e, const char* name, double value);
 

@@ -81,7 +81,8 @@ int mxe_create(int device, mxe_t** out)
     MXE_CUDA(cudaSetDevice(device));
     mxe_engine* e = new mxe_engine();
     e->device = device;
-    MXE_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    MXE_CUDA(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+    e->stream = e->own_stream;
     cudaDeviceProp prop;
     MXE_CUDA(cudaGetDeviceProperties(&prop, device));
     e->sm_count = prop.multiProcessorCount;
@@ -105,8 +106,16 @@ void mxe_destroy(mxe_t* e)
         for (auto& sp : kv.second.spans) { cudaEventDestroy(sp.first); cudaEventDestroy(sp.second); }
     for (auto ev : e->event_pool) cudaEventDestroy(ev);
     for (auto& p : e->pinned_free) cudaFreeHost(p.p);
-    cudaStreamDestroy(e->stream);
+    cudaStreamDestroy(e->own_stream);
     delete e;
+}
+
+int mxe_set_stream(mxe_t* e, void* cuda_stream)
+{
+    if (!e) { set_error("null engine"); return MXE_ERR_ARG; }
+    cudaStreamSynchronize(e->stream);
+    e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+    return MXE_OK;
 }
 
 int mxe_set_option(mxe_t* e, const char* name, double value)

@@ -46,7 +46,8 @@ struct PhaseTimer {
 
 struct Engine {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      // stream all work is issued on
+    cudaStream_t own_stream = nullptr;  // engine-owned default
     int sm_count = 148;
     // tunables
     double tau = 10.0;       // candidate threshold: hash0>>33 <= tau * 2^31 / w

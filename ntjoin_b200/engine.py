@@ -7,6 +7,7 @@ Reference interfaces mirrored here:
                               (bin/ntjoin_utils.py:167-193, :152-165, :94-115)
 """
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -30,6 +31,7 @@ class Sketch:
         self._e, self._h, self.names = engine, handle, list(names)
         self._keep = keepalive
         self._views = None
+        engine._live.add(self)
 
     def _view(self):
         if self._views is None:
@@ -39,7 +41,7 @@ class Sketch:
             check(lib, lib.mxe_sketch_view(self._h, C.byref(n), *[C.byref(x) for x in p]))
             n = n.value
             dt = [np.uint64, np.uint64, np.uint32, np.uint32, np.uint8]
-            self._views = tuple(_np_view(x.value, n, d) for x, d in zip(p, dt))
+            self._views = tuple(_np_view(x.value, n, d).copy() for x, d in zip(p, dt))
         return self._views
 
     out_hash = property(lambda s: s._view()[0])
@@ -89,7 +91,6 @@ class Sketch:
         if self._h:
             self._e._lib.mxe_sketch_free(self._h)
             self._h = None
-            self._views = None
 
     def __del__(self):
         try:
@@ -129,9 +130,14 @@ class Engine:
         h = C.c_void_p()
         check(self._lib, self._lib.mxe_create(int(device), C.byref(h)))
         self._h = h
+        self._live = weakref.WeakSet()
         self.device = int(device)
         if timing:
             self.set_option("timing", 1)
+
+    def set_stream(self, cuda_stream):
+        """Issue all engine work on `cuda_stream` (int handle, e.g. torch.cuda.current_stream().cuda_stream)."""
+        check(self._lib, self._lib.mxe_set_stream(self._h, C.c_void_p(int(cuda_stream) if cuda_stream else None)))
 
     def set_option(self, name, value):
         check(self._lib, self._lib.mxe_set_option(self._h, name.encode(), float(value)))
@@ -216,6 +222,8 @@ class Engine:
 
     def close(self):
         if self._h:
+            for sk in list(self._live):   # sketches hold engine-owned memory: release them first
+                sk.close()
             self._lib.mxe_destroy(self._h)
             self._h = None
 

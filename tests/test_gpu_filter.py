@@ -60,4 +60,4 @@ def test_synthetic_vs_oracle(engine, oracle):
     np.testing.assert_array_equal(res.support, want["edges"]["support_mask"])
     np.testing.assert_array_equal(res.weight, want["edges"]["weight"])
     assert len(res.vertices) > 10000 and len(res.edge_u) > 10000
-    assert set(np.unique(res.support)) >= {1, 7}
+    assert 7 in set(np.unique(res.support)) and len(set(np.unique(res.support))) >= 2
