@@ -128,29 +128,6 @@ def gen_assemblies_gpu(spec, with_n, device):
     return [(ref, roffs), (tgt, toffs)]     # assembly order: reference(s) first, target last
 
 
-def shard_ranges(assemblies, world):
-    """Contiguous record ranges per rank over the pooled record list (reference records, then target
-    records), balanced by cumulative length.  Returns per rank: [(c0, c1) per assembly]."""
-    lens = np.concatenate([np.diff(o.astype(np.int64)) for _, o in assemblies])
-    cum = np.concatenate([[0], np.cumsum(lens)])
-    total = cum[-1]
-    cuts = [0]
-    for r in range(1, world):
-        cuts.append(int(np.argmin(np.abs(cum - total * r / world))))
-    cuts.append(len(lens))
-    cuts = np.maximum.accumulate(cuts)
-    starts = np.cumsum([0] + [len(o) - 1 for _, o in assemblies])
-    out = []
-    for r in range(world):
-        a0, a1 = cuts[r], cuts[r + 1]
-        per = []
-        for i in range(len(assemblies)):
-            lo, hi = max(a0, starts[i]), min(a1, starts[i + 1])
-            per.append((int(lo - starts[i]), int(max(lo, hi) - starts[i])))
-        out.append(per)
-    return out
-
-
 # ------------------------------------------------------------------------------------ clocks
 class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -234,11 +211,6 @@ def run_reference_arm(args, spec):
 
 
 # ------------------------------------------------------------------------------------ GPU arm
-class _DevArray:
-    def __init__(self, ptr, n, typestr):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
-
-
 def main():
     args = parse_args()
     spec = workload_spec(args)
@@ -249,6 +221,7 @@ def main():
     import torch
     import torch.distributed as dist
     import ntjoin_b200
+    from ntjoin_b200.dist import DeviceArray, all_gather_minimizers, shard_ranges
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -263,7 +236,7 @@ def main():
     eng.set_stream(torch.cuda.current_stream().cuda_stream)
 
     assemblies = gen_assemblies_gpu(spec, args.with_n, dev)
-    my = shard_ranges(assemblies, world)[rank]
+    my = shard_ranges([o for _, o in assemblies], world)[rank]
     shards = []            # per assembly: (device tensor, local offsets, first global record id)
     for (seq, offs), (c0, c1) in zip(assemblies, my):
         lo, hi = int(offs[c0]), int(offs[c1])
@@ -289,22 +262,9 @@ def main():
         d_hash, d_contig, counts, keep = [], [], [], []
         for sk, (_, _, c0) in zip(sks, shards):
             n, ph, _pp, pc = sk.device_pointers()
-            cnt = torch.tensor([n], dtype=torch.int64, device=dev)
-            allc = torch.empty(world, dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(allc, cnt)
-            allc = allc.cpu().numpy()
-            mx = int(allc.max())
-            hbuf = torch.zeros(mx, dtype=torch.int64, device=dev)
-            cbuf = torch.zeros(mx, dtype=torch.int32, device=dev)
-            if n:
-                hbuf[:n] = torch.as_tensor(_DevArray(ph, n, "<i8"), device=dev)
-                cbuf[:n] = torch.as_tensor(_DevArray(pc, n, "<i4"), device=dev) + c0
-            gh = torch.empty(world * mx, dtype=torch.int64, device=dev)
-            gc = torch.empty(world * mx, dtype=torch.int32, device=dev)
-            dist.all_gather_into_tensor(gh, hbuf)       # full multiset: uniqueness is per assembly, not per GPU
-            dist.all_gather_into_tensor(gc, cbuf)
-            hh = torch.cat([gh[r * mx:r * mx + int(allc[r])] for r in range(world)])
-            cc = torch.cat([gc[r * mx:r * mx + int(allc[r])] for r in range(world)])
+            hl = torch.as_tensor(DeviceArray(ph, n, "<i8"), device=dev) if n else torch.empty(0, dtype=torch.int64, device=dev)
+            cl = torch.as_tensor(DeviceArray(pc, n, "<i4"), device=dev) if n else torch.empty(0, dtype=torch.int32, device=dev)
+            hh, cc = all_gather_minimizers(hl, cl, c0)     # one exchange per assembly (NCCL over NVLink)
             keep += [hh, cc]
             d_hash.append(hh.data_ptr()); d_contig.append(cc.data_ptr()); counts.append(hh.numel())
         torch.cuda.current_stream().synchronize()
@@ -313,20 +273,21 @@ def main():
     def step_device():
         sks = [eng.sketch_device(s.data_ptr(), o, K, W) for s, o, _ in shards]
         res = gather_and_filter(sks)
+        n_tot, n_v, n_e = res.counts()        # result stays resident in HBM; sizes only
         stats["n_mx"] = [sk.n for sk in sks]
-        stats["edges"] = len(res.edge_u)
-        stats["vertices"] = len(res.vertices)
-        stats["d2h"] = sum(len(u) * 2 for u in res.uniq) + len(res.vertices) * 8 + len(res.edge_u) * 28
+        stats["edges"], stats["vertices"] = n_e, n_v
+        stats["d2h"] = n_tot * 2 + n_v * 8 + n_e * 28
         for sk in sks:
             sk.close()
-        return res
+        res.close()
 
     def step_e2e():
         sks = [eng.sketch_buffers(h, o, K, W) for h, (_, o, _) in zip(host, shards)]
         res = gather_and_filter(sks)
+        res.fetch()                           # flags + vertices + weighted edge list into host memory
         for sk in sks:
             sk.close()
-        return res
+        res.close()
 
     def barrier():
         if world > 1:
@@ -362,6 +323,7 @@ def main():
     t_pack, n_pack = eng.timing("pack")
     t_sketch, _ = eng.timing("sketch")
     t_filter, _ = eng.timing("filter")
+    phases = {nm: eng.timing(nm)[0] / args.steps for nm in ("pack", "rank", "cand", "eval", "select", "gap", "emit", "sketch", "filter")}
 
     for _ in range(min(args.warmup, 2)):
         step_e2e()
@@ -394,8 +356,7 @@ def main():
                          "frac": achieved / peak if peak else None, "traffic": None,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                          "launch_ms": cand_ms, "algorithmic_bytes_per_launch": algo_bytes_per_launch,
-                         "phase_ms_per_step": {"pack": t_pack / args.steps, "cand": t_cand / args.steps,
-                                               "sketch_total": t_sketch / args.steps, "filter": t_filter / args.steps}},
+                         "phase_ms_per_step": phases},
             "clocks": clocks,
         }
         if not args.no_cpu_baseline:

@@ -116,6 +116,9 @@ int mxe_filter_and_edges_device(mxe_t* e, const void* const* d_hash, const void*
                                 const uint64_t* n, int n_asm, const double* weights,
                                 mxe_result_t** out);
 
+/* Sizes only (no device->host copy of the arrays). */
+int mxe_result_counts(mxe_result_t* r, uint64_t* n_minimizers, uint64_t* n_vertices, uint64_t* n_edges);
+
 /* Per assembly: flags over its minimizers in sketch order.
  * uniq[i]=1: out_hash occurs once in the assembly (survives read_minimizers);
  * keep[i]=1: additionally found (unique) in every assembly (survives filter_minimizers). */

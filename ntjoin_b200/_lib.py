@@ -10,7 +10,7 @@ SYMBOLS = [
     "mxe_version", "mxe_last_error", "mxe_create", "mxe_destroy", "mxe_set_stream", "mxe_set_option",
     "mxe_sketch_file", "mxe_sketch_buffers", "mxe_sketch_device", "mxe_sketch_view",
     "mxe_sketch_device_view", "mxe_sketch_contig_name", "mxe_sketch_counts", "mxe_write_tsv", "mxe_sketch_free",
-    "mxe_filter_and_edges", "mxe_filter_and_edges_device", "mxe_result_flags", "mxe_result_graph",
+    "mxe_filter_and_edges", "mxe_filter_and_edges_device", "mxe_result_counts", "mxe_result_flags", "mxe_result_graph",
     "mxe_result_free", "mxe_timing", "mxe_timing_reset", "mxe_kernel_launches",
 ]
 
@@ -58,6 +58,7 @@ def load_library():
     lib.mxe_sketch_free.restype = None
     lib.mxe_filter_and_edges.argtypes = [vp, pp, C.c_int, C.POINTER(C.c_double), pp]
     lib.mxe_filter_and_edges_device.argtypes = [vp, pp, pp, u64p, C.c_int, C.POINTER(C.c_double), pp]
+    lib.mxe_result_counts.argtypes = [vp, u64p, u64p, u64p]
     lib.mxe_result_flags.argtypes = [vp, C.c_int, u64p, pp, pp]
     lib.mxe_result_graph.argtypes = [vp, u64p, pp, u64p, pp, pp, pp, pp]
     lib.mxe_result_free.argtypes = [vp]

@@ -385,7 +385,7 @@ int mxe_filter_and_edges_device(mxe_t* e, const void* const* d_hash, const void*
     MXE_CUDA(cudaSetDevice(e->device));
     mxe_result* R = new mxe_result();
     int rc = filter_and_edges_impl(e, (const uint64_t* const*)d_hash, (const uint32_t* const*)d_contig, n, n_asm, weights, R);
-    if (rc != MXE_OK) { delete R; return rc; }
+    if (rc != MXE_OK) { mxe_result_free(R); return rc; }
     *out = R;
     return MXE_OK;
 }
@@ -402,12 +402,56 @@ int mxe_filter_and_edges(mxe_t* e, mxe_sketch_t* const* sketches, int n_asm, con
     return mxe_filter_and_edges_device(e, dh, dc, n, n_asm, weights, out);
 }
 
+static int result_ensure_host(mxe_result* R)
+{
+    if (R->h_block) return MXE_OK;
+    mxe_engine* e = R->eng;
+    MXE_CUDA(cudaSetDevice(e->device));
+    size_t bytes = 2 * R->N + 8 * R->nV + R->nE * (8 + 8 + 4 + 8) + 256;
+    char* blk = (char*)e->pinned_alloc(bytes);
+    if (!blk) { set_error("pinned host allocation of %zu bytes failed", bytes); return MXE_ERR_NOMEM; }
+    R->h_block = blk; R->h_bytes = bytes;
+    char* p = blk;
+    R->h_vertices = (uint64_t*)p; p += 8 * R->nV;
+    R->h_eu = (uint64_t*)p; p += 8 * R->nE;
+    R->h_ev = (uint64_t*)p; p += 8 * R->nE;
+    R->h_ew = (double*)p; p += 8 * R->nE;
+    R->h_emask = (uint32_t*)p; p += 4 * R->nE;
+    R->h_uniq = (uint8_t*)p; p += R->N;
+    R->h_keep = (uint8_t*)p;
+    cudaStream_t st = e->stream;
+    if (R->N && R->d_uniq) {
+        MXE_CUDA(cudaMemcpyAsync(R->h_uniq, R->d_uniq, R->N, cudaMemcpyDeviceToHost, st));
+        MXE_CUDA(cudaMemcpyAsync(R->h_keep, R->d_keep, R->N, cudaMemcpyDeviceToHost, st));
+    }
+    if (R->nV) MXE_CUDA(cudaMemcpyAsync(R->h_vertices, R->d_vertices, 8 * R->nV, cudaMemcpyDeviceToHost, st));
+    if (R->nE) {
+        MXE_CUDA(cudaMemcpyAsync(R->h_eu, R->d_eu, 8 * R->nE, cudaMemcpyDeviceToHost, st));
+        MXE_CUDA(cudaMemcpyAsync(R->h_ev, R->d_ev, 8 * R->nE, cudaMemcpyDeviceToHost, st));
+        MXE_CUDA(cudaMemcpyAsync(R->h_ew, R->d_ew, 8 * R->nE, cudaMemcpyDeviceToHost, st));
+        MXE_CUDA(cudaMemcpyAsync(R->h_emask, R->d_emask, 4 * R->nE, cudaMemcpyDeviceToHost, st));
+    }
+    MXE_CUDA(cudaStreamSynchronize(st));
+    return MXE_OK;
+}
+
+int mxe_result_counts(mxe_result_t* r, uint64_t* n_minimizers, uint64_t* n_vertices, uint64_t* n_edges)
+{
+    if (!r) { set_error("null result"); return MXE_ERR_ARG; }
+    if (r->eng) MXE_CUDA(cudaStreamSynchronize(r->eng->stream));
+    if (n_minimizers) *n_minimizers = r->N;
+    if (n_vertices) *n_vertices = r->nV;
+    if (n_edges) *n_edges = r->nE;
+    return MXE_OK;
+}
+
 int mxe_result_flags(mxe_result_t* r, int a, uint64_t* n, const uint8_t** uniq, const uint8_t** keep)
 {
     if (!r || a < 0 || a >= r->n_asm) { set_error("bad assembly index"); return MXE_ERR_ARG; }
-    if (n) *n = r->uniq[a].size();
-    if (uniq) *uniq = r->uniq[a].data();
-    if (keep) *keep = r->keep[a].data();
+    MXE_TRY(result_ensure_host(r));
+    if (n) *n = r->asm_off[a + 1] - r->asm_off[a];
+    if (uniq) *uniq = r->h_uniq + r->asm_off[a];
+    if (keep) *keep = r->h_keep + r->asm_off[a];
     return MXE_OK;
 }
 
@@ -415,17 +459,29 @@ int mxe_result_graph(mxe_result_t* r, uint64_t* n_vertices, const uint64_t** ver
                      const uint64_t** edge_u, const uint64_t** edge_v, const uint32_t** support_mask, const double** weight)
 {
     if (!r) { set_error("null result"); return MXE_ERR_ARG; }
-    if (n_vertices) *n_vertices = r->vertices.size();
-    if (vertices) *vertices = r->vertices.data();
-    if (n_edges) *n_edges = r->edge_u.size();
-    if (edge_u) *edge_u = r->edge_u.data();
-    if (edge_v) *edge_v = r->edge_v.data();
-    if (support_mask) *support_mask = r->support.data();
-    if (weight) *weight = r->weight.data();
+    MXE_TRY(result_ensure_host(r));
+    if (n_vertices) *n_vertices = r->nV;
+    if (vertices) *vertices = r->h_vertices;
+    if (n_edges) *n_edges = r->nE;
+    if (edge_u) *edge_u = r->h_eu;
+    if (edge_v) *edge_v = r->h_ev;
+    if (support_mask) *support_mask = r->h_emask;
+    if (weight) *weight = r->h_ew;
     return MXE_OK;
 }
 
-void mxe_result_free(mxe_result_t* r) { delete r; }
+void mxe_result_free(mxe_result_t* r)
+{
+    if (!r) return;
+    if (r->eng) {
+        cudaSetDevice(r->eng->device);
+        cudaStream_t st = r->eng->stream;
+        void* ptrs[] = {r->d_uniq, r->d_keep, r->d_vertices, r->d_eu, r->d_ev, r->d_emask, r->d_ew};
+        for (void* p : ptrs) if (p) cudaFreeAsync(p, st);
+        r->eng->pinned_release(r->h_block, r->h_bytes);
+    }
+    delete r;
+}
 
 // ------------------------------------------------------------------ measurement
 int mxe_timing(mxe_t* e, const char* name, double* ms, uint64_t* launches)

@@ -36,10 +36,17 @@ struct mxe_sketch {
 struct mxe_result {
     mxe_engine* eng = nullptr;
     int n_asm = 0;
-    std::vector<std::vector<uint8_t>> uniq, keep;
-    std::vector<uint64_t> vertices, edge_u, edge_v;
-    std::vector<uint32_t> support;
-    std::vector<double> weight;
+    uint64_t N = 0, nV = 0, nE = 0;
+    uint64_t asm_off[33] = {0};
+    // device-resident result
+    uint8_t* d_uniq = nullptr; uint8_t* d_keep = nullptr;      // N flags, concatenated in assembly order
+    uint64_t* d_vertices = nullptr;                             // nV
+    uint64_t* d_eu = nullptr; uint64_t* d_ev = nullptr;         // nE
+    uint32_t* d_emask = nullptr; double* d_ew = nullptr;        // nE
+    // lazy host copy (one pinned block)
+    void* h_block = nullptr; size_t h_bytes = 0;
+    uint8_t* h_uniq = nullptr; uint8_t* h_keep = nullptr; uint64_t* h_vertices = nullptr;
+    uint64_t* h_eu = nullptr; uint64_t* h_ev = nullptr; uint32_t* h_emask = nullptr; double* h_ew = nullptr;
 };
 
 namespace mxe {

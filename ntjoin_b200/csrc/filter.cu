@@ -182,13 +182,6 @@ __global__ void __launch_bounds__(256) edge_gather_kernel(const uint32_t* __rest
 static inline unsigned gridf(uint64_t n) { return (unsigned)((n + 255) / 256); }
 static inline int bits_for(uint64_t v) { int b = 1; while (b < 32 && (1ULL << b) <= v) b++; return ((b + 7) / 8) * 8; }
 
-template <typename T>
-static int d2h(std::vector<T>& dst, const T* src, size_t n, cudaStream_t st)
-{
-    dst.resize(n);
-    if (n) MXE_CUDA(cudaMemcpyAsync(dst.data(), src, n * sizeof(T), cudaMemcpyDeviceToHost, st));
-    return MXE_OK;
-}
 
 int filter_and_edges_impl(mxe_engine* e, const uint64_t* const* d_hash, const uint32_t* const* d_contig,
                           const uint64_t* n, int n_asm, const double* weights, mxe_result* R)
@@ -202,8 +195,8 @@ int filter_and_edges_impl(mxe_engine* e, const uint64_t* const* d_hash, const ui
     for (int a = 0; a < n_asm; a++) { A.off[a + 1] = A.off[a] + n[a]; A.weight[a] = weights[a]; }
     const uint64_t N = A.off[n_asm];
     if (N >= (1ULL << 32)) { set_error("too many minimizers (%llu)", (unsigned long long)N); return MXE_ERR_ARG; }
-    R->eng = e; R->n_asm = n_asm;
-    R->uniq.assign(n_asm, {}); R->keep.assign(n_asm, {});
+    R->eng = e; R->n_asm = n_asm; R->N = N;
+    for (int a = 0; a <= n_asm; a++) R->asm_off[a] = A.off[a];
     if (N == 0) return MXE_OK;
 
     DBuf<uint64_t> keys, keys2, hprefix, kprefix, vertices;
@@ -213,6 +206,7 @@ int filter_and_edges_impl(mxe_engine* e, const uint64_t* const* d_hash, const ui
     MXE_TRY(vals.alloc(N, st)); MXE_TRY(vals2.alloc(N, st));
     MXE_TRY(contig.alloc(N, st)); MXE_TRY(head.alloc(N, st)); MXE_TRY(vid.alloc(N, st)); MXE_TRY(kflag.alloc(N, st));
     MXE_TRY(uniq.alloc(N, st)); MXE_TRY(keep.alloc(N, st));
+    uint8_t* const keep_p = keep.p;
     MXE_TRY(hprefix.alloc(N + 1, st)); MXE_TRY(kprefix.alloc(N + 1, st));
     for (int a = 0; a < n_asm; a++) {
         if (!n[a]) continue;
@@ -220,9 +214,9 @@ int filter_and_edges_impl(mxe_engine* e, const uint64_t* const* d_hash, const ui
         MXE_LAUNCH(e, copy_contig_kernel, gridf(n[a]), 256, 0, d_contig[a], n[a], A.off[a], contig.p);
     }
     MXE_TRY(radix_sort_pairs(e, keys.p, vals.p, keys2.p, vals2.p, N, 0, 64));
-    MXE_LAUNCH(e, mark_kernel, gridf(N), 256, 0, keys.p, vals.p, N, A, uniq.p, keep.p, head.p);
+    MXE_LAUNCH(e, mark_kernel, gridf(N), 256, 0, keys.p, vals.p, N, A, uniq.p, keep_p, head.p);
     MXE_TRY(exclusive_scan_u32_u64(e, head.p, hprefix.p, N));
-    MXE_LAUNCH(e, widen_flags_kernel, gridf(N), 256, 0, keep.p, N, kflag.p);
+    MXE_LAUNCH(e, widen_flags_kernel, gridf(N), 256, 0, keep_p, N, kflag.p);
     MXE_TRY(exclusive_scan_u32_u64(e, kflag.p, kprefix.p, N));
     uint64_t tot[2];
     MXE_CUDA(cudaMemcpyAsync(&tot[0], hprefix.p + N, 8, cudaMemcpyDeviceToHost, st));
@@ -230,28 +224,24 @@ int filter_and_edges_impl(mxe_engine* e, const uint64_t* const* d_hash, const ui
     MXE_CUDA(cudaStreamSynchronize(st));
     const uint64_t nV = tot[0], n_keep = tot[1];
 
-    // flags back to the host, split per assembly
-    for (int a = 0; a < n_asm; a++) {
-        MXE_TRY(d2h(R->uniq[a], uniq.p + A.off[a], n[a], st));
-        MXE_TRY(d2h(R->keep[a], keep.p + A.off[a], n[a], st));
-    }
-    if (nV == 0) { MXE_CUDA(cudaStreamSynchronize(st)); return MXE_OK; }
+    R->d_uniq = uniq.detach(); R->d_keep = keep.detach();
+    if (nV == 0) return MXE_OK;
 
     MXE_TRY(vertices.alloc(nV, st));
-    MXE_LAUNCH(e, vertex_kernel, gridf(N), 256, 0, keys.p, vals.p, N, A, keep.p, hprefix.p, vid.p, vertices.p);
-    MXE_TRY(d2h(R->vertices, vertices.p, nV, st));
+    MXE_LAUNCH(e, vertex_kernel, gridf(N), 256, 0, keys.p, vals.p, N, A, keep_p, hprefix.p, vid.p, vertices.p);
+    R->nV = nV;
 
     DBuf<uint32_t> cvid, cidx, eflag;
     DBuf<uint64_t> eprefix;
     MXE_TRY(cvid.alloc(n_keep + 1, st)); MXE_TRY(cidx.alloc(n_keep + 1, st)); MXE_TRY(eflag.alloc(n_keep, st));
     MXE_TRY(eprefix.alloc(n_keep + 1, st));
-    MXE_LAUNCH(e, compact_kernel, gridf(N), 256, 0, keep.p, kprefix.p, N, vid.p, cvid.p, cidx.p);
+    MXE_LAUNCH(e, compact_kernel, gridf(N), 256, 0, keep_p, kprefix.p, N, vid.p, cvid.p, cidx.p);
     MXE_LAUNCH(e, pair_flag_kernel, gridf(n_keep), 256, 0, cidx.p, n_keep, A, contig.p, eflag.p);
     MXE_TRY(exclusive_scan_u32_u64(e, eflag.p, eprefix.p, n_keep));
     uint64_t n_pairs = 0;
     MXE_CUDA(cudaMemcpyAsync(&n_pairs, eprefix.p + n_keep, 8, cudaMemcpyDeviceToHost, st));
     MXE_CUDA(cudaStreamSynchronize(st));
-    if (n_pairs == 0) return MXE_OK;
+    if (n_pairs == 0) { R->d_vertices = vertices.detach(); return MXE_OK; }
 
     DBuf<uint64_t> ekey, ekey2, uprefix;
     DBuf<uint32_t> eval, eval2, ehead, srcmin;
@@ -283,11 +273,9 @@ int filter_and_edges_impl(mxe_engine* e, const uint64_t* const* d_hash, const ui
     MXE_TRY(radix_sort_pairs(e, okey.p, oval.p, okey2.p, oval2.p, nE, 0, kb));
     MXE_TRY(radix_sort_pairs(e, okey.p, oval.p, okey2.p, oval2.p, nE, 32, 32 + kb));
     MXE_LAUNCH(e, edge_gather_kernel, gridf(nE), 256, 0, oval.p, nE, ue_q0.p, ue_mask.p, cvid.p, vertices.p, A, eu.p, ev.p, emask.p, ew.p);
-    MXE_TRY(d2h(R->edge_u, eu.p, nE, st));
-    MXE_TRY(d2h(R->edge_v, ev.p, nE, st));
-    MXE_TRY(d2h(R->support, emask.p, nE, st));
-    MXE_TRY(d2h(R->weight, ew.p, nE, st));
-    MXE_CUDA(cudaStreamSynchronize(st));
+    R->nE = nE;
+    R->d_vertices = vertices.detach();
+    R->d_eu = eu.detach(); R->d_ev = ev.detach(); R->d_emask = emask.detach(); R->d_ew = ew.detach();
     MXE_CUDA(cudaGetLastError());
     return MXE_OK;
 }

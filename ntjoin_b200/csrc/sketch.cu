@@ -89,6 +89,9 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
         MXE_LAUNCH(e, pack_kernel, grid_for(nW, 256), 256, 0, d_seq, P, pk.p, B.p);
         MXE_LAUNCH(e, vmask_kernel, grid_for(nW, 256), 256, 0, B.p, P, V.p);
         if (n_contigs > 1) MXE_LAUNCH(e, boundary_kernel, grid_for(n_contigs - 1, 128), 128, 0, d_offsets.p, n_contigs, P, V.p);
+    }
+    {
+        Span sp(e, "rank");
         MXE_TRY(bitmap_rank_build(e, V.p, nW, vprefix.p));
         MXE_LAUNCH(e, contig_bounds_kernel, grid_for(n_contigs + 1, 128), 128, 0, d_offsets.p, n_contigs, P, V.p, vprefix.p, ostart.p);
     }
@@ -105,7 +108,10 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
             MXE_LAUNCH(e, cand_generic_kernel, grid_for(n_threads, 128), 128, 0, pk.p, V.p, P, Tb, C.p);
         }
     }
-    MXE_TRY(bitmap_rank_build(e, C.p, nW, cprefix.p));
+    {
+        Span sp(e, "rank");
+        MXE_TRY(bitmap_rank_build(e, C.p, nW, cprefix.p));
+    }
 
     uint64_t totals[2] = {0, 0};
     MXE_CUDA(cudaMemcpyAsync(&totals[0], vprefix.p + n_vblocks, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
@@ -127,11 +133,14 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
     uint64_t gap_cap = std::max<uint64_t>(65536, n_cand / 8 + n_contigs);
     unsigned long long gc[2] = {0, 0};
     {
-        Span sp(e, "select");
+        Span sp(e, "eval");
         MXE_TRY(bitmap_extract(e, C.p, nW, cprefix.p, cpos.p));
         if (n_cand)
             MXE_LAUNCH(e, cand_eval_kernel, grid_for(n_cand, 256), 256, 0, cpos.p, n_cand, pk.p, V.p, vprefix.p,
                        d_offsets.p, n_contigs, P, Tb, ch0.p, cord.p, cctg.p);
+    }
+    {
+        Span sp(e, "select");
         for (int attempt = 0; attempt < 2; attempt++) {
             MXE_TRY(gaps.alloc(gap_cap, st));
             MXE_CUDA(cudaMemsetAsync(gcount.p, 0, 2 * sizeof(unsigned long long), st));
@@ -159,7 +168,10 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
     }
 
     // ---- ordered emission
-    MXE_TRY(bitmap_rank_build(e, M.p, nW, mprefix.p));
+    {
+        Span sp(e, "rank");
+        MXE_TRY(bitmap_rank_build(e, M.p, nW, mprefix.p));
+    }
     uint64_t n_mx = 0;
     MXE_CUDA(cudaMemcpyAsync(&n_mx, mprefix.p + n_vblocks, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     MXE_CUDA(cudaStreamSynchronize(st));

@@ -100,26 +100,62 @@ class Sketch:
 
 
 class FilterResult:
-    """Outcome of steps 2-3: per-assembly flags + the weighted edge list (copied to numpy)."""
+    """Outcome of steps 2-3: per-assembly flags + the weighted edge list.  Arrays stay on the device
+    until first touched (then one pinned device->host copy)."""
 
     def __init__(self, engine, handle, n_asm):
-        lib = engine._lib
-        self.uniq, self.keep = [], []
-        for a in range(n_asm):
-            n = C.c_uint64()
-            u, k = C.c_void_p(), C.c_void_p()
-            check(lib, lib.mxe_result_flags(handle, a, C.byref(n), C.byref(u), C.byref(k)))
-            self.uniq.append(_np_view(u.value, n.value, np.uint8).astype(bool))
-            self.keep.append(_np_view(k.value, n.value, np.uint8).astype(bool))
-        nv, ne = C.c_uint64(), C.c_uint64()
-        p = [C.c_void_p() for _ in range(5)]
-        check(lib, lib.mxe_result_graph(handle, C.byref(nv), C.byref(p[0]), C.byref(ne), *[C.byref(x) for x in p[1:]]))
-        self.vertices = _np_view(p[0].value, nv.value, np.uint64).copy()
-        self.edge_u = _np_view(p[1].value, ne.value, np.uint64).copy()
-        self.edge_v = _np_view(p[2].value, ne.value, np.uint64).copy()
-        self.support = _np_view(p[3].value, ne.value, np.uint32).copy()
-        self.weight = _np_view(p[4].value, ne.value, np.float64).copy()
-        lib.mxe_result_free(handle)
+        self._e, self._h, self.n_asm = engine, handle, n_asm
+        self._cache = None
+        engine._live.add(self)
+
+    def counts(self):
+        """(total minimizers, vertices, edges) without copying the arrays to the host."""
+        lib = self._e._lib
+        a = [C.c_uint64() for _ in range(3)]
+        check(lib, lib.mxe_result_counts(self._h, *[C.byref(x) for x in a]))
+        return tuple(x.value for x in a)
+
+    def fetch(self):
+        if self._cache is None:
+            lib = self._e._lib
+            uniq, keep = [], []
+            for a in range(self.n_asm):
+                n = C.c_uint64()
+                u, k = C.c_void_p(), C.c_void_p()
+                check(lib, lib.mxe_result_flags(self._h, a, C.byref(n), C.byref(u), C.byref(k)))
+                uniq.append(_np_view(u.value, n.value, np.uint8).astype(bool))
+                keep.append(_np_view(k.value, n.value, np.uint8).astype(bool))
+            nv, ne = C.c_uint64(), C.c_uint64()
+            p = [C.c_void_p() for _ in range(5)]
+            check(lib, lib.mxe_result_graph(self._h, C.byref(nv), C.byref(p[0]), C.byref(ne), *[C.byref(x) for x in p[1:]]))
+            self._cache = {
+                "uniq": uniq, "keep": keep,
+                "vertices": _np_view(p[0].value, nv.value, np.uint64).copy(),
+                "edge_u": _np_view(p[1].value, ne.value, np.uint64).copy(),
+                "edge_v": _np_view(p[2].value, ne.value, np.uint64).copy(),
+                "support": _np_view(p[3].value, ne.value, np.uint32).copy(),
+                "weight": _np_view(p[4].value, ne.value, np.float64).copy(),
+            }
+        return self._cache
+
+    uniq = property(lambda s: s.fetch()["uniq"])
+    keep = property(lambda s: s.fetch()["keep"])
+    vertices = property(lambda s: s.fetch()["vertices"])
+    edge_u = property(lambda s: s.fetch()["edge_u"])
+    edge_v = property(lambda s: s.fetch()["edge_v"])
+    support = property(lambda s: s.fetch()["support"])
+    weight = property(lambda s: s.fetch()["weight"])
+
+    def close(self):
+        if self._h:
+            self._e._lib.mxe_result_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Engine:
