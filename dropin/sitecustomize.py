@@ -1,0 +1,35 @@
+"""Activates the engine-backed ntjoin_utils functions without editing ntJoin's bin/ directory.
+
+Usage:  PYTHONPATH=<repo>/dropin:<repo>  NTJOIN_B200=1  ntJoin assemble ...
+Python imports `sitecustomize` at start-up; this one registers an import hook that patches the
+reference's `ntjoin_utils` right after it is loaded (see ntjoin_b200/dropin.py).
+"""
+import importlib.abc
+import importlib.util
+import os
+import sys
+
+if os.environ.get("NTJOIN_B200", "0") not in ("", "0"):
+    class _Patch(importlib.abc.MetaPathFinder):
+        def find_spec(self, name, path, target=None):
+            if name != "ntjoin_utils":
+                return None
+            sys.meta_path.remove(self)
+            try:
+                spec = importlib.util.find_spec(name)
+            finally:
+                sys.meta_path.insert(0, self)
+            if spec is None or spec.loader is None:
+                return None
+            loader = spec.loader
+            orig_exec = loader.exec_module
+
+            def exec_module(module):
+                orig_exec(module)
+                from ntjoin_b200 import dropin
+                dropin.install(module)
+
+            loader.exec_module = exec_module
+            return spec
+
+    sys.meta_path.insert(0, _Patch())

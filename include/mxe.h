@@ -78,6 +78,11 @@ int mxe_sketch_buffers(mxe_t* e, const uint8_t* seq, const uint64_t* offsets, ui
 int mxe_sketch_device(mxe_t* e, const void* d_seq, const uint64_t* offsets, uint32_t n_contigs,
                       const char* const* names, int k, int w, int flags, mxe_sketch_t** out);
 
+/* Load a sketch back from an `indexlr` TSV written earlier (make's resume path: ntJoin keeps
+ * <fasta>.k<k>.w<w>.tsv as .SECONDARY, ntJoin:202).  Parses id \t hash[:pos[:...]] ... exactly as
+ * bin/ntjoin_utils.py:173-185 does; the arrays are uploaded for mxe_filter_and_edges. */
+int mxe_sketch_load_tsv(mxe_t* e, const char* tsv_path, mxe_sketch_t** out);
+
 /* Host view (SoA, sorted by (contig, pos); contigs in input order).  Pointers stay valid until
  * mxe_sketch_free.  Any output pointer may be NULL. */
 int mxe_sketch_view(mxe_sketch_t* s, uint64_t* n,

@@ -242,6 +242,72 @@ int mxe_sketch_file(mxe_t* e, const char* fasta_path, int k, int w, int flags, m
     return MXE_OK;
 }
 
+int mxe_sketch_load_tsv(mxe_t* e, const char* tsv_path, mxe_sketch_t** out)
+{
+    if (!e || !tsv_path || !out) { set_error("null argument"); return MXE_ERR_ARG; }
+    MXE_CUDA(cudaSetDevice(e->device));
+    FILE* f = fopen(tsv_path, "rb");
+    if (!f) { set_error("cannot open %s: %s", tsv_path, strerror(errno)); return MXE_ERR_IO; }
+    fseek(f, 0, SEEK_END);
+    long long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    std::vector<char> buf((size_t)sz + 1);
+    if (sz && fread(buf.data(), 1, (size_t)sz, f) != (size_t)sz) { fclose(f); set_error("short read on %s", tsv_path); return MXE_ERR_IO; }
+    fclose(f);
+    buf[sz] = '\n';
+    std::vector<uint64_t> hashes;
+    std::vector<uint32_t> pos, contig;
+    mxe_sketch* S = new mxe_sketch();
+    S->eng = e;
+    const char* p = buf.data();
+    const char* end = p + sz;
+    while (p < end) {
+        const char* nl = (const char*)memchr(p, '\n', end - p + 1);
+        const char* tab = (const char*)memchr(p, '\t', nl - p);
+        const char* idend = tab ? tab : nl;
+        while (idend > p && (idend[-1] == '\r' || idend[-1] == ' ')) idend--;
+        uint32_t c = (uint32_t)S->names.size();
+        S->names.emplace_back(p, idend - p);
+        if (tab) {
+            const char* q = tab + 1;
+            while (q < nl) {
+                while (q < nl && (*q == ' ' || *q == '\r')) q++;
+                if (q >= nl) break;
+                uint64_t h = 0;
+                const char* q0 = q;
+                while (q < nl && *q >= '0' && *q <= '9') h = h * 10 + (uint64_t)(*q++ - '0');
+                if (q == q0) { mxe_sketch_free(S); set_error("%s: malformed minimizer entry in record %u", tsv_path, c); return MXE_ERR_IO; }
+                uint64_t ps = 0;
+                if (q < nl && *q == ':') { q++; while (q < nl && *q >= '0' && *q <= '9') ps = ps * 10 + (uint64_t)(*q++ - '0'); }
+                while (q < nl && *q != ' ') q++;   // :strand / :seq fields
+                hashes.push_back(h); pos.push_back((uint32_t)ps); contig.push_back(c);
+            }
+        }
+        p = nl + 1;
+    }
+    S->n_contigs = (uint32_t)S->names.size();
+    S->offsets.assign(S->n_contigs + 1, 0);
+    S->n = hashes.size();
+    if (S->n) {
+        cudaStream_t st = e->stream;
+        size_t n = S->n;
+        cudaError_t err = cudaMallocAsync((void**)&S->d_out_hash, n * 8, st);
+        if (err == cudaSuccess) err = cudaMallocAsync((void**)&S->d_min_hash, n * 8, st);
+        if (err == cudaSuccess) err = cudaMallocAsync((void**)&S->d_pos, n * 4, st);
+        if (err == cudaSuccess) err = cudaMallocAsync((void**)&S->d_contig, n * 4, st);
+        if (err == cudaSuccess) err = cudaMallocAsync((void**)&S->d_forward, n, st);
+        if (err == cudaSuccess) err = cudaMemcpyAsync(S->d_out_hash, hashes.data(), n * 8, cudaMemcpyHostToDevice, st);
+        if (err == cudaSuccess) err = cudaMemsetAsync(S->d_min_hash, 0, n * 8, st);
+        if (err == cudaSuccess) err = cudaMemcpyAsync(S->d_pos, pos.data(), n * 4, cudaMemcpyHostToDevice, st);
+        if (err == cudaSuccess) err = cudaMemcpyAsync(S->d_contig, contig.data(), n * 4, cudaMemcpyHostToDevice, st);
+        if (err == cudaSuccess) err = cudaMemsetAsync(S->d_forward, 0, n, st);
+        if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+        if (err != cudaSuccess) { mxe_sketch_free(S); set_error("upload of %s failed: %s", tsv_path, cudaGetErrorString(err)); return MXE_ERR_CUDA; }
+    }
+    *out = S;
+    return MXE_OK;
+}
+
 static int ensure_host(mxe_sketch* S)
 {
     if (S->h_block || S->n == 0) return MXE_OK;

@@ -272,12 +272,18 @@ __global__ void __launch_bounds__(128) cand_generic_kernel(const uint32_t* __res
 // Only the upper rotation group (bits 63:33) of fwd and rev is rolled, in 32-bit registers.
 //   sum mode: t = (f31 + r31 + carry) mod 2^31, carry in {0,1}  =>  superset test (f31+r31+1) mod 2^31 <= T+1
 //   min mode: t = min(f31, r31)
+// Register layouts chosen so that each roll is two ALU ops + one table XOR:
+//   F  "low aligned": value in bits 30:0, bit 31 is don't-care ("dirty")
+//   R  "top aligned": value in bits 31:1, bit 0 is dirty
+//   a = F << 1 is both the top-aligned clean copy of F (for the sum) and the funnel-shift source.
+// The 16-entry table (idx = out<<2 | in) holds {fwd term low aligned, rev term top aligned}; it is 128 B,
+// one entry per bank pair, so any mix of indices in a warp is conflict free.
 template <int CANON_MIN>
 __global__ void __launch_bounds__(128) cand31_kernel(const uint32_t* __restrict__ pk, const uint32_t* __restrict__ V,
                                                       SketchParams P, SketchTables Tb, uint32_t* __restrict__ C)
 {
     __shared__ uint2 tab[16];
-    if (threadIdx.x < 16) tab[threadIdx.x] = Tb.t16[threadIdx.x];
+    if (threadIdx.x < 16) { uint2 e = Tb.t16[threadIdx.x]; e.y <<= 1; tab[threadIdx.x] = e; }
     __syncthreads();
     uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t p0 = tid * (uint64_t)P.chunk;
@@ -290,39 +296,47 @@ __global__ void __launch_bounds__(128) cand31_kernel(const uint32_t* __restrict_
         F = rol31(F) ^ Tb.shi[cf];
         R = rol31(R) ^ Tb.shi[cr];
     }
+    R <<= 1;
     const uint64_t q0 = p0 >> 4;
     const int kq = k >> 4, ks = (k & 15) >> 2;
     const uint32_t lowmask = ks == 1 ? 0x3F3F3F3Fu : ks == 2 ? 0x0F0F0F0Fu : 0x03030303u;
     const char* tb = reinterpret_cast<const char*>(tab);
-    const uint32_t T1 = CANON_MIN ? P.T : P.T + 1u;
+    const uint32_t Tt = CANON_MIN ? ((P.T << 1) | 1u) : (((P.T + 1u) << 1) | 1u);
     const int n_g = P.chunk / 16;
     uint32_t bits = 0;
     for (int g = 0; g < n_g; g++) {
         if (p0 + (uint64_t)g * 16 >= P.n) { if (g & 1) C[(p0 >> 5) + (g >> 1)] = bits & V[(p0 >> 5) + (g >> 1)]; break; }
-        uint32_t o = pk[q0 + g];
-        uint32_t a = pk[q0 + g + kq];
-        uint32_t in = a;
+        uint32_t o = __ldg(pk + q0 + g);
+        uint32_t in = __ldg(pk + q0 + g + kq);
         if (ks) {
-            uint32_t b2 = pk[q0 + g + kq + 1];
-            in = ((a >> (2 * ks)) & lowmask) | ((b2 << (8 - 2 * ks)) & ~lowmask);
+            uint32_t b2 = __ldg(pk + q0 + g + kq + 1);
+            in = ((in >> (2 * ks)) & lowmask) | ((b2 << (8 - 2 * ks)) & ~lowmask);
         }
-        // nibble words: z1 = idx for j=0 (low nibbles) and j=2 (high nibbles); z2 = j=1, j=3
+        // table byte offsets (idx << 3), one per byte:  zl[j] low nibbles, zh[j] high nibbles of z1 (j=0,2) / z2 (j=1,3)
         uint32_t z1 = ((o << 2) & 0xCCCCCCCCu) | (in & 0x33333333u);
         uint32_t z2 = (o & 0xCCCCCCCCu) | ((in >> 2) & 0x33333333u);
-        uint32_t gb = 0;
+        uint32_t zq[4];
+        zq[0] = (z1 << 3) & 0x78787878u;
+        zq[1] = (z2 << 3) & 0x78787878u;
+        zq[2] = (z1 >> 1) & 0x78787878u;
+        zq[3] = (z2 >> 1) & 0x78787878u;
+        uint32_t key[16];
+        uint32_t m = 0xFFFFFFFFu;
 #pragma unroll
         for (int i = 0; i < 16; i++) {
-            uint32_t key;
-            if (CANON_MIN) key = min(F, R);
-            else key = (F + R + 1u) & 0x7FFFFFFFu;
-            if (key <= T1) gb |= 1u << i;
-            const int j = i >> 2, b = i & 3;
-            const uint32_t z = (j & 1) ? z2 : z1;
-            const int off = 8 * b + ((j & 2) ? 4 : 0);
-            uint32_t addr = off >= 3 ? ((z >> (off - 3)) & 0x78u) : ((z << (3 - off)) & 0x78u);
-            uint2 e = *reinterpret_cast<const uint2*>(tb + addr);
-            F = rol31(F) ^ e.x;
-            R = ror31(R ^ e.y);
+            const uint32_t a = F << 1;
+            key[i] = CANON_MIN ? min(a, R) : a + R + 2u;
+            m = min(m, key[i]);
+            const uint32_t addr = __byte_perm(zq[i >> 2], 0, 0x4440 | (i & 3));
+            const uint2 e = *reinterpret_cast<const uint2*>(tb + addr);
+            F = __funnelshift_l(a, F, 1) ^ e.x;
+            const uint32_t u = R ^ e.y;
+            R = __funnelshift_r(u, u >> 1, 1);
+        }
+        uint32_t gb = 0;
+        if (m <= Tt) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) gb |= (key[i] <= Tt ? 1u : 0u) << i;
         }
         if (g & 1) {
             bits |= gb << 16;

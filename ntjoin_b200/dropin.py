@@ -1,0 +1,121 @@
+"""Engine-backed replacements for ntJoin's three step-2/3 Python functions (seam S3).
+
+Reference signatures (bin/ntjoin_utils.py):
+    read_minimizers(tsv_filename, repeat_bf=False) -> (mx_info: dict[str,(str,int)], mxs: list[list[str]])   :167-193
+    filter_minimizers(list_mxs: dict[asm, list[list[str]]]) -> same shape                                     :152-165
+    build_graph(list_mxs, weights, graph=None, black_list=None) -> igraph.Graph (vs['name'], es['support'],
+                                                                               es['weight'])                 :83-141
+
+`install(ntjoin_utils_module)` swaps them in.  Return types and contents are identical to the
+reference's; the arithmetic (uniqueness counting, intersection, adjacent-pair edge reduction, weights)
+runs on the GPU through the C ABI.  The lists returned by read_minimizers / filter_minimizers carry a
+hidden handle to the device-resident arrays so the next stage does not re-parse strings.  Calls the
+engine cannot serve (repeat_bf, black_list, an existing graph, plain lists from other callers such as
+bin/ntjoin_overlap.py:25-28) fall through to the reference's original functions.
+"""
+import numpy as np
+
+_ENGINE = None
+
+
+def _engine():
+    global _ENGINE
+    if _ENGINE is None:
+        import os
+        from .engine import Engine
+        _ENGINE = Engine(int(os.environ.get("MXE_DEVICE", "0")))
+    return _ENGINE
+
+
+class MxLists(list):
+    """list[list[str]] plus the arrays it was built from."""
+    _sketch = None      # Sketch (device-resident out_hash / contig)
+    _mask = None        # bool mask over the sketch selecting the entries present in these lists
+    _result = None      # FilterResult shared by all assemblies after filter_minimizers
+    _asm_index = None
+
+
+def _lists_from(sk, mask):
+    """per-record lists (records with at least one minimizer in the TSV) of decimal strings"""
+    oh, cg = sk.out_hash, sk.contig
+    strs = np.array([str(h) for h in oh.tolist()], dtype=object)
+    present = np.unique(cg)
+    bounds = np.searchsorted(cg, np.arange(len(sk.names) + 1))
+    out = MxLists()
+    for c in present:
+        s, e = bounds[c], bounds[c + 1]
+        out.append(strs[s:e][mask[s:e]].tolist())
+    return out, strs
+
+
+def make_read_minimizers(original):
+    def read_minimizers(tsv_filename, repeat_bf=False):
+        if repeat_bf:
+            return original(tsv_filename, repeat_bf)
+        eng = _engine()
+        sk = eng.load_tsv(tsv_filename)
+        res = eng.filter_and_edges([sk], [1.0])
+        uniq = res.uniq[0]
+        mxs, strs = _lists_from(sk, uniq)
+        names = sk.names
+        cg, ps = sk.contig[uniq].tolist(), sk.pos[uniq].tolist()
+        mx_info = {h: (names[c], p) for h, c, p in zip(strs[uniq].tolist(), cg, ps)}
+        mxs._sketch, mxs._mask = sk, uniq
+        res.close()
+        return mx_info, mxs
+    read_minimizers.__doc__ = original.__doc__
+    return read_minimizers
+
+
+def make_filter_minimizers(original):
+    def filter_minimizers(list_mxs):
+        vals = list(list_mxs.values())
+        if not vals or not all(isinstance(v, MxLists) and v._sketch is not None for v in vals):
+            return original(list_mxs)
+        eng = _engine()
+        sks = [v._sketch for v in vals]
+        res = eng.filter_and_edges(sks, [1.0] * len(sks))
+        out = {}
+        for a, (asm, v) in enumerate(list_mxs.items()):
+            keep = res.keep[a]
+            lists, _ = _lists_from(v._sketch, keep)
+            lists._sketch, lists._mask, lists._asm_index = v._sketch, keep, a
+            out[asm] = lists
+        return out
+    filter_minimizers.__doc__ = original.__doc__
+    return filter_minimizers
+
+
+def make_build_graph(original, ig):
+    def build_graph(list_mxs, weights, graph=None, black_list=None):
+        vals = list(list_mxs.values())
+        if graph is not None or black_list is not None or not vals or \
+                not all(isinstance(v, MxLists) and v._sketch is not None and v._asm_index is not None for v in vals):
+            return original(list_mxs, weights, graph, black_list)
+        eng = _engine()
+        keys = list(list_mxs.keys())
+        res = eng.filter_and_edges([v._sketch for v in vals], [weights[k] for k in keys])
+        g = ig.Graph()
+        vs = res.vertices
+        g.add_vertices([str(v) for v in vs.tolist()])
+        eu = np.searchsorted(vs, res.edge_u)
+        ev = np.searchsorted(vs, res.edge_v)
+        g.add_edges(list(zip(eu.tolist(), ev.tolist())))
+        n_asm = len(keys)
+        g.es["support"] = [[keys[a] for a in range(n_asm) if m >> a & 1] for m in res.support.tolist()]
+        g.es["weight"] = res.weight.tolist()
+        res.close()
+        return g
+    build_graph.__doc__ = original.__doc__
+    return build_graph
+
+
+def install(module):
+    """Patch a loaded `ntjoin_utils` module in place (idempotent)."""
+    if getattr(module, "_mxe_installed", False):
+        return module
+    module.read_minimizers = make_read_minimizers(module.read_minimizers)
+    module.filter_minimizers = make_filter_minimizers(module.filter_minimizers)
+    module.build_graph = make_build_graph(module.build_graph, module.ig)
+    module._mxe_installed = True
+    return module

@@ -189,9 +189,7 @@ class Engine:
         arr = (C.c_char_p * n)(*[str(x).encode() for x in names])
         return arr, [str(x) for x in names]
 
-    def sketch_file(self, path, k, w, canonical="sum"):
-        out = C.c_void_p()
-        check(self._lib, self._lib.mxe_sketch_file(self._h, str(path).encode(), int(k), int(w), self._flags(canonical), C.byref(out)))
+    def _named(self, out):
         sk = Sketch(self, out, [])
         nm = C.c_char_p()
         n_contigs = sk.counts_raw()[4]
@@ -199,6 +197,17 @@ class Engine:
             check(self._lib, self._lib.mxe_sketch_contig_name(out, i, C.byref(nm)))
             sk.names.append(nm.value.decode("utf-8", "replace"))
         return sk
+
+    def sketch_file(self, path, k, w, canonical="sum"):
+        out = C.c_void_p()
+        check(self._lib, self._lib.mxe_sketch_file(self._h, str(path).encode(), int(k), int(w), self._flags(canonical), C.byref(out)))
+        return self._named(out)
+
+    def load_tsv(self, path):
+        """Sketch object from an existing <fasta>.k<k>.w<w>.tsv (out_hash, pos, record ids and names only)."""
+        out = C.c_void_p()
+        check(self._lib, self._lib.mxe_sketch_load_tsv(self._h, str(path).encode(), C.byref(out)))
+        return self._named(out)
 
     def sketch_buffers(self, seq, offsets, k, w, names=None, canonical="sum"):
         """seq: host bytes / numpy uint8 / CPU torch uint8 tensor (pinned memory is copied fastest)."""

@@ -1,0 +1,108 @@
+"""Pure-Python restatement of ntJoin's step-2/3 functions (small cases only; TEST INFRASTRUCTURE).
+
+Follows bin/ntjoin_utils.py:167-193 (read_minimizers), :152-165 (filter_minimizers), :83-141
+(build_graph) in behaviour; written independently.  Checked against the golden vectors produced by
+the reference's own functions (tests/golden/steps23_*.json).  Also provides the recording stand-in
+for python-igraph used where igraph is not installed.
+"""
+import types
+
+
+class RecordingGraph:
+    """Just enough of igraph.Graph for build_graph: names, edges by name or index, es attributes."""
+
+    def __init__(self):
+        self.vnames, self.edges, self.eattr = [], [], {}
+        self._index, self._eid = {}, {}
+
+    def add_vertices(self, names):
+        for n in names:
+            self._index[n] = len(self.vnames)
+            self.vnames.append(n)
+
+    def _name(self, v):
+        return self.vnames[v] if isinstance(v, int) else v
+
+    def add_edges(self, pairs):
+        for s, t in pairs:
+            s, t = self._name(s), self._name(t)
+            self._eid[(s, t)] = self._eid[(t, s)] = len(self.edges)
+            self.edges.append((s, t))
+
+    def get_eid(self, s, t):
+        return self._eid[(self._name(s), self._name(t))]
+
+    class _ES:
+        def __init__(self, g):
+            self.g = g
+
+        def __setitem__(self, k, v):
+            self.g.eattr[k] = list(v)
+
+        def __getitem__(self, k):
+            return self.g.eattr[k]
+
+        def __iter__(self):
+            return iter(())
+
+    @property
+    def es(self):
+        return RecordingGraph._ES(self)
+
+
+def read_minimizers(tsv_filename, repeat_bf=False):
+    first, dup, per_record = {}, set(), []
+    with open(tsv_filename, encoding="utf-8") as fh:
+        for raw in fh:
+            cols = raw.strip().split("\t")
+            if len(cols) < 2:
+                continue
+            entries = [e.split(":") for e in cols[1].split(" ")]
+            per_record.append([e[0] for e in entries])
+            for mx, pos, seq in entries:
+                if mx in first or (repeat_bf and repeat_bf.contains(seq)):
+                    dup.add(mx)
+                else:
+                    first[mx] = (cols[0], int(pos))
+    info = {m: v for m, v in first.items() if m not in dup}
+    return info, [[m for m in rec if m not in dup] for rec in per_record]
+
+
+def filter_minimizers(list_mxs):
+    sets = [set(m for rec in recs for m in rec) for recs in list_mxs.values()]
+    common = set.intersection(*sets)
+    return {asm: [[m for m in rec if m in common] for rec in recs] for asm, recs in list_mxs.items()}
+
+
+def build_graph(list_mxs, weights, graph=None, black_list=None):
+    assert graph is None
+    g = RecordingGraph()
+    adj, verts = {}, set()
+    for asm, recs in list_mxs.items():
+        for rec in recs:
+            for a, b in zip(rec, rec[1:]):
+                if a in adj and b in adj[a]:
+                    adj[a][b].append(asm)
+                elif b in adj and a in adj[b]:
+                    adj[b][a].append(asm)
+                else:
+                    adj.setdefault(a, {})[b] = [asm]
+            for m in rec:
+                if black_list is None or m not in black_list:
+                    verts.add(m)
+    pairs = [(s, t) for s in adj for t in adj[s]]
+    g.add_vertices(sorted(verts, key=int))
+    g.add_edges(pairs)
+    g.es["support"] = [adj[s][t] for s, t in pairs]
+    g.es["weight"] = [sum(weights[f] for f in adj[s][t]) for s, t in pairs]
+    return g
+
+
+def as_module():
+    """a module object shaped like the reference's ntjoin_utils (for ntjoin_b200.dropin.install)"""
+    m = types.ModuleType("ntjoin_utils")
+    ig = types.ModuleType("igraph")
+    ig.Graph = RecordingGraph
+    m.ig = ig
+    m.read_minimizers, m.filter_minimizers, m.build_graph = read_minimizers, filter_minimizers, build_graph
+    return m

@@ -1,0 +1,70 @@
+"""GPU: the two drop-in seams -- the `indexlr` executable (S1/S2) and the patched ntjoin_utils
+functions (S3) -- against the oracle CLI and the reference-generated golden vectors."""
+import glob
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+import oracle_lib
+import ref_py
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+INDEXLR = os.path.join(ROOT, "bin", "indexlr")
+
+
+def test_indexlr_cli_both_argv_forms(golden_dir, tmp_path):
+    fa = os.path.join(golden_dir, "inputs", "scaf.more_seqs.fa")
+    want = subprocess.check_output([oracle_lib.CLI, "--seq", "--long", "--pos", "-k", "32", "-w", "500", fa])
+    got = subprocess.check_output([sys.executable, INDEXLR, "--seq", "--long", "--pos", "-k", "32", "-w", "500", "-t", "4", fa])   # ntJoin:205
+    assert got == want
+    out = tmp_path / "o.tsv"
+    subprocess.check_call([sys.executable, INDEXLR, fa, "--seq", "--long", "--pos", "-k32", "-w500", "-t4", "-o", str(out)])     # ntjoin_utils.py:198
+    assert out.read_bytes() == want
+
+
+def test_indexlr_cli_fails_nonzero(tmp_path):
+    r = subprocess.run([sys.executable, INDEXLR, "-k", "32", "-w", "10", str(tmp_path / "missing.fa")], capture_output=True)
+    assert r.returncode != 0 and b"cannot open" in r.stderr
+    assert subprocess.run([sys.executable, INDEXLR, "-k", "32"], capture_output=True).returncode != 0
+
+
+def test_dropin_functions_vs_golden(golden_dir, tmp_path):
+    from ntjoin_b200 import dropin
+    mod = dropin.install(ref_py.as_module())
+    for path in sorted(glob.glob(os.path.join(golden_dir, "steps23_*.json"))):
+        g = json.load(open(path))
+        list_mxs, weights = {}, {}
+        for i, f in enumerate(g["files"]):
+            tsv = str(tmp_path / f"{i}.{f}.k{g['k']}.w{g['w']}.tsv")
+            subprocess.check_call([sys.executable, INDEXLR, "--seq", "--long", "--pos", "-k", str(g["k"]), "-w", str(g["w"]),
+                                   os.path.join(golden_dir, "inputs", f), "-o", tsv])
+            info, mxs = mod.read_minimizers(tsv)
+            assert type(info) is dict and isinstance(mxs, list)
+            assert {k: list(v) for k, v in info.items()} == g["read_minimizers"][i]["mx_info"], path
+            assert list(info) == list(g["read_minimizers"][i]["mx_info"]), path
+            assert mxs == g["read_minimizers"][i]["mxs"], path
+            assert all(isinstance(v, tuple) and isinstance(v[0], str) and isinstance(v[1], int) for v in info.values())
+            list_mxs[tsv], weights[tsv] = mxs, g["weights"][i]
+        filt = mod.filter_minimizers(list_mxs)
+        assert list(filt) == list(list_mxs) and [filt[t] for t in list_mxs] == g["filter_minimizers"], path
+        gr = mod.build_graph(filt, weights)
+        keys = list(list_mxs)
+        assert sorted(gr.vnames, key=int) == g["vertices"], path
+        assert [list(e) for e in gr.edges] == g["edges"], path
+        assert [[keys.index(f) for f in s] for s in gr.eattr["support"]] == g["support"], path
+        assert gr.eattr["weight"] == g["weight"], path
+
+
+def test_dropin_falls_through_for_plain_lists():
+    """callers like bin/ntjoin_overlap.py:25-28 pass plain lists keyed by ints: the originals must run"""
+    from ntjoin_b200 import dropin
+    mod = dropin.install(ref_py.as_module())
+    lm = {0: [["1", "2", "3"]], 1: [["3", "2", "9"]]}
+    f = mod.filter_minimizers(lm)
+    assert f == {0: [["2", "3"]], 1: [["3", "2"]]}
+    g = mod.build_graph(f, {0: 1, 1: 1})
+    assert g.edges == [("2", "3")] and g.eattr["weight"] == [2]
