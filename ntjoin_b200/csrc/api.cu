@@ -122,7 +122,7 @@ int mxe_set_option(mxe_t* e, const char* name, double value)
 {
     if (!e || !name) { set_error("null argument"); return MXE_ERR_ARG; }
     if (!strcmp(name, "tau")) { if (value <= 0) { set_error("tau must be > 0"); return MXE_ERR_ARG; } e->tau = value; }
-    else if (!strcmp(name, "chunk")) { if (value < 32) { set_error("chunk must be >= 32"); return MXE_ERR_ARG; } e->chunk = (int)value; }
+    else if (!strcmp(name, "chunk")) { if (value != 0 && value < 32) { set_error("chunk must be 0 (auto) or >= 32"); return MXE_ERR_ARG; } e->chunk = (int)value; }
     else if (!strcmp(name, "cand_variant")) e->cand_variant = (int)value;
     else if (!strcmp(name, "timing")) e->timing = value != 0;
     else { set_error("unknown option %s", name); return MXE_ERR_ARG; }

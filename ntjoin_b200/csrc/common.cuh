@@ -51,7 +51,7 @@ struct Engine {
     int sm_count = 148;
     // tunables
     double tau = 10.0;       // candidate threshold: hash0>>33 <= tau * 2^31 / w
-    int chunk = 256;         // positions per thread in the candidate kernel (multiple of 32)
+    int chunk = 0;           // positions per thread in the candidate kernel (multiple of 32; 0 = auto)
     int cand_variant = 1;    // 0 = generic 64-bit, 1 = 31-bit lane prefilter
     bool timing = false;
     // accounting

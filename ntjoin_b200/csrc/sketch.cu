@@ -19,6 +19,11 @@ static void build_tables(int k, SketchTables* T)
         T->shi[c] = (uint32_t)(seed[c] >> 33);
         shi_rolk[c] = (uint32_t)(x >> 33);
     }
+    T->f0 = 0; T->r0 = 0;
+    for (int i = 0; i < k; i++) {
+        T->f0 = rol31(T->f0) ^ T->shi[0];      // fwd of A^k
+        T->r0 = rol31(T->r0) ^ T->shi[2];      // rev of A^k = fwd-style fold of T^k
+    }
     for (int o = 0; o < 4; o++)
         for (int in = 0; in < 4; in++) {
             uint2 e;
@@ -58,7 +63,11 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
         double t = e->tau * 2147483648.0 / (double)w;
         P.T = t >= 2147483646.0 ? 2147483646u : (uint32_t)t;
     }
-    P.chunk = std::max(32, (e->chunk / 32) * 32);
+    if (e->chunk > 0) P.chunk = std::max(32, (e->chunk / 32) * 32);
+    else {   // auto: long runs amortise the k-step warm-up, but keep >= ~4 waves of threads in flight
+        uint64_t want = n / ((uint64_t)e->sm_count * 2048 * 2) + 1;
+        P.chunk = (int)std::min<uint64_t>(1024, std::max<uint64_t>(128, (want + 31) / 32 * 32));
+    }
     SketchTables Tb;
     build_tables(k, &Tb);
 
@@ -134,10 +143,11 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
     unsigned long long gc[2] = {0, 0};
     {
         Span sp(e, "eval");
-        MXE_TRY(bitmap_extract(e, C.p, nW, cprefix.p, cpos.p));
-        if (n_cand)
-            MXE_LAUNCH(e, cand_eval_kernel, grid_for(n_cand, 256), 256, 0, cpos.p, n_cand, pk.p, V.p, vprefix.p,
-                       d_offsets.p, n_contigs, P, Tb, ch0.p, cord.p, cctg.p);
+        if (n_cand) {
+            MXE_LAUNCH(e, cand_extract_kernel, grid_for(n_vblocks * 32, 256), 256, 0, C.p, V.p, nW, cprefix.p, vprefix.p, n_vblocks,
+                       d_offsets.p, n_contigs, cpos.p, cord.p, cctg.p);
+            MXE_LAUNCH(e, cand_hash_kernel, grid_for(n_cand, 256), 256, 0, cpos.p, n_cand, pk.p, P, Tb, ch0.p);
+        }
     }
     {
         Span sp(e, "select");
@@ -178,15 +188,12 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
     S->n = n_mx;
     if (n_mx) {
         Span sp(e, "emit");
-        DBuf<uint64_t> mpos;
-        MXE_TRY(mpos.alloc(n_mx, st));
-        MXE_TRY(bitmap_extract(e, M.p, nW, mprefix.p, mpos.p));
         MXE_CUDA(cudaMallocAsync((void**)&S->d_out_hash, n_mx * sizeof(uint64_t), st));
         MXE_CUDA(cudaMallocAsync((void**)&S->d_min_hash, n_mx * sizeof(uint64_t), st));
         MXE_CUDA(cudaMallocAsync((void**)&S->d_pos, n_mx * sizeof(uint32_t), st));
         MXE_CUDA(cudaMallocAsync((void**)&S->d_contig, n_mx * sizeof(uint32_t), st));
         MXE_CUDA(cudaMallocAsync((void**)&S->d_forward, n_mx * sizeof(uint8_t), st));
-        MXE_LAUNCH(e, final_eval_kernel, grid_for(n_mx, 256), 256, 0, mpos.p, n_mx, pk.p, d_offsets.p, n_contigs, P, Tb,
+        MXE_LAUNCH(e, final_emit_kernel, grid_for(n_vblocks * 32, 256), 256, 0, M.p, nW, mprefix.p, n_vblocks, pk.p, d_offsets.p, n_contigs, P, Tb,
                    S->d_out_hash, S->d_min_hash, S->d_pos, S->d_contig, S->d_forward);
     }
     MXE_CUDA(cudaGetLastError());

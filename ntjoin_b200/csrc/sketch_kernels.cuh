@@ -26,6 +26,7 @@ struct SketchTables {
     uint64_t seed_rolk[4]; // srol^k(seed)
     uint2 t16[16];         // 31-bit lane roll table: idx = out<<2|in -> {fwd term, rev term}
     uint32_t shi[4];       // seed >> 33 by code
+    uint32_t f0, r0;       // 31-bit lane hashes of the all-A k-mer (warm-up seed of cand31)
 };
 
 struct SketchParams {
@@ -90,6 +91,96 @@ __device__ __forceinline__ void kmer_hash64(const uint32_t* __restrict__ pk, uin
 __device__ __forceinline__ uint64_t canon(uint64_t f, uint64_t r, int canon_min)
 {
     return canon_min ? (r < f ? r : f) : f + r;
+}
+
+// ---------------------------------------------------------------- table-driven exact k-mer hash
+// srol^n / sror^n for 0 < n < 31 on the 33|31 split word
+__host__ __device__ __forceinline__ uint64_t sroln(uint64_t x, int n)
+{
+    uint64_t g33 = x & 0x1FFFFFFFFULL, g31 = x >> 33;
+    g33 = ((g33 << n) | (g33 >> (33 - n))) & 0x1FFFFFFFFULL;
+    g31 = ((g31 << n) | (g31 >> (31 - n))) & 0x7FFFFFFFULL;
+    return g33 | (g31 << 33);
+}
+__host__ __device__ __forceinline__ uint64_t srorn(uint64_t x, int n)
+{
+    uint64_t g33 = x & 0x1FFFFFFFFULL, g31 = x >> 33;
+    g33 = ((g33 >> n) | (g33 << (33 - n))) & 0x1FFFFFFFFULL;
+    g31 = ((g31 >> n) | (g31 << (31 - n))) & 0x7FFFFFFFULL;
+    return g33 | (g31 << 33);
+}
+
+// pk word (byte-interleaved) -> natural order (base i at bits 2i): 4x4 transpose of 2-bit fields
+__device__ __forceinline__ uint32_t pk_to_natural(uint32_t x)
+{
+    uint32_t t = ((x >> 12) ^ x) & 0x0000F0F0u;
+    x ^= t ^ (t << 12);
+    t = ((x >> 6) ^ x) & 0x00CC00CCu;
+    x ^= t ^ (t << 6);
+    return x;
+}
+
+// Shared-memory tables for 4 bases per lookup (index = natural byte, base j at bits 2j):
+//   f4[v]  = XOR_j srol^(3-j)(seed[c_j])                    fwd:  f = srol^4(f) ^ f4[v]
+//   r4[v]  = srol^(k-4)( XOR_j srol^j(seed[c_j ^ 2]) )      rev:  r = sror^4(r) ^ r4[v]
+//   s1[c]  = seed[c] ,  s1[4+c] = srol^(k-1)(seed[c ^ 2])   single-base steps for k % 4 != 0
+struct HashTabs { uint64_t f4[256]; uint64_t r4[256]; uint64_t s1[8]; };
+
+__device__ __forceinline__ void build_hash_tabs(HashTabs* H, const SketchTables& Tb, int k)
+{
+    for (int v = threadIdx.x; v < 256; v += blockDim.x) {
+        uint64_t f = 0, r = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t c = (v >> (2 * j)) & 3;
+            f = srol1(f) ^ sel4(c, Tb.seed);
+            uint64_t sc = sel4(c ^ 2u, Tb.seed);
+            for (int q = 0; q < j; q++) sc = srol1(sc);
+            r ^= sc;
+        }
+        for (int q = 0; q < k - 4; q++) r = srol1(r);      // k >= 4 whenever r4 is used
+        H->f4[v] = f;
+        H->r4[v] = r;
+    }
+    if (threadIdx.x < 4) {
+        H->s1[threadIdx.x] = Tb.seed[threadIdx.x];
+        uint64_t sc = Tb.seed[threadIdx.x ^ 2];
+        for (int q = 0; q < k - 1; q++) sc = srol1(sc);
+        H->s1[4 + threadIdx.x] = sc;
+    }
+    __syncthreads();
+}
+
+// exact base hashes of the k-mer at p (all bases assumed valid), 4 bases per table lookup
+__device__ __forceinline__ void kmer_hash64_tab(const uint32_t* __restrict__ pk, uint64_t p, int k, const HashTabs* H,
+                                                uint64_t& fwd, uint64_t& rev)
+{
+    const uint64_t q = p >> 4;
+    const uint32_t sh = ((uint32_t)p & 15u) * 2u;
+    uint64_t f = 0, r = 0;
+    uint32_t cur = pk_to_natural(__ldg(pk + q));
+    int left = k;
+    for (int m = 0; left > 0; m++) {
+        uint32_t nxt = pk_to_natural(__ldg(pk + q + m + 1));
+        uint32_t N = __funnelshift_r(cur, nxt, sh);      // 16 bases starting at p + 16 m, natural order
+        cur = nxt;
+        int nb = left < 16 ? left : 16;
+        left -= nb;
+        for (; nb >= 4; nb -= 4) {
+            uint32_t v = N & 0xFFu;
+            N >>= 8;
+            f = sroln(f, 4) ^ H->f4[v];
+            r = srorn(r, 4) ^ H->r4[v];
+        }
+        for (; nb > 0; nb--) {
+            uint32_t c = N & 3u;
+            N >>= 2;
+            f = srol1(f) ^ H->s1[c];
+            r = sror1(r) ^ H->s1[4 + c];
+        }
+    }
+    fwd = f;
+    rev = r;
 }
 
 // rank of position p in bitmap V (number of set bits strictly before p)
@@ -278,6 +369,19 @@ __global__ void __launch_bounds__(128) cand_generic_kernel(const uint32_t* __res
 //   a = F << 1 is both the top-aligned clean copy of F (for the sum) and the funnel-shift source.
 // The 16-entry table (idx = out<<2 | in) holds {fwd term low aligned, rev term top aligned}; it is 128 B,
 // one entry per bank pair, so any mix of indices in a warp is conflict free.
+#define MXE_CAND_STEP(i)                                                                              \
+    {                                                                                                 \
+        const uint32_t a = F << 1;                                                                    \
+        const uint32_t key = CANON_MIN ? min(a, R) : a + R + 2u;                                      \
+        asm("{ .reg .pred p; setp.le.u32 p, %1, %2; @p or.b32 %0, %0, %3; }"                          \
+            : "+r"(gb) : "r"(key), "r"(Tt), "n"(1u << (i)));                                          \
+        const uint32_t addr = __byte_perm(zq[(i) >> 2], 0, 0x4440 | ((i) & 3));                       \
+        const uint2 e = *reinterpret_cast<const uint2*>(tb + addr);                                   \
+        F = __funnelshift_l(a, F, 1) ^ e.x;                                                           \
+        const uint32_t u = R ^ e.y;                                                                   \
+        R = __funnelshift_r(u, u >> 1, 1);                                                            \
+    }
+
 template <int CANON_MIN>
 __global__ void __launch_bounds__(128) cand31_kernel(const uint32_t* __restrict__ pk, const uint32_t* __restrict__ V,
                                                       SketchParams P, SketchTables Tb, uint32_t* __restrict__ C)
@@ -289,30 +393,36 @@ __global__ void __launch_bounds__(128) cand31_kernel(const uint32_t* __restrict_
     uint64_t p0 = tid * (uint64_t)P.chunk;
     if (p0 >= P.n) return;
     const int k = P.k;
-    // direct 31-bit hash of the first k-mer
-    uint32_t F = 0, R = 0;
-    for (int i = 0; i < k; i++) {
-        uint32_t cf = pk_code(pk, p0 + i), cr = pk_code(pk, p0 + k - 1 - i) ^ 2u;
-        F = rol31(F) ^ Tb.shi[cf];
-        R = rol31(R) ^ Tb.shi[cr];
-    }
-    R <<= 1;
     const uint64_t q0 = p0 >> 4;
     const int kq = k >> 4, ks = (k & 15) >> 2;
+    uint32_t F, R;
+    int g = 0;
+    if (ks == 0) {
+        // warm-up by rolling: start from the all-A k-mer and roll k steps with out = A, in = first k bases
+        F = Tb.f0; R = Tb.r0; g = -kq;
+    } else {
+        F = 0; R = 0;
+        for (int i = 0; i < k; i++) {
+            uint32_t cf = pk_code(pk, p0 + i), cr = pk_code(pk, p0 + k - 1 - i) ^ 2u;
+            F = rol31(F) ^ Tb.shi[cf];
+            R = rol31(R) ^ Tb.shi[cr];
+        }
+    }
+    R <<= 1;
     const uint32_t lowmask = ks == 1 ? 0x3F3F3F3Fu : ks == 2 ? 0x0F0F0F0Fu : 0x03030303u;
     const char* tb = reinterpret_cast<const char*>(tab);
     const uint32_t Tt = CANON_MIN ? ((P.T << 1) | 1u) : (((P.T + 1u) << 1) | 1u);
     const int n_g = P.chunk / 16;
     uint32_t bits = 0;
-    for (int g = 0; g < n_g; g++) {
-        if (p0 + (uint64_t)g * 16 >= P.n) { if (g & 1) C[(p0 >> 5) + (g >> 1)] = bits & V[(p0 >> 5) + (g >> 1)]; break; }
-        uint32_t o = __ldg(pk + q0 + g);
+    for (; g < n_g; g++) {
+        if (g >= 0 && p0 + (uint64_t)g * 16 >= P.n) { if (g & 1) C[(p0 >> 5) + (g >> 1)] = bits & V[(p0 >> 5) + (g >> 1)]; break; }
+        uint32_t o = g < 0 ? 0u : __ldg(pk + q0 + g);
         uint32_t in = __ldg(pk + q0 + g + kq);
         if (ks) {
             uint32_t b2 = __ldg(pk + q0 + g + kq + 1);
             in = ((in >> (2 * ks)) & lowmask) | ((b2 << (8 - 2 * ks)) & ~lowmask);
         }
-        // table byte offsets (idx << 3), one per byte:  zl[j] low nibbles, zh[j] high nibbles of z1 (j=0,2) / z2 (j=1,3)
+        // table byte offsets (idx << 3), one per byte: zq[j] serves positions 4j..4j+3 of the group
         uint32_t z1 = ((o << 2) & 0xCCCCCCCCu) | (in & 0x33333333u);
         uint32_t z2 = (o & 0xCCCCCCCCu) | ((in >> 2) & 0x33333333u);
         uint32_t zq[4];
@@ -320,24 +430,12 @@ __global__ void __launch_bounds__(128) cand31_kernel(const uint32_t* __restrict_
         zq[1] = (z2 << 3) & 0x78787878u;
         zq[2] = (z1 >> 1) & 0x78787878u;
         zq[3] = (z2 >> 1) & 0x78787878u;
-        uint32_t key[16];
-        uint32_t m = 0xFFFFFFFFu;
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-            const uint32_t a = F << 1;
-            key[i] = CANON_MIN ? min(a, R) : a + R + 2u;
-            m = min(m, key[i]);
-            const uint32_t addr = __byte_perm(zq[i >> 2], 0, 0x4440 | (i & 3));
-            const uint2 e = *reinterpret_cast<const uint2*>(tb + addr);
-            F = __funnelshift_l(a, F, 1) ^ e.x;
-            const uint32_t u = R ^ e.y;
-            R = __funnelshift_r(u, u >> 1, 1);
-        }
         uint32_t gb = 0;
-        if (m <= Tt) {
-#pragma unroll
-            for (int i = 0; i < 16; i++) gb |= (key[i] <= Tt ? 1u : 0u) << i;
-        }
+        MXE_CAND_STEP(0) MXE_CAND_STEP(1) MXE_CAND_STEP(2) MXE_CAND_STEP(3)
+        MXE_CAND_STEP(4) MXE_CAND_STEP(5) MXE_CAND_STEP(6) MXE_CAND_STEP(7)
+        MXE_CAND_STEP(8) MXE_CAND_STEP(9) MXE_CAND_STEP(10) MXE_CAND_STEP(11)
+        MXE_CAND_STEP(12) MXE_CAND_STEP(13) MXE_CAND_STEP(14) MXE_CAND_STEP(15)
+        if (g < 0) continue;
         if (g & 1) {
             bits |= gb << 16;
             uint64_t wi = (p0 >> 5) + (g >> 1);
@@ -347,23 +445,59 @@ __global__ void __launch_bounds__(128) cand31_kernel(const uint32_t* __restrict_
         }
     }
 }
+#undef MXE_CAND_STEP
 
-// ---------------------------------------------------------------- cand_eval
-__global__ void __launch_bounds__(256) cand_eval_kernel(const uint64_t* __restrict__ cpos, uint64_t n_cand,
-                                                         const uint32_t* __restrict__ pk, const uint32_t* __restrict__ V,
-                                                         const uint64_t* __restrict__ vprefix,
-                                                         const uint64_t* __restrict__ offsets, uint32_t n_contigs,
-                                                         SketchParams P, SketchTables Tb,
-                                                         uint64_t* __restrict__ h0, uint64_t* __restrict__ gord, uint32_t* __restrict__ ctg)
+// ---------------------------------------------------------------- candidate extraction + evaluation
+// One warp per 1024-bit block of C: ordered positions, valid-k-mer ordinals (warp scan over V, no
+// per-candidate rank walk) and record ids (one binary search per block).
+__global__ void __launch_bounds__(256) cand_extract_kernel(const uint32_t* __restrict__ C, const uint32_t* __restrict__ V, uint64_t n_words,
+                                                            const uint64_t* __restrict__ cprefix, const uint64_t* __restrict__ vprefix, uint64_t n_blocks,
+                                                            const uint64_t* __restrict__ offsets, uint32_t n_contigs,
+                                                            uint64_t* __restrict__ cpos, uint64_t* __restrict__ cord, uint32_t* __restrict__ cctg)
 {
+    uint64_t blk = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (blk >= n_blocks) return;
+    const uint64_t c_base = cprefix[blk];
+    if (cprefix[blk + 1] == c_base) return;          // warp-uniform
+    const uint64_t wi = blk * RANK_BLOCK_WORDS + lane;
+    uint32_t cw = wi < n_words ? C[wi] : 0;
+    const uint32_t vw = wi < n_words ? V[wi] : 0;
+    uint32_t cc = __popc(cw), vc = __popc(vw), cx = cc, vx = vc;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t y1 = __shfl_up_sync(0xffffffffu, cx, d), y2 = __shfl_up_sync(0xffffffffu, vx, d);
+        if (lane >= d) { cx += y1; vx += y2; }
+    }
+    uint32_t c0 = 0;
+    if (lane == 0) c0 = contig_of(offsets, n_contigs, blk * RANK_BLOCK_BITS);
+    c0 = __shfl_sync(0xffffffffu, c0, 0);
+    uint64_t o = c_base + (cx - cc);
+    const uint64_t v_base = vprefix[blk] + (vx - vc);
+    const uint64_t base = wi << 5;
+    while (cw) {
+        const int b = __ffs(cw) - 1;
+        cw &= cw - 1;
+        const uint64_t p = base + b;
+        uint32_t c = c0;
+        while (c + 1 < n_contigs && offsets[c + 1] <= p) c++;
+        cpos[o] = p;
+        cord[o] = v_base + __popc(vw & ((1u << b) - 1u));
+        cctg[o] = c;
+        o++;
+    }
+}
+
+__global__ void __launch_bounds__(256) cand_hash_kernel(const uint64_t* __restrict__ cpos, uint64_t n_cand, const uint32_t* __restrict__ pk,
+                                                         SketchParams P, SketchTables Tb, uint64_t* __restrict__ h0)
+{
+    __shared__ HashTabs H;
+    build_hash_tabs(&H, Tb, P.k);
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_cand) return;
-    uint64_t p = cpos[i];
     uint64_t f, r;
-    kmer_hash64(pk, p, P.k, Tb.seed, f, r);
+    kmer_hash64_tab(pk, cpos[i], P.k, &H, f, r);
     h0[i] = canon(f, r, P.canon_min);
-    gord[i] = bitmap_rank(V, vprefix, p);
-    ctg[i] = contig_of(offsets, n_contigs, p);
 }
 
 // ---------------------------------------------------------------- select
@@ -459,6 +593,8 @@ __global__ void __launch_bounds__(256) gap_kernel(const Gap* __restrict__ gaps, 
                                                    uint64_t* __restrict__ scratch_h, uint64_t* __restrict__ scratch_p,
                                                    uint32_t* __restrict__ M)
 {
+    __shared__ HashTabs Ht;
+    build_hash_tabs(&Ht, Tb, P.k);
     const uint64_t w = (uint64_t)P.w;
     const uint64_t stride = (uint64_t)GAP_CHUNK + w;
     uint64_t* H = scratch_h + (uint64_t)blockIdx.x * stride;
@@ -473,7 +609,7 @@ __global__ void __launch_bounds__(256) gap_kernel(const Gap* __restrict__ gaps, 
             for (uint64_t e = threadIdx.x; e < m; e += blockDim.x) {
                 uint64_t p = bitmap_select(V, vprefix, n_vblocks, o0 + e);
                 uint64_t f, r;
-                kmer_hash64(pk, p, P.k, Tb.seed, f, r);
+                kmer_hash64_tab(pk, p, P.k, &Ht, f, r);
                 H[e] = canon(f, r, P.canon_min);
                 Q[e] = p;
             }
@@ -497,27 +633,52 @@ __global__ void __launch_bounds__(256) gap_kernel(const Gap* __restrict__ gaps, 
     }
 }
 
-// ---------------------------------------------------------------- final_eval
-__global__ void __launch_bounds__(256) final_eval_kernel(const uint64_t* __restrict__ mpos, uint64_t n_mx,
-                                                          const uint32_t* __restrict__ pk,
+// ---------------------------------------------------------------- final emission
+// One warp per 1024-bit block of M: ordered minimizer records.
+__global__ void __launch_bounds__(256) final_emit_kernel(const uint32_t* __restrict__ M, uint64_t n_words, const uint64_t* __restrict__ mprefix,
+                                                          uint64_t n_blocks, const uint32_t* __restrict__ pk,
                                                           const uint64_t* __restrict__ offsets, uint32_t n_contigs,
                                                           SketchParams P, SketchTables Tb,
                                                           uint64_t* __restrict__ out_hash, uint64_t* __restrict__ min_hash,
                                                           uint32_t* __restrict__ pos, uint32_t* __restrict__ contig,
                                                           uint8_t* __restrict__ forward)
 {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_mx) return;
-    uint64_t p = mpos[i];
-    uint64_t f, r;
-    kmer_hash64(pk, p, P.k, Tb.seed, f, r);
-    uint64_t h0 = canon(f, r, P.canon_min);
-    uint32_t c = contig_of(offsets, n_contigs, p);
-    out_hash[i] = mix_out_hash(h0, P.k);
-    min_hash[i] = h0;
-    pos[i] = (uint32_t)(p - offsets[c]);
-    contig[i] = c;
-    forward[i] = f <= r;
+    __shared__ HashTabs H;
+    build_hash_tabs(&H, Tb, P.k);
+    uint64_t blk = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (blk >= n_blocks) return;
+    const uint64_t m_base = mprefix[blk];
+    if (mprefix[blk + 1] == m_base) return;
+    const uint64_t wi = blk * RANK_BLOCK_WORDS + lane;
+    uint32_t mw = wi < n_words ? M[wi] : 0;
+    uint32_t mc = __popc(mw), mx = mc;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, mx, d);
+        if (lane >= d) mx += y;
+    }
+    uint32_t c0 = 0;
+    if (lane == 0) c0 = contig_of(offsets, n_contigs, blk * RANK_BLOCK_BITS);
+    c0 = __shfl_sync(0xffffffffu, c0, 0);
+    uint64_t o = m_base + (mx - mc);
+    const uint64_t base = wi << 5;
+    while (mw) {
+        const int b = __ffs(mw) - 1;
+        mw &= mw - 1;
+        const uint64_t p = base + b;
+        uint32_t c = c0;
+        while (c + 1 < n_contigs && offsets[c + 1] <= p) c++;
+        uint64_t f, r;
+        kmer_hash64_tab(pk, p, P.k, &H, f, r);
+        const uint64_t h0 = canon(f, r, P.canon_min);
+        out_hash[o] = mix_out_hash(h0, P.k);
+        min_hash[o] = h0;
+        pos[o] = (uint32_t)(p - offsets[c]);
+        contig[o] = c;
+        forward[o] = f <= r;
+        o++;
+    }
 }
 
 }  // namespace mxe

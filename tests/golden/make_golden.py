@@ -123,6 +123,7 @@ def main():
             out = {
                 "files": files, "k": k, "w": w, "weights": weights,
                 "read_minimizers": [{"mx_info": {mx: [c, p] for mx, (c, p) in list_mx_info[t].items()},
+                                     "mx_order": list(list_mx_info[t]),       # dict insertion order
                                      "mxs": list_mxs[t]} for t in tsvs],
                 "filter_minimizers": [filtered[t] for t in tsvs],
                 "vertices": sorted(graph.vnames, key=int),

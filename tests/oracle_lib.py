@@ -91,6 +91,7 @@ class Oracle:
             raise RuntimeError(f"oracle filter failed: {rc}")
         edges = np.ctypeslib.as_array(C.cast(E, C.POINTER(C.c_uint8)), shape=(ne.value * C.sizeof(MxoEdge),)).view(EDGE_DTYPE).copy() \
             if ne.value else np.empty(0, dtype=EDGE_DTYPE)
+        edges["_pad"] = 0     # struct padding is uninitialised on the C side
         verts = np.ctypeslib.as_array(V, shape=(nv.value,)).copy() if nv.value else np.empty(0, dtype=np.uint64)
         self.lib.mxo_free(E)
         self.lib.mxo_free(V)
