@@ -66,7 +66,7 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
     if (e->chunk > 0) P.chunk = std::max(32, (e->chunk / 32) * 32);
     else {   // auto: long runs amortise the k-step warm-up, but keep >= ~4 waves of threads in flight
         uint64_t want = n / ((uint64_t)e->sm_count * 2048 * 2) + 1;
-        P.chunk = (int)std::min<uint64_t>(1024, std::max<uint64_t>(128, (want + 31) / 32 * 32));
+        P.chunk = want >= 512 ? 512 : want >= 256 ? 256 : 128;
     }
     SketchTables Tb;
     build_tables(k, &Tb);
@@ -74,6 +74,7 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
     const uint64_t nW = P.n_words;
     const uint64_t n_vblocks = (nW + RANK_BLOCK_WORDS - 1) / RANK_BLOCK_WORDS;
     const uint64_t pk_words = 2 * nW + (uint64_t)(k / 16) + 16;
+    P.pk_words = pk_words;
 
     DBuf<uint32_t> pk, B, V, C, M;
     DBuf<uint64_t> vprefix, cprefix, mprefix, d_offsets, ostart;
@@ -111,8 +112,19 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
         uint64_t n_threads = (n + P.chunk - 1) / P.chunk;
         bool fast = e->cand_variant >= 1 && (k % 4 == 0) && k >= 4;
         if (fast) {
-            if (P.canon_min) MXE_LAUNCH(e, cand31_kernel<1>, grid_for(n_threads, 128), 128, 0, pk.p, V.p, P, Tb, C.p);
-            else MXE_LAUNCH(e, cand31_kernel<0>, grid_for(n_threads, 128), 128, 0, pk.p, V.p, P, Tb, C.p);
+            // the staged kernel needs a power-of-two run length between 128 and 1024
+            int c = 128;
+            while (c * 2 <= P.chunk && c < 1024) c *= 2;
+            P.chunk = c;
+            n_threads = (n + P.chunk - 1) / P.chunk;
+            size_t smem = cand31_smem_bytes(P.chunk, k);
+            if (P.canon_min) {
+                MXE_CUDA(cudaFuncSetAttribute(cand31_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                MXE_LAUNCH(e, cand31_kernel<1>, grid_for(n_threads, CAND_THREADS), CAND_THREADS, smem, pk.p, V.p, P, Tb, C.p);
+            } else {
+                MXE_CUDA(cudaFuncSetAttribute(cand31_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                MXE_LAUNCH(e, cand31_kernel<0>, grid_for(n_threads, CAND_THREADS), CAND_THREADS, smem, pk.p, V.p, P, Tb, C.p);
+            }
         } else {
             MXE_LAUNCH(e, cand_generic_kernel, grid_for(n_threads, 128), 128, 0, pk.p, V.p, P, Tb, C.p);
         }
@@ -193,7 +205,10 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
         MXE_CUDA(cudaMallocAsync((void**)&S->d_pos, n_mx * sizeof(uint32_t), st));
         MXE_CUDA(cudaMallocAsync((void**)&S->d_contig, n_mx * sizeof(uint32_t), st));
         MXE_CUDA(cudaMallocAsync((void**)&S->d_forward, n_mx * sizeof(uint8_t), st));
-        MXE_LAUNCH(e, final_emit_kernel, grid_for(n_vblocks * 32, 256), 256, 0, M.p, nW, mprefix.p, n_vblocks, pk.p, d_offsets.p, n_contigs, P, Tb,
+        DBuf<uint64_t> mpos;
+        MXE_TRY(mpos.alloc(n_mx, st));
+        MXE_TRY(bitmap_extract(e, M.p, nW, mprefix.p, mpos.p));
+        MXE_LAUNCH(e, final_eval_kernel, grid_for(n_mx, 256), 256, 0, mpos.p, n_mx, pk.p, d_offsets.p, n_contigs, P, Tb,
                    S->d_out_hash, S->d_min_hash, S->d_pos, S->d_contig, S->d_forward);
     }
     MXE_CUDA(cudaGetLastError());

@@ -36,6 +36,7 @@ struct SketchParams {
     int canon_min;         // 0 sum, 1 min
     uint32_t T;            // candidate threshold on hash0>>33
     int chunk;             // positions per thread in cand kernels
+    uint64_t pk_words;     // allocated words of pk (zero padded past the sequence)
 };
 
 // ---------------------------------------------------------------- bit helpers
@@ -382,67 +383,109 @@ __global__ void __launch_bounds__(128) cand_generic_kernel(const uint32_t* __res
         R = __funnelshift_r(u, u >> 1, 1);                                                            \
     }
 
-template <int CANON_MIN>
-__global__ void __launch_bounds__(128) cand31_kernel(const uint32_t* __restrict__ pk, const uint32_t* __restrict__ V,
-                                                      SketchParams P, SketchTables Tb, uint32_t* __restrict__ C)
+// Shared-memory staging: every thread walks its own run of `chunk` consecutive positions, which as
+// direct global loads is one scattered 4-byte access per lane (measured: L1TEX 99 % busy, 10x DRAM
+// over-fetch).  The CTA instead copies its contiguous slice of pk (plus a k-base halo) and of V into
+// shared memory with coalesced loads; rows are padded by one word per thread-run so that the per-thread
+// walk (lane stride = run length + 1 words, odd) is bank-conflict free.  C is written back through the
+// same buffer, coalesced.
+constexpr int CAND_THREADS = 128;
+
+__host__ __device__ inline size_t cand31_smem_bytes(int chunk, int k)
 {
-    __shared__ uint2 tab[16];
-    if (threadIdx.x < 16) { uint2 e = Tb.t16[threadIdx.x]; e.y <<= 1; tab[threadIdx.x] = e; }
-    __syncthreads();
-    uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint64_t p0 = tid * (uint64_t)P.chunk;
-    if (p0 >= P.n) return;
+    const int wpt = chunk / 16, wv = chunk / 32;
+    const size_t n_pk = (size_t)CAND_THREADS * wpt + (size_t)(k / 16) + 2;
+    const size_t n_v = (size_t)CAND_THREADS * wv;
+    return (32 + n_pk + n_pk / wpt + 1 + n_v + n_v / wv + 1) * sizeof(uint32_t);
+}
+
+template <int CANON_MIN>
+__global__ void __launch_bounds__(CAND_THREADS) cand31_kernel(const uint32_t* __restrict__ pk, const uint32_t* __restrict__ V,
+                                                               SketchParams P, SketchTables Tb, uint32_t* __restrict__ C)
+{
+    extern __shared__ uint32_t smem[];
+    uint2* tab = reinterpret_cast<uint2*>(smem);                 // 16 entries
+    const int wpt = P.chunk >> 4, wv = P.chunk >> 5;             // pk / V words per thread-run (powers of two)
+    const int lw = 31 - __clz(wpt), lv = 31 - __clz(wv);
     const int k = P.k;
-    const uint64_t q0 = p0 >> 4;
     const int kq = k >> 4, ks = (k & 15) >> 2;
-    uint32_t F, R;
-    int g = 0;
-    if (ks == 0) {
-        // warm-up by rolling: start from the all-A k-mer and roll k steps with out = A, in = first k bases
-        F = Tb.f0; R = Tb.r0; g = -kq;
-    } else {
-        F = 0; R = 0;
-        for (int i = 0; i < k; i++) {
-            uint32_t cf = pk_code(pk, p0 + i), cr = pk_code(pk, p0 + k - 1 - i) ^ 2u;
-            F = rol31(F) ^ Tb.shi[cf];
-            R = rol31(R) ^ Tb.shi[cr];
-        }
+    const uint32_t n_pk = CAND_THREADS * wpt + kq + 2;
+    uint32_t* pkS = smem + 32;
+    uint32_t* vcS = pkS + n_pk + (n_pk >> lw) + 1;
+    const uint32_t n_v = CAND_THREADS * wv;
+
+    if (threadIdx.x < 16) { uint2 e = Tb.t16[threadIdx.x]; e.y <<= 1; tab[threadIdx.x] = e; }
+    const uint64_t cta_p0 = (uint64_t)blockIdx.x * CAND_THREADS * (uint64_t)P.chunk;
+    const uint64_t q_cta = cta_p0 >> 4, v_cta = cta_p0 >> 5;
+    for (uint32_t i = threadIdx.x; i < n_pk; i += CAND_THREADS) {
+        uint64_t gw = q_cta + i;
+        pkS[i + (i >> lw)] = gw < P.pk_words ? __ldg(pk + gw) : 0u;
     }
-    R <<= 1;
-    const uint32_t lowmask = ks == 1 ? 0x3F3F3F3Fu : ks == 2 ? 0x0F0F0F0Fu : 0x03030303u;
-    const char* tb = reinterpret_cast<const char*>(tab);
-    const uint32_t Tt = CANON_MIN ? ((P.T << 1) | 1u) : (((P.T + 1u) << 1) | 1u);
-    const int n_g = P.chunk / 16;
-    uint32_t bits = 0;
-    for (; g < n_g; g++) {
-        if (g >= 0 && p0 + (uint64_t)g * 16 >= P.n) { if (g & 1) C[(p0 >> 5) + (g >> 1)] = bits & V[(p0 >> 5) + (g >> 1)]; break; }
-        uint32_t o = g < 0 ? 0u : __ldg(pk + q0 + g);
-        uint32_t in = __ldg(pk + q0 + g + kq);
-        if (ks) {
-            uint32_t b2 = __ldg(pk + q0 + g + kq + 1);
-            in = ((in >> (2 * ks)) & lowmask) | ((b2 << (8 - 2 * ks)) & ~lowmask);
-        }
-        // table byte offsets (idx << 3), one per byte: zq[j] serves positions 4j..4j+3 of the group
-        uint32_t z1 = ((o << 2) & 0xCCCCCCCCu) | (in & 0x33333333u);
-        uint32_t z2 = (o & 0xCCCCCCCCu) | ((in >> 2) & 0x33333333u);
-        uint32_t zq[4];
-        zq[0] = (z1 << 3) & 0x78787878u;
-        zq[1] = (z2 << 3) & 0x78787878u;
-        zq[2] = (z1 >> 1) & 0x78787878u;
-        zq[3] = (z2 >> 1) & 0x78787878u;
-        uint32_t gb = 0;
-        MXE_CAND_STEP(0) MXE_CAND_STEP(1) MXE_CAND_STEP(2) MXE_CAND_STEP(3)
-        MXE_CAND_STEP(4) MXE_CAND_STEP(5) MXE_CAND_STEP(6) MXE_CAND_STEP(7)
-        MXE_CAND_STEP(8) MXE_CAND_STEP(9) MXE_CAND_STEP(10) MXE_CAND_STEP(11)
-        MXE_CAND_STEP(12) MXE_CAND_STEP(13) MXE_CAND_STEP(14) MXE_CAND_STEP(15)
-        if (g < 0) continue;
-        if (g & 1) {
-            bits |= gb << 16;
-            uint64_t wi = (p0 >> 5) + (g >> 1);
-            C[wi] = bits & V[wi];
+    for (uint32_t i = threadIdx.x; i < n_v; i += CAND_THREADS) {
+        uint64_t gv = v_cta + i;
+        vcS[i + (i >> lv)] = gv < P.n_words ? __ldg(V + gv) : 0u;
+    }
+    __syncthreads();
+
+    const uint64_t p0 = cta_p0 + (uint64_t)threadIdx.x * P.chunk;
+    if (p0 < P.n) {
+        uint32_t F, R;
+        int g = 0;
+        if (ks == 0) {
+            // warm-up by rolling: start from the all-A k-mer and roll k steps with out = A, in = first k bases
+            F = Tb.f0; R = Tb.r0; g = -kq;
         } else {
-            bits = gb;
+            F = 0; R = 0;
+            for (int i = 0; i < k; i++) {
+                uint32_t cf = pk_code(pk, p0 + i), cr = pk_code(pk, p0 + k - 1 - i) ^ 2u;
+                F = rol31(F) ^ Tb.shi[cf];
+                R = rol31(R) ^ Tb.shi[cr];
+            }
         }
+        R <<= 1;
+        const uint32_t lowmask = ks == 1 ? 0x3F3F3F3Fu : ks == 2 ? 0x0F0F0F0Fu : 0x03030303u;
+        const char* tb = reinterpret_cast<const char*>(tab);
+        const uint32_t Tt = CANON_MIN ? ((P.T << 1) | 1u) : (((P.T + 1u) << 1) | 1u);
+        const int n_g = P.chunk / 16;
+        const uint32_t row = threadIdx.x * wpt;
+        const uint32_t vrow = threadIdx.x * wv + threadIdx.x;   // padded index of this run's first V word
+        uint32_t bits = 0;
+        for (; g < n_g; g++) {
+            const uint32_t io = row + g, ii = row + g + kq;
+            uint32_t o = g < 0 ? 0u : pkS[io + (io >> lw)];
+            uint32_t in = pkS[ii + (ii >> lw)];
+            if (ks) {
+                uint32_t b2 = pkS[ii + 1 + ((ii + 1) >> lw)];
+                in = ((in >> (2 * ks)) & lowmask) | ((b2 << (8 - 2 * ks)) & ~lowmask);
+            }
+            // table byte offsets (idx << 3), one per byte: zq[j] serves positions 4j..4j+3 of the group
+            uint32_t z1 = ((o << 2) & 0xCCCCCCCCu) | (in & 0x33333333u);
+            uint32_t z2 = (o & 0xCCCCCCCCu) | ((in >> 2) & 0x33333333u);
+            uint32_t zq[4];
+            zq[0] = (z1 << 3) & 0x78787878u;
+            zq[1] = (z2 << 3) & 0x78787878u;
+            zq[2] = (z1 >> 1) & 0x78787878u;
+            zq[3] = (z2 >> 1) & 0x78787878u;
+            uint32_t gb = 0;
+            MXE_CAND_STEP(0) MXE_CAND_STEP(1) MXE_CAND_STEP(2) MXE_CAND_STEP(3)
+            MXE_CAND_STEP(4) MXE_CAND_STEP(5) MXE_CAND_STEP(6) MXE_CAND_STEP(7)
+            MXE_CAND_STEP(8) MXE_CAND_STEP(9) MXE_CAND_STEP(10) MXE_CAND_STEP(11)
+            MXE_CAND_STEP(12) MXE_CAND_STEP(13) MXE_CAND_STEP(14) MXE_CAND_STEP(15)
+            if (g < 0) continue;
+            if (g & 1) {
+                bits |= gb << 16;
+                vcS[vrow + (g >> 1)] &= bits;        // C = candidates & valid starts (bits beyond n are not valid starts)
+            } else {
+                bits = gb;
+            }
+        }
+    } else {
+        for (int j = 0; j < wv; j++) vcS[threadIdx.x * wv + threadIdx.x + j] = 0;
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n_v; i += CAND_THREADS) {
+        uint64_t gv = v_cta + i;
+        if (gv < P.n_words) C[gv] = vcS[i + (i >> lv)];
     }
 }
 #undef MXE_CAND_STEP
@@ -633,10 +676,9 @@ __global__ void __launch_bounds__(256) gap_kernel(const Gap* __restrict__ gaps, 
     }
 }
 
-// ---------------------------------------------------------------- final emission
-// One warp per 1024-bit block of M: ordered minimizer records.
-__global__ void __launch_bounds__(256) final_emit_kernel(const uint32_t* __restrict__ M, uint64_t n_words, const uint64_t* __restrict__ mprefix,
-                                                          uint64_t n_blocks, const uint32_t* __restrict__ pk,
+// ---------------------------------------------------------------- final_eval: one thread per minimizer
+__global__ void __launch_bounds__(256) final_eval_kernel(const uint64_t* __restrict__ mpos, uint64_t n_mx,
+                                                          const uint32_t* __restrict__ pk,
                                                           const uint64_t* __restrict__ offsets, uint32_t n_contigs,
                                                           SketchParams P, SketchTables Tb,
                                                           uint64_t* __restrict__ out_hash, uint64_t* __restrict__ min_hash,
@@ -645,40 +687,18 @@ __global__ void __launch_bounds__(256) final_emit_kernel(const uint32_t* __restr
 {
     __shared__ HashTabs H;
     build_hash_tabs(&H, Tb, P.k);
-    uint64_t blk = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (blk >= n_blocks) return;
-    const uint64_t m_base = mprefix[blk];
-    if (mprefix[blk + 1] == m_base) return;
-    const uint64_t wi = blk * RANK_BLOCK_WORDS + lane;
-    uint32_t mw = wi < n_words ? M[wi] : 0;
-    uint32_t mc = __popc(mw), mx = mc;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        uint32_t y = __shfl_up_sync(0xffffffffu, mx, d);
-        if (lane >= d) mx += y;
-    }
-    uint32_t c0 = 0;
-    if (lane == 0) c0 = contig_of(offsets, n_contigs, blk * RANK_BLOCK_BITS);
-    c0 = __shfl_sync(0xffffffffu, c0, 0);
-    uint64_t o = m_base + (mx - mc);
-    const uint64_t base = wi << 5;
-    while (mw) {
-        const int b = __ffs(mw) - 1;
-        mw &= mw - 1;
-        const uint64_t p = base + b;
-        uint32_t c = c0;
-        while (c + 1 < n_contigs && offsets[c + 1] <= p) c++;
-        uint64_t f, r;
-        kmer_hash64_tab(pk, p, P.k, &H, f, r);
-        const uint64_t h0 = canon(f, r, P.canon_min);
-        out_hash[o] = mix_out_hash(h0, P.k);
-        min_hash[o] = h0;
-        pos[o] = (uint32_t)(p - offsets[c]);
-        contig[o] = c;
-        forward[o] = f <= r;
-        o++;
-    }
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_mx) return;
+    const uint64_t p = mpos[i];
+    uint64_t f, r;
+    kmer_hash64_tab(pk, p, P.k, &H, f, r);
+    const uint64_t h0 = canon(f, r, P.canon_min);
+    const uint32_t c = contig_of(offsets, n_contigs, p);
+    out_hash[i] = mix_out_hash(h0, P.k);
+    min_hash[i] = h0;
+    pos[i] = (uint32_t)(p - offsets[c]);
+    contig[i] = c;
+    forward[i] = f <= r;
 }
 
 }  // namespace mxe
