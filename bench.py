@@ -121,8 +121,8 @@ def gen_assemblies_gpu(spec, with_n, device):
         at += b - a
         toffs[i + 1] = at
     n_sub = int(G * 0.001)
-    idx = torch.randint(0, G, (n_sub,), device=device, generator=g)
-    sub = lut[torch.randint(0, 4, (n_sub,), dtype=torch.uint8, device=device, generator=g).long()]
+    idx = torch.unique(torch.randint(0, G, (n_sub,), device=device, generator=g))   # unique: deterministic scatter
+    sub = lut[torch.randint(0, 4, (idx.numel(),), dtype=torch.uint8, device=device, generator=g).long()]
     keep = tgt[idx] != ord("N")
     tgt[idx[keep]] = sub[keep]
     return [(ref, roffs), (tgt, toffs)]     # assembly order: reference(s) first, target last
@@ -130,13 +130,27 @@ def gen_assemblies_gpu(spec, with_n, device):
 
 # ------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """Samples SM clock, power and throttle reasons of one GPU every few ms DURING the timed region
+    (NVML in a thread; falls back to `nvidia-smi -lms` when pynvml is unavailable)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.index, self.rows, self.stop_flag, self.proc, self.t, self.nvml = index, [], False, None, None, None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nvml = pynvml
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -145,22 +159,40 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        bits = {"hw_slowdown": n.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": n.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": n.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": n.nvmlClocksThrottleReasonSwPowerCap}
+        while not self.stop_flag:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+                mx = n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)
+                pw = n.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((float(sm), float(mx), pw, [k for k, b in bits.items() if r & b]))
+            except Exception:
+                pass
+            time.sleep(0.004)
+
     def _read(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            r = [x.strip() for x in line.split(",")]
+            if len(r) >= 7 and r[0].replace(".", "").isdigit():
+                self.rows.append((float(r[0]), float(r[1]), float(r[2]) if r[2].replace(".", "").isdigit() else 0.0,
+                                  [names[i] for i in range(4) if r[3 + i].lower() == "active"]))
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        self.t.join(timeout=2)
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower() == "active"})
-        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        if self.t:
+            self.t.join(timeout=2)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median([r[0] for r in self.rows])), "sm_max_mhz": max(r[1] for r in self.rows),
+                "power_w_max": max(r[2] for r in self.rows), "samples": len(self.rows),
+                "reasons": sorted({x for r in self.rows for x in r[3]})}
 
 
 # ------------------------------------------------------------------------------------ CPU arm

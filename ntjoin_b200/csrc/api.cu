@@ -162,7 +162,7 @@ int mxe_sketch_buffers(mxe_t* e, const uint8_t* seq, const uint64_t* offsets, ui
 int mxe_sketch_device(mxe_t* e, const void* d_seq, const uint64_t* offsets, uint32_t n_contigs,
                       const char* const* names, int k, int w, int flags, mxe_sketch_t** out)
 {
-    if (!e || !out || !offsets || !d_seq) { set_error("null argument"); return MXE_ERR_ARG; }
+    if (!e || !out || !offsets || (!d_seq && n_contigs && offsets[n_contigs])) { set_error("null argument"); return MXE_ERR_ARG; }
     MXE_CUDA(cudaSetDevice(e->device));
     mxe_sketch* S = new mxe_sketch();
     set_names(S, names, n_contigs);

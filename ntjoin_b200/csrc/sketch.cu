@@ -45,7 +45,7 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
         if (offsets[c + 1] - offsets[c] >= (1ULL << 32)) { set_error("record %u longer than 2^32-1 bases", c); return MXE_ERR_ARG; }
     }
     if (n_contigs && offsets[n_contigs] != n) { set_error("offsets[n_contigs] != n"); return MXE_ERR_ARG; }
-    if (((uintptr_t)d_seq & 15) != 0) { set_error("device sequence pointer must be 16-byte aligned"); return MXE_ERR_ARG; }
+    if (n && ((uintptr_t)d_seq & 15) != 0) { set_error("device sequence pointer must be 16-byte aligned"); return MXE_ERR_ARG; }
 
     cudaStream_t st = e->stream;
     S->eng = e; S->k = k; S->w = w; S->flags = flags;
