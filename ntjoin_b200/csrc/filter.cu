@@ -42,6 +42,35 @@ __global__ void __launch_bounds__(256) copy_contig_kernel(const uint32_t* __rest
     if (i < n) dst[base + i] = src[i];
 }
 
+// The hash sort only covers the top SORT_BITS bits (out_hash is uniformly mixed, so ties in the top 32 bits between
+// DIFFERENT hashes are rare: ~n^2/2^33 pairs).  This pass finishes the job: inside every run of equal top bits it
+// orders the elements by full key (stable insertion sort; the input order inside a run is the concatenation order,
+// i.e. by assembly).  Runs whose keys are all equal (true duplicates, any length) need nothing.  A mixed run longer
+// than FIXUP_MAX raises the fallback flag and the caller redoes the sort on all 64 bits.
+constexpr int SORT_LOW_BIT = 32;
+constexpr int FIXUP_MAX = 64;
+
+__global__ void __launch_bounds__(256) fixup_kernel(uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, uint64_t N, int* __restrict__ fallback)
+{
+    uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= N) return;
+    const uint64_t top = keys[s] >> SORT_LOW_BIT;
+    if (s > 0 && (keys[s - 1] >> SORT_LOW_BIT) == top) return;      // not a run head
+    if (s + 1 >= N || (keys[s + 1] >> SORT_LOW_BIT) != top) return; // run of one
+    const uint64_t k0 = keys[s];
+    uint64_t e = s + 1;
+    bool mixed = false;
+    while (e < N && (keys[e] >> SORT_LOW_BIT) == top) { mixed |= keys[e] != k0; e++; }
+    if (!mixed) return;
+    if (e - s > FIXUP_MAX) { *fallback = 1; return; }
+    for (uint64_t i = s + 1; i < e; i++) {
+        uint64_t kk = keys[i]; uint32_t vv = vals[i];
+        uint64_t j = i;
+        while (j > s && keys[j - 1] > kk) { keys[j] = keys[j - 1]; vals[j] = vals[j - 1]; j--; }
+        keys[j] = kk; vals[j] = vv;
+    }
+}
+
 // per sorted element: uniqueness inside its assembly, membership in a found-in-all run, run head
 __global__ void __launch_bounds__(256) mark_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t N,
                                                     AsmOffsets A, uint8_t* __restrict__ uniq, uint8_t* __restrict__ keep,
@@ -213,7 +242,19 @@ int filter_and_edges_impl(mxe_engine* e, const uint64_t* const* d_hash, const ui
         MXE_LAUNCH(e, concat_kernel, gridf(n[a]), 256, 0, d_hash[a], n[a], A.off[a], keys.p, vals.p);
         MXE_LAUNCH(e, copy_contig_kernel, gridf(n[a]), 256, 0, d_contig[a], n[a], A.off[a], contig.p);
     }
-    MXE_TRY(radix_sort_pairs(e, keys.p, vals.p, keys2.p, vals2.p, N, 0, 64));
+    {
+        // sort the top 32 bits, finish inside the (tiny) tied runs; full 64-bit sort only if that is not enough
+        DBuf<int> fallback;
+        MXE_TRY(fallback.alloc(1, st));
+        MXE_CUDA(cudaMemsetAsync(fallback.p, 0, sizeof(int), st));
+        MXE_TRY(radix_sort_pairs(e, keys.p, vals.p, keys2.p, vals2.p, N, SORT_LOW_BIT, 64));
+        MXE_LAUNCH(e, fixup_kernel, gridf(N), 256, 0, keys.p, vals.p, N, fallback.p);
+        int fb = 0;
+        MXE_CUDA(cudaMemcpyAsync(&fb, fallback.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        MXE_CUDA(cudaStreamSynchronize(st));
+        if (fb) MXE_TRY(radix_sort_pairs(e, keys.p, vals.p, keys2.p, vals2.p, N, 0, SORT_LOW_BIT));   // LSD: low bits, then...
+        if (fb) MXE_TRY(radix_sort_pairs(e, keys.p, vals.p, keys2.p, vals2.p, N, SORT_LOW_BIT, 64));  // ...high bits again (stable)
+    }
     MXE_LAUNCH(e, mark_kernel, gridf(N), 256, 0, keys.p, vals.p, N, A, uniq.p, keep_p, head.p);
     MXE_TRY(exclusive_scan_u32_u64(e, head.p, hprefix.p, N));
     MXE_LAUNCH(e, widen_flags_kernel, gridf(N), 256, 0, keep_p, N, kflag.p);

@@ -78,6 +78,9 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
 
     DBuf<uint32_t> pk, B, V, C, M;
     DBuf<uint64_t> vprefix, cprefix, mprefix, d_offsets, ostart;
+    DBuf<uint32_t> vcounts, ccounts;
+    MXE_TRY(vcounts.alloc(n_vblocks + 1, st));
+    MXE_TRY(ccounts.alloc(n_vblocks + 1, st));
     MXE_TRY(pk.alloc(pk_words, st));
     MXE_TRY(B.alloc(nW, st));
     MXE_TRY(V.alloc(nW, st));
@@ -97,16 +100,17 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
     {
         Span sp(e, "pack");
         MXE_LAUNCH(e, pack_kernel, grid_for(nW, 256), 256, 0, d_seq, P, pk.p, B.p);
-        MXE_LAUNCH(e, vmask_kernel, grid_for(nW, 256), 256, 0, B.p, P, V.p);
-        if (n_contigs > 1) MXE_LAUNCH(e, boundary_kernel, grid_for(n_contigs - 1, 128), 128, 0, d_offsets.p, n_contigs, P, V.p);
+        MXE_LAUNCH(e, vmask_kernel, grid_for(nW, 256), 256, 0, B.p, P, V.p, vcounts.p);
+        if (n_contigs > 1) MXE_LAUNCH(e, boundary_kernel, grid_for(n_contigs - 1, 128), 128, 0, d_offsets.p, n_contigs, P, V.p, vcounts.p);
     }
     {
         Span sp(e, "rank");
-        MXE_TRY(bitmap_rank_build(e, V.p, nW, vprefix.p));
+        MXE_TRY(exclusive_scan_u32_u64(e, vcounts.p, vprefix.p, n_vblocks));
         MXE_LAUNCH(e, contig_bounds_kernel, grid_for(n_contigs + 1, 128), 128, 0, d_offsets.p, n_contigs, P, V.p, vprefix.p, ostart.p);
     }
 
     // ---- candidates
+    bool c_counted = false;
     {
         Span sp(e, "cand");
         uint64_t n_threads = (n + P.chunk - 1) / P.chunk;
@@ -118,12 +122,13 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
             P.chunk = c;
             n_threads = (n + P.chunk - 1) / P.chunk;
             size_t smem = cand31_smem_bytes(P.chunk, k);
+            c_counted = true;
             if (P.canon_min) {
                 MXE_CUDA(cudaFuncSetAttribute(cand31_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                MXE_LAUNCH(e, cand31_kernel<1>, grid_for(n_threads, CAND_THREADS), CAND_THREADS, smem, pk.p, V.p, P, Tb, C.p);
+                MXE_LAUNCH(e, cand31_kernel<1>, grid_for(n_threads, CAND_THREADS), CAND_THREADS, smem, pk.p, V.p, P, Tb, C.p, ccounts.p);
             } else {
                 MXE_CUDA(cudaFuncSetAttribute(cand31_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                MXE_LAUNCH(e, cand31_kernel<0>, grid_for(n_threads, CAND_THREADS), CAND_THREADS, smem, pk.p, V.p, P, Tb, C.p);
+                MXE_LAUNCH(e, cand31_kernel<0>, grid_for(n_threads, CAND_THREADS), CAND_THREADS, smem, pk.p, V.p, P, Tb, C.p, ccounts.p);
             }
         } else {
             MXE_LAUNCH(e, cand_generic_kernel, grid_for(n_threads, 128), 128, 0, pk.p, V.p, P, Tb, C.p);
@@ -131,7 +136,8 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
     }
     {
         Span sp(e, "rank");
-        MXE_TRY(bitmap_rank_build(e, C.p, nW, cprefix.p));
+        if (c_counted) MXE_TRY(exclusive_scan_u32_u64(e, ccounts.p, cprefix.p, n_vblocks));
+        else MXE_TRY(bitmap_rank_build(e, C.p, nW, cprefix.p));
     }
 
     uint64_t totals[2] = {0, 0};

@@ -287,10 +287,8 @@ __global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ s
 }
 
 // ---------------------------------------------------------------- vmask: V = valid k-mer starts
-__global__ void __launch_bounds__(256) vmask_kernel(const uint32_t* __restrict__ B, SketchParams P, uint32_t* __restrict__ V)
+__device__ __forceinline__ uint32_t vmask_word(const uint32_t* __restrict__ B, const SketchParams& P, uint64_t t)
 {
-    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= P.n_words) return;
     const int reach = (31 + P.k - 1) / 32;     // last word touched = t + reach
     uint32_t any = 0;
     for (int j = 0; j <= reach; j++) any |= (t + j < P.n_words) ? B[t + j] : 0xFFFFFFFFu;
@@ -308,18 +306,37 @@ __global__ void __launch_bounds__(256) vmask_kernel(const uint32_t* __restrict__
             }
         }
     }
-    V[t] = v;
+    return v;
 }
 
+// Also emits the rank-directory block counts of V (one warp = 32 consecutive words = one 1024-bit block).
+__global__ void __launch_bounds__(256) vmask_kernel(const uint32_t* __restrict__ B, SketchParams P, uint32_t* __restrict__ V,
+                                                    uint32_t* __restrict__ vcounts)
+{
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t v = 0;
+    if (t < P.n_words) v = vmask_word(B, P, t);
+    uint32_t c = __popc(v);
+#pragma unroll
+    for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if (t < P.n_words) V[t] = v;
+    if ((threadIdx.x & 31) == 0 && (t >> 5) * RANK_BLOCK_WORDS < P.n_words) vcounts[t >> 5] = c;
+}
+
+
 // contig boundaries: a k-mer may not straddle two records
-__global__ void boundary_kernel(const uint64_t* __restrict__ offsets, uint32_t n_contigs, SketchParams P, uint32_t* __restrict__ V)
+__global__ void boundary_kernel(const uint64_t* __restrict__ offsets, uint32_t n_contigs, SketchParams P, uint32_t* __restrict__ V,
+                                uint32_t* __restrict__ vcounts)
 {
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x + 1;
     if (c >= n_contigs) return;
     uint64_t q = offsets[c];
     if (q == 0 || q >= P.n) return;
     uint64_t lo = q >= (uint64_t)(P.k - 1) ? q - (P.k - 1) : 0;
-    for (uint64_t p = lo; p < q; p++) atomicAnd(&V[p >> 5], ~(1u << (p & 31)));
+    for (uint64_t p = lo; p < q; p++) {
+        uint32_t bit = 1u << (p & 31);
+        if (atomicAnd(&V[p >> 5], ~bit) & bit) atomicSub(&vcounts[p >> 10], 1u);   // keep the block count exact
+    }
 }
 
 // ostart[c] = ordinal of the first valid k-mer at or after offsets[c]  (n_contigs+1 entries)
@@ -401,7 +418,8 @@ __host__ __device__ inline size_t cand31_smem_bytes(int chunk, int k)
 
 template <int CANON_MIN>
 __global__ void __launch_bounds__(CAND_THREADS) cand31_kernel(const uint32_t* __restrict__ pk, const uint32_t* __restrict__ V,
-                                                               SketchParams P, SketchTables Tb, uint32_t* __restrict__ C)
+                                                               SketchParams P, SketchTables Tb, uint32_t* __restrict__ C,
+                                                               uint32_t* __restrict__ ccounts)
 {
     extern __shared__ uint32_t smem[];
     uint2* tab = reinterpret_cast<uint2*>(smem);                 // 16 entries
@@ -483,9 +501,14 @@ __global__ void __launch_bounds__(CAND_THREADS) cand31_kernel(const uint32_t* __
         for (int j = 0; j < wv; j++) vcS[threadIdx.x * wv + threadIdx.x + j] = 0;
     }
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < n_v; i += CAND_THREADS) {
+    for (uint32_t i = threadIdx.x; i < n_v; i += CAND_THREADS) {     // n_v is a multiple of 128: warps stay converged
         uint64_t gv = v_cta + i;
-        if (gv < P.n_words) C[gv] = vcS[i + (i >> lv)];
+        uint32_t cw = gv < P.n_words ? vcS[i + (i >> lv)] : 0u;
+        if (gv < P.n_words) C[gv] = cw;
+        uint32_t c = __popc(cw);
+#pragma unroll
+        for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+        if ((threadIdx.x & 31) == 0 && gv < P.n_words) ccounts[gv >> 5] = c;   // rank-directory block count of C
     }
 }
 #undef MXE_CAND_STEP

@@ -61,3 +61,35 @@ def test_synthetic_vs_oracle(engine, oracle):
     np.testing.assert_array_equal(res.weight, want["edges"]["weight"])
     assert len(res.vertices) > 10000 and len(res.edge_u) > 10000
     assert 7 in set(np.unique(res.support)) and len(set(np.unique(res.support))) >= 2
+
+
+@pytest.mark.parametrize("n_top", [40, 40_000])
+def test_hash_sort_tied_top_bits(engine, oracle, n_top):
+    """steps 2-3 sort only the top 32 bits and repair tied runs in place; long mixed runs force the full 64-bit
+    sort (n_top=40: runs of thousands of different hashes sharing their top 32 bits), short ones the fix-up path"""
+    import torch
+    rng = np.random.default_rng(n_top)
+    tops = rng.integers(0, 2**32, n_top, dtype=np.uint64) << np.uint64(32)
+    base = tops[rng.integers(0, n_top, 120_000)] | rng.integers(0, 2**12, 120_000, dtype=np.uint64)
+    hashes, contigs = [], []
+    for a in range(3):
+        h = base.copy()
+        rng.shuffle(h)
+        h = h[: 100_000 + 1000 * a]
+        hashes.append(h)
+        contigs.append(np.sort(rng.integers(0, 50, len(h))).astype(np.uint32))
+    weights = [1.0, 0.25, 3.0]
+    dh = [torch.from_numpy(h.view(np.int64)).cuda() for h in hashes]
+    dc = [torch.from_numpy(c.view(np.int32)).cuda() for c in contigs]
+    torch.cuda.synchronize()
+    res = engine.filter_and_edges_device([t.data_ptr() for t in dh], [t.data_ptr() for t in dc], [len(h) for h in hashes], weights)
+    want = oracle.filter_and_edges(hashes, contigs, weights)
+    for a in range(3):
+        np.testing.assert_array_equal(res.uniq[a], want["uniq"][a])
+        np.testing.assert_array_equal(res.keep[a], want["keep"][a])
+    np.testing.assert_array_equal(res.vertices, want["vertices"])
+    np.testing.assert_array_equal(res.edge_u, want["edges"]["u"])
+    np.testing.assert_array_equal(res.edge_v, want["edges"]["v"])
+    np.testing.assert_array_equal(res.support, want["edges"]["support_mask"])
+    np.testing.assert_array_equal(res.weight, want["edges"]["weight"])
+    assert len(res.vertices) > 100
