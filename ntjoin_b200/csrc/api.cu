@@ -17,6 +17,43 @@ void set_error(const char* fmt, ...)
     va_end(ap);
 }
 
+static thread_local Arena* g_arena = nullptr;
+Arena* current_arena() { return g_arena; }
+ArenaScope::ArenaScope(Engine* e_) : e(e_) { e->arena.begin(e->stream); g_arena = &e->arena; }
+ArenaScope::~ArenaScope() { g_arena = nullptr; e->arena.end(); }
+
+void Arena::begin(cudaStream_t st)
+{
+    active = true;
+    if (chunks.size() > 1) {
+        size_t total = 0;
+        for (auto& c : chunks) total += c.bytes;
+        cudaStreamSynchronize(st);
+        for (auto& c : chunks) cudaFree(c.p);
+        chunks.clear();
+        char* p = nullptr;
+        if (cudaMalloc((void**)&p, total) == cudaSuccess) chunks.push_back({p, total, 0});
+        else cudaGetLastError();
+    }
+    for (auto& c : chunks) c.used = 0;
+}
+void* Arena::alloc(size_t bytes)
+{
+    bytes = (bytes + 511) & ~(size_t)511;
+    for (auto& c : chunks)
+        if (c.bytes - c.used >= bytes) { void* q = c.p + c.used; c.used += bytes; return q; }
+    size_t want = bytes > ((size_t)64 << 20) ? bytes : ((size_t)64 << 20);
+    char* p = nullptr;
+    if (cudaMalloc((void**)&p, want) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    chunks.push_back({p, want, bytes});
+    return p;
+}
+void Arena::destroy()
+{
+    for (auto& c : chunks) cudaFree(c.p);
+    chunks.clear();
+}
+
 cudaEvent_t Engine::get_event()
 {
     if (!event_pool.empty()) { cudaEvent_t ev = event_pool.back(); event_pool.pop_back(); return ev; }
@@ -106,6 +143,7 @@ void mxe_destroy(mxe_t* e)
         for (auto& sp : kv.second.spans) { cudaEventDestroy(sp.first); cudaEventDestroy(sp.second); }
     for (auto ev : e->event_pool) cudaEventDestroy(ev);
     for (auto& p : e->pinned_free) cudaFreeHost(p.p);
+    e->arena.destroy();
     cudaStreamDestroy(e->own_stream);
     delete e;
 }
@@ -133,6 +171,7 @@ int mxe_set_option(mxe_t* e, const char* name, double value)
 static int sketch_from_host(mxe_t* e, const uint8_t* seq, uint64_t n, const uint64_t* offsets, uint32_t n_contigs,
                             int k, int w, int flags, mxe_sketch* S)
 {
+    ArenaScope scope(e);
     DBuf<uint8_t> d_seq;
     MXE_TRY(d_seq.alloc(n + 64, e->stream));
     if (n) MXE_CUDA(cudaMemcpyAsync(d_seq.p, seq, n, cudaMemcpyHostToDevice, e->stream));
@@ -166,7 +205,11 @@ int mxe_sketch_device(mxe_t* e, const void* d_seq, const uint64_t* offsets, uint
     MXE_CUDA(cudaSetDevice(e->device));
     mxe_sketch* S = new mxe_sketch();
     set_names(S, names, n_contigs);
-    int rc = sketch_device_impl(e, (const uint8_t*)d_seq, n_contigs ? offsets[n_contigs] : 0, offsets, n_contigs, k, w, flags, S);
+    int rc;
+    {
+        ArenaScope scope(e);
+        rc = sketch_device_impl(e, (const uint8_t*)d_seq, n_contigs ? offsets[n_contigs] : 0, offsets, n_contigs, k, w, flags, S);
+    }
     if (rc != MXE_OK) { mxe_sketch_free(S); return rc; }
     *out = S;
     return MXE_OK;
@@ -450,7 +493,11 @@ int mxe_filter_and_edges_device(mxe_t* e, const void* const* d_hash, const void*
     if (!e || !d_hash || !d_contig || !n || !weights || !out) { set_error("null argument"); return MXE_ERR_ARG; }
     MXE_CUDA(cudaSetDevice(e->device));
     mxe_result* R = new mxe_result();
-    int rc = filter_and_edges_impl(e, (const uint64_t* const*)d_hash, (const uint32_t* const*)d_contig, n, n_asm, weights, R);
+    int rc;
+    {
+        ArenaScope scope(e);
+        rc = filter_and_edges_impl(e, (const uint64_t* const*)d_hash, (const uint32_t* const*)d_contig, n, n_asm, weights, R);
+    }
     if (rc != MXE_OK) { mxe_result_free(R); return rc; }
     *out = R;
     return MXE_OK;

@@ -44,8 +44,22 @@ struct PhaseTimer {
     uint64_t launches = 0;
 };
 
+// Grow-only device workspace for per-call temporaries: bump allocation, no allocator calls in steady state.
+// Chunks are kept until the next call starts; if a call needed more than one chunk they are merged into one
+// chunk of the total size, so from the second step of a fixed workload on there is exactly one chunk.
+struct Arena {
+    struct Chunk { char* p; size_t bytes, used; };
+    std::vector<Chunk> chunks;
+    bool active = false;
+    void* alloc(size_t bytes);          // nullptr on out-of-memory
+    void begin(cudaStream_t st);        // start of an API call: recycle (and merge) the chunks
+    void end() { active = false; }
+    void destroy();
+};
+
 struct Engine {
     int device = 0;
+    Arena arena;
     cudaStream_t stream = nullptr;      // stream all work is issued on
     cudaStream_t own_stream = nullptr;  // engine-owned default
     int sm_count = 148;
@@ -71,23 +85,48 @@ struct Span {
     ~Span() { if (a) e->span_end(name, a, e->launches - l0); }
 };
 
-// stream-ordered device buffer
+Arena* current_arena();                 // arena of the API call running on this thread, or nullptr
+struct ArenaScope {
+    Engine* e;
+    ArenaScope(Engine* e_);
+    ~ArenaScope();
+};
+
+// device buffer: workspace arena inside an API call, stream-ordered allocation otherwise
 template <typename T>
 struct DBuf {
     T* p = nullptr; size_t n = 0; cudaStream_t s = nullptr;
     DBuf() {}
     DBuf(const DBuf&) = delete;
     DBuf& operator=(const DBuf&) = delete;
+    bool from_arena = false;
     int alloc(size_t count, cudaStream_t st) {
         release();
         s = st; n = count;
         if (count == 0) count = 1;
+        if (Arena* a = current_arena()) {
+            p = (T*)a->alloc(count * sizeof(T));
+            from_arena = true;
+            if (!p) { set_error("device workspace allocation of %zu bytes failed", count * sizeof(T)); return MXE_ERR_NOMEM; }
+            return MXE_OK;
+        }
+        from_arena = false;
         cudaError_t err = cudaMallocAsync((void**)&p, count * sizeof(T), st);
         if (err != cudaSuccess) { p = nullptr; set_error("cudaMallocAsync(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(err)); return MXE_ERR_NOMEM; }
         return MXE_OK;
     }
-    void release() { if (p) { cudaFreeAsync(p, s); p = nullptr; n = 0; } }
-    T* detach() { T* q = p; p = nullptr; n = 0; return q; }
+    void release() { if (p) { if (!from_arena) cudaFreeAsync(p, s); p = nullptr; n = 0; } }
+    // hand the buffer to a longer-lived owner: arena memory is copied out into a stream-ordered allocation
+    T* detach() {
+        T* q = p;
+        if (p && from_arena) {
+            q = nullptr;
+            if (cudaMallocAsync((void**)&q, (n ? n : 1) * sizeof(T), s) == cudaSuccess)
+                cudaMemcpyAsync(q, p, n * sizeof(T), cudaMemcpyDeviceToDevice, s);
+        }
+        p = nullptr; n = 0;
+        return q;
+    }
     ~DBuf() { release(); }
 };
 
