@@ -1,0 +1,118 @@
+"""btllib-shaped Python objects backed by the engine.
+
+ntJoin uses two btllib classes from Python after the hot path:
+  * btllib.Indexlr(path, k, w, IndexlrFlag.LONG_MODE, threads)  -- overlap re-sketch at k=15, w=10 on
+    <prefix>.segments.fa; consumers read record.id and record.minimizers[i].out_hash / .pos
+    (bin/ntjoin_assemble.py:478-481, 506-507)
+  * btllib.SeqReader(path, SeqReaderFlag.LONG_MODE, threads)     -- record.id / record.seq
+    (bin/ntjoin_assemble.py:313-316)
+These stand-ins expose the same attribute names so that `import ntjoin_b200.btllib_compat as btllib` works for
+those call sites; the minimizers come from the same CUDA kernels as step 1.
+"""
+import os
+from collections import namedtuple
+
+Minimizer = namedtuple("Minimizer", ["min_hash", "out_hash", "pos", "forward", "seq"])
+IndexlrRecord = namedtuple("IndexlrRecord", ["num", "id", "barcode", "readlen", "minimizers"])
+SeqRecord = namedtuple("SeqRecord", ["num", "id", "comment", "seq", "qual"])
+
+
+class IndexlrFlag:
+    NO_ID, BX, SEQ, FILTER_IN, FILTER_OUT, SHORT_MODE, LONG_MODE = 1, 2, 4, 8, 16, 32, 64
+
+
+class SeqReaderFlag:
+    FOLD_CASE, NO_FOLD_CASE, NO_TRIM_MASKED, TRIM_MASKED, SHORT_MODE, LONG_MODE = 0, 1, 0, 2, 4, 8
+
+
+_ENGINE = None
+
+
+def _engine():
+    global _ENGINE
+    if _ENGINE is None:
+        from .engine import Engine
+        _ENGINE = Engine(int(os.environ.get("MXE_DEVICE", "0")))
+    return _ENGINE
+
+
+class Indexlr:
+    """Iterates records of a FASTA file with their ordered minimizers (context manager like btllib's)."""
+
+    def __init__(self, seqfile, k, w, flags=IndexlrFlag.LONG_MODE, threads=5, verbose=False, canonical="sum"):
+        if not os.path.exists(seqfile):
+            raise FileNotFoundError(seqfile)
+        self._sk = _engine().sketch_file(seqfile, k, w, canonical=canonical)
+        self._k, self._flags = k, flags
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+    def close(self):
+        if self._sk is not None:
+            self._sk.close()
+            self._sk = None
+
+    def __iter__(self):
+        sk = self._sk
+        oh, mh, ps, fw = sk.out_hash, sk.min_hash, sk.pos, sk.forward
+        cg = sk.contig
+        import numpy as np
+        bounds = np.searchsorted(cg, np.arange(len(sk.names) + 1))
+        for c, name in enumerate(sk.names):
+            s, e = int(bounds[c]), int(bounds[c + 1])
+            mxs = [Minimizer(int(mh[i]), int(oh[i]), int(ps[i]), bool(fw[i]), "") for i in range(s, e)]
+            yield IndexlrRecord(c, name, "", 0, mxs)
+
+
+class SeqReader:
+    """FASTA/FASTQ records with upper-cased sequence (btllib folds case by default)."""
+
+    def __init__(self, seqfile, flags=SeqReaderFlag.LONG_MODE, threads=5):
+        if not os.path.exists(seqfile):
+            raise FileNotFoundError(seqfile)
+        self._path = seqfile
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+    def close(self):
+        pass
+
+    def __iter__(self):
+        import gzip
+        op = gzip.open if str(self._path).endswith(".gz") else open
+        num, name, comment, parts = 0, None, "", []
+        with op(self._path, "rt") as fh:
+            first = fh.read(1)
+            fh.seek(0)
+            if first == "@":
+                while True:
+                    h = fh.readline()
+                    if not h:
+                        break
+                    seq = fh.readline().strip()
+                    fh.readline()
+                    qual = fh.readline().strip()
+                    f = h[1:].split(None, 1)
+                    yield SeqRecord(num, f[0] if f else "", f[1].strip() if len(f) > 1 else "", seq.upper(), qual)
+                    num += 1
+                return
+            for line in fh:
+                if line.startswith(">"):
+                    if name is not None:
+                        yield SeqRecord(num, name, comment, "".join(parts).upper(), "")
+                        num += 1
+                    f = line[1:].split(None, 1)
+                    name, comment, parts = (f[0] if f else ""), (f[1].strip() if len(f) > 1 else ""), []
+                else:
+                    parts.append(line.strip())
+            if name is not None:
+                yield SeqRecord(num, name, comment, "".join(parts).upper(), "")

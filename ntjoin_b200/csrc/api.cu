@@ -130,6 +130,7 @@ int mxe_create(int device, mxe_t** out)
     if (const char* s = getenv("MXE_TAU")) e->tau = atof(s);
     if (const char* s = getenv("MXE_CHUNK")) e->chunk = atoi(s);
     if (const char* s = getenv("MXE_CAND_VARIANT")) e->cand_variant = atoi(s);
+    if (const char* s = getenv("MXE_PRUNE")) e->prune = atoi(s) != 0;
     *out = e;
     return MXE_OK;
 }
@@ -162,6 +163,7 @@ int mxe_set_option(mxe_t* e, const char* name, double value)
     if (!strcmp(name, "tau")) { if (value <= 0) { set_error("tau must be > 0"); return MXE_ERR_ARG; } e->tau = value; }
     else if (!strcmp(name, "chunk")) { if (value != 0 && value < 32) { set_error("chunk must be 0 (auto) or >= 32"); return MXE_ERR_ARG; } e->chunk = (int)value; }
     else if (!strcmp(name, "cand_variant")) e->cand_variant = (int)value;
+    else if (!strcmp(name, "prune")) e->prune = value != 0;
     else if (!strcmp(name, "timing")) e->timing = value != 0;
     else { set_error("unknown option %s", name); return MXE_ERR_ARG; }
     return MXE_OK;

@@ -64,9 +64,10 @@ struct Engine {
     cudaStream_t own_stream = nullptr;  // engine-owned default
     int sm_count = 148;
     // tunables
-    double tau = 10.0;       // candidate threshold: hash0>>33 <= tau * 2^31 / w
+    double tau = 9.0;        // candidate threshold: hash0>>33 <= tau * 2^31 / w
     int chunk = 0;           // positions per thread in the candidate kernel (multiple of 32; 0 = auto)
     int cand_variant = 1;    // 0 = generic 64-bit, 1 = 31-bit lane prefilter
+    bool prune = false;      // drop dominated candidates on 31-bit bounds before the exact stages
     bool timing = false;
     // accounting
     uint64_t launches = 0;

@@ -157,14 +157,32 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
     MXE_TRY(cord.alloc(n_cand, st));
     MXE_TRY(cctg.alloc(n_cand, st));
     MXE_TRY(gcount.alloc(2, st));
-    uint64_t gap_cap = std::max<uint64_t>(65536, n_cand / 8 + n_contigs);
+    uint64_t gap_cap = std::max<uint64_t>(65536, n_cand / 8 + n_contigs);   // grown on demand below
     unsigned long long gc[2] = {0, 0};
+    uint64_t n_sel = n_cand;        // candidates that reach the exact stages
+    uint64_t *s_pos = cpos.p, *s_ord = cord.p;
+    uint32_t* s_ctg = cctg.p;
+    DBuf<uint64_t> cpos2, cord2, pprefix;
+    DBuf<uint32_t> cctg2, klo, khi, pflag;
     {
         Span sp(e, "eval");
         if (n_cand) {
             MXE_LAUNCH(e, cand_extract_kernel, grid_for(n_vblocks * 32, 256), 256, 0, C.p, V.p, nW, cprefix.p, vprefix.p, n_vblocks,
                        d_offsets.p, n_contigs, cpos.p, cord.p, cctg.p);
-            MXE_LAUNCH(e, cand_hash_kernel, grid_for(n_cand, 256), 256, 0, cpos.p, n_cand, pk.p, P, Tb, ch0.p);
+            if (e->prune) {
+                MXE_TRY(klo.alloc(n_cand, st)); MXE_TRY(khi.alloc(n_cand, st)); MXE_TRY(pflag.alloc(n_cand, st));
+                MXE_TRY(pprefix.alloc(n_cand + 1, st));
+                MXE_LAUNCH(e, cand_key31_kernel, grid_for(n_cand, 256), 256, 0, cpos.p, n_cand, pk.p, P, Tb, klo.p, khi.p);
+                MXE_LAUNCH(e, prune_kernel, grid_for(n_cand, 256), 256, 0, klo.p, khi.p, cord.p, cctg.p, n_cand, ostart.p, P, pflag.p);
+                MXE_TRY(exclusive_scan_u32_u64(e, pflag.p, pprefix.p, n_cand));
+                MXE_CUDA(cudaMemcpyAsync(&n_sel, pprefix.p + n_cand, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+                MXE_CUDA(cudaStreamSynchronize(st));
+                MXE_TRY(cpos2.alloc(n_sel, st)); MXE_TRY(cord2.alloc(n_sel, st)); MXE_TRY(cctg2.alloc(n_sel, st));
+                MXE_LAUNCH(e, cand_compact_kernel, grid_for(n_cand, 256), 256, 0, pflag.p, pprefix.p, n_cand, cpos.p, cord.p, cctg.p,
+                           cpos2.p, cord2.p, cctg2.p);
+                s_pos = cpos2.p; s_ord = cord2.p; s_ctg = cctg2.p;
+            }
+            if (n_sel) MXE_LAUNCH(e, cand_hash_kernel, grid_for(n_sel, 256), 256, 0, s_pos, n_sel, pk.p, P, Tb, ch0.p);
         }
     }
     {
@@ -173,9 +191,9 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
             MXE_TRY(gaps.alloc(gap_cap, st));
             MXE_CUDA(cudaMemsetAsync(gcount.p, 0, 2 * sizeof(unsigned long long), st));
             GapList G{gaps.p, gcount.p, gcount.p + 1, gap_cap};
-            if (n_cand)
-                MXE_LAUNCH(e, select_kernel, grid_for(n_cand, 256), 256, 0, cpos.p, ch0.p, cord.p, cctg.p, n_cand, ostart.p, P, M.p, G);
-            MXE_LAUNCH(e, empty_contig_gap_kernel, grid_for(n_contigs, 128), 128, 0, cpos.p, n_cand, d_offsets.p, n_contigs, ostart.p, P, G);
+            if (n_sel)
+                MXE_LAUNCH(e, select_kernel, grid_for(n_sel, 256), 256, 0, s_pos, ch0.p, s_ord, s_ctg, n_sel, ostart.p, P, M.p, G);
+            MXE_LAUNCH(e, empty_contig_gap_kernel, grid_for(n_contigs, 128), 128, 0, s_pos, n_sel, d_offsets.p, n_contigs, ostart.p, P, G);
             MXE_CUDA(cudaMemcpyAsync(gc, gcount.p, sizeof(gc), cudaMemcpyDeviceToHost, st));
             MXE_CUDA(cudaStreamSynchronize(st));
             if (gc[0] <= gap_cap) break;
@@ -188,11 +206,13 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
     if (gc[0]) {
         Span sp(e, "gap");
         unsigned grid = (unsigned)std::min<uint64_t>(gc[0], (uint64_t)e->sm_count * 4);
-        DBuf<uint64_t> sh, sq;
+        DBuf<uint64_t> sh, sq, sbm, sbi;
         uint64_t stride = (uint64_t)GAP_CHUNK + (uint64_t)w;
         MXE_TRY(sh.alloc(stride * grid, st));
         MXE_TRY(sq.alloc(stride * grid, st));
-        MXE_LAUNCH(e, gap_kernel, grid, 256, 0, gaps.p, (uint64_t)gc[0], pk.p, V.p, vprefix.p, n_vblocks, P, Tb, sh.p, sq.p, M.p);
+        MXE_TRY(sbm.alloc((stride / 32 + 2) * grid, st));
+        MXE_TRY(sbi.alloc((stride / 32 + 2) * grid, st));
+        MXE_LAUNCH(e, gap_kernel, grid, 256, 0, gaps.p, (uint64_t)gc[0], pk.p, V.p, vprefix.p, n_vblocks, P, Tb, sh.p, sq.p, sbm.p, sbi.p, M.p);
     }
 
     // ---- ordered emission

@@ -566,6 +566,125 @@ __global__ void __launch_bounds__(256) cand_hash_kernel(const uint64_t* __restri
     h0[i] = canon(f, r, P.canon_min);
 }
 
+// ---------------------------------------------------------------- candidate pruning on 31-bit bounds
+// Most candidates (~1 % of positions) are not minimizers (~0.2 %).  Before paying for exact 64-bit hashes, each
+// candidate gets cheap bounds lo <= t <= hi on t = hash0 >> 33 from the 31-bit lanes alone (sum: t in {s1-1, s1},
+// s1 = (f31+r31+1) mod 2^31; min: t = min(f31,r31) exactly).  Candidate j DOMINATES i when hi_j < lo_i (then
+// hash0_j < hash0_i whatever the low bits are).  A candidate that has a dominator inside every window containing it
+// can never be a window arg-min and is dropped; every window's true candidate arg-min survives (nothing dominates
+// it), so the exact selection over the survivors returns the same arg-min for every window.
+struct HashTabs31 { uint32_t f4[256]; uint32_t r4[256]; uint32_t s1[8]; };
+
+__device__ __forceinline__ void build_hash_tabs31(HashTabs31* H, const SketchTables& Tb, int k)
+{
+    for (int v = threadIdx.x; v < 256; v += blockDim.x) {
+        uint32_t f = 0, r = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t c = (v >> (2 * j)) & 3;
+            f = rol31(f) ^ Tb.shi[c];
+            uint32_t sc = Tb.shi[c ^ 2u];
+            for (int q = 0; q < j; q++) sc = rol31(sc);
+            r ^= sc;
+        }
+        for (int q = 0; q < k - 4; q++) r = rol31(r);
+        H->f4[v] = f;
+        H->r4[v] = r;
+    }
+    if (threadIdx.x < 4) {
+        H->s1[threadIdx.x] = Tb.shi[threadIdx.x];
+        uint32_t sc = Tb.shi[threadIdx.x ^ 2];
+        for (int q = 0; q < k - 1; q++) sc = rol31(sc);
+        H->s1[4 + threadIdx.x] = sc;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) cand_key31_kernel(const uint64_t* __restrict__ cpos, uint64_t n_cand, const uint32_t* __restrict__ pk,
+                                                          SketchParams P, SketchTables Tb, uint32_t* __restrict__ klo, uint32_t* __restrict__ khi)
+{
+    __shared__ HashTabs31 H;
+    build_hash_tabs31(&H, Tb, P.k);
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cand) return;
+    const uint64_t p = cpos[i];
+    const uint64_t q = p >> 4;
+    const uint32_t sh = ((uint32_t)p & 15u) * 2u;
+    uint32_t f = 0, r = 0;
+    uint32_t cur = pk_to_natural(__ldg(pk + q));
+    int left = P.k;
+    for (int m = 0; left > 0; m++) {
+        uint32_t nxt = pk_to_natural(__ldg(pk + q + m + 1));
+        uint32_t N = __funnelshift_r(cur, nxt, sh);
+        cur = nxt;
+        int nb = left < 16 ? left : 16;
+        left -= nb;
+        for (; nb >= 4; nb -= 4) {
+            uint32_t v = N & 0xFFu;
+            N >>= 8;
+            f = (((f << 4) | (f >> 27)) & 0x7FFFFFFFu) ^ H.f4[v];
+            r = (((r >> 4) | (r << 27)) & 0x7FFFFFFFu) ^ H.r4[v];
+        }
+        for (; nb > 0; nb--) {
+            uint32_t c = N & 3u;
+            N >>= 2;
+            f = rol31(f) ^ H.s1[c];
+            r = ror31(r) ^ H.s1[4 + c];
+        }
+    }
+    uint32_t lo, hi;
+    if (P.canon_min) { lo = hi = min(f, r); }
+    else {
+        uint32_t s1 = (f + r + 1u) & 0x7FFFFFFFu;
+        lo = s1 ? s1 - 1u : 0u;
+        hi = s1 ? s1 : 0x7FFFFFFFu;
+    }
+    klo[i] = lo;
+    khi[i] = hi;
+}
+
+__global__ void __launch_bounds__(256) prune_kernel(const uint32_t* __restrict__ klo, const uint32_t* __restrict__ khi,
+                                                     const uint64_t* __restrict__ gord, const uint32_t* __restrict__ ctg, uint64_t n_cand,
+                                                     const uint64_t* __restrict__ ostart, SketchParams P, uint32_t* __restrict__ flag)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cand) return;
+    const uint32_t c = ctg[i];
+    const uint64_t os = ostart[c], oe = ostart[c + 1];
+    const uint64_t w = (uint64_t)P.w;
+    uint32_t keep = 0;
+    if (oe - os >= w) {
+        const uint64_t o = gord[i];
+        const uint32_t lo = klo[i];
+        const uint64_t jmin = os + w - 1, jmax = oe - 1;
+        uint64_t jlo = o > jmin ? o : jmin;
+        uint64_t jhi = o + w - 1 < jmax ? o + w - 1 : jmax;
+        for (uint64_t j = i; j-- > 0;) {
+            if (ctg[j] != c || gord[j] + w <= o) break;
+            if (khi[j] < lo) { uint64_t b = gord[j] + w; if (b > jlo) jlo = b; break; }
+        }
+        if (jlo <= jhi)
+            for (uint64_t j = i + 1; j < n_cand; j++) {
+                if (ctg[j] != c || gord[j] >= o + w) break;
+                if (khi[j] < lo) { uint64_t b = gord[j] - 1; if (b < jhi) jhi = b; break; }
+            }
+        keep = jlo <= jhi;
+    }
+    flag[i] = keep;
+}
+
+__global__ void __launch_bounds__(256) cand_compact_kernel(const uint32_t* __restrict__ flag, const uint64_t* __restrict__ prefix, uint64_t n_cand,
+                                                            const uint64_t* __restrict__ cpos, const uint64_t* __restrict__ gord, const uint32_t* __restrict__ ctg,
+                                                            uint64_t* __restrict__ cpos2, uint64_t* __restrict__ gord2, uint32_t* __restrict__ ctg2)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cand || !flag[i]) return;
+    uint64_t o = prefix[i];
+    cpos2[o] = cpos[i];
+    gord2[o] = gord[i];
+    ctg2[o] = ctg[i];
+}
+
 // ---------------------------------------------------------------- select
 struct Gap { uint64_t ja, jb; };
 
@@ -651,12 +770,14 @@ __global__ void empty_contig_gap_kernel(const uint64_t* __restrict__ cpos, uint6
 
 // ---------------------------------------------------------------- gap: dense exact windows
 constexpr int GAP_CHUNK = 1024;   // window ends per chunk
+constexpr int GAP_RUN = 16;       // consecutive ordinals hashed by one thread (rolling)
 
 __global__ void __launch_bounds__(256) gap_kernel(const Gap* __restrict__ gaps, uint64_t n_gaps,
                                                    const uint32_t* __restrict__ pk, const uint32_t* __restrict__ V,
                                                    const uint64_t* __restrict__ vprefix, uint64_t n_vblocks,
                                                    SketchParams P, SketchTables Tb,
                                                    uint64_t* __restrict__ scratch_h, uint64_t* __restrict__ scratch_p,
+                                                   uint64_t* __restrict__ scratch_bm, uint64_t* __restrict__ scratch_bi,
                                                    uint32_t* __restrict__ M)
 {
     __shared__ HashTabs Ht;
@@ -665,6 +786,8 @@ __global__ void __launch_bounds__(256) gap_kernel(const Gap* __restrict__ gaps, 
     const uint64_t stride = (uint64_t)GAP_CHUNK + w;
     uint64_t* H = scratch_h + (uint64_t)blockIdx.x * stride;
     uint64_t* Q = scratch_p + (uint64_t)blockIdx.x * stride;
+    uint64_t* BM = scratch_bm + (uint64_t)blockIdx.x * (stride / 32 + 2);
+    uint64_t* BI = scratch_bi + (uint64_t)blockIdx.x * (stride / 32 + 2);
     for (uint64_t g = blockIdx.x; g < n_gaps; g += gridDim.x) {
         const uint64_t ja = gaps[g].ja, jb = gaps[g].jb;
         for (uint64_t ca = ja; ca <= jb; ca += GAP_CHUNK) {
@@ -672,26 +795,53 @@ __global__ void __launch_bounds__(256) gap_kernel(const Gap* __restrict__ gaps, 
             uint64_t o0 = ca - (w - 1);
             uint64_t m = cb - o0 + 1;
             __syncthreads();
-            for (uint64_t e = threadIdx.x; e < m; e += blockDim.x) {
-                uint64_t p = bitmap_select(V, vprefix, n_vblocks, o0 + e);
+            // each thread fills a run of GAP_RUN consecutive ordinals: one select + one table hash, then rolling
+            for (uint64_t e0 = (uint64_t)threadIdx.x * GAP_RUN; e0 < m; e0 += (uint64_t)blockDim.x * GAP_RUN) {
+                uint64_t p = bitmap_select(V, vprefix, n_vblocks, o0 + e0);
                 uint64_t f, r;
                 kmer_hash64_tab(pk, p, P.k, &Ht, f, r);
-                H[e] = canon(f, r, P.canon_min);
-                Q[e] = p;
+                H[e0] = canon(f, r, P.canon_min);
+                Q[e0] = p;
+                const uint64_t e1 = e0 + GAP_RUN < m ? e0 + GAP_RUN : m;
+                for (uint64_t e = e0 + 1; e < e1; e++) {
+                    // next valid k-mer start after p
+                    uint64_t q = p + 1;
+                    uint32_t wv = V[q >> 5] >> (q & 31);
+                    while (!wv) { q = ((q >> 5) + 1) << 5; wv = V[q >> 5]; }
+                    q += __ffs(wv) - 1;
+                    if (q == p + 1) {
+                        const uint32_t o = pk_code(pk, p), in = pk_code(pk, p + P.k);
+                        f = srol1(f) ^ Tb.seed_rolk[o] ^ Tb.seed[in];
+                        r = sror1(r ^ Tb.seed_rolk[in ^ 2u] ^ Tb.seed[o ^ 2u]);
+                    } else {
+                        kmer_hash64_tab(pk, q, P.k, &Ht, f, r);
+                    }
+                    p = q;
+                    H[e] = canon(f, r, P.canon_min);
+                    Q[e] = p;
+                }
             }
             __syncthreads();
-            for (uint64_t e = threadIdx.x; e < m; e += blockDim.x) {
-                const uint64_t h = H[e];
-                if (h == ~0ULL) continue;
-                uint64_t jlo = e > w - 1 ? e : w - 1;
-                uint64_t jhi = e + w - 1 < m - 1 ? e + w - 1 : m - 1;
-                for (uint64_t d = 1; d < w && d <= e; d++)
-                    if (H[e - d] < h) { uint64_t b = e - d + w; if (b > jlo) jlo = b; break; }
-                if (jlo > jhi) continue;
-                for (uint64_t d = 1; d < w && e + d < m; d++)
-                    if (H[e + d] <= h) { uint64_t b = e + d - 1; if (b < jhi) jhi = b; break; }
-                if (jlo <= jhi) {
-                    uint64_t p = Q[e];
+            // block minima (32 elements, rightmost on ties), then one thread per window end: partial right block,
+            // whole blocks right to left, partial left block; strict '<' while moving left keeps the rightmost minimum
+            const uint64_t nb = (m + 31) >> 5;
+            for (uint64_t b = threadIdx.x; b < nb; b += blockDim.x) {
+                const uint64_t s0 = b << 5, s1 = s0 + 32 < m ? s0 + 32 : m;
+                uint64_t best = H[s0], bi = s0;
+                for (uint64_t x = s0 + 1; x < s1; x++) { uint64_t hx = H[x]; if (hx <= best) { best = hx; bi = x; } }
+                BM[b] = best;
+                BI[b] = bi;
+            }
+            __syncthreads();
+            for (uint64_t je = w - 1 + threadIdx.x; je < m; je += blockDim.x) {
+                const uint64_t lo = je - (w - 1);
+                uint64_t best = H[je], bi = je;
+                uint64_t x = je;
+                while (x > lo && (x & 31) != 0) { x--; uint64_t hx = H[x]; if (hx < best) { best = hx; bi = x; } }   // down to a block boundary
+                while (x >= lo + 32) { uint64_t bb = (x >> 5) - 1; if (BM[bb] < best) { best = BM[bb]; bi = BI[bb]; } x -= 32; }
+                while (x > lo) { x--; uint64_t hx = H[x]; if (hx < best) { best = hx; bi = x; } }
+                if (best != ~0ULL) {
+                    uint64_t p = Q[bi];
                     atomicOr(&M[p >> 5], 1u << (p & 31));
                 }
             }

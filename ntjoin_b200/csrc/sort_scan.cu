@@ -179,7 +179,7 @@ int bitmap_extract(Engine* e, const uint32_t* d_bits, size_t n_words, const uint
 // ------------------------------------------------------------------------------------------
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS = 16;
+constexpr int RS_ITEMS = 8;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;   // 4096 keys per CTA
 
 __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint64_t* __restrict__ keys, size_t n, int shift,

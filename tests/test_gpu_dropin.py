@@ -68,3 +68,23 @@ def test_dropin_falls_through_for_plain_lists():
     assert f == {0: [["2", "3"]], 1: [["3", "2"]]}
     g = mod.build_graph(f, {0: 1, 1: 1})
     assert g.edges == [("2", "3")] and g.eattr["weight"] == [2]
+
+
+def test_btllib_compat_overlap_resketch(golden_dir, oracle):
+    """bin/ntjoin_assemble.py:478-481 shape: Indexlr(path, k=15, w=10, LONG_MODE, threads) -> .id, .minimizers[].out_hash/.pos"""
+    import numpy as np
+    from ntjoin_b200 import btllib_compat as btllib
+    fa = os.path.join(golden_dir, "inputs", "scaf.f-f.overlapping.fa")
+    names, seq, offs = oracle_lib.read_fasta(fa)
+    ref = oracle.sketch(seq, offs, 15, 10)
+    got = []
+    with btllib.Indexlr(fa, 15, 10, btllib.IndexlrFlag.LONG_MODE, 4) as ix:
+        for rec in ix:
+            assert rec.id == names[rec.num]
+            got += [(rec.num, m.out_hash, m.pos) for m in rec.minimizers]
+    assert got == [(int(c), int(h), int(p)) for c, h, p in zip(ref["contig"], ref["out_hash"], ref["pos"])]
+    with btllib.SeqReader(fa, btllib.SeqReaderFlag.LONG_MODE, 4) as rd:
+        recs = list(rd)
+    assert [r.id for r in recs] == names and "".join(r.seq for r in recs).encode() == seq
+    with pytest.raises(FileNotFoundError):
+        btllib.SeqReader(fa + ".missing", btllib.SeqReaderFlag.LONG_MODE, 1)

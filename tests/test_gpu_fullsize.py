@@ -78,7 +78,7 @@ def test_config3_properties(engine, oracle):
         np.testing.assert_array_equal(sk2.pos, pos)
         np.testing.assert_array_equal(sk2.contig, ctg)
     finally:
-        engine.set_option("tau", 10.0)
+        engine.set_option("tau", 9.0)
     # slice consistency against the oracle
     gpos = offs[ctg] + pos.astype(np.uint64)
     margin = 4 * (W + K)

@@ -73,11 +73,13 @@ def _messy(n, seed):
 def test_messy_synthetic(engine, oracle, canonical, variant):
     seq, offs = _messy(1_500_000, 7)
     engine.set_option("cand_variant", variant)
+    engine.set_option("prune", variant)          # variant 0 also exercises the unpruned exact path
     for k, w in [(32, 1000), (32, 100), (16, 50), (20, 10), (40, 250), (15, 10), (32, 5000)]:
         ref = oracle.sketch(seq, offs, k, w, canonical=canonical)
         sk = engine.sketch_buffers(seq, offs, k, w, canonical=canonical)
         assert_same(sk, ref)
     engine.set_option("cand_variant", 1)
+    engine.set_option("prune", 1)
 
 
 @pytest.mark.parametrize("tau", [0.5, 3.0, 10.0, 1e9])
@@ -90,7 +92,7 @@ def test_threshold_independence(engine, oracle, tau):
         sk = engine.sketch_buffers(seq, offs, 32, 500)
         assert_same(sk, ref)
     finally:
-        engine.set_option("tau", 10.0)
+        engine.set_option("tau", 9.0)
 
 
 def test_config2_scale_down(engine, oracle):
