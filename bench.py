@@ -316,7 +316,7 @@ def main():
     def step_e2e():
         sks = [eng.sketch_buffers(h, o, K, W) for h, (_, o, _) in zip(host, shards)]
         res = gather_and_filter(sks)
-        res.fetch()                           # flags + vertices + weighted edge list into host memory
+        res.fetch(copy=False)                 # flags + vertices + weighted edge list into (pinned) host memory
         for sk in sks:
             sk.close()
         res.close()

@@ -120,6 +120,10 @@ int mxe_create(int device, mxe_t** out)
     e->device = device;
     MXE_CUDA(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
     e->stream = e->own_stream;
+    for (int c = 0; c < 2; c++) MXE_CUDA(cudaStreamCreateWithFlags(&e->copy_stream[c], cudaStreamNonBlocking));
+    MXE_CUDA(cudaEventCreateWithFlags(&e->ev_ready, cudaEventDisableTiming));
+    for (int i = 0; i < MXE_N_CHUNK_EVENTS; i++) MXE_CUDA(cudaEventCreateWithFlags(&e->ev_chunk[i], cudaEventDisableTiming));
+    if (const char* s = getenv("MXE_H2D_CHUNK_MB")) e->h2d_chunk_mb = std::max(1, atoi(s));
     cudaDeviceProp prop;
     MXE_CUDA(cudaGetDeviceProperties(&prop, device));
     e->sm_count = prop.multiProcessorCount;
@@ -145,6 +149,9 @@ void mxe_destroy(mxe_t* e)
     for (auto ev : e->event_pool) cudaEventDestroy(ev);
     for (auto& p : e->pinned_free) cudaFreeHost(p.p);
     e->arena.destroy();
+    for (int c = 0; c < 2; c++) if (e->copy_stream[c]) cudaStreamDestroy(e->copy_stream[c]);
+    if (e->ev_ready) cudaEventDestroy(e->ev_ready);
+    for (int i = 0; i < MXE_N_CHUNK_EVENTS; i++) if (e->ev_chunk[i]) cudaEventDestroy(e->ev_chunk[i]);
     cudaStreamDestroy(e->own_stream);
     delete e;
 }
@@ -176,8 +183,7 @@ static int sketch_from_host(mxe_t* e, const uint8_t* seq, uint64_t n, const uint
     ArenaScope scope(e);
     DBuf<uint8_t> d_seq;
     MXE_TRY(d_seq.alloc(n + 64, e->stream));
-    if (n) MXE_CUDA(cudaMemcpyAsync(d_seq.p, seq, n, cudaMemcpyHostToDevice, e->stream));
-    return sketch_device_impl(e, d_seq.p, n, offsets, n_contigs, k, w, flags, S);
+    return sketch_device_impl(e, d_seq.p, n, offsets, n_contigs, k, w, flags, S, seq);   // chunked H2D inside, overlapped with pack
 }
 
 static void set_names(mxe_sketch* S, const char* const* names, uint32_t n_contigs)

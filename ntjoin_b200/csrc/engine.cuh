@@ -2,7 +2,14 @@
 #pragma once
 #include "common.cuh"
 
+constexpr int MXE_N_CHUNK_EVENTS = 64;
+
 struct mxe_engine : public mxe::Engine {
+    // host-input path: two copy streams (two copy engines) + events
+    cudaStream_t copy_stream[2] = {nullptr, nullptr};
+    cudaEvent_t ev_ready = nullptr;
+    cudaEvent_t ev_chunk[MXE_N_CHUNK_EVENTS] = {nullptr};
+    int h2d_chunk_mb = 256;
     // pinned host block pool (grow-only, reused across steps)
     struct Pinned { void* p; size_t bytes; };
     std::vector<Pinned> pinned_free;
@@ -51,7 +58,7 @@ struct mxe_result {
 
 namespace mxe {
 int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const uint64_t* offsets, uint32_t n_contigs,
-                       int k, int w, int flags, mxe_sketch* out);
+                       int k, int w, int flags, mxe_sketch* out, const uint8_t* h_seq = nullptr);
 int filter_and_edges_impl(mxe_engine* e, const uint64_t* const* d_hash, const uint32_t* const* d_contig,
                           const uint64_t* n, int n_asm, const double* weights, mxe_result* out);
 }

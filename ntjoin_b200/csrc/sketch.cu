@@ -36,7 +36,7 @@ static void build_tables(int k, SketchTables* T)
 static inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
 
 int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const uint64_t* offsets, uint32_t n_contigs,
-                       int k, int w, int flags, mxe_sketch* S)
+                       int k, int w, int flags, mxe_sketch* S, const uint8_t* h_seq)
 {
     if (k < 1 || k > 1024 || w < 1) { set_error("bad k/w (k=%d w=%d)", k, w); return MXE_ERR_ARG; }
     if (n_contigs && offsets[0] != 0) { set_error("offsets[0] must be 0"); return MXE_ERR_ARG; }
@@ -99,7 +99,26 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
     // ---- pack + validity
     {
         Span sp(e, "pack");
-        MXE_LAUNCH(e, pack_kernel, grid_for(nW, 256), 256, 0, d_seq, P, pk.p, B.p);
+        if (!h_seq) {
+            MXE_LAUNCH(e, pack_kernel, grid_for(nW, 256), 256, 0, d_seq, P, pk.p, B.p, (uint64_t)0, nW);
+        } else {
+            // host input: chunked H2D on two copy streams, each chunk packed as soon as it has landed
+            const uint64_t CH = (uint64_t)e->h2d_chunk_mb << 20;
+            MXE_CUDA(cudaEventRecord(e->ev_ready, st));                 // the staging buffer may still be in use by earlier work
+            for (int c = 0; c < 2; c++) MXE_CUDA(cudaStreamWaitEvent(e->copy_stream[c], e->ev_ready, 0));
+            int i = 0;
+            for (uint64_t off = 0; off < n; off += CH, i++) {
+                const uint64_t len = std::min<uint64_t>(CH, n - off);
+                cudaStream_t cs = e->copy_stream[i & 1];
+                cudaEvent_t ev = e->ev_chunk[i % MXE_N_CHUNK_EVENTS];
+                MXE_CUDA(cudaMemcpyAsync(const_cast<uint8_t*>(d_seq) + off, h_seq + off, len, cudaMemcpyHostToDevice, cs));
+                MXE_CUDA(cudaEventRecord(ev, cs));
+                MXE_CUDA(cudaStreamWaitEvent(st, ev, 0));
+                const uint64_t t0 = off >> 5, t1 = (off + len + 31) >> 5;
+                MXE_LAUNCH(e, pack_kernel, grid_for(t1 - t0, 256), 256, 0, d_seq, P, pk.p, B.p, t0, t1);
+                if ((i % MXE_N_CHUNK_EVENTS) == MXE_N_CHUNK_EVENTS - 1) MXE_CUDA(cudaStreamSynchronize(st));   // events are reused
+            }
+        }
         MXE_LAUNCH(e, vmask_kernel, grid_for(nW, 256), 256, 0, B.p, P, V.p, vcounts.p);
         if (n_contigs > 1) MXE_LAUNCH(e, boundary_kernel, grid_for(n_contigs - 1, 128), 128, 0, d_offsets.p, n_contigs, P, V.p, vcounts.p);
     }

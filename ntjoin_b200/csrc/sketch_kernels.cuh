@@ -236,11 +236,12 @@ __device__ __forceinline__ uint32_t bad_bytes(uint32_t x)
     return (x & 0xF9F9F9F9u) ^ (m >> 2) ^ (m << 2);    // non-zero byte <=> invalid base
 }
 
+// Processes words [t0, t1) so that the host path can pack each chunk as soon as its H2D copy has landed.
 __global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ seq, SketchParams P,
-                                                   uint32_t* __restrict__ pk, uint32_t* __restrict__ B)
+                                                   uint32_t* __restrict__ pk, uint32_t* __restrict__ B, uint64_t t0, uint64_t t1)
 {
-    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= P.n_words) return;
+    uint64_t t = t0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= t1) return;
     uint64_t p0 = t << 5;
     uint32_t pkw[2] = {0, 0};
     uint32_t bad = 0;

@@ -115,7 +115,11 @@ class FilterResult:
         check(lib, lib.mxe_result_counts(self._h, *[C.byref(x) for x in a]))
         return tuple(x.value for x in a)
 
-    def fetch(self):
+    def fetch(self, copy=True):
+        """Bring flags, vertices and the weighted edge list to host memory (one pinned device->host copy).
+        copy=False returns views into the engine's pinned block, valid until close()."""
+        if not copy:
+            return self._fetch_views()
         if self._cache is None:
             lib = self._e._lib
             uniq, keep = [], []
@@ -137,6 +141,23 @@ class FilterResult:
                 "weight": _np_view(p[4].value, ne.value, np.float64).copy(),
             }
         return self._cache
+
+    def _fetch_views(self):
+        lib = self._e._lib
+        out = {"uniq": [], "keep": []}
+        for a in range(self.n_asm):
+            n = C.c_uint64()
+            u, k = C.c_void_p(), C.c_void_p()
+            check(lib, lib.mxe_result_flags(self._h, a, C.byref(n), C.byref(u), C.byref(k)))
+            out["uniq"].append(_np_view(u.value, n.value, np.uint8))
+            out["keep"].append(_np_view(k.value, n.value, np.uint8))
+        nv, ne = C.c_uint64(), C.c_uint64()
+        p = [C.c_void_p() for _ in range(5)]
+        check(lib, lib.mxe_result_graph(self._h, C.byref(nv), C.byref(p[0]), C.byref(ne), *[C.byref(x) for x in p[1:]]))
+        for key, ptr, n, dt in (("vertices", p[0], nv, np.uint64), ("edge_u", p[1], ne, np.uint64), ("edge_v", p[2], ne, np.uint64),
+                                ("support", p[3], ne, np.uint32), ("weight", p[4], ne, np.float64)):
+            out[key] = _np_view(ptr.value, n.value, dt)
+        return out
 
     uniq = property(lambda s: s.fetch()["uniq"])
     keep = property(lambda s: s.fetch()["keep"])
