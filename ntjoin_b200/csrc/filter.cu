@@ -9,9 +9,10 @@
 // Method: one stable radix sort of all assemblies' out_hash (input concatenated in assembly
 // order, so equal hashes stay grouped by assembly) -> run analysis gives `uniq`, `keep` and a
 // dense vertex id per surviving hash; ordered compaction of survivors -> adjacent pairs ->
-// stable sort by (min id, max id) -> run reduction gives support masks and the first sighting;
-// a last sort by (first sighting of the source, first sighting of the edge) reproduces the
-// insertion order of the reference's dict-of-dicts (formatted_edges, :115).
+// per-assembly successor/predecessor tables indexed by vertex id give every edge's support
+// mask and its first sighting without sorting (a surviving hash occurs once per assembly);
+// a stable sort on the source's first-creation index then reproduces the insertion order of
+// the reference's dict-of-dicts (formatted_edges, :115).
 #include "engine.cuh"
 
 #include <algorithm>
@@ -141,51 +142,62 @@ __global__ void __launch_bounds__(256) pair_flag_kernel(const uint32_t* __restri
     eflag[j] = f;
 }
 
-__global__ void __launch_bounds__(256) pair_emit_kernel(const uint32_t* __restrict__ cvid, const uint32_t* __restrict__ eflag,
-                                                         const uint64_t* __restrict__ eprefix, uint64_t n_keep,
-                                                         uint64_t* __restrict__ ekey, uint32_t* __restrict__ eval)
+// Edge de-duplication without sorting.  Every surviving hash occurs exactly once per assembly, so a vertex has at
+// most one successor and one predecessor per assembly.  The sightings (v -> x) of the undirected edge {v,x} are found
+// by looking v up in every assembly's succ/pred table; the sighting in the first supporting assembly owns the edge
+// (that is the reference's first-seen orientation, bin/ntjoin_utils.py:101-108), so ordered compaction of the owning
+// sightings yields the distinct edges already in first-seen order.
+__global__ void __launch_bounds__(256) adjacency_kernel(const uint32_t* __restrict__ cvid, const uint32_t* __restrict__ cidx,
+                                                         const uint32_t* __restrict__ eflag, uint64_t n_keep, AsmOffsets A, uint64_t nV,
+                                                         uint32_t* __restrict__ succ, uint32_t* __restrict__ pred)
 {
     uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_keep || !eflag[j]) return;
-    uint32_t a = cvid[j], b = cvid[j + 1];
-    uint32_t lo = a < b ? a : b, hi = a < b ? b : a;
-    uint64_t q = eprefix[j];
-    ekey[q] = ((uint64_t)lo << 32) | hi;
-    eval[q] = (uint32_t)j;
+    const uint64_t a = (uint64_t)asm_of(A, cidx[j]);
+    succ[a * nV + cvid[j]] = cvid[j + 1];
+    pred[a * nV + cvid[j + 1]] = cvid[j];
 }
 
-__global__ void __launch_bounds__(256) edge_head_kernel(const uint64_t* __restrict__ ekey, uint64_t n_pairs, uint32_t* __restrict__ ehead)
+__global__ void __launch_bounds__(256) edge_owner_kernel(const uint32_t* __restrict__ cvid, const uint32_t* __restrict__ cidx,
+                                                          const uint32_t* __restrict__ eflag, uint64_t n_keep, AsmOffsets A, uint64_t nV,
+                                                          const uint32_t* __restrict__ succ, const uint32_t* __restrict__ pred,
+                                                          uint32_t* __restrict__ own, uint32_t* __restrict__ mask_out)
 {
-    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < n_pairs) ehead[r] = r == 0 || ekey[r] != ekey[r - 1];
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_keep) return;
+    uint32_t is_owner = 0;
+    if (eflag[j]) {
+        const int a = asm_of(A, cidx[j]);
+        const uint32_t v = cvid[j], x = cvid[j + 1];
+        uint32_t mask = 0;
+        for (int b = 0; b < A.n; b++)
+            if (succ[(uint64_t)b * nV + v] == x || pred[(uint64_t)b * nV + v] == x) mask |= 1u << b;
+        is_owner = (__ffs(mask) - 1) == a;
+        mask_out[j] = mask;
+    }
+    own[j] = is_owner;
 }
 
-// one thread per distinct edge: support mask over its run, first sighting, source's first appearance
-__global__ void __launch_bounds__(256) edge_reduce_kernel(const uint64_t* __restrict__ ekey, const uint32_t* __restrict__ eval,
-                                                           const uint32_t* __restrict__ ehead, const uint64_t* __restrict__ uprefix,
-                                                           uint64_t n_pairs, const uint32_t* __restrict__ cidx, const uint32_t* __restrict__ cvid,
-                                                           AsmOffsets A, uint32_t* __restrict__ ue_q0, uint32_t* __restrict__ ue_mask,
-                                                           uint32_t* __restrict__ srcmin)
+__global__ void __launch_bounds__(256) edge_compact_kernel(const uint32_t* __restrict__ own, const uint64_t* __restrict__ uprefix,
+                                                            const uint32_t* __restrict__ mask_in, uint64_t n_keep, const uint32_t* __restrict__ cvid,
+                                                            uint32_t* __restrict__ ue_q0, uint32_t* __restrict__ ue_mask, uint32_t* __restrict__ srcmin)
 {
-    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_pairs || !ehead[r]) return;
-    const uint64_t K = ekey[r];
-    uint32_t mask = 0;
-    for (uint64_t x = r; x < n_pairs && ekey[x] == K; x++) mask |= 1u << asm_of(A, cidx[eval[x]]);
-    uint32_t q0 = eval[r];               // stable sort => smallest sighting index first
-    uint64_t t = uprefix[r];
-    ue_q0[t] = q0;
-    ue_mask[t] = mask;
-    atomicMin(&srcmin[cvid[q0]], q0);
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_keep || !own[j]) return;
+    uint64_t t = uprefix[j];
+    ue_q0[t] = (uint32_t)j;
+    ue_mask[t] = mask_in[j];
+    atomicMin(&srcmin[cvid[j]], (uint32_t)j);     // first time this vertex becomes the source of a new edge
 }
 
+// formatted_edges order (bin/ntjoin_utils.py:115): sources in order of their first edge, edges of a source in creation
+// order.  Edges are already in creation order, so a STABLE sort on the source's first-creation index suffices.
 __global__ void __launch_bounds__(256) edge_order_key_kernel(const uint32_t* __restrict__ ue_q0, uint64_t n_edges, const uint32_t* __restrict__ cvid,
                                                               const uint32_t* __restrict__ srcmin, uint64_t* __restrict__ okey, uint32_t* __restrict__ oval)
 {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_edges) return;
-    uint32_t q0 = ue_q0[t];
-    okey[t] = ((uint64_t)srcmin[cvid[q0]] << 32) | q0;
+    okey[t] = srcmin[cvid[ue_q0[t]]];
     oval[t] = (uint32_t)t;
 }
 
@@ -284,21 +296,19 @@ int filter_and_edges_impl(mxe_engine* e, const uint64_t* const* d_hash, const ui
     MXE_CUDA(cudaStreamSynchronize(st));
     if (n_pairs == 0) { R->d_vertices = vertices.detach(); return MXE_OK; }
 
-    DBuf<uint64_t> ekey, ekey2, uprefix;
-    DBuf<uint32_t> eval, eval2, ehead, srcmin;
-    MXE_TRY(ekey.alloc(n_pairs, st)); MXE_TRY(ekey2.alloc(n_pairs, st));
-    MXE_TRY(eval.alloc(n_pairs, st)); MXE_TRY(eval2.alloc(n_pairs, st));
-    MXE_TRY(ehead.alloc(n_pairs, st)); MXE_TRY(uprefix.alloc(n_pairs + 1, st));
+    DBuf<uint32_t> succ, pred, own, emask_j, srcmin;
+    DBuf<uint64_t> uprefix;
+    MXE_TRY(succ.alloc((uint64_t)n_asm * nV, st)); MXE_TRY(pred.alloc((uint64_t)n_asm * nV, st));
+    MXE_TRY(own.alloc(n_keep, st)); MXE_TRY(emask_j.alloc(n_keep, st)); MXE_TRY(uprefix.alloc(n_keep + 1, st));
     MXE_TRY(srcmin.alloc(nV, st));
-    MXE_LAUNCH(e, pair_emit_kernel, gridf(n_keep), 256, 0, cvid.p, eflag.p, eprefix.p, n_keep, ekey.p, eval.p);
-    const int vb = bits_for(nV);
-    MXE_TRY(radix_sort_pairs(e, ekey.p, eval.p, ekey2.p, eval2.p, n_pairs, 0, vb));
-    MXE_TRY(radix_sort_pairs(e, ekey.p, eval.p, ekey2.p, eval2.p, n_pairs, 32, 32 + vb));
-    MXE_LAUNCH(e, edge_head_kernel, gridf(n_pairs), 256, 0, ekey.p, n_pairs, ehead.p);
-    MXE_TRY(exclusive_scan_u32_u64(e, ehead.p, uprefix.p, n_pairs));
-    uint64_t nE = 0;
-    MXE_CUDA(cudaMemcpyAsync(&nE, uprefix.p + n_pairs, 8, cudaMemcpyDeviceToHost, st));
+    MXE_CUDA(cudaMemsetAsync(succ.p, 0xFF, (uint64_t)n_asm * nV * sizeof(uint32_t), st));
+    MXE_CUDA(cudaMemsetAsync(pred.p, 0xFF, (uint64_t)n_asm * nV * sizeof(uint32_t), st));
     MXE_CUDA(cudaMemsetAsync(srcmin.p, 0xFF, nV * sizeof(uint32_t), st));
+    MXE_LAUNCH(e, adjacency_kernel, gridf(n_keep), 256, 0, cvid.p, cidx.p, eflag.p, n_keep, A, nV, succ.p, pred.p);
+    MXE_LAUNCH(e, edge_owner_kernel, gridf(n_keep), 256, 0, cvid.p, cidx.p, eflag.p, n_keep, A, nV, succ.p, pred.p, own.p, emask_j.p);
+    MXE_TRY(exclusive_scan_u32_u64(e, own.p, uprefix.p, n_keep));
+    uint64_t nE = 0;
+    MXE_CUDA(cudaMemcpyAsync(&nE, uprefix.p + n_keep, 8, cudaMemcpyDeviceToHost, st));
     MXE_CUDA(cudaStreamSynchronize(st));
 
     DBuf<uint32_t> ue_q0, ue_mask, oval, oval2, emask;
@@ -307,12 +317,9 @@ int filter_and_edges_impl(mxe_engine* e, const uint64_t* const* d_hash, const ui
     MXE_TRY(ue_q0.alloc(nE, st)); MXE_TRY(ue_mask.alloc(nE, st)); MXE_TRY(oval.alloc(nE, st)); MXE_TRY(oval2.alloc(nE, st));
     MXE_TRY(okey.alloc(nE, st)); MXE_TRY(okey2.alloc(nE, st));
     MXE_TRY(eu.alloc(nE, st)); MXE_TRY(ev.alloc(nE, st)); MXE_TRY(emask.alloc(nE, st)); MXE_TRY(ew.alloc(nE, st));
-    MXE_LAUNCH(e, edge_reduce_kernel, gridf(n_pairs), 256, 0, ekey.p, eval.p, ehead.p, uprefix.p, n_pairs, cidx.p, cvid.p, A,
-               ue_q0.p, ue_mask.p, srcmin.p);
+    MXE_LAUNCH(e, edge_compact_kernel, gridf(n_keep), 256, 0, own.p, uprefix.p, emask_j.p, n_keep, cvid.p, ue_q0.p, ue_mask.p, srcmin.p);
     MXE_LAUNCH(e, edge_order_key_kernel, gridf(nE), 256, 0, ue_q0.p, nE, cvid.p, srcmin.p, okey.p, oval.p);
-    const int kb = bits_for(n_keep);
-    MXE_TRY(radix_sort_pairs(e, okey.p, oval.p, okey2.p, oval2.p, nE, 0, kb));
-    MXE_TRY(radix_sort_pairs(e, okey.p, oval.p, okey2.p, oval2.p, nE, 32, 32 + kb));
+    MXE_TRY(radix_sort_pairs(e, okey.p, oval.p, okey2.p, oval2.p, nE, 0, bits_for(n_keep)));
     MXE_LAUNCH(e, edge_gather_kernel, gridf(nE), 256, 0, oval.p, nE, ue_q0.p, ue_mask.p, cvid.p, vertices.p, A, eu.p, ev.p, emask.p, ew.p);
     R->nE = nE;
     R->d_vertices = vertices.detach();
