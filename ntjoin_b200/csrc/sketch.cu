@@ -1,6 +1,7 @@
 // sketch.cu -- host orchestration of step 1 (see sketch_kernels.cuh for the algorithm).
 #include "engine.cuh"
 #include "sketch_kernels.cuh"
+#include "bitslice_kernels.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -134,7 +135,32 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
         Span sp(e, "cand");
         uint64_t n_threads = (n + P.chunk - 1) / P.chunk;
         bool fast = e->cand_variant >= 1 && (k % 4 == 0) && k >= 4;
-        if (fast) {
+        const int kmod = k % 31;
+        bool sliced = e->cand_variant >= 2 && !P.canon_min && (kmod == 1 || kmod == 9 || kmod == 24) && k >= 16 && k <= 256 &&
+                      (e->cand_variant >= 3 || n >= ((uint64_t)1 << 29));
+        if (sliced) {
+            // bit-sliced kernel: transpose pk into bit planes, run 32 streams per thread, then C &= V with counts
+            BsParams BP;
+            BP.n = n; BP.k = k; BP.iters = bs_iters(k); BP.rows = bs_rows(k);
+            BP.n_tiles = (n + BS_TILE - 1) / BS_TILE;
+            BP.f0 = Tb.f0; BP.r0 = Tb.r0;
+            const uint32_t TH = P.T >> (31 - BS_H);
+            uint32_t Q = (TH + 1) >> (BS_H - BS_HS);
+            if (Q > (1u << BS_HS) - 1) Q = (1u << BS_HS) - 1;
+            const uint32_t K = ((1u << BS_HS) - 1) - Q;
+            for (int i = 0; i < BS_HS; i++) BP.kmask[i] = ((K >> i) & 1u) ? 0xFFFFFFFFu : 0u;
+            DBuf<uint32_t> PL;
+            const uint64_t n_groups = (BP.n_tiles + 3) / 4;
+            MXE_TRY(PL.alloc(n_groups * (uint64_t)BP.rows * 8, st));
+            const int n_in = PLANE_SLICE + BP.rows / 16;
+            const size_t psm = (4 * (size_t)(n_in + n_in / 32 + 1) + 128) * sizeof(uint32_t);
+            MXE_LAUNCH(e, plane_kernel, (unsigned)n_groups, 128, psm, pk.p, pk_words, BP.n_tiles, BP.rows, PL.p);
+            if (kmod == 1) MXE_LAUNCH(e, cand_bs_kernel<1>, grid_for(BP.n_tiles, 128), 128, 0, PL.p, BP, C.p);
+            else if (kmod == 9) MXE_LAUNCH(e, cand_bs_kernel<9>, grid_for(BP.n_tiles, 128), 128, 0, PL.p, BP, C.p);
+            else MXE_LAUNCH(e, cand_bs_kernel<24>, grid_for(BP.n_tiles, 128), 128, 0, PL.p, BP, C.p);
+            MXE_LAUNCH(e, cand_mask_count_kernel, grid_for(nW, 256), 256, 0, C.p, V.p, nW, ccounts.p);
+            c_counted = true;
+        } else if (fast) {
             // the staged kernel needs a power-of-two run length between 128 and 1024
             int c = 128;
             while (c * 2 <= P.chunk && c < 1024) c *= 2;

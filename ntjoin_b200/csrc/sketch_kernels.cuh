@@ -227,6 +227,24 @@ __device__ __forceinline__ uint32_t contig_of(const uint64_t* __restrict__ offse
     return lo;
 }
 
+// warp-cooperative version: 32-ary search, two or three dependent loads instead of log2(n) (all lanes get the result)
+__device__ __forceinline__ uint32_t contig_of_warp(const uint64_t* __restrict__ offsets, uint32_t n_contigs, uint64_t p, int lane)
+{
+    uint32_t lo = 0, hi = n_contigs;          // answer in [lo, hi): last c with offsets[c] <= p
+    while (hi - lo > 1) {
+        const uint32_t span = hi - lo;
+        const uint32_t step = (span + 31) / 32;
+        const uint32_t idx = lo + (uint32_t)(lane + 1) * step;      // probes lo+step, lo+2*step, ...
+        const bool le = idx < hi && offsets[idx] <= p;
+        const uint32_t cnt = __popc(__ballot_sync(0xffffffffu, le));   // probes are monotone: first cnt are true
+        const uint32_t nlo = lo + cnt * step;
+        const uint32_t nhi = nlo + step < hi ? nlo + step : hi;
+        lo = nlo;
+        hi = nhi;
+    }
+    return lo;
+}
+
 // ---------------------------------------------------------------- pack: ASCII -> pk, B
 // One thread per 32 bases.  Valid bytes are ACGTacgt; everything else sets its bit in B.
 // Byte-SIMD validity: x = (byte & 0xDF) ^ 0x41 is one of 00 02 06 15 for A C G T.
@@ -536,9 +554,7 @@ __global__ void __launch_bounds__(256) cand_extract_kernel(const uint32_t* __res
         uint32_t y1 = __shfl_up_sync(0xffffffffu, cx, d), y2 = __shfl_up_sync(0xffffffffu, vx, d);
         if (lane >= d) { cx += y1; vx += y2; }
     }
-    uint32_t c0 = 0;
-    if (lane == 0) c0 = contig_of(offsets, n_contigs, blk * RANK_BLOCK_BITS);
-    c0 = __shfl_sync(0xffffffffu, c0, 0);
+    const uint32_t c0 = contig_of_warp(offsets, n_contigs, blk * RANK_BLOCK_BITS, lane);
     uint64_t o = c_base + (cx - cc);
     const uint64_t v_base = vprefix[blk] + (vx - vc);
     const uint64_t base = wi << 5;

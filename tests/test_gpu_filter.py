@@ -93,3 +93,28 @@ def test_hash_sort_tied_top_bits(engine, oracle, n_top):
     np.testing.assert_array_equal(res.support, want["edges"]["support_mask"])
     np.testing.assert_array_equal(res.weight, want["edges"]["weight"])
     assert len(res.vertices) > 100
+
+
+def test_config4_four_way(engine, oracle):
+    """BASELINE configs[3] scaled down: target + 3 references (0.1-0.5 % divergence), k=32 w=500, weights 2 2 2 / 1"""
+    anc, aoffs, _ = synth.make_reference(8_000_000, n_chrom=6, dup_frac=0.02)
+    asms = []
+    for i, rate in enumerate((0.001, 0.003, 0.005)):
+        asms.append(synth.derive_target(anc, aoffs, seed=500 + i, min_len=200_000, max_len=3_000_000, sub_rate=rate, rc_frac=0.2)[:2])
+    asms.append(synth.derive_target(anc, aoffs, seed=600, min_len=10_000, max_len=500_000, sub_rate=0.002)[:2])      # target last
+    weights = [2.0, 2.0, 2.0, 1.0]
+    sks = [engine.sketch_buffers(s, o, 32, 500) for s, o in asms]
+    res = engine.filter_and_edges(sks, weights)
+    want = oracle.filter_and_edges([s.out_hash for s in sks], [s.contig for s in sks], weights)
+    for a in range(4):
+        np.testing.assert_array_equal(res.uniq[a], want["uniq"][a])
+        np.testing.assert_array_equal(res.keep[a], want["keep"][a])
+    np.testing.assert_array_equal(res.vertices, want["vertices"])
+    np.testing.assert_array_equal(res.edge_u, want["edges"]["u"])
+    np.testing.assert_array_equal(res.edge_v, want["edges"]["v"])
+    np.testing.assert_array_equal(res.support, want["edges"]["support_mask"])
+    np.testing.assert_array_equal(res.weight, want["edges"]["weight"])
+    masks = set(int(m) for m in np.unique(res.support))
+    assert 15 in masks and len(masks) >= 4 and set(np.unique(res.weight)) >= {7.0}
+    # n=2 filtering downstream (bin/ntjoin.py:80-89) keeps edges with weight >= 2: every edge seen only in the target is dropped
+    assert (res.weight[res.support == 8] == 1.0).all()

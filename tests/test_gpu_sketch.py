@@ -33,7 +33,7 @@ def test_golden_tsv_bytes(engine, golden_dir, tmp_path, fname):
     assert out.read_bytes() == want
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 3])
 @pytest.mark.parametrize("canonical", ["sum", "min"])
 @pytest.mark.parametrize("fname", FIXTURES)
 def test_fixture_vs_oracle(engine, oracle, golden_dir, fname, canonical, variant):
@@ -68,12 +68,12 @@ def _messy(n, seed):
     return seq, offs
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 3])
 @pytest.mark.parametrize("canonical", ["sum", "min"])
 def test_messy_synthetic(engine, oracle, canonical, variant):
     seq, offs = _messy(1_500_000, 7)
     engine.set_option("cand_variant", variant)
-    engine.set_option("prune", variant)          # variant 0 also exercises the unpruned exact path
+    engine.set_option("prune", variant == 1)     # also exercises the pruned exact path
     for k, w in [(32, 1000), (32, 100), (16, 50), (20, 10), (40, 250), (15, 10), (32, 5000)]:
         ref = oracle.sketch(seq, offs, k, w, canonical=canonical)
         sk = engine.sketch_buffers(seq, offs, k, w, canonical=canonical)
@@ -130,3 +130,17 @@ def test_tsv_with_seq_matches_oracle_cli(engine, golden_dir, tmp_path):
     out = tmp_path / "o.tsv"
     sk.write_tsv(out, pos=True, strand=False, seq=True)
     assert out.read_bytes() == want
+
+
+@pytest.mark.parametrize("variant", [1, 3])
+def test_config5_kw_sweep(engine, oracle, variant):
+    """BASELINE configs[4]: k in {24,32,40} x w in {250,500,1000,5000}, scaled down, both candidate kernels"""
+    rseq, roffs, _ = synth.make_reference(6_000_000, n_chrom=5, dup_frac=0.02, n_frac=0.005)
+    engine.set_option("cand_variant", variant)
+    try:
+        for k in (24, 32, 40):
+            for w in (250, 500, 1000, 5000):
+                ref = oracle.sketch(rseq, roffs, k, w, threads=8)
+                assert_same(engine.sketch_buffers(rseq, roffs, k, w), ref)
+    finally:
+        engine.set_option("cand_variant", 1)
