@@ -77,13 +77,12 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
     const uint64_t pk_words = 2 * nW + (uint64_t)(k / 16) + 16;
     P.pk_words = pk_words;
 
-    DBuf<uint32_t> pk, B, V, C, M;
+    DBuf<uint32_t> pk, V, C, M;
     DBuf<uint64_t> vprefix, cprefix, mprefix, d_offsets, ostart;
     DBuf<uint32_t> vcounts, ccounts;
     MXE_TRY(vcounts.alloc(n_vblocks + 1, st));
     MXE_TRY(ccounts.alloc(n_vblocks + 1, st));
     MXE_TRY(pk.alloc(pk_words, st));
-    MXE_TRY(B.alloc(nW, st));
     MXE_TRY(V.alloc(nW, st));
     MXE_TRY(C.alloc(nW, st));
     MXE_TRY(M.alloc(nW, st));
@@ -101,7 +100,7 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
     {
         Span sp(e, "pack");
         if (!h_seq) {
-            MXE_LAUNCH(e, pack_kernel, grid_for(nW, 256), 256, 0, d_seq, P, pk.p, B.p, (uint64_t)0, nW);
+            MXE_LAUNCH(e, pack_kernel, grid_for(nW, 256), 256, 0, d_seq, P, pk.p, V.p, vcounts.p, (uint64_t)0, nW);
         } else {
             // host input: chunked H2D on two copy streams, each chunk packed as soon as it has landed
             const uint64_t CH = (uint64_t)e->h2d_chunk_mb << 20;
@@ -115,12 +114,14 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
                 MXE_CUDA(cudaMemcpyAsync(const_cast<uint8_t*>(d_seq) + off, h_seq + off, len, cudaMemcpyHostToDevice, cs));
                 MXE_CUDA(cudaEventRecord(ev, cs));
                 MXE_CUDA(cudaStreamWaitEvent(st, ev, 0));
-                const uint64_t t0 = off >> 5, t1 = (off + len + 31) >> 5;
-                MXE_LAUNCH(e, pack_kernel, grid_for(t1 - t0, 256), 256, 0, d_seq, P, pk.p, B.p, t0, t1);
+                // ranges lag one warp (32 words) behind the copied bytes: the V halo of a warp reads the next words
+                const bool last = off + len >= n;
+                const uint64_t t0 = off ? (off >> 5) - 32 : 0;
+                const uint64_t t1 = last ? nW : ((off + len) >> 5) - 32;
+                if (t1 > t0) MXE_LAUNCH(e, pack_kernel, grid_for(t1 - t0, 256), 256, 0, d_seq, P, pk.p, V.p, vcounts.p, t0, t1);
                 if ((i % MXE_N_CHUNK_EVENTS) == MXE_N_CHUNK_EVENTS - 1) MXE_CUDA(cudaStreamSynchronize(st));   // events are reused
             }
         }
-        MXE_LAUNCH(e, vmask_kernel, grid_for(nW, 256), 256, 0, B.p, P, V.p, vcounts.p);
         if (n_contigs > 1) MXE_LAUNCH(e, boundary_kernel, grid_for(n_contigs - 1, 128), 128, 0, d_offsets.p, n_contigs, P, V.p, vcounts.p);
     }
     {
@@ -227,7 +228,21 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
                            cpos2.p, cord2.p, cctg2.p);
                 s_pos = cpos2.p; s_ord = cord2.p; s_ctg = cctg2.p;
             }
-            if (n_sel) MXE_LAUNCH(e, cand_hash_kernel, grid_for(n_sel, 256), 256, 0, s_pos, n_sel, pk.p, P, Tb, ch0.p);
+            if (n_sel) {
+                const int G = k / 4;
+                if (G >= 1 && G <= HASHPOS_MAX_GROUPS) {
+                    // position-specific tables (built once per sketch) -> no rotations per candidate
+                    DBuf<uint64_t> PF, PR;
+                    MXE_TRY(PF.alloc((size_t)G * 256, st)); MXE_TRY(PR.alloc((size_t)G * 256, st));
+                    MXE_LAUNCH(e, hash_pos_tables_kernel, G, 256, 0, Tb, k, PF.p, PR.p);
+                    const size_t hsm = (size_t)2 * G * 256 * sizeof(uint64_t);
+                    MXE_CUDA(cudaFuncSetAttribute(cand_hash_pos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
+                    const unsigned grid = (unsigned)std::min<uint64_t>(grid_for(n_sel, 256), (uint64_t)e->sm_count * 5);
+                    MXE_LAUNCH(e, cand_hash_pos_kernel, grid, 256, hsm, s_pos, n_sel, pk.p, P, Tb, PF.p, PR.p, ch0.p);
+                } else {
+                    MXE_LAUNCH(e, cand_hash_kernel, grid_for(n_sel, 256), 256, 0, s_pos, n_sel, pk.p, P, Tb, ch0.p);
+                }
+            }
         }
     }
     {

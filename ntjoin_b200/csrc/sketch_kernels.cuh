@@ -245,8 +245,8 @@ __device__ __forceinline__ uint32_t contig_of_warp(const uint64_t* __restrict__ 
     return lo;
 }
 
-// ---------------------------------------------------------------- pack: ASCII -> pk, B
-// One thread per 32 bases.  Valid bytes are ACGTacgt; everything else sets its bit in B.
+// ---------------------------------------------------------------- pack: ASCII -> pk, V (+ rank counts of V)
+// One thread per 32 bases.  Valid bytes are ACGTacgt; everything else is a "bad" base.
 // Byte-SIMD validity: x = (byte & 0xDF) ^ 0x41 is one of 00 02 06 15 for A C G T.
 __device__ __forceinline__ uint32_t bad_bytes(uint32_t x)
 {
@@ -254,16 +254,13 @@ __device__ __forceinline__ uint32_t bad_bytes(uint32_t x)
     return (x & 0xF9F9F9F9u) ^ (m >> 2) ^ (m << 2);    // non-zero byte <=> invalid base
 }
 
-// Processes words [t0, t1) so that the host path can pack each chunk as soon as its H2D copy has landed.
-__global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ seq, SketchParams P,
-                                                   uint32_t* __restrict__ pk, uint32_t* __restrict__ B, uint64_t t0, uint64_t t1)
+// 32 bases at word t: 2-bit codes (two pk words) and the exact bad-base mask (bases beyond n are bad)
+__device__ __forceinline__ uint32_t pack_word(const uint8_t* __restrict__ seq, uint64_t n, uint64_t t, uint32_t pkw[2])
 {
-    uint64_t t = t0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= t1) return;
-    uint64_t p0 = t << 5;
-    uint32_t pkw[2] = {0, 0};
+    const uint64_t p0 = t << 5;
     uint32_t bad = 0;
-    if (p0 + 32 <= P.n) {
+    pkw[0] = pkw[1] = 0;
+    if (p0 + 32 <= n) {
         const uint4* src = reinterpret_cast<const uint4*>(seq + p0);
         uint4 a = __ldg(src), b = __ldg(src + 1);
         uint32_t wv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
@@ -291,7 +288,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ s
             uint64_t p = p0 + i;
             uint32_t code = 0;
             bool ok = false;
-            if (p < P.n) {
+            if (p < n) {
                 uint32_t x = ((uint32_t)seq[p] & 0xDFu) ^ 0x41u;
                 ok = (x == 0x00u) | (x == 0x02u) | (x == 0x06u) | (x == 0x15u);
                 code = (x >> 1) & 3u;
@@ -301,47 +298,90 @@ __global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ s
             pkw[i >> 4] |= code << (((ii & 3u) << 3) | ((ii >> 2) << 1));
         }
     }
-    reinterpret_cast<uint2*>(pk)[t] = make_uint2(pkw[0], pkw[1]);
-    B[t] = bad;
+    return bad;
 }
 
-// ---------------------------------------------------------------- vmask: V = valid k-mer starts
-__device__ __forceinline__ uint32_t vmask_word(const uint32_t* __restrict__ B, const SketchParams& P, uint64_t t)
+// V word = positions p of this word with no bad base in [p, p+k); `nb(j)` returns the bad mask of word t+j
+template <typename F>
+__device__ __forceinline__ uint32_t vmask_from(F nb, int reach, int k)
 {
-    const int reach = (31 + P.k - 1) / 32;     // last word touched = t + reach
     uint32_t any = 0;
-    for (int j = 0; j <= reach; j++) any |= (t + j < P.n_words) ? B[t + j] : 0xFFFFFFFFu;
-    uint32_t v = 0xFFFFFFFFu;
-    if (any) {
-        v = 0;
-        // distance from bit position to the next bad position, scanning right to left
-        long long next_bad = -1;   // absolute bit index (relative to word t) of nearest bad at or after current
-        for (int j = reach; j >= 0; j--) {
-            uint32_t bw = (t + j < P.n_words) ? B[t + j] : 0xFFFFFFFFu;
-            for (int b = 31; b >= 0; b--) {
-                int idx = j * 32 + b;
-                if ((bw >> b) & 1u) next_bad = idx;
-                if (j == 0 && (next_bad < 0 || next_bad >= idx + P.k)) v |= 1u << b;
-            }
+    for (int j = 0; j <= reach; j++) any |= nb(j);
+    if (!any) return 0xFFFFFFFFu;
+    uint32_t v = 0;
+    long long next_bad = -1;     // bit index (relative to this word) of the nearest bad base at or after the cursor
+    for (int j = reach; j >= 0; j--) {
+        const uint32_t bw = nb(j);
+        for (int b = 31; b >= 0; b--) {
+            const int idx = j * 32 + b;
+            if ((bw >> b) & 1u) next_bad = idx;
+            if (j == 0 && (next_bad < 0 || next_bad >= idx + k)) v |= 1u << b;
         }
     }
     return v;
 }
 
-// Also emits the rank-directory block counts of V (one warp = 32 consecutive words = one 1024-bit block).
-__global__ void __launch_bounds__(256) vmask_kernel(const uint32_t* __restrict__ B, SketchParams P, uint32_t* __restrict__ V,
-                                                    uint32_t* __restrict__ vcounts)
+// Words [t0, t1) (t0 a multiple of 32).  Each warp also classifies the `reach` words that follow its 32 words, so V
+// needs no second pass over a bad-base bitmap; the host path shifts chunk ranges by one warp so that this halo has
+// always landed.  Emits the rank-directory block counts of V (one warp = one 1024-bit block).
+__global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ seq, SketchParams P,
+                                                   uint32_t* __restrict__ pk, uint32_t* __restrict__ V, uint32_t* __restrict__ vcounts,
+                                                   uint64_t t0, uint64_t t1)
 {
-    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t v = 0;
-    if (t < P.n_words) v = vmask_word(B, P, t);
+    const uint64_t t = t0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const uint64_t tw = t - lane;                       // first word of this warp
+    if (tw >= t1) return;                               // warp-uniform
+    const int reach = (31 + P.k - 1) / 32;              // V of word t looks at words t .. t+reach   (reach <= 32)
+    uint32_t pkw[2], tmp[2];
+    uint32_t bad = 0xFFFFFFFFu, bad_halo = 0xFFFFFFFFu; // words beyond the sequence are all bad
+    if (t < P.n_words) {
+        bad = pack_word(seq, P.n, t, pkw);
+        if (t < t1) reinterpret_cast<uint2*>(pk)[t] = make_uint2(pkw[0], pkw[1]);
+    }
+    {
+        // halo = the `reach` words after this warp's 32: cooperative screening (one u32 per lane and round); only if a bad
+        // base shows up (or the sequence ends inside the halo) do the first `reach` lanes classify their word exactly
+        const uint64_t hb = (tw + 32) << 5;                 // first halo base
+        bool suspicious = false;
+        for (int i = lane; i < reach * 8; i += 32) {
+            const uint64_t p = hb + 4 * (uint64_t)i;
+            if (p + 4 <= P.n) {
+                const uint32_t x = (__ldg(reinterpret_cast<const uint32_t*>(seq + p)) & 0xDFDFDFDFu) ^ 0x41414141u;
+                suspicious |= bad_bytes(x) != 0;
+            } else suspicious = true;
+        }
+        if (__any_sync(0xffffffffu, suspicious)) {
+            if (lane < reach && tw + 32 + lane < P.n_words) bad_halo = pack_word(seq, P.n, tw + 32 + lane, tmp);
+        } else {
+            bad_halo = 0;
+        }
+    }
+    uint32_t any = bad;
+    for (int j = 1; j <= reach; j++) {
+        const int src = lane + j;
+        const uint32_t a = __shfl_sync(0xffffffffu, bad, src & 31), h = __shfl_sync(0xffffffffu, bad_halo, src & 31);
+        any |= src < 32 ? a : h;
+    }
+    uint32_t v = 0xFFFFFFFFu;
+    const bool slow = any != 0;
+    if (__any_sync(0xffffffffu, slow)) {                // rare: some lane has a bad base within reach
+        uint32_t nbw[33];
+        nbw[0] = bad;
+        for (int j = 1; j <= reach; j++) {
+            const int src = lane + j;
+            const uint32_t a = __shfl_sync(0xffffffffu, bad, src & 31), h = __shfl_sync(0xffffffffu, bad_halo, src & 31);
+            nbw[j] = src < 32 ? a : h;
+        }
+        if (slow) v = vmask_from([&](int j) { return nbw[j]; }, reach, P.k);
+    }
+    if (t >= P.n_words) v = 0;
     uint32_t c = __popc(v);
 #pragma unroll
     for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-    if (t < P.n_words) V[t] = v;
-    if ((threadIdx.x & 31) == 0 && (t >> 5) * RANK_BLOCK_WORDS < P.n_words) vcounts[t >> 5] = c;
+    if (t < P.n_words && t < t1) V[t] = v;
+    if (lane == 0 && tw < P.n_words) vcounts[tw >> 5] = c;
 }
-
 
 // contig boundaries: a k-mer may not straddle two records
 __global__ void boundary_kernel(const uint64_t* __restrict__ offsets, uint32_t n_contigs, SketchParams P, uint32_t* __restrict__ V,
@@ -581,6 +621,73 @@ __global__ void __launch_bounds__(256) cand_hash_kernel(const uint64_t* __restri
     uint64_t f, r;
     kmer_hash64_tab(pk, cpos[i], P.k, &H, f, r);
     h0[i] = canon(f, r, P.canon_min);
+}
+
+// ---------------------------------------------------------------- exact hash with position-specific tables
+// hash = XOR over 4-base groups of a table entry that already carries the group's rotation, so the per-candidate work
+// is one byte extract, two LDS.64 and two 64-bit XORs per group (no rotations).  Tables: PF[g][v] = srol^(4(G-1-g))(f4[v]),
+// PR[g][v] = sror^(4(G-1-g))(r4[v]), G = k/4 groups; the k % 4 trailing bases use the single-base recurrences.
+constexpr int HASHPOS_MAX_GROUPS = 10;       // 2 * 10 * 2 KB = 40 KB of shared memory (k <= 43)
+
+__global__ void __launch_bounds__(256) hash_pos_tables_kernel(SketchTables Tb, int k, uint64_t* __restrict__ PF, uint64_t* __restrict__ PR)
+{
+    __shared__ HashTabs H;
+    build_hash_tabs(&H, Tb, k);
+    const int G = k / 4;
+    for (int idx = threadIdx.x + blockIdx.x * blockDim.x; idx < G * 256; idx += blockDim.x * gridDim.x) {
+        const int g = idx >> 8, v = idx & 255;
+        uint64_t f = H.f4[v], r = H.r4[v];
+        for (int q = 0; q < 4 * (G - 1 - g); q++) { f = srol1(f); r = sror1(r); }
+        PF[idx] = f;
+        PR[idx] = r;
+    }
+}
+
+__global__ void __launch_bounds__(256) cand_hash_pos_kernel(const uint64_t* __restrict__ cpos, uint64_t n_cand, const uint32_t* __restrict__ pk,
+                                                             SketchParams P, SketchTables Tb, const uint64_t* __restrict__ PF,
+                                                             const uint64_t* __restrict__ PR, uint64_t* __restrict__ h0)
+{
+    extern __shared__ uint64_t hp[];
+    const int G = P.k / 4;
+    uint64_t* pf = hp;
+    uint64_t* pr = hp + G * 256;
+    __shared__ uint64_t s1[8];
+    for (int i = threadIdx.x; i < G * 256; i += blockDim.x) { pf[i] = PF[i]; pr[i] = PR[i]; }
+    if (threadIdx.x < 4) {
+        s1[threadIdx.x] = Tb.seed[threadIdx.x];
+        uint64_t sc = Tb.seed[threadIdx.x ^ 2];
+        for (int q = 0; q < P.k - 1; q++) sc = srol1(sc);
+        s1[4 + threadIdx.x] = sc;
+    }
+    __syncthreads();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cand; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t p = cpos[i];
+        const uint64_t q = p >> 4;
+        const uint32_t sh = ((uint32_t)p & 15u) * 2u;
+        uint64_t f = 0, r = 0;
+        uint32_t cur = pk_to_natural(__ldg(pk + q));
+        int g = 0, left = P.k;
+        for (int m = 0; left > 0; m++) {
+            const uint32_t nxt = pk_to_natural(__ldg(pk + q + m + 1));
+            uint32_t N = __funnelshift_r(cur, nxt, sh);          // 16 bases starting at p + 16 m, natural order
+            cur = nxt;
+            int nb = left < 16 ? left : 16;
+            left -= nb;
+            for (; nb >= 4; nb -= 4, g++) {
+                const uint32_t v = N & 0xFFu;
+                N >>= 8;
+                f ^= pf[g * 256 + v];
+                r ^= pr[g * 256 + v];
+            }
+            for (; nb > 0; nb--) {                               // k % 4 trailing bases (last word only)
+                const uint32_t c = N & 3u;
+                N >>= 2;
+                f = srol1(f) ^ s1[c];
+                r = sror1(r) ^ s1[4 + c];
+            }
+        }
+        h0[i] = canon(f, r, P.canon_min);
+    }
 }
 
 // ---------------------------------------------------------------- candidate pruning on 31-bit bounds
