@@ -368,6 +368,12 @@ def main():
         except OSError:
             pass
         peak = peaks.get("hbm_gbs", 6650.0)
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["cand31_kernel"]
+            traffic = (tj["dram_read_bytes_per_base"] + tj["dram_write_bytes_per_base"]) * my_bases / n_asm   # ncu-measured DRAM bytes per launch
+        except (OSError, KeyError):
+            pass
         # algorithmic bytes of the sketch: 1 B per base read + 16 B per emitted minimizer
         n_mx_local = sum(stats["n_mx"])
         algo_bytes_per_launch = (my_bases + 16.0 * n_mx_local) / n_asm
@@ -385,7 +391,7 @@ def main():
                     "h2d_bytes_per_step": my_bases, "d2h_bytes_per_step": stats["d2h"]},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "cand31_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None, "traffic": None,
+                         "frac": achieved / peak if peak else None, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                          "launch_ms": cand_ms, "algorithmic_bytes_per_launch": algo_bytes_per_launch,
                          "phase_ms_per_step": phases},
