@@ -169,7 +169,7 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
             n_threads = (n + P.chunk - 1) / P.chunk;
             size_t smem = cand31_smem_bytes(P.chunk, k);
             c_counted = true;
-            if (P.canon_min) {
+if (P.canon_min) {
                 MXE_CUDA(cudaFuncSetAttribute(cand31_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 MXE_LAUNCH(e, cand31_kernel<1>, grid_for(n_threads, CAND_THREADS), CAND_THREADS, smem, pk.p, V.p, P, Tb, C.p, ccounts.p);
             } else {
@@ -213,7 +213,7 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
     {
         Span sp(e, "eval");
         if (n_cand) {
-            MXE_LAUNCH(e, cand_extract_kernel, grid_for(n_vblocks * 32, 256), 256, 0, C.p, V.p, nW, cprefix.p, vprefix.p, n_vblocks,
+            MXE_LAUNCH(e, cand_extract_kernel, grid_for((n_vblocks + XBLOCKS - 1) / XBLOCKS * 32, 256), 256, 0, C.p, V.p, nW, cprefix.p, vprefix.p, n_vblocks,
                        d_offsets.p, n_contigs, cpos.p, cord.p, cctg.p);
             if (e->prune) {
                 MXE_TRY(klo.alloc(n_cand, st)); MXE_TRY(khi.alloc(n_cand, st)); MXE_TRY(pflag.alloc(n_cand, st));

@@ -573,41 +573,68 @@ __global__ void __launch_bounds__(CAND_THREADS) cand31_kernel(const uint32_t* __
 #undef MXE_CAND_STEP
 
 // ---------------------------------------------------------------- candidate extraction + evaluation
-// One warp per 1024-bit block of C: ordered positions, valid-k-mer ordinals (warp scan over V, no
-// per-candidate rank walk) and record ids (one binary search per block).
+// One warp per 8192 bits of C (8 rank blocks), one lane per 8 consecutive words: two 16-byte loads of C and of V per
+// lane are in flight together and one warp scan serves eight rank blocks (the one-warp-per-block version was latency
+// bound: a chain of dependent loads per 9 candidates).  Emits ordered positions, valid-k-mer ordinals (popcounts of V,
+// no per-candidate rank walk) and record ids (one 32-ary search per warp, then a monotone walk).
+constexpr int XW = 8;                        // words per lane
+constexpr int XBLOCKS = XW * 32 / RANK_BLOCK_WORDS;   // rank blocks per warp (8)
+
+__device__ __forceinline__ void load_words8(const uint32_t* __restrict__ bits, uint64_t w0, uint64_t n_words, uint32_t out[XW])
+{
+    if (w0 + XW <= n_words) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(bits + w0)), b = __ldg(reinterpret_cast<const uint4*>(bits + w0) + 1);
+        out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w; out[4] = b.x; out[5] = b.y; out[6] = b.z; out[7] = b.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < XW; j++) out[j] = w0 + j < n_words ? __ldg(bits + w0 + j) : 0u;
+    }
+}
+
 __global__ void __launch_bounds__(256) cand_extract_kernel(const uint32_t* __restrict__ C, const uint32_t* __restrict__ V, uint64_t n_words,
                                                             const uint64_t* __restrict__ cprefix, const uint64_t* __restrict__ vprefix, uint64_t n_blocks,
                                                             const uint64_t* __restrict__ offsets, uint32_t n_contigs,
                                                             uint64_t* __restrict__ cpos, uint64_t* __restrict__ cord, uint32_t* __restrict__ cctg)
 {
-    uint64_t blk = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t sb = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (blk >= n_blocks) return;
-    const uint64_t c_base = cprefix[blk];
-    if (cprefix[blk + 1] == c_base) return;          // warp-uniform
-    const uint64_t wi = blk * RANK_BLOCK_WORDS + lane;
-    uint32_t cw = wi < n_words ? C[wi] : 0;
-    const uint32_t vw = wi < n_words ? V[wi] : 0;
-    uint32_t cc = __popc(cw), vc = __popc(vw), cx = cc, vx = vc;
+    const uint64_t blk0 = sb * XBLOCKS;
+    if (blk0 >= n_blocks) return;
+    const uint64_t blk1 = blk0 + XBLOCKS < n_blocks ? blk0 + XBLOCKS : n_blocks;
+    const uint64_t c_base = cprefix[blk0];
+    if (cprefix[blk1] == c_base) return;             // warp-uniform
+    const uint64_t w0 = sb * (32 * XW) + (uint64_t)lane * XW;
+    uint32_t cw[XW], vw[XW];
+    load_words8(C, w0, n_words, cw);
+    load_words8(V, w0, n_words, vw);
+    uint32_t cc = 0, vc = 0;
+#pragma unroll
+    for (int j = 0; j < XW; j++) { cc += __popc(cw[j]); vc += __popc(vw[j]); }
+    uint32_t cx = cc, vx = vc;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         uint32_t y1 = __shfl_up_sync(0xffffffffu, cx, d), y2 = __shfl_up_sync(0xffffffffu, vx, d);
         if (lane >= d) { cx += y1; vx += y2; }
     }
-    const uint32_t c0 = contig_of_warp(offsets, n_contigs, blk * RANK_BLOCK_BITS, lane);
+    uint32_t c = contig_of_warp(offsets, n_contigs, sb * (uint64_t)(32 * XW * 32), lane);
+    if (cc == 0) return;                              // after the collectives
     uint64_t o = c_base + (cx - cc);
-    const uint64_t v_base = vprefix[blk] + (vx - vc);
-    const uint64_t base = wi << 5;
-    while (cw) {
-        const int b = __ffs(cw) - 1;
-        cw &= cw - 1;
-        const uint64_t p = base + b;
-        uint32_t c = c0;
-        while (c + 1 < n_contigs && offsets[c + 1] <= p) c++;
-        cpos[o] = p;
-        cord[o] = v_base + __popc(vw & ((1u << b) - 1u));
-        cctg[o] = c;
-        o++;
+    uint64_t vb = vprefix[blk0] + (vx - vc);
+#pragma unroll
+    for (int j = 0; j < XW; j++) {
+        uint32_t wv = cw[j];
+        const uint64_t base = (w0 + j) << 5;
+        while (wv) {
+            const int b = __ffs(wv) - 1;
+            wv &= wv - 1;
+            const uint64_t p = base + b;
+            while (c + 1 < n_contigs && offsets[c + 1] <= p) c++;
+            cpos[o] = p;
+            cord[o] = vb + __popc(vw[j] & ((1u << b) - 1u));
+            cctg[o] = c;
+            o++;
+        }
+        vb += __popc(vw[j]);
     }
 }
 

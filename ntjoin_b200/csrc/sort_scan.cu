@@ -107,18 +107,37 @@ int exclusive_scan_u32_u64(Engine* e, const uint32_t* d_in, uint64_t* d_out, siz
 // ------------------------------------------------------------------------------------------
 // bitmap rank directory + ordered extraction
 // ------------------------------------------------------------------------------------------
+// One warp per 8192 bits (8 rank blocks), one lane per 8 consecutive words (two 16-byte loads in flight per lane).
+constexpr int BW = 8;                                    // words per lane
+constexpr int BBLOCKS = BW * 32 / RANK_BLOCK_WORDS;      // rank blocks per warp
+
+__device__ __forceinline__ void bm_load8(const uint32_t* __restrict__ bits, size_t w0, size_t n_words, uint32_t out[BW])
+{
+    if (w0 + BW <= n_words) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(bits + w0)), b = __ldg(reinterpret_cast<const uint4*>(bits + w0) + 1);
+        out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w; out[4] = b.x; out[5] = b.y; out[6] = b.z; out[7] = b.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < BW; j++) out[j] = w0 + j < n_words ? __ldg(bits + w0 + j) : 0u;
+    }
+}
+
 __global__ void __launch_bounds__(256) bitmap_block_count_kernel(const uint32_t* __restrict__ bits, size_t n_words,
                                                                   uint32_t* __restrict__ counts, size_t n_blocks)
 {
-    // one warp per 1024-bit block
-    size_t blk = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int lane = threadIdx.x & 31;
-    if (blk >= n_blocks) return;
-    size_t wi = blk * RANK_BLOCK_WORDS + lane;
-    uint32_t c = wi < n_words ? __popc(bits[wi]) : 0;
+    const size_t sb = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const size_t blk0 = sb * BBLOCKS;
+    if (blk0 >= n_blocks) return;
+    uint32_t wv[BW];
+    bm_load8(bits, sb * (32 * BW) + (size_t)lane * BW, n_words, wv);
+    uint32_t c = 0;
 #pragma unroll
-    for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-    if (lane == 0) counts[blk] = c;
+    for (int j = 0; j < BW; j++) c += __popc(wv[j]);
+    c += __shfl_xor_sync(0xffffffffu, c, 1);             // four lanes = one 1024-bit rank block
+    c += __shfl_xor_sync(0xffffffffu, c, 2);
+    const size_t blk = blk0 + (lane >> 2);
+    if ((lane & 3) == 0 && blk < n_blocks) counts[blk] = c;
 }
 
 int bitmap_rank_build(Engine* e, const uint32_t* d_bits, size_t n_words, uint64_t* d_prefix)
@@ -127,7 +146,7 @@ int bitmap_rank_build(Engine* e, const uint32_t* d_bits, size_t n_words, uint64_
     DBuf<uint32_t> counts;
     MXE_TRY(counts.alloc(n_blocks, e->stream));
     if (n_blocks) {
-        unsigned grid = (unsigned)((n_blocks * 32 + 255) / 256);
+        unsigned grid = (unsigned)(((n_blocks + BBLOCKS - 1) / BBLOCKS * 32 + 255) / 256);
         MXE_LAUNCH(e, bitmap_block_count_kernel, grid, 256, 0, d_bits, n_words, counts.p, n_blocks);
     }
     MXE_TRY(exclusive_scan_u32_u64(e, counts.p, d_prefix, n_blocks));
@@ -138,25 +157,35 @@ __global__ void __launch_bounds__(256) bitmap_extract_kernel(const uint32_t* __r
                                                               const uint64_t* __restrict__ prefix, size_t n_blocks,
                                                               uint64_t* __restrict__ out)
 {
-    size_t blk = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int lane = threadIdx.x & 31;
-    if (blk >= n_blocks) return;
-    uint64_t b0 = prefix[blk];
-    if (prefix[blk + 1] == b0) return;   // empty block (warp-uniform)
-    size_t wi = blk * RANK_BLOCK_WORDS + lane;
-    uint32_t wv = wi < n_words ? bits[wi] : 0;
-    uint32_t c = __popc(wv), x = c;
+    const size_t sb = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const size_t blk0 = sb * BBLOCKS;
+    if (blk0 >= n_blocks) return;
+    const size_t blk1 = blk0 + BBLOCKS < n_blocks ? blk0 + BBLOCKS : n_blocks;
+    const uint64_t b0 = prefix[blk0];
+    if (prefix[blk1] == b0) return;      // empty (warp-uniform)
+    const size_t w0 = sb * (32 * BW) + (size_t)lane * BW;
+    uint32_t wv[BW];
+    bm_load8(bits, w0, n_words, wv);
+    uint32_t c = 0;
+#pragma unroll
+    for (int j = 0; j < BW; j++) c += __popc(wv[j]);
+    uint32_t x = c;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
         if (lane >= d) x += y;
     }
     uint64_t o = b0 + (x - c);
-    uint64_t base = (uint64_t)wi << 5;
-    while (wv) {
-        int b = __ffs(wv) - 1;
-        wv &= wv - 1;
-        out[o++] = base + b;
+#pragma unroll
+    for (int j = 0; j < BW; j++) {
+        uint32_t v = wv[j];
+        const uint64_t base = (uint64_t)(w0 + j) << 5;
+        while (v) {
+            int b = __ffs(v) - 1;
+            v &= v - 1;
+            out[o++] = base + b;
+        }
     }
 }
 
@@ -164,7 +193,7 @@ int bitmap_extract(Engine* e, const uint32_t* d_bits, size_t n_words, const uint
 {
     size_t n_blocks = (n_words + RANK_BLOCK_WORDS - 1) / RANK_BLOCK_WORDS;
     if (!n_blocks) return MXE_OK;
-    unsigned grid = (unsigned)((n_blocks * 32 + 255) / 256);
+    unsigned grid = (unsigned)(((n_blocks + BBLOCKS - 1) / BBLOCKS * 32 + 255) / 256);
     MXE_LAUNCH(e, bitmap_extract_kernel, grid, 256, 0, d_bits, n_words, d_prefix, n_blocks, d_out);
     MXE_CUDA(cudaGetLastError());
     return MXE_OK;
