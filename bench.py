@@ -11,8 +11,10 @@ adjacent-minimizer edge list, with the result (flags, vertices, edges) delivered
   roofline / cpu_baseline : see DESIGN.md "Measurement"
 
 N>1 (torchrun, one rank per GPU): records are sharded over ranks in contiguous ranges (strong
-scaling, total work fixed); one NCCL all-gather per assembly moves the per-rank minimizer lists
-(full multiset: uniqueness is per assembly, not per GPU) before steps 2-3.
+scaling, total work fixed).  Steps 2-3 run distributed (ntjoin_b200.dist): one NCCL all-gather of the
+per-rank minimizer hashes (full multiset: uniqueness is per assembly, not per GPU), then every rank
+marks its hash range and processes its own records, combined by three integer all-reduces; each rank
+ends with its shard of the result (flags of its records, vertices of its hash range, its edges).
 
 `--impl reference` times the CPU restatement of the reference path (oracle/, all host threads) on
 a bounded sample of the same workload.
@@ -253,7 +255,7 @@ def main():
     import torch
     import torch.distributed as dist
     import ntjoin_b200
-    from ntjoin_b200.dist import DeviceArray, all_gather_minimizers, shard_ranges
+    from ntjoin_b200.dist import DeviceArray, TorchComm, distributed_filter_and_edges, shard_ranges
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -265,7 +267,11 @@ def main():
     dev = torch.device("cuda", local)
 
     eng = ntjoin_b200.Engine(local, timing=True)
-    eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    stream = torch.cuda.Stream()          # one real stream for the engine, the torch ops and the timing events
+    torch.cuda.set_stream(stream)
+    eng.set_stream(stream.cuda_stream)
+    comm = TorchComm(dev) if world > 1 else None
+    stages = eng.dist_stages() if world > 1 else None
 
     assemblies = gen_assemblies_gpu(spec, args.with_n, dev)
     my = shard_ranges([o for _, o in assemblies], world)[rank]
@@ -291,16 +297,12 @@ def main():
         if world == 1:
             res = eng.filter_and_edges(sks, WEIGHTS)
             return res
-        d_hash, d_contig, counts, keep = [], [], [], []
-        for sk, (_, _, c0) in zip(sks, shards):
+        hashes, contigs = [], []
+        for sk in sks:
             n, ph, _pp, pc = sk.device_pointers()
-            hl = torch.as_tensor(DeviceArray(ph, n, "<i8"), device=dev) if n else torch.empty(0, dtype=torch.int64, device=dev)
-            cl = torch.as_tensor(DeviceArray(pc, n, "<i4"), device=dev) if n else torch.empty(0, dtype=torch.int32, device=dev)
-            hh, cc = all_gather_minimizers(hl, cl, c0)     # one exchange per assembly (NCCL over NVLink)
-            keep += [hh, cc]
-            d_hash.append(hh.data_ptr()); d_contig.append(cc.data_ptr()); counts.append(hh.numel())
-        torch.cuda.current_stream().synchronize()
-        return eng.filter_and_edges_device(d_hash, d_contig, counts, WEIGHTS)
+            hashes.append(torch.as_tensor(DeviceArray(ph, n, "<i8"), device=dev) if n else torch.empty(0, dtype=torch.int64, device=dev))
+            contigs.append(torch.as_tensor(DeviceArray(pc, n, "<i4"), device=dev) if n else torch.empty(0, dtype=torch.int32, device=dev))
+        return distributed_filter_and_edges(stages, hashes, contigs, WEIGHTS, comm)   # this rank's shard of the result
 
     def step_device():
         sks = [eng.sketch_device(s.data_ptr(), o, K, W) for s, o, _ in shards]
@@ -308,7 +310,7 @@ def main():
         n_tot, n_v, n_e = res.counts()        # result stays resident in HBM; sizes only
         stats["n_mx"] = [sk.n for sk in sks]
         stats["edges"], stats["vertices"] = n_e, n_v
-        stats["d2h"] = n_tot * 2 + n_v * 8 + n_e * 28
+        stats["d2h"] = n_tot * 2 + n_v * 8 + n_e * (28 if world == 1 else 36)
         for sk in sks:
             sk.close()
         res.close()
@@ -361,6 +363,13 @@ def main():
         step_e2e()
     sec_e2e = timed(step_e2e, args.steps)
 
+    if world > 1:   # whole-job totals for the report (outside the timed regions)
+        tot = torch.tensor(stats["n_mx"] + [stats["vertices"], stats["edges"], stats["d2h"], my_bases], dtype=torch.int64, device=dev)
+        dist.all_reduce(tot)
+        tot = tot.cpu().tolist()
+        stats["n_mx_total"], stats["vertices"], stats["edges"] = tot[:n_asm], tot[n_asm], tot[n_asm + 1]
+        stats["d2h_total"], stats["h2d_total"] = tot[n_asm + 2], tot[n_asm + 3]
+
     if rank == 0:
         peaks = {}
         try:
@@ -385,10 +394,11 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec / args.steps * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": spec["name"], "k": K, "w": W, "bases_per_step": total_bases, "n_free": not args.with_n,
-                       "l2": "inputs larger than L2 (>= 200 MB per assembly)", "sharding": f"contiguous record ranges over {world} rank(s)",
-                       "minimizers": stats["n_mx"], "vertices": stats["vertices"], "edges": stats["edges"]},
+                       "l2": "inputs larger than L2 (>= 200 MB per assembly)", "sharding": f"contiguous record ranges over {world} rank(s)" +
+                       ("; steps 2-3 by hash range / own records, 1 all-gather + 3 all-reduces (NCCL)" if world > 1 else ""),
+                       "minimizers": stats.get("n_mx_total", stats["n_mx"]), "vertices": stats["vertices"], "edges": stats["edges"]},
             "e2e": {"value": total_bases * args.steps / sec_e2e / 1e9, "unit": "Gbases/s", "ms_per_step": sec_e2e / args.steps * 1e3,
-                    "h2d_bytes_per_step": my_bases, "d2h_bytes_per_step": stats["d2h"]},
+                    "h2d_bytes_per_step": stats.get("h2d_total", my_bases), "d2h_bytes_per_step": stats.get("d2h_total", stats["d2h"])},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "cand31_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic,

@@ -30,6 +30,7 @@ extern "C" {
 typedef struct mxe_engine mxe_t;
 typedef struct mxe_sketch mxe_sketch_t;
 typedef struct mxe_result mxe_result_t;
+typedef struct mxe_dist mxe_dist_t;
 
 enum {
     MXE_OK = 0,
@@ -137,6 +138,51 @@ int mxe_result_graph(mxe_result_t* r, uint64_t* n_vertices, const uint64_t** ver
                      const uint32_t** support_mask, const double** weight);
 
 void mxe_result_free(mxe_result_t* r);
+
+/* ---- steps 2-3 across GPUs (one process per GPU) ------------------------------------------
+ *
+ * Uniqueness is per ASSEMBLY, not per GPU (bin/ntjoin_utils.py:182-187), and the intersection is
+ * over all assemblies (:155-157), so the path has real exchange steps.  The collectives belong to
+ * the caller (torch.distributed / NCCL over NVLink); these four stages run between them on
+ * GLOBALLY indexed device arrays, each rank doing 1/world of the single-GPU work:
+ *
+ *   all-gather(hashes)   -> mxe_dist_mark       (owned hash range: unique / found-in-all / vertex ids)
+ *   all-reduce(sum, mk)  -> mxe_dist_adjacency  (own records: survivors, adjacent pairs -> succ/pred)
+ *   all-reduce(sum, s/p) -> mxe_dist_edges      (support masks, edge ownership, first-source table)
+ *   all-reduce(min, src) -> mxe_dist_finish     (local edge shard with global order keys)
+ *
+ * Global index space: assemblies in order (references ..., target last); inside an assembly the
+ * ranks in order (rank r holds a contiguous range of records); N = asm_off[n_asm] < 0x7f000000.
+ * Rank r owns the hashes h with ((h >> 32) * world) >> 32 == r.
+ */
+
+/* d_keys: N uint64 out_hash in global order (must stay alive until mxe_dist_finish).
+ * d_mk (out): N uint32, zero outside the owned entries; bit 31 = unique in its assembly
+ * (read_minimizers), bits 30:0 = 1 + local vertex id if found unique in every assembly. */
+int mxe_dist_mark(mxe_t* e, const void* d_keys, const uint64_t* asm_off, int n_asm, int rank, int world,
+                  void* d_mk, mxe_dist_t** out, uint64_t* n_vertices_local);
+
+/* d_mk: summed over ranks.  vbase: world+1 exclusive prefix of the per-rank vertex counts.
+ * loc_off[a] / loc_n[a]: this rank's slice of assembly a in the global index space;
+ * d_contig[a]: its loc_n[a] uint32 record ids.  d_succ / d_pred (out): n_asm * nV uint32 each,
+ * entries 1 + global vertex id of the successor / predecessor of a vertex in an assembly, zero
+ * outside this rank's sightings (so the tables of all ranks combine by summation). */
+int mxe_dist_adjacency(mxe_dist_t* d, const void* d_mk, const uint64_t* vbase, const uint64_t* loc_off,
+                       const uint64_t* loc_n, const void* const* d_contig, void* d_succ, void* d_pred);
+
+/* d_succ / d_pred: summed over ranks.  d_srcmin (out): nV uint32, for every vertex the creation
+ * index of the first edge this rank owns with that vertex as source (0x7f7f7f7f = none). */
+int mxe_dist_edges(mxe_dist_t* d, const void* d_succ, const void* d_pred, void* d_srcmin, uint64_t* n_edges_local);
+
+/* d_srcmin: minimum over ranks.  The result is this rank's SHARD: flags of its own slices
+ * (mxe_result_flags), its vertices (owned hash range, ascending), its edges ordered by
+ * mxe_result_edge_keys; concatenating flags / vertices in rank order and merging the edge shards
+ * by key gives exactly the single-GPU result. */
+int mxe_dist_finish(mxe_dist_t* d, const void* d_srcmin, const double* weights, mxe_result_t** out);
+void mxe_dist_free(mxe_dist_t* d);
+
+/* Global order key of every edge of a multi-GPU shard (ascending inside the shard). */
+int mxe_result_edge_keys(mxe_result_t* r, uint64_t* n_edges, const uint64_t** keys);
 
 /* ---- measurement hooks (bench.py) -------------------------------------------------------- */
 

@@ -12,6 +12,7 @@ SYMBOLS = [
     "mxe_sketch_device_view", "mxe_sketch_contig_name", "mxe_sketch_counts", "mxe_write_tsv", "mxe_sketch_free",
     "mxe_filter_and_edges", "mxe_filter_and_edges_device", "mxe_result_counts", "mxe_result_flags", "mxe_result_graph",
     "mxe_result_free", "mxe_timing", "mxe_timing_reset", "mxe_kernel_launches",
+    "mxe_dist_mark", "mxe_dist_adjacency", "mxe_dist_edges", "mxe_dist_finish", "mxe_dist_free", "mxe_result_edge_keys",
 ]
 
 
@@ -64,6 +65,13 @@ def load_library():
     lib.mxe_result_graph.argtypes = [vp, u64p, pp, u64p, pp, pp, pp, pp]
     lib.mxe_result_free.argtypes = [vp]
     lib.mxe_result_free.restype = None
+    lib.mxe_dist_mark.argtypes = [vp, vp, u64p, C.c_int, C.c_int, C.c_int, vp, pp, u64p]
+    lib.mxe_dist_adjacency.argtypes = [vp, vp, u64p, u64p, u64p, pp, vp, vp]
+    lib.mxe_dist_edges.argtypes = [vp, vp, vp, vp, u64p]
+    lib.mxe_dist_finish.argtypes = [vp, vp, C.POINTER(C.c_double), pp]
+    lib.mxe_dist_free.argtypes = [vp]
+    lib.mxe_dist_free.restype = None
+    lib.mxe_result_edge_keys.argtypes = [vp, u64p, pp]
     lib.mxe_timing.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), u64p]
     lib.mxe_timing_reset.argtypes = [vp]
     lib.mxe_kernel_launches.argtypes = [vp]

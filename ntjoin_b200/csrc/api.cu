@@ -528,7 +528,7 @@ static int result_ensure_host(mxe_result* R)
     if (R->h_block) return MXE_OK;
     mxe_engine* e = R->eng;
     MXE_CUDA(cudaSetDevice(e->device));
-    size_t bytes = 2 * R->N + 8 * R->nV + R->nE * (8 + 8 + 4 + 8) + 256;
+    size_t bytes = 2 * R->N + 8 * R->nV + R->nE * (8 + 8 + 4 + 8 + 8) + 256;
     char* blk = (char*)e->pinned_alloc(bytes);
     if (!blk) { set_error("pinned host allocation of %zu bytes failed", bytes); return MXE_ERR_NOMEM; }
     R->h_block = blk; R->h_bytes = bytes;
@@ -537,6 +537,7 @@ static int result_ensure_host(mxe_result* R)
     R->h_eu = (uint64_t*)p; p += 8 * R->nE;
     R->h_ev = (uint64_t*)p; p += 8 * R->nE;
     R->h_ew = (double*)p; p += 8 * R->nE;
+    R->h_ekey = (uint64_t*)p; p += 8 * R->nE;
     R->h_emask = (uint32_t*)p; p += 4 * R->nE;
     R->h_uniq = (uint8_t*)p; p += R->N;
     R->h_keep = (uint8_t*)p;
@@ -551,6 +552,7 @@ static int result_ensure_host(mxe_result* R)
         MXE_CUDA(cudaMemcpyAsync(R->h_ev, R->d_ev, 8 * R->nE, cudaMemcpyDeviceToHost, st));
         MXE_CUDA(cudaMemcpyAsync(R->h_ew, R->d_ew, 8 * R->nE, cudaMemcpyDeviceToHost, st));
         MXE_CUDA(cudaMemcpyAsync(R->h_emask, R->d_emask, 4 * R->nE, cudaMemcpyDeviceToHost, st));
+        if (R->d_ekey) MXE_CUDA(cudaMemcpyAsync(R->h_ekey, R->d_ekey, 8 * R->nE, cudaMemcpyDeviceToHost, st));
     }
     MXE_CUDA(cudaStreamSynchronize(st));
     return MXE_OK;
@@ -597,11 +599,81 @@ void mxe_result_free(mxe_result_t* r)
     if (r->eng) {
         cudaSetDevice(r->eng->device);
         cudaStream_t st = r->eng->stream;
-        void* ptrs[] = {r->d_uniq, r->d_keep, r->d_vertices, r->d_eu, r->d_ev, r->d_emask, r->d_ew};
+        void* ptrs[] = {r->d_uniq, r->d_keep, r->d_vertices, r->d_eu, r->d_ev, r->d_emask, r->d_ew, r->d_ekey};
         for (void* p : ptrs) if (p) cudaFreeAsync(p, st);
         r->eng->pinned_release(r->h_block, r->h_bytes);
     }
     delete r;
+}
+
+int mxe_result_edge_keys(mxe_result_t* r, uint64_t* n_edges, const uint64_t** keys)
+{
+    if (!r) { set_error("null result"); return MXE_ERR_ARG; }
+    if (r->nE && !r->d_ekey) { set_error("edge order keys exist only on multi-GPU result shards"); return MXE_ERR_ARG; }
+    MXE_TRY(result_ensure_host(r));
+    if (n_edges) *n_edges = r->nE;
+    if (keys) *keys = r->h_ekey;
+    return MXE_OK;
+}
+
+// ------------------------------------------------------------------ multi-GPU steps 2-3 (stages between the caller's collectives)
+int mxe_dist_mark(mxe_t* e, const void* d_keys, const uint64_t* asm_off, int n_asm, int rank, int world,
+                  void* d_mk, mxe_dist_t** out, uint64_t* n_vertices_local)
+{
+    if (!e || !asm_off || !out || !n_vertices_local || !d_mk || (!d_keys && n_asm > 0 && asm_off[n_asm])) { set_error("null argument"); return MXE_ERR_ARG; }
+    MXE_CUDA(cudaSetDevice(e->device));
+    mxe_dist* X = new mxe_dist();
+    X->eng = e;
+    int rc;
+    {
+        ArenaScope scope(e);
+        rc = dist_mark_impl(e, (const uint64_t*)d_keys, asm_off, n_asm, rank, world, (uint32_t*)d_mk, X, n_vertices_local);
+    }
+    if (rc != MXE_OK) { mxe_dist_free(X); return rc; }
+    *out = X;
+    return MXE_OK;
+}
+
+int mxe_dist_adjacency(mxe_dist_t* X, const void* d_mk, const uint64_t* vbase, const uint64_t* loc_off, const uint64_t* loc_n,
+                       const void* const* d_contig, void* d_succ, void* d_pred)
+{
+    if (!X || !d_mk || !vbase || !loc_off || !loc_n || !d_contig || !d_succ || !d_pred) { set_error("null argument"); return MXE_ERR_ARG; }
+    MXE_CUDA(cudaSetDevice(X->eng->device));
+    ArenaScope scope(X->eng);
+    return dist_adjacency_impl(X, (const uint32_t*)d_mk, vbase, loc_off, loc_n, (const uint32_t* const*)d_contig, (uint32_t*)d_succ, (uint32_t*)d_pred);
+}
+
+int mxe_dist_edges(mxe_dist_t* X, const void* d_succ, const void* d_pred, void* d_srcmin, uint64_t* n_edges_local)
+{
+    if (!X || !d_succ || !d_pred || !d_srcmin || !n_edges_local) { set_error("null argument"); return MXE_ERR_ARG; }
+    MXE_CUDA(cudaSetDevice(X->eng->device));
+    ArenaScope scope(X->eng);
+    return dist_edges_impl(X, (const uint32_t*)d_succ, (const uint32_t*)d_pred, (uint32_t*)d_srcmin, n_edges_local);
+}
+
+int mxe_dist_finish(mxe_dist_t* X, const void* d_srcmin, const double* weights, mxe_result_t** out)
+{
+    if (!X || !d_srcmin || !weights || !out) { set_error("null argument"); return MXE_ERR_ARG; }
+    MXE_CUDA(cudaSetDevice(X->eng->device));
+    mxe_result* R = new mxe_result();
+    int rc;
+    {
+        ArenaScope scope(X->eng);
+        rc = dist_finish_impl(X, (const uint32_t*)d_srcmin, weights, R);
+    }
+    if (rc != MXE_OK) { mxe_result_free(R); return rc; }
+    *out = R;
+    return MXE_OK;
+}
+
+void mxe_dist_free(mxe_dist_t* X)
+{
+    if (!X) return;
+    if (X->eng) {
+        cudaSetDevice(X->eng->device);
+        for (void* p : X->owned) if (p) cudaFreeAsync(p, X->eng->stream);
+    }
+    delete X;
 }
 
 // ------------------------------------------------------------------ measurement

@@ -40,6 +40,12 @@ struct mxe_sketch {
     const uint8_t* seq_borrowed = nullptr;   // caller buffer (mxe_sketch_buffers), valid while caller keeps it
 };
 
+namespace mxe {
+struct AsmOffsets { uint64_t off[33]; int n; double weight[32]; };
+struct DistInfo { uint64_t vbase[33]; int world; };                     // exclusive prefix of the per-rank vertex counts
+struct LocalSlices { uint64_t lofs[33]; uint64_t goff[32]; int n; };    // local concat offsets, global index of each local slice
+}
+
 struct mxe_result {
     mxe_engine* eng = nullptr;
     int n_asm = 0;
@@ -50,10 +56,36 @@ struct mxe_result {
     uint64_t* d_vertices = nullptr;                             // nV
     uint64_t* d_eu = nullptr; uint64_t* d_ev = nullptr;         // nE
     uint32_t* d_emask = nullptr; double* d_ew = nullptr;        // nE
+    uint64_t* d_ekey = nullptr;                                 // nE, multi-GPU shards only: global order key of each edge
     // lazy host copy (one pinned block)
     void* h_block = nullptr; size_t h_bytes = 0;
     uint8_t* h_uniq = nullptr; uint8_t* h_keep = nullptr; uint64_t* h_vertices = nullptr;
     uint64_t* h_eu = nullptr; uint64_t* h_ev = nullptr; uint32_t* h_emask = nullptr; double* h_ew = nullptr;
+    uint64_t* h_ekey = nullptr;
+};
+
+// multi-GPU steps 2-3: state carried between the stages (stream-ordered allocations: they outlive one API call)
+struct mxe_dist {
+    mxe_engine* eng = nullptr;
+    mxe::AsmOffsets A;
+    mxe::LocalSlices S;
+    mxe::DistInfo D;
+    int rank = 0, world = 1;
+    uint64_t N = 0, L = 0, nV_local = 0, nV = 0, n_keep = 0, nE = 0;
+    const uint64_t* d_keys = nullptr;      // caller-owned, must stay alive until mxe_dist_finish
+    std::vector<void*> owned;              // everything below, released by mxe_dist_free
+    uint64_t* vertices = nullptr;          // nV_local, ascending
+    uint8_t* luniq = nullptr; uint8_t* lkeep = nullptr;                               // L
+    uint32_t *cvid = nullptr, *cidx = nullptr, *cloc = nullptr, *eflag = nullptr;     // n_keep (+1)
+    uint32_t *ue_q0 = nullptr, *ue_mask = nullptr;                                    // nE
+    template <typename T> int alloc(T** p, size_t n)
+    {
+        *p = nullptr;
+        cudaError_t err = cudaMallocAsync((void**)p, (n ? n : 1) * sizeof(T), eng->stream);
+        if (err != cudaSuccess) { mxe::set_error("cudaMallocAsync(%zu bytes): %s", n * sizeof(T), cudaGetErrorString(err)); return MXE_ERR_NOMEM; }
+        owned.push_back(*p);
+        return MXE_OK;
+    }
 };
 
 namespace mxe {
@@ -61,4 +93,10 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
                        int k, int w, int flags, mxe_sketch* out, const uint8_t* h_seq = nullptr);
 int filter_and_edges_impl(mxe_engine* e, const uint64_t* const* d_hash, const uint32_t* const* d_contig,
                           const uint64_t* n, int n_asm, const double* weights, mxe_result* out);
+int dist_mark_impl(mxe_engine* e, const uint64_t* d_keys, const uint64_t* asm_off, int n_asm, int rank, int world,
+                   uint32_t* d_mk, mxe_dist* X, uint64_t* nv_local);
+int dist_adjacency_impl(mxe_dist* X, const uint32_t* d_mk, const uint64_t* vbase, const uint64_t* loc_off, const uint64_t* loc_n,
+                        const uint32_t* const* d_contig, uint32_t* d_succ, uint32_t* d_pred);
+int dist_edges_impl(mxe_dist* X, const uint32_t* d_succ, const uint32_t* d_pred, uint32_t* d_srcmin, uint64_t* n_edges_local);
+int dist_finish_impl(mxe_dist* X, const uint32_t* d_srcmin, const double* weights, mxe_result* out);
 }

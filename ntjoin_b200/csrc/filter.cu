@@ -19,8 +19,6 @@
 
 namespace mxe {
 
-struct AsmOffsets { uint64_t off[33]; int n; double weight[32]; };
-
 __device__ __forceinline__ int asm_of(const AsmOffsets& A, uint64_t idx)
 {
     int a = 0;
@@ -324,6 +322,335 @@ int filter_and_edges_impl(mxe_engine* e, const uint64_t* const* d_hash, const ui
     R->nE = nE;
     R->d_vertices = vertices.detach();
     R->d_eu = eu.detach(); R->d_ev = ev.detach(); R->d_emask = emask.detach(); R->d_ew = ew.detach();
+    MXE_CUDA(cudaGetLastError());
+    return MXE_OK;
+}
+
+
+// ====================================================================================================
+// Multi-GPU steps 2-3 (one process per GPU).  The collectives between the stages belong
+// to the caller (torch.distributed / NCCL over NVLink); every stage works on GLOBALLY indexed arrays,
+// so each rank does 1/world of the single-GPU work and the partial tables are combined exactly by
+// integer all-reduces:
+//   global index space  : assemblies in order, inside an assembly the ranks in order (each rank holds
+//                         a contiguous range of records), N = all minimizers of all assemblies
+//   hash ownership      : rank r owns the hashes h with ((h >> 32) * world) >> 32 == r  (monotone in h,
+//                         so per-rank vertex lists concatenate to the ascending single-GPU order)
+//   stage 1 mark        : uniqueness / found-in-all / local vertex ids for the owned hash range -> mk[N]
+//                         (zero outside the owned entries)                        -> all-reduce(sum) mk
+//   stage 2 adjacency   : this rank's survivors (its own records) -> succ/pred tables indexed by
+//                         GLOBAL vertex id (zero outside own sightings)           -> all-reduce(sum)
+//   stage 3 edges       : support mask + ownership of the local sightings, srcmin -> all-reduce(min)
+//   stage 4 finish      : local edge shard ordered by (first-creation index of the source, creation
+//                         index); merging the shards by that key reproduces formatted_edges order.
+// Uniqueness is per ASSEMBLY, not per GPU (bin/ntjoin_utils.py:182-187): stage 1 sees the full multiset.
+// ====================================================================================================
+__device__ __forceinline__ uint32_t hash_owner(uint64_t h, int world) { return (uint32_t)(((h >> 32) * (uint64_t)world) >> 32); }
+
+__global__ void __launch_bounds__(256) owner_flag_kernel(const uint64_t* __restrict__ keys, uint64_t N, int rank, int world, uint32_t* __restrict__ flag)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) flag[i] = hash_owner(keys[i], world) == (uint32_t)rank;
+}
+
+__global__ void __launch_bounds__(256) owner_compact_kernel(const uint64_t* __restrict__ keys, uint64_t N, const uint32_t* __restrict__ flag,
+                                                             const uint64_t* __restrict__ prefix, uint64_t* __restrict__ skeys, uint32_t* __restrict__ svals)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N || !flag[i]) return;
+    uint64_t j = prefix[i];
+    skeys[j] = keys[i];
+    svals[j] = (uint32_t)i;
+}
+
+// mk[idx] = uniq << 31 | (keep ? 1 + local vertex id : 0) for the owned entries (the rest of mk stays zero)
+__global__ void __launch_bounds__(256) pack_mk_kernel(const uint32_t* __restrict__ svals, uint64_t n_sel, const uint8_t* __restrict__ uniq,
+                                                       const uint8_t* __restrict__ keep, const uint32_t* __restrict__ vid, uint32_t* __restrict__ mk)
+{
+    uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_sel) return;
+    const uint32_t idx = svals[s];
+    mk[idx] = ((uint32_t)uniq[idx] << 31) | (keep[idx] ? vid[idx] + 1u : 0u);
+}
+
+__device__ __forceinline__ int slice_of(const LocalSlices& S, uint64_t l)
+{
+    int a = 0;
+    while (a + 1 < S.n && l >= S.lofs[a + 1]) a++;
+    return a;
+}
+
+__global__ void __launch_bounds__(256) local_flag_kernel(const uint32_t* __restrict__ mk, LocalSlices S, uint64_t L,
+                                                          uint32_t* __restrict__ kflag, uint8_t* __restrict__ luniq, uint8_t* __restrict__ lkeep)
+{
+    uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= L) return;
+    const int a = slice_of(S, l);
+    const uint32_t m = mk[S.goff[a] + (l - S.lofs[a])];
+    const uint32_t k = (m & 0x7FFFFFFFu) != 0;
+    kflag[l] = k;
+    luniq[l] = (uint8_t)(m >> 31);
+    lkeep[l] = (uint8_t)k;
+}
+
+__global__ void __launch_bounds__(256) local_compact_kernel(const uint32_t* __restrict__ mk, const uint64_t* __restrict__ keys, LocalSlices S, uint64_t L,
+                                                             const uint32_t* __restrict__ kflag, const uint64_t* __restrict__ kprefix, DistInfo D,
+                                                             uint32_t* __restrict__ cvid, uint32_t* __restrict__ cidx, uint32_t* __restrict__ cloc)
+{
+    uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= L || !kflag[l]) return;
+    const int a = slice_of(S, l);
+    const uint64_t g = S.goff[a] + (l - S.lofs[a]);
+    const uint64_t j = kprefix[l];
+    cvid[j] = (uint32_t)(D.vbase[hash_owner(keys[g], D.world)] + ((mk[g] & 0x7FFFFFFFu) - 1u));
+    cidx[j] = (uint32_t)g;
+    cloc[j] = (uint32_t)l;
+}
+
+__global__ void __launch_bounds__(256) local_pair_flag_kernel(const uint32_t* __restrict__ cloc, uint64_t n_keep, LocalSlices S,
+                                                               const uint32_t* __restrict__ lcontig, uint32_t* __restrict__ eflag)
+{
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_keep) return;
+    uint32_t f = 0;
+    if (j + 1 < n_keep) {
+        const uint32_t l1 = cloc[j], l2 = cloc[j + 1];
+        f = slice_of(S, l1) == slice_of(S, l2) && lcontig[l1] == lcontig[l2];
+    }
+    eflag[j] = f;
+}
+
+// succ/pred entries are 1 + vertex id (0 = none) so that the tables of all ranks combine by summation
+__global__ void __launch_bounds__(256) dist_adjacency_kernel(const uint32_t* __restrict__ cvid, const uint32_t* __restrict__ cidx,
+                                                              const uint32_t* __restrict__ eflag, uint64_t n_keep, AsmOffsets A, uint64_t nV,
+                                                              uint32_t* __restrict__ succ, uint32_t* __restrict__ pred)
+{
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_keep || !eflag[j]) return;
+    const uint64_t a = (uint64_t)asm_of(A, cidx[j]);
+    succ[a * nV + cvid[j]] = cvid[j + 1] + 1u;
+    pred[a * nV + cvid[j + 1]] = cvid[j] + 1u;
+}
+
+__global__ void __launch_bounds__(256) dist_edge_owner_kernel(const uint32_t* __restrict__ cvid, const uint32_t* __restrict__ cidx,
+                                                               const uint32_t* __restrict__ eflag, uint64_t n_keep, AsmOffsets A, uint64_t nV,
+                                                               const uint32_t* __restrict__ succ, const uint32_t* __restrict__ pred,
+                                                               uint32_t* __restrict__ own, uint32_t* __restrict__ mask_out)
+{
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_keep) return;
+    uint32_t is_owner = 0;
+    if (eflag[j]) {
+        const int a = asm_of(A, cidx[j]);
+        const uint32_t v = cvid[j], x1 = cvid[j + 1] + 1u;
+        uint32_t mask = 0;
+        for (int b = 0; b < A.n; b++)
+            if (succ[(uint64_t)b * nV + v] == x1 || pred[(uint64_t)b * nV + v] == x1) mask |= 1u << b;
+        is_owner = (__ffs(mask) - 1) == a;
+        mask_out[j] = mask;
+    }
+    own[j] = is_owner;
+}
+
+// creation index of an edge = global index of its source element (monotone in the single-GPU sighting order)
+__global__ void __launch_bounds__(256) dist_edge_compact_kernel(const uint32_t* __restrict__ own, const uint64_t* __restrict__ uprefix,
+                                                                 const uint32_t* __restrict__ mask_in, uint64_t n_keep, const uint32_t* __restrict__ cvid,
+                                                                 const uint32_t* __restrict__ cidx, uint32_t* __restrict__ ue_q0, uint32_t* __restrict__ ue_mask,
+                                                                 uint32_t* __restrict__ srcmin)
+{
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_keep || !own[j]) return;
+    uint64_t t = uprefix[j];
+    ue_q0[t] = (uint32_t)j;
+    ue_mask[t] = mask_in[j];
+    atomicMin(&srcmin[cvid[j]], cidx[j]);
+}
+
+__global__ void __launch_bounds__(256) dist_edge_key_kernel(const uint32_t* __restrict__ ue_q0, uint64_t n_edges, const uint32_t* __restrict__ cvid,
+                                                             const uint32_t* __restrict__ srcmin, uint64_t* __restrict__ okey, uint32_t* __restrict__ oval)
+{
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_edges) return;
+    okey[t] = srcmin[cvid[ue_q0[t]]];
+    oval[t] = (uint32_t)t;
+}
+
+__global__ void __launch_bounds__(256) dist_edge_gather_kernel(const uint32_t* __restrict__ oval, const uint64_t* __restrict__ okey, uint64_t n_edges,
+                                                                const uint32_t* __restrict__ ue_q0, const uint32_t* __restrict__ ue_mask,
+                                                                const uint32_t* __restrict__ cidx, const uint64_t* __restrict__ keys, AsmOffsets A,
+                                                                uint64_t* __restrict__ eu, uint64_t* __restrict__ ev, uint32_t* __restrict__ emask,
+                                                                double* __restrict__ ew, uint64_t* __restrict__ ekey)
+{
+    uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n_edges) return;
+    const uint32_t t = oval[o];
+    const uint32_t q0 = ue_q0[t], mask = ue_mask[t];
+    eu[o] = keys[cidx[q0]];
+    ev[o] = keys[cidx[q0 + 1]];
+    emask[o] = mask;
+    double wsum = 0.0;
+    for (int a = 0; a < A.n; a++)
+        if (mask & (1u << a)) wsum += A.weight[a];
+    ew[o] = wsum;
+    ekey[o] = (okey[o] << 32) | (uint64_t)cidx[q0];
+}
+
+int dist_mark_impl(mxe_engine* e, const uint64_t* d_keys, const uint64_t* asm_off, int n_asm, int rank, int world,
+                   uint32_t* d_mk, mxe_dist* X, uint64_t* nv_local)
+{
+    if (n_asm < 1 || n_asm > 32 || world < 1 || world > 32 || rank < 0 || rank >= world) { set_error("bad n_asm/rank/world"); return MXE_ERR_ARG; }
+    cudaStream_t st = e->stream;
+    Span whole(e, "filter");
+    AsmOffsets& A = X->A;
+    A.n = n_asm;
+    for (int a = 0; a <= n_asm; a++) A.off[a] = asm_off[a];
+    for (int a = 0; a < n_asm; a++) A.weight[a] = 0.0;
+    const uint64_t N = A.off[n_asm];
+    if (N >= 0x7F000000ULL) { set_error("too many minimizers for the multi-GPU path (%llu)", (unsigned long long)N); return MXE_ERR_ARG; }
+    X->eng = e; X->rank = rank; X->world = world; X->N = N; X->d_keys = d_keys;
+    *nv_local = 0;
+    MXE_CUDA(cudaMemsetAsync(d_mk, 0, (N ? N : 1) * sizeof(uint32_t), st));
+    if (N == 0) return MXE_OK;
+
+    DBuf<uint32_t> flag, svals, svals2, head, vid;
+    DBuf<uint64_t> prefix, skeys, skeys2, hprefix;
+    DBuf<uint8_t> uniq, keep;
+    MXE_TRY(flag.alloc(N, st)); MXE_TRY(prefix.alloc(N + 1, st));
+    MXE_LAUNCH(e, owner_flag_kernel, gridf(N), 256, 0, d_keys, N, rank, world, flag.p);
+    MXE_TRY(exclusive_scan_u32_u64(e, flag.p, prefix.p, N));
+    uint64_t n_sel = 0;
+    MXE_CUDA(cudaMemcpyAsync(&n_sel, prefix.p + N, 8, cudaMemcpyDeviceToHost, st));
+    MXE_CUDA(cudaStreamSynchronize(st));
+    if (n_sel == 0) return MXE_OK;
+    MXE_TRY(skeys.alloc(n_sel, st)); MXE_TRY(skeys2.alloc(n_sel, st)); MXE_TRY(svals.alloc(n_sel, st)); MXE_TRY(svals2.alloc(n_sel, st));
+    MXE_LAUNCH(e, owner_compact_kernel, gridf(N), 256, 0, d_keys, N, flag.p, prefix.p, skeys.p, svals.p);
+    {
+        DBuf<int> fallback;
+        MXE_TRY(fallback.alloc(1, st));
+        MXE_CUDA(cudaMemsetAsync(fallback.p, 0, sizeof(int), st));
+        MXE_TRY(radix_sort_pairs(e, skeys.p, svals.p, skeys2.p, svals2.p, n_sel, SORT_LOW_BIT, 64));
+        MXE_LAUNCH(e, fixup_kernel, gridf(n_sel), 256, 0, skeys.p, svals.p, n_sel, fallback.p);
+        int fb = 0;
+        MXE_CUDA(cudaMemcpyAsync(&fb, fallback.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        MXE_CUDA(cudaStreamSynchronize(st));
+        if (fb) MXE_TRY(radix_sort_pairs(e, skeys.p, svals.p, skeys2.p, svals2.p, n_sel, 0, SORT_LOW_BIT));
+        if (fb) MXE_TRY(radix_sort_pairs(e, skeys.p, svals.p, skeys2.p, svals2.p, n_sel, SORT_LOW_BIT, 64));
+    }
+    // the compaction kept the global order, so equal hashes are still grouped by assembly after the stable sort
+    MXE_TRY(uniq.alloc(N, st)); MXE_TRY(keep.alloc(N, st)); MXE_TRY(head.alloc(n_sel, st)); MXE_TRY(hprefix.alloc(n_sel + 1, st));
+    MXE_TRY(vid.alloc(N, st));
+    MXE_LAUNCH(e, mark_kernel, gridf(n_sel), 256, 0, skeys.p, svals.p, n_sel, A, uniq.p, keep.p, head.p);
+    MXE_TRY(exclusive_scan_u32_u64(e, head.p, hprefix.p, n_sel));
+    uint64_t nV = 0;
+    MXE_CUDA(cudaMemcpyAsync(&nV, hprefix.p + n_sel, 8, cudaMemcpyDeviceToHost, st));
+    MXE_CUDA(cudaStreamSynchronize(st));
+    MXE_TRY(X->alloc(&X->vertices, nV));
+    MXE_LAUNCH(e, vertex_kernel, gridf(n_sel), 256, 0, skeys.p, svals.p, n_sel, A, keep.p, hprefix.p, vid.p, X->vertices);
+    MXE_LAUNCH(e, pack_mk_kernel, gridf(n_sel), 256, 0, svals.p, n_sel, uniq.p, keep.p, vid.p, d_mk);
+    X->nV_local = nV;
+    *nv_local = nV;
+    MXE_CUDA(cudaGetLastError());
+    return MXE_OK;
+}
+
+int dist_adjacency_impl(mxe_dist* X, const uint32_t* d_mk, const uint64_t* vbase, const uint64_t* loc_off, const uint64_t* loc_n,
+                        const uint32_t* const* d_contig, uint32_t* d_succ, uint32_t* d_pred)
+{
+    mxe_engine* e = X->eng;
+    cudaStream_t st = e->stream;
+    Span whole(e, "filter");
+    const int n_asm = X->A.n;
+    LocalSlices& S = X->S;
+    S.n = n_asm; S.lofs[0] = 0;
+    for (int a = 0; a < n_asm; a++) {
+        if (loc_off[a] + loc_n[a] > X->A.off[a + 1] || loc_off[a] < X->A.off[a]) { set_error("local slice of assembly %d outside its global range", a); return MXE_ERR_ARG; }
+        S.goff[a] = loc_off[a]; S.lofs[a + 1] = S.lofs[a] + loc_n[a];
+    }
+    const uint64_t L = S.lofs[n_asm];
+    X->L = L;
+    X->D.world = X->world;
+    for (int r = 0; r <= X->world; r++) X->D.vbase[r] = vbase[r];
+    const uint64_t nV = vbase[X->world];
+    X->nV = nV;
+    if (nV >= 0x7FFFFFFFULL) { set_error("too many vertices"); return MXE_ERR_ARG; }
+    MXE_CUDA(cudaMemsetAsync(d_succ, 0, (size_t)n_asm * (nV ? nV : 1) * sizeof(uint32_t), st));
+    MXE_CUDA(cudaMemsetAsync(d_pred, 0, (size_t)n_asm * (nV ? nV : 1) * sizeof(uint32_t), st));
+    MXE_TRY(X->alloc(&X->luniq, L)); MXE_TRY(X->alloc(&X->lkeep, L));
+    X->n_keep = 0;
+    if (L == 0) return MXE_OK;
+
+    DBuf<uint32_t> kflag, lcontig;
+    DBuf<uint64_t> kprefix;
+    MXE_TRY(kflag.alloc(L, st)); MXE_TRY(kprefix.alloc(L + 1, st)); MXE_TRY(lcontig.alloc(L, st));
+    for (int a = 0; a < n_asm; a++)
+        if (loc_n[a]) MXE_LAUNCH(e, copy_contig_kernel, gridf(loc_n[a]), 256, 0, d_contig[a], loc_n[a], S.lofs[a], lcontig.p);
+    MXE_LAUNCH(e, local_flag_kernel, gridf(L), 256, 0, d_mk, S, L, kflag.p, X->luniq, X->lkeep);
+    MXE_TRY(exclusive_scan_u32_u64(e, kflag.p, kprefix.p, L));
+    uint64_t n_keep = 0;
+    MXE_CUDA(cudaMemcpyAsync(&n_keep, kprefix.p + L, 8, cudaMemcpyDeviceToHost, st));
+    MXE_CUDA(cudaStreamSynchronize(st));
+    X->n_keep = n_keep;
+    MXE_TRY(X->alloc(&X->cvid, n_keep + 1)); MXE_TRY(X->alloc(&X->cidx, n_keep + 1)); MXE_TRY(X->alloc(&X->cloc, n_keep + 1));
+    MXE_TRY(X->alloc(&X->eflag, n_keep + 1));
+    if (n_keep == 0) return MXE_OK;
+    MXE_LAUNCH(e, local_compact_kernel, gridf(L), 256, 0, d_mk, X->d_keys, S, L, kflag.p, kprefix.p, X->D, X->cvid, X->cidx, X->cloc);
+    MXE_LAUNCH(e, local_pair_flag_kernel, gridf(n_keep), 256, 0, X->cloc, n_keep, S, lcontig.p, X->eflag);
+    MXE_LAUNCH(e, dist_adjacency_kernel, gridf(n_keep), 256, 0, X->cvid, X->cidx, X->eflag, n_keep, X->A, nV, d_succ, d_pred);
+    MXE_CUDA(cudaGetLastError());
+    return MXE_OK;
+}
+
+int dist_edges_impl(mxe_dist* X, const uint32_t* d_succ, const uint32_t* d_pred, uint32_t* d_srcmin, uint64_t* n_edges_local)
+{
+    mxe_engine* e = X->eng;
+    cudaStream_t st = e->stream;
+    Span whole(e, "filter");
+    const uint64_t n_keep = X->n_keep, nV = X->nV;
+    *n_edges_local = 0;
+    X->nE = 0;
+    MXE_CUDA(cudaMemsetAsync(d_srcmin, 0x7F, (nV ? nV : 1) * sizeof(uint32_t), st));     // 0x7f7f7f7f > any global index (N < 0x7f000000)
+    if (n_keep == 0) return MXE_OK;
+    DBuf<uint32_t> own, emask_j;
+    DBuf<uint64_t> uprefix;
+    MXE_TRY(own.alloc(n_keep, st)); MXE_TRY(emask_j.alloc(n_keep, st)); MXE_TRY(uprefix.alloc(n_keep + 1, st));
+    MXE_LAUNCH(e, dist_edge_owner_kernel, gridf(n_keep), 256, 0, X->cvid, X->cidx, X->eflag, n_keep, X->A, nV, d_succ, d_pred, own.p, emask_j.p);
+    MXE_TRY(exclusive_scan_u32_u64(e, own.p, uprefix.p, n_keep));
+    uint64_t nE = 0;
+    MXE_CUDA(cudaMemcpyAsync(&nE, uprefix.p + n_keep, 8, cudaMemcpyDeviceToHost, st));
+    MXE_CUDA(cudaStreamSynchronize(st));
+    X->nE = nE;
+    *n_edges_local = nE;
+    MXE_TRY(X->alloc(&X->ue_q0, nE)); MXE_TRY(X->alloc(&X->ue_mask, nE));
+    if (nE) MXE_LAUNCH(e, dist_edge_compact_kernel, gridf(n_keep), 256, 0, own.p, uprefix.p, emask_j.p, n_keep, X->cvid, X->cidx, X->ue_q0, X->ue_mask, d_srcmin);
+    MXE_CUDA(cudaGetLastError());
+    return MXE_OK;
+}
+
+int dist_finish_impl(mxe_dist* X, const uint32_t* d_srcmin, const double* weights, mxe_result* R)
+{
+    mxe_engine* e = X->eng;
+    cudaStream_t st = e->stream;
+    Span whole(e, "filter");
+    const int n_asm = X->A.n;
+    for (int a = 0; a < n_asm; a++) X->A.weight[a] = weights[a];
+    R->eng = e; R->n_asm = n_asm; R->N = X->L; R->nV = X->nV_local; R->nE = X->nE;
+    for (int a = 0; a <= n_asm; a++) R->asm_off[a] = X->S.lofs[a];
+    // hand the per-rank shard over to the result object (ownership moves out of X)
+    auto take = [&](void* p) { for (auto& q : X->owned) if (q == p) q = nullptr; return p; };
+    R->d_uniq = (uint8_t*)take(X->luniq); R->d_keep = (uint8_t*)take(X->lkeep);
+    R->d_vertices = (uint64_t*)take(X->vertices);
+    const uint64_t nE = X->nE;
+    if (nE == 0) return MXE_OK;
+    DBuf<uint32_t> oval, oval2, emask;
+    DBuf<uint64_t> okey, okey2, eu, ev, ekey;
+    DBuf<double> ew;
+    MXE_TRY(oval.alloc(nE, st)); MXE_TRY(oval2.alloc(nE, st)); MXE_TRY(okey.alloc(nE, st)); MXE_TRY(okey2.alloc(nE, st));
+    MXE_TRY(eu.alloc(nE, st)); MXE_TRY(ev.alloc(nE, st)); MXE_TRY(emask.alloc(nE, st)); MXE_TRY(ew.alloc(nE, st)); MXE_TRY(ekey.alloc(nE, st));
+    MXE_LAUNCH(e, dist_edge_key_kernel, gridf(nE), 256, 0, X->ue_q0, nE, X->cvid, d_srcmin, okey.p, oval.p);
+    MXE_TRY(radix_sort_pairs(e, okey.p, oval.p, okey2.p, oval2.p, nE, 0, bits_for(X->N)));
+    MXE_LAUNCH(e, dist_edge_gather_kernel, gridf(nE), 256, 0, oval.p, okey.p, nE, X->ue_q0, X->ue_mask, X->cidx, X->d_keys, X->A,
+               eu.p, ev.p, emask.p, ew.p, ekey.p);
+    R->d_eu = eu.detach(); R->d_ev = ev.detach(); R->d_emask = emask.detach(); R->d_ew = ew.detach(); R->d_ekey = ekey.detach();
     MXE_CUDA(cudaGetLastError());
     return MXE_OK;
 }

@@ -1,13 +1,27 @@
-"""Multi-GPU plumbing: record sharding and the single exchange step of the path.
+"""Multi-GPU plumbing: record sharding and the exchange steps of the path.
 
 Step 1 is independent per record, so records are sharded over ranks in CONTIGUOUS ranges of the
 pooled record list (reference records, then target records).  Concatenating the per-rank minimizer
 lists in rank order therefore reproduces the single-GPU (record, pos) order exactly, and the
 result does not depend on the GPU count.
 
-Steps 2-3 need one exchange: uniqueness is per ASSEMBLY, not per GPU (bin/ntjoin_utils.py:182-187),
-so the FULL per-rank lists (the multiset, not the locally-unique set) are all-gathered before the
-global count.  torch.distributed carries it (NCCL over NVLink on GPUs, gloo in the CPU tests).
+Steps 2-3 need exchanges: uniqueness is per ASSEMBLY, not per GPU (bin/ntjoin_utils.py:182-187), and
+the intersection is over all assemblies (:155-157).  `distributed_filter_and_edges` runs them with
+every rank doing 1/world of the work on globally indexed arrays:
+
+    all-gather(hashes)      FULL per-rank lists (the multiset, not the locally-unique sets)
+    stage mark              rank r owns the hash range r: unique / found-in-all / vertex ids
+    all-reduce(sum, mk)     N x u32 marks, zero outside the owned entries
+    stage adjacency         own records: ordered survivors, adjacent pairs -> succ/pred tables
+    all-reduce(sum, s/p)    n_asm x nV x u32 x 2, zero outside own sightings
+    stage edges             support masks + ownership of the local sightings, first-source table
+    all-reduce(min, srcmin) nV x u32
+    stage finish            local edge shard with global order keys
+
+The stages are device kernels behind the C ABI (Engine.dist_stages()); the collectives are
+torch.distributed (NCCL over NVLink on GPUs, gloo in the CPU tests).  The orchestration is a
+generator that yields one request per collective, so the same code is driven by a real process
+group (`TorchComm`) or, in tests, by several simulated ranks in lock-step (`run_lockstep`).
 """
 import numpy as np
 
@@ -68,3 +82,189 @@ class DeviceArray:
 
     def __init__(self, ptr, n, typestr):
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+# ------------------------------------------------------------------------------------------------
+# distributed steps 2-3
+# ------------------------------------------------------------------------------------------------
+class Layout:
+    """Global minimizer index space: assemblies in order, inside an assembly the ranks in order."""
+
+    def __init__(self, counts):
+        self.counts = np.asarray(counts, dtype=np.int64)            # [world, n_asm]
+        self.world, self.n_asm = self.counts.shape
+        self.asm_off = np.concatenate([[0], np.cumsum(self.counts.sum(axis=0))]).astype(np.int64)
+        before = np.cumsum(self.counts, axis=0) - self.counts      # minimizers of lower ranks, per assembly
+        self.goff = self.asm_off[:-1][None, :] + before             # [world, n_asm] global index of each slice
+        self.N = int(self.asm_off[-1])
+
+
+def _filter_steps(stages, hashes, contigs, weights, rank, world, device):
+    """Generator: yields (op, payload) per collective and receives its result.
+    hashes[a]: int64 tensor (bit pattern of the uint64 out_hash) of this rank's minimizers of assembly a
+    in (record, pos) order; contigs[a]: int32 tensor of their (local) record ids."""
+    import torch
+    n_asm = len(hashes)
+    counts = yield ("counts", [int(h.numel()) for h in hashes])
+    lay = Layout(counts)
+    keys = yield ("keys", (hashes, lay))                         # int64[N] in the global layout
+    mk = torch.empty(max(1, lay.N), dtype=torch.int32, device=device)
+    handle, nv_local = stages.mark(keys, lay.asm_off, rank, world, mk)
+    try:
+        nvs = yield ("counts", [int(nv_local)])
+        vbase = np.concatenate([[0], np.cumsum(nvs[:, 0])]).astype(np.int64)
+        n_v = int(vbase[-1])
+        yield ("sum", mk)
+        table = torch.empty(2 * n_asm * max(1, n_v), dtype=torch.int32, device=device)
+        succ, pred = table[:n_asm * max(1, n_v)], table[n_asm * max(1, n_v):]
+        stages.adjacency(handle, mk, vbase, lay.goff[rank], lay.counts[rank], contigs, succ, pred)
+        yield ("sum", table)
+        srcmin = torch.empty(max(1, n_v), dtype=torch.int32, device=device)
+        n_e_local = stages.edges(handle, succ, pred, srcmin)
+        yield ("min", srcmin)
+    except BaseException:
+        stages.abort(handle)
+        raise
+    shard = stages.finish(handle, srcmin, weights)
+    return DistShard(shard, lay, rank, vbase, int(n_e_local), keep=(keys, mk, table, srcmin))
+
+
+class DistShard:
+    """This rank's part of the result of steps 2-3: flags of its own minimizers, the vertices of its
+    hash range (ascending) and its edges with global order keys.  `merge_shards` reassembles the
+    single-GPU result from the fetched shards of all ranks."""
+
+    def __init__(self, result, layout, rank, vbase, n_edges_local, keep=None):
+        self.result, self.layout, self.rank, self.vbase, self.n_edges_local = result, layout, rank, vbase, n_edges_local
+        self._keep = keep
+
+    def counts(self):
+        return self.result.counts()
+
+    def fetch(self, copy=True):
+        d = dict(self.result.fetch(copy=copy))
+        d["edge_key"] = self.result.edge_keys if self.n_edges_local else np.empty(0, dtype=np.uint64)
+        return d
+
+    def close(self):
+        self.result.close()
+        self._keep = None
+
+
+def merge_shards(shards):
+    """shards: fetched dicts of all ranks, in rank order.  Returns the single-GPU result layout:
+    uniq/keep per assembly, vertices ascending, edges in the order of bin/ntjoin_utils.py:115."""
+    n_asm = len(shards[0]["uniq"])
+    out = {"uniq": [np.concatenate([s["uniq"][a] for s in shards]) for a in range(n_asm)],
+           "keep": [np.concatenate([s["keep"][a] for s in shards]) for a in range(n_asm)],
+           "vertices": np.concatenate([s["vertices"] for s in shards])}
+    key = np.concatenate([s["edge_key"] for s in shards])
+    order = np.argsort(key, kind="stable")
+    for name in ("edge_u", "edge_v", "support", "weight"):
+        out[name] = np.concatenate([s[name] for s in shards])[order]
+    return out
+
+
+class TorchComm:
+    """Collectives of `_filter_steps` over a torch.distributed process group."""
+
+    def __init__(self, device, group=None):
+        import torch.distributed as dist
+        self.dist, self.group, self.device = dist, group, device
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+
+    def counts(self, values):
+        import torch
+        mine = torch.tensor(values, dtype=torch.int64, device=self.device)
+        out = torch.empty(self.world * len(values), dtype=torch.int64, device=self.device)
+        self.dist.all_gather_into_tensor(out, mine, group=self.group)
+        return out.cpu().numpy().reshape(self.world, len(values))
+
+    def keys(self, hashes, lay):
+        """one padded all-gather of the concatenated local lists, then slice copies into the global layout"""
+        import torch
+        local_n = lay.counts.sum(axis=1)
+        mx = max(1, int(local_n.max()))
+        buf = torch.empty(mx, dtype=torch.int64, device=self.device)
+        at = 0
+        for h in hashes:
+            if h.numel():
+                buf[at:at + h.numel()] = h
+            at += h.numel()
+        if at < mx:
+            buf[at:].zero_()
+        gathered = torch.empty(self.world * mx, dtype=torch.int64, device=self.device)
+        self.dist.all_gather_into_tensor(gathered, buf, group=self.group)
+        keys = torch.empty(max(1, lay.N), dtype=torch.int64, device=self.device)
+        for r in range(self.world):
+            at = r * mx
+            for a in range(lay.n_asm):
+                n = int(lay.counts[r, a])
+                if n:
+                    g = int(lay.goff[r, a])
+                    keys[g:g + n] = gathered[at:at + n]
+                at += n
+        return keys
+
+    def reduce(self, op, tensor):
+        self.dist.all_reduce(tensor, op=self.dist.ReduceOp.SUM if op == "sum" else self.dist.ReduceOp.MIN, group=self.group)
+
+    def execute(self, req):
+        op, payload = req
+        if op == "counts":
+            return self.counts(payload)
+        if op == "keys":
+            return self.keys(*payload)
+        self.reduce(op, payload)
+        return None
+
+
+def distributed_filter_and_edges(stages, hashes, contigs, weights, comm):
+    """Steps 2-3 across the ranks of `comm` (a TorchComm).  Returns this rank's DistShard."""
+    gen = _filter_steps(stages, hashes, contigs, weights, comm.rank, comm.world, comm.device)
+    try:
+        req = next(gen)
+        while True:
+            req = gen.send(comm.execute(req))
+    except StopIteration as stop:
+        return stop.value
+
+
+def run_lockstep(stage_list, hashes_per_rank, contigs_per_rank, weights, device):
+    """Drive `world` simulated ranks of `_filter_steps` in one process (tests: the same orchestration and
+    the same device stages as the real multi-process run, with the collectives done in place)."""
+    import torch
+    world = len(stage_list)
+    gens = [_filter_steps(stage_list[r], hashes_per_rank[r], contigs_per_rank[r], weights, r, world, device) for r in range(world)]
+    reqs = [next(g) for g in gens]
+    results = [None] * world
+    while any(r is not None for r in reqs):
+        op = reqs[0][0]
+        assert all(r[0] == op for r in reqs)
+        if op == "counts":
+            resp = [np.asarray([r[1] for r in reqs], dtype=np.int64)] * world
+        elif op == "keys":
+            lay = reqs[0][1][1]
+            keys = torch.empty(max(1, lay.N), dtype=torch.int64, device=device)
+            for r in range(world):
+                for a in range(lay.n_asm):
+                    n = int(lay.counts[r, a])
+                    if n:
+                        g = int(lay.goff[r, a])
+                        keys[g:g + n] = reqs[r][1][0][a]
+            resp = [keys.clone() for _ in range(world)]
+        else:
+            stack = torch.stack([r[1] for r in reqs])
+            red = stack.sum(dim=0, dtype=torch.int32) if op == "sum" else stack.min(dim=0).values
+            for r in reqs:
+                r[1].copy_(red)
+            resp = [None] * world
+        nxt = []
+        for i, g in enumerate(gens):
+            try:
+                nxt.append(g.send(resp[i]))
+            except StopIteration as stop:
+                results[i] = stop.value
+                nxt.append(None)
+        reqs = nxt
+    return results

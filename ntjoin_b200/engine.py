@@ -159,6 +159,14 @@ class FilterResult:
             out[key] = _np_view(ptr.value, n.value, dt)
         return out
 
+    @property
+    def edge_keys(self):
+        """Multi-GPU shards only: the global order key of every edge (ascending inside the shard)."""
+        lib = self._e._lib
+        n, p = C.c_uint64(), C.c_void_p()
+        check(lib, lib.mxe_result_edge_keys(self._h, C.byref(n), C.byref(p)))
+        return _np_view(p.value, n.value, np.uint64).copy()
+
     uniq = property(lambda s: s.fetch()["uniq"])
     keep = property(lambda s: s.fetch()["keep"])
     vertices = property(lambda s: s.fetch()["vertices"])
@@ -275,6 +283,10 @@ class Engine:
         check(self._lib, self._lib.mxe_filter_and_edges_device(self._h, dh, dc, cn, n, ws, C.byref(out)))
         return FilterResult(self, out, n)
 
+    def dist_stages(self):
+        """Engine-backed stages of the multi-GPU steps 2-3 (driven by ntjoin_b200.dist)."""
+        return EngineDistStages(self)
+
     def timing(self, name):
         ms, nl = C.c_double(), C.c_uint64()
         check(self._lib, self._lib.mxe_timing(self._h, name.encode(), C.byref(ms), C.byref(nl)))
@@ -298,3 +310,49 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+
+
+def _u64arr(values):
+    return (C.c_uint64 * len(values))(*[int(x) for x in values])
+
+
+class EngineDistStages:
+    """The four device stages of the multi-GPU steps 2-3 (include/mxe.h: mxe_dist_*), taking torch
+    tensors that live on this engine's device.  The collectives between them are issued by
+    ntjoin_b200.dist on the same tensors."""
+
+    def __init__(self, engine):
+        self._e = engine
+        self._lib = engine._lib
+
+    def mark(self, keys, asm_off, rank, world, mk):
+        h, nv = C.c_void_p(), C.c_uint64()
+        check(self._lib, self._lib.mxe_dist_mark(self._e._h, C.c_void_p(keys.data_ptr()), _u64arr(asm_off), len(asm_off) - 1,
+                                                 int(rank), int(world), C.c_void_p(mk.data_ptr()), C.byref(h), C.byref(nv)))
+        return h, nv.value
+
+    def adjacency(self, handle, mk, vbase, loc_off, loc_n, contigs, succ, pred):
+        n = len(contigs)
+        cp = (C.c_void_p * n)(*[c.data_ptr() if c.numel() else None for c in contigs])
+        check(self._lib, self._lib.mxe_dist_adjacency(handle, C.c_void_p(mk.data_ptr()), _u64arr(vbase), _u64arr(loc_off), _u64arr(loc_n),
+                                                      cp, C.c_void_p(succ.data_ptr()), C.c_void_p(pred.data_ptr())))
+
+    def edges(self, handle, succ, pred, srcmin):
+        ne = C.c_uint64()
+        check(self._lib, self._lib.mxe_dist_edges(handle, C.c_void_p(succ.data_ptr()), C.c_void_p(pred.data_ptr()),
+                                                  C.c_void_p(srcmin.data_ptr()), C.byref(ne)))
+        return ne.value
+
+    def finish(self, handle, srcmin, weights):
+        n = len(weights)
+        ws = (C.c_double * n)(*[float(x) for x in weights])
+        out = C.c_void_p()
+        try:
+            check(self._lib, self._lib.mxe_dist_finish(handle, C.c_void_p(srcmin.data_ptr()), ws, C.byref(out)))
+        finally:
+            self._lib.mxe_dist_free(handle)
+        return FilterResult(self._e, out, n)
+
+    def abort(self, handle):
+        self._lib.mxe_dist_free(handle)

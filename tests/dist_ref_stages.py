@@ -1,0 +1,123 @@
+"""numpy stand-ins for the four device stages of the multi-GPU steps 2-3 (include/mxe.h: mxe_dist_*).
+
+TEST INFRASTRUCTURE: lets the CPU tests drive ntjoin_b200.dist's orchestration (real gloo collectives or the
+lock-step simulator) without a GPU.  Same contracts as Engine.dist_stages(): tensors in, tensors filled in place.
+The single-process semantics they distribute are bin/ntjoin_utils.py:167-193, :152-165, :94-115.
+"""
+import numpy as np
+
+
+def _u32(t):
+    return t.numpy().view(np.uint32)
+
+
+def owner_of(h, world):
+    return ((h >> np.uint64(32)) * np.uint64(world)) >> np.uint64(32)
+
+
+class _State:
+    pass
+
+
+class _Shard:
+    """mimics FilterResult for DistShard (fetch / edge_keys / counts / close)"""
+
+    def __init__(self, d, keys):
+        self._d, self.edge_keys = d, keys
+
+    def fetch(self, copy=True):
+        return self._d
+
+    def counts(self):
+        return sum(len(u) for u in self._d["uniq"]), len(self._d["vertices"]), len(self._d["edge_u"])
+
+    def close(self):
+        pass
+
+
+class NumpyDistStages:
+    def mark(self, keys, asm_off, rank, world, mk):
+        st = _State()
+        st.keys = keys.numpy().view(np.uint64)
+        st.asm_off = np.asarray(asm_off, dtype=np.int64)
+        st.n_asm, st.world, st.rank = len(asm_off) - 1, world, rank
+        N = int(st.asm_off[-1])
+        m = _u32(mk)
+        m[:] = 0
+        h_all = st.keys[:N]
+        idx = np.nonzero(owner_of(h_all, world) == rank)[0]
+        st.vertices = np.empty(0, dtype=np.uint64)
+        if len(idx):
+            h = h_all[idx]
+            asm = np.searchsorted(st.asm_off, idx, side="right") - 1
+            _, inv, cnt = np.unique(np.stack([h, asm.astype(np.uint64)], axis=1), axis=0, return_inverse=True, return_counts=True)
+            uniq = cnt[inv.ravel()] == 1
+            hu, hinv, hcnt = np.unique(h, return_inverse=True, return_counts=True)
+            n_uniq = np.bincount(hinv, weights=uniq.astype(np.float64), minlength=len(hu))
+            keep_h = (hcnt == st.n_asm) & (n_uniq == st.n_asm)          # once in EVERY assembly
+            vid_h = np.cumsum(keep_h) - 1
+            keep = keep_h[hinv]
+            m[idx] = (uniq.astype(np.uint32) << np.uint32(31)) | np.where(keep, vid_h[hinv] + 1, 0).astype(np.uint32)
+            st.vertices = hu[keep_h]
+        return st, len(st.vertices)
+
+    def adjacency(self, st, mk, vbase, loc_off, loc_n, contigs, succ, pred):
+        m = _u32(mk)
+        s, p = _u32(succ), _u32(pred)
+        s[:] = 0
+        p[:] = 0
+        vbase = np.asarray(vbase, dtype=np.int64)
+        st.nV = int(vbase[-1])
+        st.luniq, st.lkeep, sight = [], [], []
+        cv, cg, ca, cc = [], [], [], []
+        for a in range(st.n_asm):
+            g = int(loc_off[a]) + np.arange(int(loc_n[a]), dtype=np.int64)
+            mm = m[g] if len(g) else np.empty(0, dtype=np.uint32)
+            keep = (mm & np.uint32(0x7FFFFFFF)) != 0
+            st.luniq.append((mm >> np.uint32(31)).astype(bool))
+            st.lkeep.append(keep)
+            gk = g[keep]
+            vid = vbase[owner_of(st.keys[gk], st.world).astype(np.int64)] + (mm[keep] & np.uint32(0x7FFFFFFF)).astype(np.int64) - 1
+            cv.append(vid); cg.append(gk); ca.append(np.full(len(gk), a, dtype=np.int64))
+            cc.append(contigs[a].numpy().astype(np.int64)[keep] if len(g) else np.empty(0, dtype=np.int64))
+        st.cvid, st.cidx, st.casm, ctg = map(np.concatenate, (cv, cg, ca, cc))
+        n = len(st.cvid)
+        st.eflag = np.zeros(n, dtype=bool)
+        if n > 1:
+            st.eflag[:-1] = (st.casm[:-1] == st.casm[1:]) & (ctg[:-1] == ctg[1:])
+        j = np.nonzero(st.eflag)[0]
+        s[st.casm[j] * st.nV + st.cvid[j]] = (st.cvid[j + 1] + 1).astype(np.uint32)
+        p[st.casm[j] * st.nV + st.cvid[j + 1]] = (st.cvid[j] + 1).astype(np.uint32)
+
+    def edges(self, st, succ, pred, srcmin):
+        s, p = _u32(succ), _u32(pred)
+        sm = _u32(srcmin)
+        sm[:] = 0x7F7F7F7F
+        j = np.nonzero(st.eflag)[0]
+        v, x1 = st.cvid[j], (st.cvid[j + 1] + 1).astype(np.uint32)
+        mask = np.zeros(len(j), dtype=np.uint32)
+        for b in range(st.n_asm):
+            hit = (s[b * st.nV + v] == x1) | (p[b * st.nV + v] == x1)
+            mask |= hit.astype(np.uint32) << np.uint32(b)
+        first = np.array([(int(mm) & -int(mm)).bit_length() - 1 for mm in mask], dtype=np.int64)
+        own = first == st.casm[j]
+        st.q0, st.emask = j[own], mask[own]
+        np.minimum.at(sm, st.cvid[st.q0], st.cidx[st.q0].astype(np.uint32))
+        return len(st.q0)
+
+    def finish(self, st, srcmin, weights):
+        sm = _u32(srcmin)
+        key = (sm[st.cvid[st.q0]].astype(np.uint64) << np.uint64(32)) | st.cidx[st.q0].astype(np.uint64)
+        order = np.argsort(key, kind="stable")
+        q0, mask, key = st.q0[order], st.emask[order], key[order]
+        w = np.zeros(len(q0), dtype=np.float64)
+        for a in range(st.n_asm):                       # Python's sum(): assembly order, starting from 0
+            w = np.where((mask >> np.uint32(a)) & np.uint32(1), w + float(weights[a]), w)
+        d = {"uniq": st.luniq, "keep": st.lkeep, "vertices": st.vertices,
+             "edge_u": st.keys[st.cidx[q0]] if len(q0) else np.empty(0, dtype=np.uint64),
+             "edge_v": st.keys[st.cidx[q0 + 1]] if len(q0) else np.empty(0, dtype=np.uint64),
+             "support": mask.astype(np.uint32), "weight": w}
+        return _Shard(d, key)
+
+    def abort(self, st):
+        pass
