@@ -270,7 +270,7 @@ def main():
     stream = torch.cuda.Stream()          # one real stream for the engine, the torch ops and the timing events
     torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
-    comm = TorchComm(dev) if world > 1 else None
+    comm = TorchComm(dev, timing=True) if world > 1 else None
     stages = eng.dist_stages() if world > 1 else None
 
     assemblies = gen_assemblies_gpu(spec, args.with_n, dev)
@@ -347,6 +347,8 @@ def main():
     for _ in range(args.warmup):
         step_device()
     eng.timing_reset()
+    if comm:
+        comm.timing_ms()
     l0 = eng.kernel_launches()
     sampler = ClockSampler(local)
     sampler.start()
@@ -358,6 +360,9 @@ def main():
     t_sketch, _ = eng.timing("sketch")
     t_filter, _ = eng.timing("filter")
     phases = {nm: eng.timing(nm)[0] / args.steps for nm in ("pack", "rank", "cand", "eval", "select", "gap", "emit", "sketch", "filter")}
+    if comm:
+        phases.update({nm: eng.timing(nm)[0] / args.steps for nm in ("dist_mark", "dist_adjacency", "dist_edges", "dist_finish")})
+        phases.update({"comm_" + k: v / args.steps for k, v in comm.timing_ms().items()})
 
     for _ in range(min(args.warmup, 2)):
         step_e2e()

@@ -135,6 +135,7 @@ int mxe_create(int device, mxe_t** out)
     if (const char* s = getenv("MXE_CHUNK")) e->chunk = atoi(s);
     if (const char* s = getenv("MXE_CAND_VARIANT")) e->cand_variant = atoi(s);
     if (const char* s = getenv("MXE_PRUNE")) e->prune = atoi(s) != 0;
+    if (const char* s = getenv("MXE_SORT_BITS")) e->sort_bits = atoi(s);
     *out = e;
     return MXE_OK;
 }
@@ -171,6 +172,7 @@ int mxe_set_option(mxe_t* e, const char* name, double value)
     else if (!strcmp(name, "chunk")) { if (value != 0 && value < 32) { set_error("chunk must be 0 (auto) or >= 32"); return MXE_ERR_ARG; } e->chunk = (int)value; }
     else if (!strcmp(name, "cand_variant")) e->cand_variant = (int)value;
     else if (!strcmp(name, "prune")) e->prune = value != 0;
+    else if (!strcmp(name, "sort_bits")) e->sort_bits = (int)value;
     else if (!strcmp(name, "timing")) e->timing = value != 0;
     else { set_error("unknown option %s", name); return MXE_ERR_ARG; }
     return MXE_OK;

@@ -46,10 +46,18 @@ __global__ void __launch_bounds__(256) copy_contig_kernel(const uint32_t* __rest
 // orders the elements by full key (stable insertion sort; the input order inside a run is the concatenation order,
 // i.e. by assembly).  Runs whose keys are all equal (true duplicates, any length) need nothing.  A mixed run longer
 // than FIXUP_MAX raises the fallback flag and the caller redoes the sort on all 64 bits.
-constexpr int SORT_LOW_BIT = 32;
 constexpr int FIXUP_MAX = 64;
 
-__global__ void __launch_bounds__(256) fixup_kernel(uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, uint64_t N, int* __restrict__ fallback)
+// number of low key bits left to the fix-up: sort 24 top bits (3 radix passes) while the expected run of equal top bits
+// stays short (N <= 2^25 -> about two elements per occupied bucket), else 32 (4 passes)
+static inline int sort_low_bit(const Engine* e, uint64_t N)
+{
+    if (e->sort_bits == 24 || e->sort_bits == 32 || e->sort_bits == 40) return 64 - e->sort_bits;
+    return N <= (1ULL << 25) ? 40 : 32;
+}
+
+__global__ void __launch_bounds__(256) fixup_kernel(uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, uint64_t N, int SORT_LOW_BIT,
+                                                     int* __restrict__ fallback)
 {
     uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= N) return;
@@ -257,8 +265,9 @@ int filter_and_edges_impl(mxe_engine* e, const uint64_t* const* d_hash, const ui
         DBuf<int> fallback;
         MXE_TRY(fallback.alloc(1, st));
         MXE_CUDA(cudaMemsetAsync(fallback.p, 0, sizeof(int), st));
+        const int SORT_LOW_BIT = sort_low_bit(e, N);
         MXE_TRY(radix_sort_pairs(e, keys.p, vals.p, keys2.p, vals2.p, N, SORT_LOW_BIT, 64));
-        MXE_LAUNCH(e, fixup_kernel, gridf(N), 256, 0, keys.p, vals.p, N, fallback.p);
+        MXE_LAUNCH(e, fixup_kernel, gridf(N), 256, 0, keys.p, vals.p, N, SORT_LOW_BIT, fallback.p);
         int fb = 0;
         MXE_CUDA(cudaMemcpyAsync(&fb, fallback.p, sizeof(int), cudaMemcpyDeviceToHost, st));
         MXE_CUDA(cudaStreamSynchronize(st));
@@ -501,6 +510,7 @@ int dist_mark_impl(mxe_engine* e, const uint64_t* d_keys, const uint64_t* asm_of
     if (n_asm < 1 || n_asm > 32 || world < 1 || world > 32 || rank < 0 || rank >= world) { set_error("bad n_asm/rank/world"); return MXE_ERR_ARG; }
     cudaStream_t st = e->stream;
     Span whole(e, "filter");
+    Span part(e, "dist_mark");
     AsmOffsets& A = X->A;
     A.n = n_asm;
     for (int a = 0; a <= n_asm; a++) A.off[a] = asm_off[a];
@@ -528,8 +538,10 @@ int dist_mark_impl(mxe_engine* e, const uint64_t* d_keys, const uint64_t* asm_of
         DBuf<int> fallback;
         MXE_TRY(fallback.alloc(1, st));
         MXE_CUDA(cudaMemsetAsync(fallback.p, 0, sizeof(int), st));
+        // the owned range spans 1/world of the key space: its top log2(world) bits carry (almost) no information
+        const int SORT_LOW_BIT = sort_low_bit(e, N);
         MXE_TRY(radix_sort_pairs(e, skeys.p, svals.p, skeys2.p, svals2.p, n_sel, SORT_LOW_BIT, 64));
-        MXE_LAUNCH(e, fixup_kernel, gridf(n_sel), 256, 0, skeys.p, svals.p, n_sel, fallback.p);
+        MXE_LAUNCH(e, fixup_kernel, gridf(n_sel), 256, 0, skeys.p, svals.p, n_sel, SORT_LOW_BIT, fallback.p);
         int fb = 0;
         MXE_CUDA(cudaMemcpyAsync(&fb, fallback.p, sizeof(int), cudaMemcpyDeviceToHost, st));
         MXE_CUDA(cudaStreamSynchronize(st));
@@ -559,6 +571,7 @@ int dist_adjacency_impl(mxe_dist* X, const uint32_t* d_mk, const uint64_t* vbase
     mxe_engine* e = X->eng;
     cudaStream_t st = e->stream;
     Span whole(e, "filter");
+    Span part(e, "dist_adjacency");
     const int n_asm = X->A.n;
     LocalSlices& S = X->S;
     S.n = n_asm; S.lofs[0] = 0;
@@ -605,6 +618,7 @@ int dist_edges_impl(mxe_dist* X, const uint32_t* d_succ, const uint32_t* d_pred,
     mxe_engine* e = X->eng;
     cudaStream_t st = e->stream;
     Span whole(e, "filter");
+    Span part(e, "dist_edges");
     const uint64_t n_keep = X->n_keep, nV = X->nV;
     *n_edges_local = 0;
     X->nE = 0;
@@ -631,6 +645,7 @@ int dist_finish_impl(mxe_dist* X, const uint32_t* d_srcmin, const double* weight
     mxe_engine* e = X->eng;
     cudaStream_t st = e->stream;
     Span whole(e, "filter");
+    Span part(e, "dist_finish");
     const int n_asm = X->A.n;
     for (int a = 0; a < n_asm; a++) X->A.weight[a] = weights[a];
     R->eng = e; R->n_asm = n_asm; R->N = X->L; R->nV = X->nV_local; R->nE = X->nE;

@@ -214,7 +214,7 @@ if (P.canon_min) {
         Span sp(e, "eval");
         if (n_cand) {
             MXE_LAUNCH(e, cand_extract_kernel, grid_for((n_vblocks + XBLOCKS - 1) / XBLOCKS * 32, 256), 256, 0, C.p, V.p, nW, cprefix.p, vprefix.p, n_vblocks,
-                       d_offsets.p, n_contigs, cpos.p, cord.p, cctg.p);
+                       d_offsets.p, n_contigs, (uint64_t)w, cpos.p, cord.p, cctg.p);
             if (e->prune) {
                 MXE_TRY(klo.alloc(n_cand, st)); MXE_TRY(khi.alloc(n_cand, st)); MXE_TRY(pflag.alloc(n_cand, st));
                 MXE_TRY(pprefix.alloc(n_cand + 1, st));

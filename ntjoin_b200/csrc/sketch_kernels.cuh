@@ -576,7 +576,9 @@ __global__ void __launch_bounds__(CAND_THREADS) cand31_kernel(const uint32_t* __
 // One warp per 8192 bits of C (8 rank blocks), one lane per 8 consecutive words: two 16-byte loads of C and of V per
 // lane are in flight together and one warp scan serves eight rank blocks (the one-warp-per-block version was latency
 // bound: a chain of dependent loads per 9 candidates).  Emits ordered positions, valid-k-mer ordinals (popcounts of V,
-// no per-candidate rank walk) and record ids (one 32-ary search per warp, then a monotone walk).
+// no per-candidate rank walk) and record ids (one 32-ary search per warp, then a monotone walk).  Ordinals are stored
+// PADDED: ordinal + record * w, so that candidates of different records are never within w of each other and the
+// window scans of select_kernel need no record test.
 constexpr int XW = 8;                        // words per lane
 constexpr int XBLOCKS = XW * 32 / RANK_BLOCK_WORDS;   // rank blocks per warp (8)
 
@@ -593,7 +595,7 @@ __device__ __forceinline__ void load_words8(const uint32_t* __restrict__ bits, u
 
 __global__ void __launch_bounds__(256) cand_extract_kernel(const uint32_t* __restrict__ C, const uint32_t* __restrict__ V, uint64_t n_words,
                                                             const uint64_t* __restrict__ cprefix, const uint64_t* __restrict__ vprefix, uint64_t n_blocks,
-                                                            const uint64_t* __restrict__ offsets, uint32_t n_contigs,
+                                                            const uint64_t* __restrict__ offsets, uint32_t n_contigs, uint64_t w,
                                                             uint64_t* __restrict__ cpos, uint64_t* __restrict__ cord, uint32_t* __restrict__ cctg)
 {
     const uint64_t sb = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -630,7 +632,7 @@ __global__ void __launch_bounds__(256) cand_extract_kernel(const uint32_t* __res
             const uint64_t p = base + b;
             while (c + 1 < n_contigs && offsets[c + 1] <= p) c++;
             cpos[o] = p;
-            cord[o] = vb + __popc(vw[j] & ((1u << b) - 1u));
+            cord[o] = vb + __popc(vw[j] & ((1u << b) - 1u)) + (uint64_t)c * w;     // padded ordinal (see select_kernel)
             cctg[o] = c;
             o++;
         }
@@ -801,8 +803,8 @@ __global__ void __launch_bounds__(256) prune_kernel(const uint32_t* __restrict__
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_cand) return;
     const uint32_t c = ctg[i];
-    const uint64_t os = ostart[c], oe = ostart[c + 1];
-    const uint64_t w = (uint64_t)P.w;
+    const uint64_t w = (uint64_t)P.w, pad = (uint64_t)c * w;      // gord holds padded ordinals
+    const uint64_t os = ostart[c] + pad, oe = ostart[c + 1] + pad;
     uint32_t keep = 0;
     if (oe - os >= w) {
         const uint64_t o = gord[i];
@@ -811,13 +813,15 @@ __global__ void __launch_bounds__(256) prune_kernel(const uint32_t* __restrict__
         uint64_t jlo = o > jmin ? o : jmin;
         uint64_t jhi = o + w - 1 < jmax ? o + w - 1 : jmax;
         for (uint64_t j = i; j-- > 0;) {
-            if (ctg[j] != c || gord[j] + w <= o) break;
-            if (khi[j] < lo) { uint64_t b = gord[j] + w; if (b > jlo) jlo = b; break; }
+            const uint64_t oj = gord[j];
+            if (oj + w <= o) break;
+            if (khi[j] < lo) { uint64_t b = oj + w; if (b > jlo) jlo = b; break; }
         }
         if (jlo <= jhi)
             for (uint64_t j = i + 1; j < n_cand; j++) {
-                if (ctg[j] != c || gord[j] >= o + w) break;
-                if (khi[j] < lo) { uint64_t b = gord[j] - 1; if (b < jhi) jhi = b; break; }
+                const uint64_t oj = gord[j];
+                if (oj >= o + w) break;
+                if (khi[j] < lo) { uint64_t b = oj - 1; if (b < jhi) jhi = b; break; }
             }
         keep = jlo <= jhi;
     }
@@ -853,6 +857,8 @@ __device__ __forceinline__ void push_gap(const GapList& G, uint64_t ja, uint64_t
     if (slot < G.capacity) G.items[slot] = Gap{ja, jb};
 }
 
+// gord holds PADDED ordinals (ordinal + record * w): two candidates of different records are at least w apart, so the
+// window scans stop at record boundaries by themselves and only the candidate's own record id is looked up.
 __global__ void __launch_bounds__(256) select_kernel(const uint64_t* __restrict__ cpos, const uint64_t* __restrict__ h0,
                                                       const uint64_t* __restrict__ gord, const uint32_t* __restrict__ ctg,
                                                       uint64_t n_cand, const uint64_t* __restrict__ ostart,
@@ -861,8 +867,8 @@ __global__ void __launch_bounds__(256) select_kernel(const uint64_t* __restrict_
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_cand) return;
     const uint32_t c = ctg[i];
-    const uint64_t os = ostart[c], oe = ostart[c + 1];
-    const uint64_t w = (uint64_t)P.w;
+    const uint64_t w = (uint64_t)P.w, pad = (uint64_t)c * w;
+    const uint64_t os = ostart[c] + pad, oe = ostart[c + 1] + pad;
     if (oe - os < w) return;                      // record has fewer than w valid k-mers: no window
     const uint64_t o = gord[i], h = h0[i];
     const uint64_t jmin = os + w - 1, jmax = oe - 1;
@@ -871,33 +877,34 @@ __global__ void __launch_bounds__(256) select_kernel(const uint64_t* __restrict_
     uint64_t jhi = o + w - 1 < jmax ? o + w - 1 : jmax;
     // nearest strictly smaller to the left within the window span
     for (uint64_t j = i; j-- > 0;) {
-        if (ctg[j] != c || gord[j] + w <= o) break;
-        if (h0[j] < h) { uint64_t b = gord[j] + w; if (b > jlo) jlo = b; break; }
+        const uint64_t oj = gord[j];
+        if (oj + w <= o) break;
+        if (h0[j] < h) { uint64_t b = oj + w; if (b > jlo) jlo = b; break; }
     }
     // nearest smaller-or-equal to the right (rightmost wins ties)
+    const uint64_t o_next = i + 1 < n_cand ? gord[i + 1] : ~0ULL;
     for (uint64_t j = i + 1; j < n_cand; j++) {
-        if (ctg[j] != c || gord[j] >= o + w) break;
-        if (h0[j] <= h) { uint64_t b = gord[j] - 1; if (b < jhi) jhi = b; break; }
+        const uint64_t oj = j == i + 1 ? o_next : gord[j];
+        if (oj >= o + w) break;
+        if (h0[j] <= h) { uint64_t b = oj - 1; if (b < jhi) jhi = b; break; }
     }
     if (jlo <= jhi) {
         if ((uint32_t)(h >> 33) <= P.T && h != ~0ULL) {
             uint64_t p = cpos[i];
             atomicOr(&M[p >> 5], 1u << (p & 31));
         } else {
-            push_gap(G, jlo, jhi);
+            push_gap(G, jlo - pad, jhi - pad);
         }
     }
-    // candidate-free windows to the right of this candidate
+    // candidate-free windows to the right of this candidate (a candidate of the next record lies beyond jmax)
     {
-        bool has_next = (i + 1 < n_cand) && ctg[i + 1] == c;
         uint64_t ga = o + w > jmin ? o + w : jmin;
-        uint64_t gb = has_next ? gord[i + 1] - 1 : jmax;
-        if (gb > jmax) gb = jmax;
-        if (ga <= gb) push_gap(G, ga, gb);
+        uint64_t gb = o_next - 1 < jmax ? o_next - 1 : jmax;
+        if (ga <= gb) push_gap(G, ga - pad, gb - pad);
     }
-    // ... and to the left of the first candidate of the record
-    if (i == 0 || ctg[i - 1] != c) {
-        if (o > jmin) push_gap(G, jmin, (o - 1 < jmax) ? o - 1 : jmax);
+    // ... and to the left of the first candidate of the record (the previous candidate lies before os)
+    if (i == 0 || gord[i - 1] < os) {
+        if (o > jmin) push_gap(G, jmin - pad, ((o - 1 < jmax) ? o - 1 : jmax) - pad);
     }
 }
 

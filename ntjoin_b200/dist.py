@@ -28,26 +28,37 @@ import numpy as np
 
 def shard_ranges(offsets_per_asm, world):
     """offsets_per_asm: list of uint64 arrays (n_records+1) in assembly order.
-    Returns ranges[rank][asm] = (first_record, end_record), balanced by cumulative bases."""
-    lens = np.concatenate([np.diff(np.asarray(o).astype(np.int64)) for o in offsets_per_asm])
-    cum = np.concatenate([[0], np.cumsum(lens)])
-    total = cum[-1]
-    cuts = [0]
-    for r in range(1, world):
-        cuts.append(int(np.argmin(np.abs(cum - total * r / world))))
-    cuts.append(len(lens))
-    cuts = np.maximum.accumulate(cuts)
-    starts = np.cumsum([0] + [len(o) - 1 for o in offsets_per_asm])
-    out = []
-    for r in range(world):
-        a0, a1 = cuts[r], cuts[r + 1]
-        per = []
-        for i in range(len(offsets_per_asm)):
-            lo = min(max(a0, starts[i]), starts[i + 1])
-            hi = max(lo, min(a1, starts[i + 1]))
-            per.append((int(lo - starts[i]), int(hi - starts[i])))
-        out.append(per)
-    return out
+    Returns ranges[rank][asm] = (first_record, end_record): every rank gets ONE contiguous record range of EVERY
+    assembly, so concatenating the ranks' lists per assembly keeps the (record, pos) order.  Cuts fall on record
+    boundaries; the assemblies are cut one after the other (coarsest records first) and each later assembly
+    compensates the imbalance left by the earlier ones, so the per-rank totals track total/world as closely as the
+    finest assembly allows (chromosome-scale references are evened out by the target's contigs)."""
+    offs = [np.asarray(o).astype(np.int64) for o in offsets_per_asm]
+    n_asm = len(offs)
+    totals = [int(o[-1] - o[0]) for o in offs]
+    order = sorted(range(n_asm), key=lambda a: -(int(np.diff(offs[a]).max()) if len(offs[a]) > 1 else 0))
+    loads = np.zeros(world, dtype=np.int64)
+    cuts = [None] * n_asm
+    done = 0
+    for a in order:
+        o = offs[a] - offs[a][0]
+        done += totals[a]
+        c = [0]
+        assigned = 0                                   # bases of this assembly given to lower ranks
+        for r in range(world - 1):
+            want = done * (r + 1) // world - int(loads[:r + 1].sum()) + 0   # bases this assembly should add to ranks 0..r
+            want = min(max(want, assigned), totals[a])
+            j = int(np.searchsorted(o, want))
+            if j > 0 and (j >= len(o) or want - o[j - 1] <= o[j] - want):
+                j -= 1
+            j = min(max(j, c[-1]), len(o) - 1)
+            c.append(j)
+            assigned = int(o[j])
+        c.append(len(o) - 1)
+        cuts[a] = c
+        for r in range(world):
+            loads[r] += int(o[c[r + 1]] - o[c[r]])
+    return [[(cuts[a][r], cuts[a][r + 1]) for a in range(n_asm)] for r in range(world)]
 
 
 def all_gather_minimizers(hashes, contigs, first_record, group=None):
@@ -168,10 +179,11 @@ def merge_shards(shards):
 class TorchComm:
     """Collectives of `_filter_steps` over a torch.distributed process group."""
 
-    def __init__(self, device, group=None):
+    def __init__(self, device, group=None, timing=False):
         import torch.distributed as dist
         self.dist, self.group, self.device = dist, group, device
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.timing, self.spans = timing, []          # (op, start event, end event) on the current stream
 
     def counts(self, values):
         import torch
@@ -211,12 +223,31 @@ class TorchComm:
 
     def execute(self, req):
         op, payload = req
+        if self.timing:
+            import torch
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
         if op == "counts":
-            return self.counts(payload)
-        if op == "keys":
-            return self.keys(*payload)
-        self.reduce(op, payload)
-        return None
+            out = self.counts(payload)
+        elif op == "keys":
+            out = self.keys(*payload)
+        else:
+            out = self.reduce(op, payload)
+        if self.timing:
+            ev1.record()
+            self.spans.append((op, ev0, ev1))
+        return out
+
+    def timing_ms(self, reset=True):
+        """device milliseconds per collective kind since the last reset (needs timing=True)"""
+        import torch
+        torch.cuda.synchronize()
+        out = {}
+        for op, a, b in self.spans:
+            out[op] = out.get(op, 0.0) + a.elapsed_time(b)
+        if reset:
+            self.spans = []
+        return out
 
 
 def distributed_filter_and_edges(stages, hashes, contigs, weights, comm):
