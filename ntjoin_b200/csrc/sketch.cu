@@ -60,6 +60,7 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
     SketchParams P;
     P.n = n; P.n_words = (n + 31) / 32; P.k = k; P.w = w;
     P.canon_min = (flags & MXE_CANON_MIN) ? 1 : 0;
+    P.mul1 = 1u; P.mul2 = 2u;
     {
         double t = e->tau * 2147483648.0 / (double)w;
         P.T = t >= 2147483646.0 ? 2147483646u : (uint32_t)t;
@@ -169,13 +170,15 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
             n_threads = (n + P.chunk - 1) / P.chunk;
             size_t smem = cand31_smem_bytes(P.chunk, k);
             c_counted = true;
-if (P.canon_min) {
-                MXE_CUDA(cudaFuncSetAttribute(cand31_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                MXE_LAUNCH(e, cand31_kernel<1>, grid_for(n_threads, CAND_THREADS), CAND_THREADS, smem, pk.p, V.p, P, Tb, C.p, ccounts.p);
-            } else {
-                MXE_CUDA(cudaFuncSetAttribute(cand31_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                MXE_LAUNCH(e, cand31_kernel<0>, grid_for(n_threads, CAND_THREADS), CAND_THREADS, smem, pk.p, V.p, P, Tb, C.p, ccounts.p);
-            }
+#define MXE_CAND31(CM, FO)                                                                                                  \
+    do {                                                                                                                    \
+        MXE_CUDA(cudaFuncSetAttribute(cand31_kernel<CM, FO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+        MXE_LAUNCH(e, (cand31_kernel<CM, FO>), grid_for(n_threads, CAND_THREADS), CAND_THREADS, smem, pk.p, V.p, P, Tb, C.p, ccounts.p); \
+    } while (0)
+            if (P.canon_min) MXE_CAND31(1, 0);
+            else if (e->fma_offload) MXE_CAND31(0, 1);
+            else MXE_CAND31(0, 0);
+#undef MXE_CAND31
         } else {
             MXE_LAUNCH(e, cand_generic_kernel, grid_for(n_threads, 128), 128, 0, pk.p, V.p, P, Tb, C.p);
         }

@@ -37,6 +37,7 @@ struct SketchParams {
     uint32_t T;            // candidate threshold on hash0>>33
     int chunk;             // positions per thread in cand kernels
     uint64_t pk_words;     // allocated words of pk (zero padded past the sequence)
+    uint32_t mul1, mul2;   // the constants 1 and 2 as run-time values (IMAD operands in cand31_kernel)
 };
 
 // ---------------------------------------------------------------- bit helpers
@@ -446,12 +447,23 @@ __global__ void __launch_bounds__(128) cand_generic_kernel(const uint32_t* __res
 //   a = F << 1 is both the top-aligned clean copy of F (for the sum) and the funnel-shift source.
 // The 16-entry table (idx = out<<2 | in) holds {fwd term low aligned, rev term top aligned}; it is 128 B,
 // one entry per bank pair, so any mix of indices in a warp is conflict free.
+// FMA_OFFLOAD: the kernel is bound by the ALU pipe (LOP3/SHF/IADD3/ISETP/PRMT) while the FMA pipe idles, so the two
+// additions of the test are issued as IMADs with run-time multipliers (1 and 2, opaque to ptxas, which would otherwise
+// turn them back into IADD3/VIADD): key = F*2 + R, key += 2, and the predicated accumulation gb += 2^i.
 #define MXE_CAND_STEP(i)                                                                              \
     {                                                                                                 \
         const uint32_t a = F << 1;                                                                    \
-        const uint32_t key = CANON_MIN ? min(a, R) : a + R + 2u;                                      \
-        asm("{ .reg .pred p; setp.le.u32 p, %1, %2; @p or.b32 %0, %0, %3; }"                          \
-            : "+r"(gb) : "r"(key), "r"(Tt), "n"(1u << (i)));                                          \
+        if (FMA_OFFLOAD && !CANON_MIN) {                                                              \
+            uint32_t key;                                                                             \
+            asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(key) : "r"(F), "r"(m_two), "r"(R));               \
+            asm("mad.lo.u32 %0, %1, %2, 2;" : "=r"(key) : "r"(key), "r"(m_one));                      \
+            asm("{ .reg .pred p; setp.le.u32 p, %1, %2; @p mad.lo.u32 %0, %3, %4, %0; }"              \
+                : "+r"(gb) : "r"(key), "r"(Tt), "r"(m_one), "n"(1u << (i)));                          \
+        } else {                                                                                      \
+            const uint32_t key = CANON_MIN ? min(a, R) : a + R + 2u;                                  \
+            asm("{ .reg .pred p; setp.le.u32 p, %1, %2; @p or.b32 %0, %0, %3; }"                      \
+                : "+r"(gb) : "r"(key), "r"(Tt), "n"(1u << (i)));                                      \
+        }                                                                                             \
         const uint32_t addr = __byte_perm(zq[(i) >> 2], 0, 0x4440 | ((i) & 3));                       \
         const uint2 e = *reinterpret_cast<const uint2*>(tb + addr);                                   \
         F = __funnelshift_l(a, F, 1) ^ e.x;                                                           \
@@ -475,7 +487,7 @@ __host__ __device__ inline size_t cand31_smem_bytes(int chunk, int k)
     return (32 + n_pk + n_pk / wpt + 1 + n_v + n_v / wv + 1) * sizeof(uint32_t);
 }
 
-template <int CANON_MIN>
+template <int CANON_MIN, int FMA_OFFLOAD>
 __global__ void __launch_bounds__(CAND_THREADS) cand31_kernel(const uint32_t* __restrict__ pk, const uint32_t* __restrict__ V,
                                                                SketchParams P, SketchTables Tb, uint32_t* __restrict__ C,
                                                                uint32_t* __restrict__ ccounts)
@@ -523,6 +535,7 @@ __global__ void __launch_bounds__(CAND_THREADS) cand31_kernel(const uint32_t* __
         const uint32_t lowmask = ks == 1 ? 0x3F3F3F3Fu : ks == 2 ? 0x0F0F0F0Fu : 0x03030303u;
         const char* tb = reinterpret_cast<const char*>(tab);
         const uint32_t Tt = CANON_MIN ? ((P.T << 1) | 1u) : (((P.T + 1u) << 1) | 1u);
+        const uint32_t m_one = P.mul1, m_two = P.mul2;       // 1 and 2 as run-time values (see MXE_CAND_STEP)
         const int n_g = P.chunk / 16;
         const uint32_t row = threadIdx.x * wpt;
         const uint32_t vrow = threadIdx.x * wv + threadIdx.x;   // padded index of this run's first V word
