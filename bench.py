@@ -316,7 +316,7 @@ def main():
         res.close()
 
     def step_e2e():
-        sks = [eng.sketch_buffers(h, o, K, W) for h, (_, o, _) in zip(host, shards)]
+        sks = eng.sketch_many([(h, o) for h, (_, o, _) in zip(host, shards)], K, W)   # H2D of assembly i+1 overlaps sketch i
         res = gather_and_filter(sks)
         res.fetch(copy=False)                 # flags + vertices + weighted edge list into (pinned) host memory
         for sk in sks:

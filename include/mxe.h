@@ -74,6 +74,11 @@ int mxe_sketch_file(mxe_t* e, const char* fasta_path, int k, int w, int flags, m
 int mxe_sketch_buffers(mxe_t* e, const uint8_t* seq, const uint64_t* offsets, uint32_t n_contigs,
                        const char* const* names, int k, int w, int flags, mxe_sketch_t** out);
 
+/* Optional: start the host->device copy of a buffer that a later mxe_sketch_buffers call (same
+ * pointer and length) will sketch.  Returns at once; the copy runs on the engine's copy streams
+ * while earlier work is still computing (at most two buffers in flight; further calls are no-ops). */
+int mxe_prefetch_buffers(mxe_t* e, const uint8_t* seq, uint64_t n);
+
 /* Same, with `d_seq` already resident in device memory of this engine's device (16-byte aligned).
  * `offsets` stays a host array.  `stream` = cudaStream_t as an integer (0 = engine stream). */
 int mxe_sketch_device(mxe_t* e, const void* d_seq, const uint64_t* offsets, uint32_t n_contigs,

@@ -121,8 +121,6 @@ int mxe_create(int device, mxe_t** out)
     MXE_CUDA(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
     e->stream = e->own_stream;
     for (int c = 0; c < 2; c++) MXE_CUDA(cudaStreamCreateWithFlags(&e->copy_stream[c], cudaStreamNonBlocking));
-    MXE_CUDA(cudaEventCreateWithFlags(&e->ev_ready, cudaEventDisableTiming));
-    for (int i = 0; i < MXE_N_CHUNK_EVENTS; i++) MXE_CUDA(cudaEventCreateWithFlags(&e->ev_chunk[i], cudaEventDisableTiming));
     if (const char* s = getenv("MXE_H2D_CHUNK_MB")) e->h2d_chunk_mb = std::max(1, atoi(s));
     cudaDeviceProp prop;
     MXE_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -151,9 +149,12 @@ void mxe_destroy(mxe_t* e)
     for (auto ev : e->event_pool) cudaEventDestroy(ev);
     for (auto& p : e->pinned_free) cudaFreeHost(p.p);
     e->arena.destroy();
-    for (int c = 0; c < 2; c++) if (e->copy_stream[c]) cudaStreamDestroy(e->copy_stream[c]);
-    if (e->ev_ready) cudaEventDestroy(e->ev_ready);
-    for (int i = 0; i < MXE_N_CHUNK_EVENTS; i++) if (e->ev_chunk[i]) cudaEventDestroy(e->ev_chunk[i]);
+    for (int c = 0; c < 2; c++) if (e->copy_stream[c]) { cudaStreamSynchronize(e->copy_stream[c]); cudaStreamDestroy(e->copy_stream[c]); }
+    for (auto& sl : e->slot) {
+        for (auto ev : sl.ev) cudaEventDestroy(ev);
+        if (sl.consumed) cudaEventDestroy(sl.consumed);
+        if (sl.d) cudaFree(sl.d);
+    }
     cudaStreamDestroy(e->own_stream);
     delete e;
 }
@@ -185,9 +186,18 @@ static int sketch_from_host(mxe_t* e, const uint8_t* seq, uint64_t n, const uint
                             int k, int w, int flags, mxe_sketch* S)
 {
     ArenaScope scope(e);
-    DBuf<uint8_t> d_seq;
-    MXE_TRY(d_seq.alloc(n + 64, e->stream));
-    return sketch_device_impl(e, d_seq.p, n, offsets, n_contigs, k, w, flags, S, seq);   // chunked H2D inside, overlapped with pack
+    if (n == 0) return sketch_device_impl(e, nullptr, 0, offsets, n_contigs, k, w, flags, S);
+    // a copy started by mxe_prefetch_buffers for exactly this buffer, else start one now in a free slot
+    H2DSlot* sl = nullptr;
+    for (auto& c : e->slot) if (c.h == seq && c.n == n) sl = &c;
+    if (!sl) {
+        for (auto& c : e->slot) if (!c.h) { sl = &c; break; }
+        if (!sl) { sl = &e->slot[0]; cudaStreamSynchronize(e->copy_stream[0]); cudaStreamSynchronize(e->copy_stream[1]); }   // drop a stale prefetch
+        MXE_TRY(h2d_issue(e, *sl, seq, n));
+    }
+    int rc = sketch_device_impl(e, sl->d, n, offsets, n_contigs, k, w, flags, S, sl);   // chunk-wise pack as the copy lands
+    sl->h = nullptr;
+    return rc;
 }
 
 static void set_names(mxe_sketch* S, const char* const* names, uint32_t n_contigs)
@@ -208,6 +218,17 @@ int mxe_sketch_buffers(mxe_t* e, const uint8_t* seq, const uint64_t* offsets, ui
     if (rc != MXE_OK) { mxe_sketch_free(S); return rc; }
     *out = S;
     return MXE_OK;
+}
+
+int mxe_prefetch_buffers(mxe_t* e, const uint8_t* seq, uint64_t n)
+{
+    if (!e || (!seq && n)) { set_error("null argument"); return MXE_ERR_ARG; }
+    if (n == 0) return MXE_OK;
+    MXE_CUDA(cudaSetDevice(e->device));
+    for (auto& c : e->slot) if (c.h == seq && c.n == n) return MXE_OK;      // already in flight
+    for (auto& c : e->slot)
+        if (!c.h) return h2d_issue(e, c, seq, n);
+    return MXE_OK;                                                           // both slots busy: the sketch call will copy
 }
 
 int mxe_sketch_device(mxe_t* e, const void* d_seq, const uint64_t* offsets, uint32_t n_contigs,

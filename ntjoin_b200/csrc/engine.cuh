@@ -2,13 +2,21 @@
 #pragma once
 #include "common.cuh"
 
-constexpr int MXE_N_CHUNK_EVENTS = 64;
+// Host-input path: a host buffer is copied in chunks on two copy streams into an engine-owned staging slot; the pack
+// kernel of each chunk waits for that chunk's arrival event only.  Two slots, so that the copy of the next assembly
+// (mxe_prefetch_buffers) runs while the previous one is still being sketched.
+struct H2DSlot {
+    uint8_t* d = nullptr; size_t cap = 0;            // device staging buffer (grow-only)
+    const uint8_t* h = nullptr; uint64_t n = 0;      // host buffer staged or in flight (nullptr = slot free)
+    uint64_t chunk = 0; int n_chunks = 0;
+    std::vector<cudaEvent_t> ev;                     // arrival of chunk i
+    cudaEvent_t consumed = nullptr;                  // last reader of the slot (pack) has finished
+    bool consumed_valid = false;
+};
 
 struct mxe_engine : public mxe::Engine {
-    // host-input path: two copy streams (two copy engines) + events
     cudaStream_t copy_stream[2] = {nullptr, nullptr};
-    cudaEvent_t ev_ready = nullptr;
-    cudaEvent_t ev_chunk[MXE_N_CHUNK_EVENTS] = {nullptr};
+    H2DSlot slot[2];
     int h2d_chunk_mb = 256;
     // pinned host block pool (grow-only, reused across steps)
     struct Pinned { void* p; size_t bytes; };
@@ -90,7 +98,8 @@ struct mxe_dist {
 
 namespace mxe {
 int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const uint64_t* offsets, uint32_t n_contigs,
-                       int k, int w, int flags, mxe_sketch* out, const uint8_t* h_seq = nullptr);
+                       int k, int w, int flags, mxe_sketch* out, H2DSlot* staged = nullptr);
+int h2d_issue(mxe_engine* e, H2DSlot& s, const uint8_t* h, uint64_t n);
 int filter_and_edges_impl(mxe_engine* e, const uint64_t* const* d_hash, const uint32_t* const* d_contig,
                           const uint64_t* n, int n_asm, const double* weights, mxe_result* out);
 int dist_mark_impl(mxe_engine* e, const uint64_t* d_keys, const uint64_t* asm_off, int n_asm, int rank, int world,

@@ -36,8 +36,38 @@ static void build_tables(int k, SketchTables* T)
 
 static inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
 
+// Start the chunked host->device copy of `h` into slot `s` (two copy streams = two copy engines).  Does not wait for
+// the compute stream, only for the previous reader of the slot.
+int h2d_issue(mxe_engine* e, H2DSlot& s, const uint8_t* h, uint64_t n)
+{
+    if (s.cap < n + 64) {
+        if (s.d) { MXE_CUDA(cudaDeviceSynchronize()); MXE_CUDA(cudaFree(s.d)); s.d = nullptr; s.cap = 0; }
+        MXE_CUDA(cudaMalloc((void**)&s.d, n + 64));
+        s.cap = n + 64;
+    }
+    if (!s.consumed) MXE_CUDA(cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming));
+    const uint64_t CH = (uint64_t)e->h2d_chunk_mb << 20;
+    const int n_chunks = (int)((n + CH - 1) / CH);
+    while ((int)s.ev.size() < n_chunks) {
+        cudaEvent_t ev;
+        MXE_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        s.ev.push_back(ev);
+    }
+    if (s.consumed_valid)
+        for (int c = 0; c < 2; c++) MXE_CUDA(cudaStreamWaitEvent(e->copy_stream[c], s.consumed, 0));
+    int i = 0;
+    for (uint64_t off = 0; off < n; off += CH, i++) {
+        const uint64_t len = std::min<uint64_t>(CH, n - off);
+        cudaStream_t cs = e->copy_stream[i & 1];
+        MXE_CUDA(cudaMemcpyAsync(s.d + off, h + off, len, cudaMemcpyHostToDevice, cs));
+        MXE_CUDA(cudaEventRecord(s.ev[i], cs));
+    }
+    s.h = h; s.n = n; s.chunk = CH; s.n_chunks = n_chunks;
+    return MXE_OK;
+}
+
 int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const uint64_t* offsets, uint32_t n_contigs,
-                       int k, int w, int flags, mxe_sketch* S, const uint8_t* h_seq)
+                       int k, int w, int flags, mxe_sketch* S, H2DSlot* staged)
 {
     if (k < 1 || k > 1024 || w < 1) { set_error("bad k/w (k=%d w=%d)", k, w); return MXE_ERR_ARG; }
     if (n_contigs && offsets[0] != 0) { set_error("offsets[0] must be 0"); return MXE_ERR_ARG; }
@@ -100,28 +130,26 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
     // ---- pack + validity
     {
         Span sp(e, "pack");
-        if (!h_seq) {
+        if (!staged) {
             MXE_LAUNCH(e, pack_kernel, grid_for(nW, 256), 256, 0, d_seq, P, pk.p, V.p, vcounts.p, (uint64_t)0, nW);
         } else {
-            // host input: chunked H2D on two copy streams, each chunk packed as soon as it has landed
-            const uint64_t CH = (uint64_t)e->h2d_chunk_mb << 20;
-            MXE_CUDA(cudaEventRecord(e->ev_ready, st));                 // the staging buffer may still be in use by earlier work
-            for (int c = 0; c < 2; c++) MXE_CUDA(cudaStreamWaitEvent(e->copy_stream[c], e->ev_ready, 0));
+            // host input: the chunks land one after the other on the copy streams (h2d_issue); each is packed as soon as
+            // its arrival event has fired
+            const uint64_t CH = staged->chunk;
             int i = 0;
             for (uint64_t off = 0; off < n; off += CH, i++) {
                 const uint64_t len = std::min<uint64_t>(CH, n - off);
-                cudaStream_t cs = e->copy_stream[i & 1];
-                cudaEvent_t ev = e->ev_chunk[i % MXE_N_CHUNK_EVENTS];
-                MXE_CUDA(cudaMemcpyAsync(const_cast<uint8_t*>(d_seq) + off, h_seq + off, len, cudaMemcpyHostToDevice, cs));
-                MXE_CUDA(cudaEventRecord(ev, cs));
-                MXE_CUDA(cudaStreamWaitEvent(st, ev, 0));
+                MXE_CUDA(cudaStreamWaitEvent(st, staged->ev[i], 0));
                 // ranges lag one warp (32 words) behind the copied bytes: the V halo of a warp reads the next words
                 const bool last = off + len >= n;
                 const uint64_t t0 = off ? (off >> 5) - 32 : 0;
                 const uint64_t t1 = last ? nW : ((off + len) >> 5) - 32;
                 if (t1 > t0) MXE_LAUNCH(e, pack_kernel, grid_for(t1 - t0, 256), 256, 0, d_seq, P, pk.p, V.p, vcounts.p, t0, t1);
-                if ((i % MXE_N_CHUNK_EVENTS) == MXE_N_CHUNK_EVENTS - 1) MXE_CUDA(cudaStreamSynchronize(st));   // events are reused
             }
+            // the sequence itself is not read after pack: the slot may be refilled from here on
+            MXE_CUDA(cudaEventRecord(staged->consumed, st));
+            staged->consumed_valid = true;
+            staged->h = nullptr;
         }
         if (n_contigs > 1) MXE_LAUNCH(e, boundary_kernel, grid_for(n_contigs - 1, 128), 128, 0, d_offsets.p, n_contigs, P, V.p, vcounts.p);
     }

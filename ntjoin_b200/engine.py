@@ -238,15 +238,37 @@ class Engine:
         check(self._lib, self._lib.mxe_sketch_load_tsv(self._h, str(path).encode(), C.byref(out)))
         return self._named(out)
 
+    @staticmethod
+    def _host_ptr(seq):
+        if hasattr(seq, "data_ptr"):
+            return seq.data_ptr(), seq, seq.numel()
+        a = np.frombuffer(seq, dtype=np.uint8) if isinstance(seq, (bytes, bytearray, memoryview)) else np.ascontiguousarray(seq, dtype=np.uint8)
+        return a.ctypes.data, a, a.size
+
+    def prefetch(self, seq):
+        """Start the host->device copy of a buffer that a later sketch_buffers(seq, ...) will use (the SAME object:
+        numpy uint8 array or CPU torch tensor, ideally pinned).  Returns at once; lets the copy of the next assembly
+        overlap the sketch of the previous one.  Returns the object to pass to sketch_buffers."""
+        ptr, keep, n = self._host_ptr(seq)
+        check(self._lib, self._lib.mxe_prefetch_buffers(self._h, C.c_void_p(ptr), n))
+        return keep
+
+    def sketch_many(self, assemblies, k, w, canonical="sum"):
+        """assemblies: [(seq, offsets[, names])] in assembly order.  Sketches them one after the other with the
+        host->device copy of each assembly overlapping the sketch of the one before."""
+        bufs = [self._host_ptr(a[0])[1] for a in assemblies]
+        out = []
+        for i, a in enumerate(assemblies):
+            for b in bufs[i:i + 2]:
+                self.prefetch(b)
+            out.append(self.sketch_buffers(bufs[i], a[1], k, w, names=a[2] if len(a) > 2 else None, canonical=canonical))
+        return out
+
     def sketch_buffers(self, seq, offsets, k, w, names=None, canonical="sum"):
         """seq: host bytes / numpy uint8 / CPU torch uint8 tensor (pinned memory is copied fastest)."""
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         n = len(offsets) - 1
-        if hasattr(seq, "data_ptr"):
-            ptr, keep = seq.data_ptr(), seq
-        else:
-            a = np.frombuffer(seq, dtype=np.uint8) if isinstance(seq, (bytes, bytearray, memoryview)) else np.ascontiguousarray(seq, dtype=np.uint8)
-            ptr, keep = a.ctypes.data, a
+        ptr, keep, _ = self._host_ptr(seq)
         carr, pynames = self._names(names, n)
         out = C.c_void_p()
         check(self._lib, self._lib.mxe_sketch_buffers(self._h, C.c_void_p(ptr), offsets.ctypes.data_as(C.POINTER(C.c_uint64)),
