@@ -271,7 +271,8 @@ def main():
     torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
     comm = TorchComm(dev, timing=True) if world > 1 else None
-    stages = eng.dist_stages() if world > 1 else None
+    dist_mode = os.environ.get("MXE_DIST_MODE", "alltoall")      # "allreduce": the cross-check formulation
+    stages = (eng.a2a_stages() if dist_mode == "alltoall" else eng.dist_stages()) if world > 1 else None
 
     assemblies = gen_assemblies_gpu(spec, args.with_n, dev)
     my = shard_ranges([o for _, o in assemblies], world)[rank]
@@ -361,7 +362,9 @@ def main():
     t_filter, _ = eng.timing("filter")
     phases = {nm: eng.timing(nm)[0] / args.steps for nm in ("pack", "rank", "cand", "eval", "select", "gap", "emit", "sketch", "filter")}
     if comm:
-        phases.update({nm: eng.timing(nm)[0] / args.steps for nm in ("dist_mark", "dist_adjacency", "dist_edges", "dist_finish")})
+        names = ("a2a_partition", "a2a_mark", "a2a_sightings", "a2a_finish") if dist_mode == "alltoall" else \
+            ("dist_mark", "dist_adjacency", "dist_edges", "dist_finish")
+        phases.update({nm: eng.timing(nm)[0] / args.steps for nm in names})
         phases.update({"comm_" + k: v / args.steps for k, v in comm.timing_ms().items()})
 
     for _ in range(min(args.warmup, 2)):
@@ -400,7 +403,8 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": spec["name"], "k": K, "w": W, "bases_per_step": total_bases, "n_free": not args.with_n,
                        "l2": "inputs larger than L2 (>= 200 MB per assembly)", "sharding": f"contiguous record ranges over {world} rank(s)" +
-                       ("; steps 2-3 by hash range / own records, 1 all-gather + 3 all-reduces (NCCL)" if world > 1 else ""),
+                       (("; steps 2-3 by hash owner, 3 all-to-alls (NCCL): keys, marks, sightings" if dist_mode == "alltoall" else
+                         "; steps 2-3 by hash range / own records, 1 all-gather + 3 all-reduces (NCCL)") if world > 1 else ""),
                        "minimizers": stats.get("n_mx_total", stats["n_mx"]), "vertices": stats["vertices"], "edges": stats["edges"]},
             "e2e": {"value": total_bases * args.steps / sec_e2e / 1e9, "unit": "Gbases/s", "ms_per_step": sec_e2e / args.steps * 1e3,
                     "h2d_bytes_per_step": stats.get("h2d_total", my_bases), "d2h_bytes_per_step": stats.get("d2h_total", stats["d2h"])},

@@ -31,6 +31,7 @@ typedef struct mxe_engine mxe_t;
 typedef struct mxe_sketch mxe_sketch_t;
 typedef struct mxe_result mxe_result_t;
 typedef struct mxe_dist mxe_dist_t;
+typedef struct mxe_a2a mxe_a2a_t;
 
 enum {
     MXE_OK = 0,
@@ -185,6 +186,46 @@ int mxe_dist_edges(mxe_dist_t* d, const void* d_succ, const void* d_pred, void* 
  * by key gives exactly the single-GPU result. */
 int mxe_dist_finish(mxe_dist_t* d, const void* d_srcmin, const double* weights, mxe_result_t** out);
 void mxe_dist_free(mxe_dist_t* d);
+
+/* ---- the same across GPUs with all-to-all exchanges (production path) ----------------------
+ *
+ * Every item travels once, to the rank that needs it (NVSwitch: uniform all-to-all bandwidth):
+ *
+ *   mxe_a2a_partition  own minimizers grouped by hash owner      -> all-to-all (keys, 8 B)
+ *   mxe_a2a_mark       owner: unique / found-in-all / vertex ids  -> all-to-all (marks, 4 B, same order back)
+ *   mxe_a2a_sightings  source: ordered survivors, adjacent pairs; every sighting goes to the owner
+ *                      of its source vertex (successor record) and of its target (predecessor)
+ *                                                                 -> all-to-all (records, 24 B)
+ *   mxe_a2a_finish     owner: succ/pred tables of its own vertices, support masks, edge ownership,
+ *                      order keys.  Result shard: flags of this rank's minimizers, vertices of its
+ *                      hash range, the edges whose source vertex it owns (mxe_result_edge_keys).
+ *
+ * Buffers returned through d_send_* belong to the handle (valid until mxe_a2a_free / mxe_a2a_finish);
+ * receive buffers are the caller's.  world <= 16.
+ */
+
+/* d_hash[a], n[a]: this rank's out_hash lists.  counts (out, host): world * n_asm, entry [o * n_asm + a] =
+ * minimizers of assembly a sent to owner o; *d_send_keys: sum(n) uint64 grouped by owner, assembly order inside. */
+int mxe_a2a_partition(mxe_t* e, const void* const* d_hash, const uint64_t* n, int n_asm, int rank, int world,
+                      mxe_a2a_t** out, uint64_t* counts, const void** d_send_keys);
+
+/* d_recv_keys: keys received, grouped by source rank (assembly order inside); recv_counts[r * n_asm + a].
+ * d_ret_marks (out, caller buffer of as many uint32): bit 31 = unique in its assembly, bits 30:0 = 1 + vertex id
+ * local to this owner if found unique in every assembly; same order as d_recv_keys. */
+int mxe_a2a_mark(mxe_a2a_t* x, const void* d_recv_keys, const uint64_t* recv_counts, void* d_ret_marks,
+                 uint64_t* n_vertices_local);
+
+/* d_marks: the marks of this rank's minimizers, in the order of d_send_keys.  d_contig[a]: record ids;
+ * goff[a]: global index of this rank's first minimizer of assembly a.  rec_counts (out, host): world entries;
+ * *d_send_records: 3 uint64 per record, grouped by destination. */
+int mxe_a2a_sightings(mxe_a2a_t* x, const void* d_marks, const void* const* d_contig, const uint64_t* goff,
+                      uint64_t* rec_counts, const void** d_send_records);
+
+/* d_recv_records: n_records records addressed to this owner (any order).  n_global = all minimizers of all
+ * assemblies and ranks.  Frees the handle's send buffers; the handle itself is released by mxe_a2a_free. */
+int mxe_a2a_finish(mxe_a2a_t* x, const void* d_recv_records, uint64_t n_records, uint64_t n_global,
+                   const double* weights, mxe_result_t** out);
+void mxe_a2a_free(mxe_a2a_t* x);
 
 /* Global order key of every edge of a multi-GPU shard (ascending inside the shard). */
 int mxe_result_edge_keys(mxe_result_t* r, uint64_t* n_edges, const uint64_t** keys);

@@ -13,6 +13,7 @@ SYMBOLS = [
     "mxe_filter_and_edges", "mxe_filter_and_edges_device", "mxe_result_counts", "mxe_result_flags", "mxe_result_graph",
     "mxe_result_free", "mxe_timing", "mxe_timing_reset", "mxe_kernel_launches",
     "mxe_dist_mark", "mxe_dist_adjacency", "mxe_dist_edges", "mxe_dist_finish", "mxe_dist_free", "mxe_result_edge_keys",
+    "mxe_a2a_partition", "mxe_a2a_mark", "mxe_a2a_sightings", "mxe_a2a_finish", "mxe_a2a_free",
 ]
 
 
@@ -73,6 +74,12 @@ def load_library():
     lib.mxe_dist_free.argtypes = [vp]
     lib.mxe_dist_free.restype = None
     lib.mxe_result_edge_keys.argtypes = [vp, u64p, pp]
+    lib.mxe_a2a_partition.argtypes = [vp, pp, u64p, C.c_int, C.c_int, C.c_int, pp, u64p, pp]
+    lib.mxe_a2a_mark.argtypes = [vp, vp, u64p, vp, u64p]
+    lib.mxe_a2a_sightings.argtypes = [vp, vp, pp, u64p, u64p, pp]
+    lib.mxe_a2a_finish.argtypes = [vp, vp, C.c_uint64, C.c_uint64, C.POINTER(C.c_double), pp]
+    lib.mxe_a2a_free.argtypes = [vp]
+    lib.mxe_a2a_free.restype = None
     lib.mxe_timing.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), u64p]
     lib.mxe_timing_reset.argtypes = [vp]
     lib.mxe_kernel_launches.argtypes = [vp]

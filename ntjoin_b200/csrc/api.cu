@@ -701,6 +701,66 @@ void mxe_dist_free(mxe_dist_t* X)
     delete X;
 }
 
+// ------------------------------------------------------------------ multi-GPU steps 2-3, all-to-all formulation
+int mxe_a2a_partition(mxe_t* e, const void* const* d_hash, const uint64_t* n, int n_asm, int rank, int world,
+                      mxe_a2a_t** out, uint64_t* counts, const void** d_send_keys)
+{
+    if (!e || !d_hash || !n || !out || !counts || !d_send_keys) { set_error("null argument"); return MXE_ERR_ARG; }
+    MXE_CUDA(cudaSetDevice(e->device));
+    mxe_a2a* X = new mxe_a2a();
+    X->eng = e;
+    int rc;
+    {
+        ArenaScope scope(e);
+        rc = a2a_partition_impl(e, (const uint64_t* const*)d_hash, n, n_asm, rank, world, X, counts, d_send_keys);
+    }
+    if (rc != MXE_OK) { mxe_a2a_free(X); return rc; }
+    *out = X;
+    return MXE_OK;
+}
+
+int mxe_a2a_mark(mxe_a2a_t* X, const void* d_recv_keys, const uint64_t* recv_counts, void* d_ret_marks, uint64_t* n_vertices_local)
+{
+    if (!X || !recv_counts || !n_vertices_local) { set_error("null argument"); return MXE_ERR_ARG; }
+    MXE_CUDA(cudaSetDevice(X->eng->device));
+    ArenaScope scope(X->eng);
+    return a2a_mark_impl(X, (const uint64_t*)d_recv_keys, recv_counts, (uint32_t*)d_ret_marks, n_vertices_local);
+}
+
+int mxe_a2a_sightings(mxe_a2a_t* X, const void* d_marks, const void* const* d_contig, const uint64_t* goff,
+                      uint64_t* rec_counts, const void** d_send_records)
+{
+    if (!X || !d_contig || !goff || !rec_counts || !d_send_records) { set_error("null argument"); return MXE_ERR_ARG; }
+    MXE_CUDA(cudaSetDevice(X->eng->device));
+    ArenaScope scope(X->eng);
+    return a2a_sightings_impl(X, (const uint32_t*)d_marks, (const uint32_t* const*)d_contig, goff, rec_counts, d_send_records);
+}
+
+int mxe_a2a_finish(mxe_a2a_t* X, const void* d_recv_records, uint64_t n_records, uint64_t n_global, const double* weights, mxe_result_t** out)
+{
+    if (!X || !weights || !out) { set_error("null argument"); return MXE_ERR_ARG; }
+    MXE_CUDA(cudaSetDevice(X->eng->device));
+    mxe_result* R = new mxe_result();
+    int rc;
+    {
+        ArenaScope scope(X->eng);
+        rc = a2a_finish_impl(X, (const uint64_t*)d_recv_records, n_records, n_global, weights, R);
+    }
+    if (rc != MXE_OK) { mxe_result_free(R); return rc; }
+    *out = R;
+    return MXE_OK;
+}
+
+void mxe_a2a_free(mxe_a2a_t* X)
+{
+    if (!X) return;
+    if (X->eng) {
+        cudaSetDevice(X->eng->device);
+        for (void* p : X->owned) if (p) cudaFreeAsync(p, X->eng->stream);
+    }
+    delete X;
+}
+
 // ------------------------------------------------------------------ measurement
 int mxe_timing(mxe_t* e, const char* name, double* ms, uint64_t* launches)
 {

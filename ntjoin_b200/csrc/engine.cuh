@@ -96,7 +96,34 @@ struct mxe_dist {
     }
 };
 
+// multi-GPU steps 2-3, all-to-all formulation: state carried between the stages
+struct mxe_a2a {
+    mxe_engine* eng = nullptr;
+    mxe::AsmOffsets A;                     // owner side: assembly offsets of the received (regrouped) keys
+    mxe::LocalSlices S;                    // source side: local concat offsets
+    int rank = 0, world = 1, n_asm = 0;
+    uint64_t L = 0, n_recv = 0, nV_local = 0;
+    std::vector<void*> owned;
+    uint64_t *lhash = nullptr, *send_keys = nullptr, *vertices = nullptr, *send_rec = nullptr;
+    uint32_t* perm = nullptr;
+    uint8_t *luniq = nullptr, *lkeep = nullptr;
+    template <typename T> int alloc(T** p, size_t n)
+    {
+        *p = nullptr;
+        cudaError_t err = cudaMallocAsync((void**)p, (n ? n : 1) * sizeof(T), eng->stream);
+        if (err != cudaSuccess) { mxe::set_error("cudaMallocAsync(%zu bytes): %s", n * sizeof(T), cudaGetErrorString(err)); return MXE_ERR_NOMEM; }
+        owned.push_back(*p);
+        return MXE_OK;
+    }
+};
+
 namespace mxe {
+int a2a_partition_impl(mxe_engine* e, const uint64_t* const* d_hash, const uint64_t* n, int n_asm, int rank, int world,
+                       mxe_a2a* X, uint64_t* counts, const void** d_send_keys);
+int a2a_mark_impl(mxe_a2a* X, const uint64_t* d_recv, const uint64_t* recv_counts, uint32_t* d_ret, uint64_t* nv_local);
+int a2a_sightings_impl(mxe_a2a* X, const uint32_t* d_marks, const uint32_t* const* d_contig, const uint64_t* goff,
+                       uint64_t* rec_counts, const void** d_send_records);
+int a2a_finish_impl(mxe_a2a* X, const uint64_t* d_rec, uint64_t n_rec, uint64_t N_global, const double* weights, mxe_result* out);
 int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const uint64_t* offsets, uint32_t n_contigs,
                        int k, int w, int flags, mxe_sketch* out, H2DSlot* staged = nullptr);
 int h2d_issue(mxe_engine* e, H2DSlot& s, const uint8_t* h, uint64_t n);

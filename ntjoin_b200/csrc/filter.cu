@@ -670,4 +670,447 @@ int dist_finish_impl(mxe_dist* X, const uint32_t* d_srcmin, const double* weight
     return MXE_OK;
 }
 
+
+// ====================================================================================================
+// Multi-GPU steps 2-3, all-to-all formulation (the production path; the all-reduce formulation above is
+// kept as a cross-check).  Every exchange moves each item exactly once, to the rank that needs it:
+//
+//   A partition   (source)   own minimizers grouped by HASH OWNER            -> all-to-all(keys, 8 B each)
+//   B mark        (owner)    unique / found-in-all / vertex ids of the range  -> all-to-all(marks, 4 B, same order back)
+//   C sightings   (source)   ordered survivors of own records, adjacent pairs;
+//                            each sighting (a: v -> x) goes to owner(v) as SUCC
+//                            and to owner(x) as PRED                         -> all-to-all(records, 24 B)
+//   D finish      (owner)    succ/pred tables of OWN vertices, support masks, edge ownership, first-source
+//                            index, order keys: all local.  Result shard = edges whose source vertex is owned.
+//
+// A vertex is named (owner << 27 | local id) everywhere, so no global vertex numbering is needed on the
+// device.  Creation index of a sighting = GLOBAL index of its source element (assemblies in order, ranks
+// in order inside an assembly), which is what makes the merged edge order independent of the GPU count.
+// ====================================================================================================
+constexpr int A2A_VBITS = 27;                    // local vertex id bits (world <= 16)
+struct PtrTable { const void* p[32]; };
+struct SegTable { uint64_t dst[1025]; uint64_t src[1024]; int n; };   // segments sorted by dst; dst[n] = total
+
+__global__ void __launch_bounds__(256) a2a_owner_key_kernel(PtrTable H, LocalSlices S, uint64_t L, int world, int n_asm,
+                                                             uint64_t* __restrict__ lhash, uint64_t* __restrict__ okey, uint32_t* __restrict__ oval,
+                                                             unsigned long long* __restrict__ counts)
+{
+    uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = l < L;
+    uint32_t bucket = 0xFFFFFFFFu;
+    if (ok) {
+        const int a = slice_of(S, l);
+        const uint64_t h = reinterpret_cast<const uint64_t*>(H.p[a])[l - S.lofs[a]];
+        const uint32_t o = hash_owner(h, world);
+        lhash[l] = h;
+        okey[l] = o;
+        oval[l] = (uint32_t)l;
+        bucket = o * (uint32_t)n_asm + (uint32_t)a;
+    }
+    // warp-aggregated count per (owner, assembly)
+    const uint32_t peers = __match_any_sync(0xffffffffu, bucket);
+    if (ok && (__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&counts[bucket], (unsigned long long)__popc(peers));
+}
+
+__global__ void __launch_bounds__(256) gather_u64_kernel(const uint64_t* __restrict__ src, const uint32_t* __restrict__ idx, uint64_t n, uint64_t* __restrict__ dst)
+{
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) dst[j] = src[idx[j]];
+}
+
+__device__ __forceinline__ int seg_of(const SegTable& T, uint64_t p)
+{
+    int lo = 0, hi = T.n;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (T.dst[mid] <= p) lo = mid; else hi = mid; }
+    return lo;
+}
+
+// received order (source rank, assembly, i) -> assembly-major order (assembly, source rank, i): equal hashes must stay
+// grouped by assembly through the stable sort (mark_kernel)
+__global__ void __launch_bounds__(256) a2a_regroup_kernel(const uint64_t* __restrict__ recv, uint64_t n, const SegTable* __restrict__ Tp,
+                                                           uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ srcpos)
+{
+    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const SegTable& T = *Tp;
+    const int sg = seg_of(T, p);
+    const uint64_t src = T.src[sg] + (p - T.dst[sg]);
+    keys[p] = recv[src];
+    vals[p] = (uint32_t)p;
+    srcpos[p] = (uint32_t)src;
+}
+
+__global__ void __launch_bounds__(256) a2a_marks_return_kernel(const uint32_t* __restrict__ srcpos, uint64_t n, const uint8_t* __restrict__ uniq,
+                                                                const uint8_t* __restrict__ keep, const uint32_t* __restrict__ vid, uint32_t* __restrict__ ret)
+{
+    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    ret[srcpos[p]] = ((uint32_t)uniq[p] << 31) | (keep[p] ? vid[p] + 1u : 0u);
+}
+
+// marks come back in send order; perm[j] = local index of send position j
+__global__ void __launch_bounds__(256) a2a_local_marks_kernel(const uint32_t* __restrict__ marks_in, const uint32_t* __restrict__ perm, uint64_t L,
+                                                               uint32_t* __restrict__ kflag, uint32_t* __restrict__ lmark,
+                                                               uint8_t* __restrict__ luniq, uint8_t* __restrict__ lkeep)
+{
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= L) return;
+    const uint32_t l = perm[j], m = marks_in[j];
+    const uint32_t k = (m & 0x7FFFFFFFu) != 0;
+    lmark[l] = m;
+    kflag[l] = k;
+    luniq[l] = (uint8_t)(m >> 31);
+    lkeep[l] = (uint8_t)k;
+}
+
+struct GlobalOffsets { uint64_t g[32]; };
+
+__global__ void __launch_bounds__(256) a2a_compact_kernel(const uint32_t* __restrict__ lmark, const uint64_t* __restrict__ lhash, LocalSlices S, uint64_t L,
+                                                           const uint32_t* __restrict__ kflag, const uint64_t* __restrict__ kprefix, GlobalOffsets G, int world,
+                                                           uint32_t* __restrict__ cid, uint64_t* __restrict__ chash, uint32_t* __restrict__ cg, uint32_t* __restrict__ cloc)
+{
+    uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= L || !kflag[l]) return;
+    const int a = slice_of(S, l);
+    const uint64_t j = kprefix[l];
+    const uint64_t h = lhash[l];
+    cid[j] = (hash_owner(h, world) << A2A_VBITS) | ((lmark[l] & 0x7FFFFFFFu) - 1u);
+    chash[j] = h;
+    cg[j] = (uint32_t)(G.g[a] + (l - S.lofs[a]));
+    cloc[j] = (uint32_t)l;
+}
+
+// two records per sighting (a: v -> x, creation index g):
+//   SUCC -> owner(v): { hash(x), local(v) << 32 | id(x), g << 8 | a << 1 | 0 }
+//   PRED -> owner(x): { hash(v), local(x) << 32 | id(v),          a << 1 | 1 }
+// written at 2*e, 2*e+1 (e = rank of the sighting among this rank's sightings) with their destination as sort key
+__global__ void __launch_bounds__(256) a2a_records_kernel(const uint32_t* __restrict__ cid, const uint64_t* __restrict__ chash, const uint32_t* __restrict__ cg,
+                                                           const uint32_t* __restrict__ cloc, const uint32_t* __restrict__ eflag, const uint64_t* __restrict__ eprefix,
+                                                           uint64_t n_keep, LocalSlices S, uint64_t* __restrict__ rec, uint64_t* __restrict__ dkey,
+                                                           uint32_t* __restrict__ dval, unsigned long long* __restrict__ counts)
+{
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = j < n_keep && eflag[j];
+    uint32_t d0 = 0xFFFFFFFFu, d1 = 0xFFFFFFFFu;
+    if (ok) {
+        const uint64_t e = eprefix[j];
+        const uint32_t v = cid[j], x = cid[j + 1];
+        const uint64_t a = (uint64_t)slice_of(S, cloc[j]);
+        d0 = v >> A2A_VBITS;
+        d1 = x >> A2A_VBITS;
+        const uint32_t vmask = (1u << A2A_VBITS) - 1u;
+        uint64_t* r0 = rec + 6 * e;
+        r0[0] = chash[j + 1]; r0[1] = ((uint64_t)(v & vmask) << 32) | x; r0[2] = ((uint64_t)cg[j] << 8) | (a << 1);
+        r0[3] = chash[j];     r0[4] = ((uint64_t)(x & vmask) << 32) | v; r0[5] = (a << 1) | 1ULL;
+        dkey[2 * e] = d0; dval[2 * e] = (uint32_t)(2 * e);
+        dkey[2 * e + 1] = d1; dval[2 * e + 1] = (uint32_t)(2 * e + 1);
+    }
+    uint32_t peers = __match_any_sync(0xffffffffu, d0);
+    if (ok && (__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&counts[d0], (unsigned long long)__popc(peers));
+    peers = __match_any_sync(0xffffffffu, d1);
+    if (ok && (__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&counts[d1], (unsigned long long)__popc(peers));
+}
+
+__global__ void __launch_bounds__(256) gather_rec_kernel(const uint64_t* __restrict__ rec, const uint32_t* __restrict__ idx, uint64_t n, uint64_t* __restrict__ dst)
+{
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint64_t* r = rec + 3 * (uint64_t)idx[j];
+    dst[3 * j] = r[0]; dst[3 * j + 1] = r[1]; dst[3 * j + 2] = r[2];
+}
+
+// owner side: successor / predecessor of every own vertex in every assembly (entries 1 + vertex name, 0 = none)
+__global__ void __launch_bounds__(256) a2a_table_kernel(const uint64_t* __restrict__ rec, uint64_t n_rec, uint64_t nV,
+                                                         uint32_t* __restrict__ succ, uint32_t* __restrict__ pred)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rec) return;
+    const uint64_t w1 = rec[3 * i + 1], w2 = rec[3 * i + 2];
+    const uint64_t a = (w2 >> 1) & 0x7F, vloc = w1 >> 32;
+    const uint32_t other = (uint32_t)w1 + 1u;
+    if (w2 & 1ULL) pred[a * nV + vloc] = other; else succ[a * nV + vloc] = other;
+}
+
+__global__ void __launch_bounds__(256) a2a_edge_owner_kernel(const uint64_t* __restrict__ rec, uint64_t n_rec, uint64_t nV, int n_asm,
+                                                              const uint32_t* __restrict__ succ, const uint32_t* __restrict__ pred,
+                                                              uint32_t* __restrict__ own, uint32_t* __restrict__ mask_out)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rec) return;
+    const uint64_t w1 = rec[3 * i + 1], w2 = rec[3 * i + 2];
+    uint32_t is_owner = 0;
+    if (!(w2 & 1ULL)) {
+        const int a = (int)((w2 >> 1) & 0x7F);
+        const uint64_t vloc = w1 >> 32;
+        const uint32_t x1 = (uint32_t)w1 + 1u;
+        uint32_t mask = 0;
+        for (int b = 0; b < n_asm; b++)
+            if (succ[(uint64_t)b * nV + vloc] == x1 || pred[(uint64_t)b * nV + vloc] == x1) mask |= 1u << b;
+        is_owner = (__ffs(mask) - 1) == a;
+        mask_out[i] = mask;
+    }
+    own[i] = is_owner;
+}
+
+__global__ void __launch_bounds__(256) a2a_edge_compact_kernel(const uint64_t* __restrict__ rec, uint64_t n_rec, const uint32_t* __restrict__ own,
+                                                                const uint64_t* __restrict__ uprefix, const uint32_t* __restrict__ mask_in,
+                                                                uint32_t* __restrict__ e_rec, uint32_t* __restrict__ e_mask, uint32_t* __restrict__ srcmin)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rec || !own[i]) return;
+    const uint64_t t = uprefix[i];
+    e_rec[t] = (uint32_t)i;
+    e_mask[t] = mask_in[i];
+    atomicMin(&srcmin[rec[3 * i + 1] >> 32], (uint32_t)(rec[3 * i + 2] >> 8));
+}
+
+// a source owns at most one edge per assembly and its edges are created in assembly order, so (first creation index of
+// the source, assembly) orders the shard exactly like the reference's dict-of-dicts
+__global__ void __launch_bounds__(256) a2a_edge_key_kernel(const uint64_t* __restrict__ rec, const uint32_t* __restrict__ e_rec, uint64_t n_edges,
+                                                            const uint32_t* __restrict__ srcmin, uint64_t* __restrict__ okey, uint32_t* __restrict__ oval)
+{
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_edges) return;
+    const uint64_t i = e_rec[t];
+    okey[t] = ((uint64_t)srcmin[rec[3 * i + 1] >> 32] << 5) | ((rec[3 * i + 2] >> 1) & 0x1F);
+    oval[t] = (uint32_t)t;
+}
+
+__global__ void __launch_bounds__(256) a2a_edge_gather_kernel(const uint32_t* __restrict__ oval, const uint64_t* __restrict__ okey, uint64_t n_edges,
+                                                               const uint64_t* __restrict__ rec, const uint32_t* __restrict__ e_rec, const uint32_t* __restrict__ e_mask,
+                                                               const uint64_t* __restrict__ vertices, AsmOffsets A,
+                                                               uint64_t* __restrict__ eu, uint64_t* __restrict__ ev, uint32_t* __restrict__ emask,
+                                                               double* __restrict__ ew, uint64_t* __restrict__ ekey)
+{
+    uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n_edges) return;
+    const uint32_t t = oval[o];
+    const uint64_t i = e_rec[t];
+    const uint32_t mask = e_mask[t];
+    eu[o] = vertices[rec[3 * i + 1] >> 32];
+    ev[o] = rec[3 * i];
+    emask[o] = mask;
+    double wsum = 0.0;
+    for (int a = 0; a < A.n; a++)
+        if (mask & (1u << a)) wsum += A.weight[a];
+    ew[o] = wsum;
+    ekey[o] = ((okey[o] >> 5) << 32) | (rec[3 * i + 2] >> 8);
+}
+
+int a2a_partition_impl(mxe_engine* e, const uint64_t* const* d_hash, const uint64_t* n, int n_asm, int rank, int world,
+                       mxe_a2a* X, uint64_t* counts, const void** d_send_keys)
+{
+    if (n_asm < 1 || n_asm > 32 || world < 1 || world > 16 || rank < 0 || rank >= world) { set_error("bad n_asm/rank/world (world <= 16)"); return MXE_ERR_ARG; }
+    cudaStream_t st = e->stream;
+    Span whole(e, "filter");
+    Span part(e, "a2a_partition");
+    X->eng = e; X->rank = rank; X->world = world; X->n_asm = n_asm;
+    LocalSlices& S = X->S;
+    S.n = n_asm; S.lofs[0] = 0;
+    PtrTable H;
+    for (int a = 0; a < n_asm; a++) { S.lofs[a + 1] = S.lofs[a] + n[a]; S.goff[a] = 0; H.p[a] = d_hash[a]; }
+    const uint64_t L = S.lofs[n_asm];
+    X->L = L;
+    if (L >= (1ULL << 31)) { set_error("too many local minimizers"); return MXE_ERR_ARG; }
+    for (int i = 0; i < world * n_asm; i++) counts[i] = 0;
+    *d_send_keys = nullptr;
+    MXE_TRY(X->alloc(&X->lhash, L)); MXE_TRY(X->alloc(&X->perm, L)); MXE_TRY(X->alloc(&X->send_keys, L));
+    *d_send_keys = X->send_keys;
+    if (L == 0) return MXE_OK;
+    DBuf<uint64_t> okey, okey2;
+    DBuf<uint32_t> oval2;
+    DBuf<unsigned long long> cnt;
+    MXE_TRY(okey.alloc(L, st)); MXE_TRY(okey2.alloc(L, st)); MXE_TRY(oval2.alloc(L, st)); MXE_TRY(cnt.alloc((size_t)world * n_asm, st));
+    MXE_CUDA(cudaMemsetAsync(cnt.p, 0, (size_t)world * n_asm * sizeof(unsigned long long), st));
+    MXE_LAUNCH(e, a2a_owner_key_kernel, gridf(L), 256, 0, H, S, L, world, n_asm, X->lhash, okey.p, X->perm, cnt.p);
+    MXE_TRY(radix_sort_pairs(e, okey.p, X->perm, okey2.p, oval2.p, L, 0, 8));        // stable partition by owner
+    MXE_LAUNCH(e, gather_u64_kernel, gridf(L), 256, 0, X->lhash, X->perm, L, X->send_keys);
+    MXE_CUDA(cudaMemcpyAsync(counts, cnt.p, (size_t)world * n_asm * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    MXE_CUDA(cudaStreamSynchronize(st));
+    MXE_CUDA(cudaGetLastError());
+    return MXE_OK;
+}
+
+int a2a_mark_impl(mxe_a2a* X, const uint64_t* d_recv, const uint64_t* recv_counts, uint32_t* d_ret, uint64_t* nv_local)
+{
+    mxe_engine* e = X->eng;
+    cudaStream_t st = e->stream;
+    Span whole(e, "filter");
+    Span part(e, "a2a_mark");
+    const int n_asm = X->n_asm, world = X->world;
+    // segment table: destination order (assembly, source rank), source order (source rank, assembly)
+    SegTable T;
+    T.n = 0;
+    AsmOffsets& A = X->A;
+    A.n = n_asm;
+    uint64_t at = 0;
+    std::vector<uint64_t> srcoff((size_t)world * n_asm);
+    {
+        uint64_t s = 0;
+        for (int r = 0; r < world; r++) for (int a = 0; a < n_asm; a++) { srcoff[(size_t)r * n_asm + a] = s; s += recv_counts[(size_t)r * n_asm + a]; }
+    }
+    for (int a = 0; a < n_asm; a++) {
+        A.off[a] = at;
+        for (int r = 0; r < world; r++) {
+            const uint64_t c = recv_counts[(size_t)r * n_asm + a];
+            if (!c) continue;
+            T.dst[T.n] = at; T.src[T.n] = srcoff[(size_t)r * n_asm + a]; T.n++;
+            at += c;
+        }
+    }
+    A.off[n_asm] = at;
+    T.dst[T.n] = at;
+    const uint64_t n_recv = at;
+    X->n_recv = n_recv;
+    *nv_local = 0;
+    X->nV_local = 0;
+    if (n_recv >= (1ULL << 31)) { set_error("too many minimizers in one hash range"); return MXE_ERR_ARG; }
+    if (n_recv == 0) return MXE_OK;
+    DBuf<SegTable> dT;
+    MXE_TRY(dT.alloc(1, st));
+    MXE_CUDA(cudaMemcpyAsync(dT.p, &T, sizeof(SegTable), cudaMemcpyHostToDevice, st));
+    DBuf<uint64_t> keys, keys2, hprefix;
+    DBuf<uint32_t> vals, vals2, srcpos, head, vid;
+    DBuf<uint8_t> uniq, keep;
+    MXE_TRY(keys.alloc(n_recv, st)); MXE_TRY(keys2.alloc(n_recv, st)); MXE_TRY(vals.alloc(n_recv, st)); MXE_TRY(vals2.alloc(n_recv, st));
+    MXE_TRY(srcpos.alloc(n_recv, st)); MXE_TRY(head.alloc(n_recv, st)); MXE_TRY(vid.alloc(n_recv, st));
+    MXE_TRY(uniq.alloc(n_recv, st)); MXE_TRY(keep.alloc(n_recv, st)); MXE_TRY(hprefix.alloc(n_recv + 1, st));
+    MXE_LAUNCH(e, a2a_regroup_kernel, gridf(n_recv), 256, 0, d_recv, n_recv, dT.p, keys.p, vals.p, srcpos.p);
+    {
+        DBuf<int> fallback;
+        MXE_TRY(fallback.alloc(1, st));
+        MXE_CUDA(cudaMemsetAsync(fallback.p, 0, sizeof(int), st));
+        const int SORT_LOW_BIT = sort_low_bit(e, n_recv * (uint64_t)world);
+        MXE_TRY(radix_sort_pairs(e, keys.p, vals.p, keys2.p, vals2.p, n_recv, SORT_LOW_BIT, 64));
+        MXE_LAUNCH(e, fixup_kernel, gridf(n_recv), 256, 0, keys.p, vals.p, n_recv, SORT_LOW_BIT, fallback.p);
+        int fb = 0;
+        MXE_CUDA(cudaMemcpyAsync(&fb, fallback.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        MXE_CUDA(cudaStreamSynchronize(st));        // also orders the host-side SegTable upload before T goes out of scope
+        if (fb) MXE_TRY(radix_sort_pairs(e, keys.p, vals.p, keys2.p, vals2.p, n_recv, 0, SORT_LOW_BIT));
+        if (fb) MXE_TRY(radix_sort_pairs(e, keys.p, vals.p, keys2.p, vals2.p, n_recv, SORT_LOW_BIT, 64));
+    }
+    MXE_LAUNCH(e, mark_kernel, gridf(n_recv), 256, 0, keys.p, vals.p, n_recv, A, uniq.p, keep.p, head.p);
+    MXE_TRY(exclusive_scan_u32_u64(e, head.p, hprefix.p, n_recv));
+    uint64_t nV = 0;
+    MXE_CUDA(cudaMemcpyAsync(&nV, hprefix.p + n_recv, 8, cudaMemcpyDeviceToHost, st));
+    MXE_CUDA(cudaStreamSynchronize(st));
+    if (nV >= (1ULL << A2A_VBITS)) { set_error("too many vertices in one hash range (%llu)", (unsigned long long)nV); return MXE_ERR_ARG; }
+    MXE_TRY(X->alloc(&X->vertices, nV));
+    MXE_LAUNCH(e, vertex_kernel, gridf(n_recv), 256, 0, keys.p, vals.p, n_recv, A, keep.p, hprefix.p, vid.p, X->vertices);
+    MXE_LAUNCH(e, a2a_marks_return_kernel, gridf(n_recv), 256, 0, srcpos.p, n_recv, uniq.p, keep.p, vid.p, d_ret);
+    X->nV_local = nV;
+    *nv_local = nV;
+    MXE_CUDA(cudaGetLastError());
+    return MXE_OK;
+}
+
+int a2a_sightings_impl(mxe_a2a* X, const uint32_t* d_marks, const uint32_t* const* d_contig, const uint64_t* goff,
+                       uint64_t* rec_counts, const void** d_send_records)
+{
+    mxe_engine* e = X->eng;
+    cudaStream_t st = e->stream;
+    Span whole(e, "filter");
+    Span part(e, "a2a_sightings");
+    const int n_asm = X->n_asm, world = X->world;
+    const LocalSlices& S = X->S;
+    const uint64_t L = X->L;
+    for (int r = 0; r < world; r++) rec_counts[r] = 0;
+    *d_send_records = nullptr;
+    MXE_TRY(X->alloc(&X->luniq, L)); MXE_TRY(X->alloc(&X->lkeep, L));
+    if (L == 0) return MXE_OK;
+    GlobalOffsets G;
+    for (int a = 0; a < n_asm; a++) G.g[a] = goff[a];
+    DBuf<uint32_t> kflag, lmark, lcontig;
+    DBuf<uint64_t> kprefix;
+    MXE_TRY(kflag.alloc(L, st)); MXE_TRY(lmark.alloc(L, st)); MXE_TRY(lcontig.alloc(L, st)); MXE_TRY(kprefix.alloc(L + 1, st));
+    for (int a = 0; a < n_asm; a++) {
+        const uint64_t na = S.lofs[a + 1] - S.lofs[a];
+        if (na) MXE_LAUNCH(e, copy_contig_kernel, gridf(na), 256, 0, d_contig[a], na, S.lofs[a], lcontig.p);
+    }
+    MXE_LAUNCH(e, a2a_local_marks_kernel, gridf(L), 256, 0, d_marks, X->perm, L, kflag.p, lmark.p, X->luniq, X->lkeep);
+    MXE_TRY(exclusive_scan_u32_u64(e, kflag.p, kprefix.p, L));
+    uint64_t n_keep = 0;
+    MXE_CUDA(cudaMemcpyAsync(&n_keep, kprefix.p + L, 8, cudaMemcpyDeviceToHost, st));
+    MXE_CUDA(cudaStreamSynchronize(st));
+    if (n_keep < 2) return MXE_OK;
+    DBuf<uint32_t> cid, cg, cloc, eflag, dval, dval2;
+    DBuf<uint64_t> chash, eprefix, rec, dkey, dkey2;
+    DBuf<unsigned long long> cnt;
+    MXE_TRY(cid.alloc(n_keep + 1, st)); MXE_TRY(cg.alloc(n_keep + 1, st)); MXE_TRY(cloc.alloc(n_keep + 1, st)); MXE_TRY(chash.alloc(n_keep + 1, st));
+    MXE_TRY(eflag.alloc(n_keep, st)); MXE_TRY(eprefix.alloc(n_keep + 1, st));
+    MXE_LAUNCH(e, a2a_compact_kernel, gridf(L), 256, 0, lmark.p, X->lhash, S, L, kflag.p, kprefix.p, G, world, cid.p, chash.p, cg.p, cloc.p);
+    MXE_LAUNCH(e, local_pair_flag_kernel, gridf(n_keep), 256, 0, cloc.p, n_keep, S, lcontig.p, eflag.p);
+    MXE_TRY(exclusive_scan_u32_u64(e, eflag.p, eprefix.p, n_keep));
+    // at most n_keep - 1 sightings: size the record buffers for the worst case instead of waiting for the count
+    const uint64_t cap = 2 * (n_keep - 1);
+    MXE_TRY(rec.alloc(3 * cap, st)); MXE_TRY(dkey.alloc(cap, st)); MXE_TRY(dkey2.alloc(cap, st)); MXE_TRY(dval.alloc(cap, st)); MXE_TRY(dval2.alloc(cap, st));
+    MXE_TRY(cnt.alloc(world, st));
+    MXE_CUDA(cudaMemsetAsync(cnt.p, 0, world * sizeof(unsigned long long), st));
+    MXE_LAUNCH(e, a2a_records_kernel, gridf(n_keep), 256, 0, cid.p, chash.p, cg.p, cloc.p, eflag.p, eprefix.p, n_keep, S, rec.p, dkey.p, dval.p, cnt.p);
+    uint64_t n_sight = 0;
+    MXE_CUDA(cudaMemcpyAsync(&n_sight, eprefix.p + n_keep, 8, cudaMemcpyDeviceToHost, st));
+    MXE_CUDA(cudaMemcpyAsync(rec_counts, cnt.p, world * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    MXE_CUDA(cudaStreamSynchronize(st));
+    const uint64_t n_rec = 2 * n_sight;
+    if (n_rec == 0) return MXE_OK;
+    MXE_TRY(X->alloc(&X->send_rec, 3 * n_rec));
+    MXE_TRY(radix_sort_pairs(e, dkey.p, dval.p, dkey2.p, dval2.p, n_rec, 0, 8));       // group by destination
+    MXE_LAUNCH(e, gather_rec_kernel, gridf(n_rec), 256, 0, rec.p, dval.p, n_rec, X->send_rec);
+    *d_send_records = X->send_rec;
+    MXE_CUDA(cudaGetLastError());
+    return MXE_OK;
+}
+
+int a2a_finish_impl(mxe_a2a* X, const uint64_t* d_rec, uint64_t n_rec, uint64_t N_global, const double* weights, mxe_result* R)
+{
+    mxe_engine* e = X->eng;
+    cudaStream_t st = e->stream;
+    Span whole(e, "filter");
+    Span part(e, "a2a_finish");
+    const int n_asm = X->n_asm;
+    AsmOffsets A = X->A;
+    A.n = n_asm;
+    for (int a = 0; a < n_asm; a++) A.weight[a] = weights[a];
+    R->eng = e; R->n_asm = n_asm; R->N = X->L; R->nV = X->nV_local; R->nE = 0;
+    for (int a = 0; a <= n_asm; a++) R->asm_off[a] = X->S.lofs[a];
+    auto take = [&](void* p) { for (auto& q : X->owned) if (q == p) q = nullptr; return p; };
+    R->d_uniq = (uint8_t*)take(X->luniq); R->d_keep = (uint8_t*)take(X->lkeep);
+    R->d_vertices = (uint64_t*)take(X->vertices);
+    const uint64_t nV = X->nV_local;
+    if (n_rec == 0 || nV == 0) return MXE_OK;
+    if (N_global >= (1ULL << 32)) { set_error("too many minimizers"); return MXE_ERR_ARG; }
+    DBuf<uint32_t> succ, pred, own, mask_i, srcmin;
+    DBuf<uint64_t> uprefix;
+    MXE_TRY(succ.alloc((uint64_t)n_asm * nV, st)); MXE_TRY(pred.alloc((uint64_t)n_asm * nV, st)); MXE_TRY(srcmin.alloc(nV, st));
+    MXE_TRY(own.alloc(n_rec, st)); MXE_TRY(mask_i.alloc(n_rec, st)); MXE_TRY(uprefix.alloc(n_rec + 1, st));
+    MXE_CUDA(cudaMemsetAsync(succ.p, 0, (uint64_t)n_asm * nV * sizeof(uint32_t), st));
+    MXE_CUDA(cudaMemsetAsync(pred.p, 0, (uint64_t)n_asm * nV * sizeof(uint32_t), st));
+    MXE_CUDA(cudaMemsetAsync(srcmin.p, 0xFF, nV * sizeof(uint32_t), st));
+    MXE_LAUNCH(e, a2a_table_kernel, gridf(n_rec), 256, 0, d_rec, n_rec, nV, succ.p, pred.p);
+    MXE_LAUNCH(e, a2a_edge_owner_kernel, gridf(n_rec), 256, 0, d_rec, n_rec, nV, n_asm, succ.p, pred.p, own.p, mask_i.p);
+    MXE_TRY(exclusive_scan_u32_u64(e, own.p, uprefix.p, n_rec));
+    uint64_t nE = 0;
+    MXE_CUDA(cudaMemcpyAsync(&nE, uprefix.p + n_rec, 8, cudaMemcpyDeviceToHost, st));
+    MXE_CUDA(cudaStreamSynchronize(st));
+    R->nE = nE;
+    if (nE == 0) return MXE_OK;
+    DBuf<uint32_t> e_rec, e_mask, oval, oval2, emask;
+    DBuf<uint64_t> okey, okey2, eu, ev, ekey;
+    DBuf<double> ew;
+    MXE_TRY(e_rec.alloc(nE, st)); MXE_TRY(e_mask.alloc(nE, st)); MXE_TRY(oval.alloc(nE, st)); MXE_TRY(oval2.alloc(nE, st));
+    MXE_TRY(okey.alloc(nE, st)); MXE_TRY(okey2.alloc(nE, st));
+    MXE_TRY(eu.alloc(nE, st)); MXE_TRY(ev.alloc(nE, st)); MXE_TRY(emask.alloc(nE, st)); MXE_TRY(ew.alloc(nE, st)); MXE_TRY(ekey.alloc(nE, st));
+    MXE_LAUNCH(e, a2a_edge_compact_kernel, gridf(n_rec), 256, 0, d_rec, n_rec, own.p, uprefix.p, mask_i.p, e_rec.p, e_mask.p, srcmin.p);
+    MXE_LAUNCH(e, a2a_edge_key_kernel, gridf(nE), 256, 0, d_rec, e_rec.p, nE, srcmin.p, okey.p, oval.p);
+    int kb = 1;
+    while (kb < 32 && (1ULL << kb) <= N_global) kb++;
+    kb = ((kb + 5 + 7) / 8) * 8;
+    MXE_TRY(radix_sort_pairs(e, okey.p, oval.p, okey2.p, oval2.p, nE, 0, kb));
+    MXE_LAUNCH(e, a2a_edge_gather_kernel, gridf(nE), 256, 0, oval.p, okey.p, nE, d_rec, e_rec.p, e_mask.p, R->d_vertices, A,
+               eu.p, ev.p, emask.p, ew.p, ekey.p);
+    R->d_eu = eu.detach(); R->d_ev = ev.detach(); R->d_emask = emask.detach(); R->d_ew = ew.detach(); R->d_ekey = ekey.detach();
+    MXE_CUDA(cudaGetLastError());
+    return MXE_OK;
+}
+
 }  // namespace mxe

@@ -140,6 +140,37 @@ def _filter_steps(stages, hashes, contigs, weights, rank, world, device):
     return DistShard(shard, lay, rank, vbase, int(n_e_local), keep=(keys, mk, table, srcmin))
 
 
+def _a2a_steps(stages, hashes, contigs, weights, rank, world, device):
+    """All-to-all formulation (production).  Same inputs and result as `_filter_steps`; every item travels once:
+    keys to their hash owner, marks back, sightings to the owners of their two vertices."""
+    import torch
+    n_asm = len(hashes)
+    handle, cnt, send_keys = stages.partition(hashes, rank, world)            # cnt[owner][asm]
+    try:
+        allc = yield ("counts", [int(x) for x in cnt.reshape(-1)])
+        c3 = allc.reshape(world, world, n_asm)                                # [source][owner][asm]
+        send_splits = c3[rank].sum(axis=1)
+        recv_counts = np.ascontiguousarray(c3[:, rank, :])                    # [source][asm] addressed to this owner
+        recv_splits = recv_counts.sum(axis=1)
+        n_recv = int(recv_splits.sum())
+        recv_keys = yield ("a2a", (send_keys, send_splits, recv_splits, 1))
+        ret_marks = torch.empty(max(1, n_recv), dtype=torch.int32, device=device)
+        nv_local = stages.mark(handle, recv_keys, recv_counts, ret_marks)
+        marks = yield ("a2a", (ret_marks[:n_recv], recv_splits, send_splits, 1))   # same order as send_keys
+        lay = Layout(c3.sum(axis=1))                                          # local counts of every rank -> global indices
+        rec_cnt, send_rec = stages.sightings(handle, marks, contigs, lay.goff[rank], world)
+        allr = yield ("counts", [int(x) for x in rec_cnt] + [int(nv_local)])
+        rec_send, rec_recv = allr[rank, :world], allr[:, rank]
+        vbase = np.concatenate([[0], np.cumsum(allr[:, world])]).astype(np.int64)
+        recv_rec = yield ("a2a", (send_rec, rec_send, rec_recv, 3))
+    except BaseException:
+        stages.abort(handle)
+        raise
+    n_rec = int(rec_recv.sum())
+    shard = stages.finish(handle, recv_rec, n_rec, lay.N, weights)
+    return DistShard(shard, lay, rank, vbase, None, keep=(recv_keys, ret_marks, marks, recv_rec))
+
+
 class DistShard:
     """This rank's part of the result of steps 2-3: flags of its own minimizers, the vertices of its
     hash range (ascending) and its edges with global order keys.  `merge_shards` reassembles the
@@ -154,7 +185,8 @@ class DistShard:
 
     def fetch(self, copy=True):
         d = dict(self.result.fetch(copy=copy))
-        d["edge_key"] = self.result.edge_keys if self.n_edges_local else np.empty(0, dtype=np.uint64)
+        n_e = self.result.counts()[2] if self.n_edges_local is None else self.n_edges_local
+        d["edge_key"] = self.result.edge_keys if n_e else np.empty(0, dtype=np.uint64)
         return d
 
     def close(self):
@@ -218,6 +250,15 @@ class TorchComm:
                 at += n
         return keys
 
+    def a2a(self, send, send_splits, recv_splits, width):
+        """all_to_all_single of `width` elements per item; splits in items"""
+        import torch
+        n_out = int(np.sum(recv_splits)) * width
+        out = torch.empty(max(1, n_out), dtype=send.dtype, device=self.device)[:n_out]
+        self.dist.all_to_all_single(out, send, output_split_sizes=[int(x) * width for x in recv_splits],
+                                    input_split_sizes=[int(x) * width for x in send_splits], group=self.group)
+        return out
+
     def reduce(self, op, tensor):
         self.dist.all_reduce(tensor, op=self.dist.ReduceOp.SUM if op == "sum" else self.dist.ReduceOp.MIN, group=self.group)
 
@@ -231,6 +272,8 @@ class TorchComm:
             out = self.counts(payload)
         elif op == "keys":
             out = self.keys(*payload)
+        elif op == "a2a":
+            out = self.a2a(*payload)
         else:
             out = self.reduce(op, payload)
         if self.timing:
@@ -251,8 +294,11 @@ class TorchComm:
 
 
 def distributed_filter_and_edges(stages, hashes, contigs, weights, comm):
-    """Steps 2-3 across the ranks of `comm` (a TorchComm).  Returns this rank's DistShard."""
-    gen = _filter_steps(stages, hashes, contigs, weights, comm.rank, comm.world, comm.device)
+    """Steps 2-3 across the ranks of `comm` (a TorchComm).  Returns this rank's DistShard.
+    `stages` selects the formulation: Engine.a2a_stages() (all-to-all, production) or Engine.dist_stages()
+    (all-reduce cross-check).  The engine must run on torch's current stream (Engine.set_stream)."""
+    steps = _a2a_steps if hasattr(stages, "partition") else _filter_steps
+    gen = steps(stages, hashes, contigs, weights, comm.rank, comm.world, comm.device)
     try:
         req = next(gen)
         while True:
@@ -266,7 +312,8 @@ def run_lockstep(stage_list, hashes_per_rank, contigs_per_rank, weights, device)
     the same device stages as the real multi-process run, with the collectives done in place)."""
     import torch
     world = len(stage_list)
-    gens = [_filter_steps(stage_list[r], hashes_per_rank[r], contigs_per_rank[r], weights, r, world, device) for r in range(world)]
+    steps = _a2a_steps if hasattr(stage_list[0], "partition") else _filter_steps
+    gens = [steps(stage_list[r], hashes_per_rank[r], contigs_per_rank[r], weights, r, world, device) for r in range(world)]
     reqs = [next(g) for g in gens]
     results = [None] * world
     while any(r is not None for r in reqs):
@@ -284,6 +331,15 @@ def run_lockstep(stage_list, hashes_per_rank, contigs_per_rank, weights, device)
                         g = int(lay.goff[r, a])
                         keys[g:g + n] = reqs[r][1][0][a]
             resp = [keys.clone() for _ in range(world)]
+        elif op == "a2a":
+            resp = []
+            for d in range(world):
+                parts = []
+                for src in range(world):
+                    send, send_splits, _recv, width = reqs[src][1]
+                    at = int(np.sum(send_splits[:d])) * width
+                    parts.append(send[at:at + int(send_splits[d]) * width])
+                resp.append(torch.cat(parts) if parts else torch.empty(0, dtype=reqs[0][1][0].dtype, device=device))
         else:
             stack = torch.stack([r[1] for r in reqs])
             red = stack.sum(dim=0, dtype=torch.int32) if op == "sum" else stack.min(dim=0).values

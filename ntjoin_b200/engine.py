@@ -306,8 +306,12 @@ class Engine:
         return FilterResult(self, out, n)
 
     def dist_stages(self):
-        """Engine-backed stages of the multi-GPU steps 2-3 (driven by ntjoin_b200.dist)."""
+        """Engine-backed stages of the multi-GPU steps 2-3, all-reduce formulation (ntjoin_b200.dist, cross-check)."""
         return EngineDistStages(self)
+
+    def a2a_stages(self):
+        """Engine-backed stages of the multi-GPU steps 2-3, all-to-all formulation (ntjoin_b200.dist, production)."""
+        return EngineA2AStages(self)
 
     def timing(self, name):
         ms, nl = C.c_double(), C.c_uint64()
@@ -378,3 +382,64 @@ class EngineDistStages:
 
     def abort(self, handle):
         self._lib.mxe_dist_free(handle)
+
+
+class EngineA2AStages:
+    """The four device stages of the all-to-all formulation (include/mxe.h: mxe_a2a_*).  Tensors live on this engine's
+    device; send buffers returned by a stage are engine-owned views valid until finish()."""
+
+    def __init__(self, engine):
+        self._e = engine
+        self._lib = engine._lib
+
+    def _view(self, ptr, n, dtype):
+        import torch
+        from .dist import DeviceArray
+        dev = torch.device("cuda", self._e.device)
+        if not n:
+            return torch.empty(0, dtype=dtype, device=dev)
+        return torch.as_tensor(DeviceArray(ptr, n, "<i8"), device=dev)
+
+    def partition(self, hashes, rank, world):
+        import torch
+        n_asm = len(hashes)
+        hp = (C.c_void_p * n_asm)(*[h.data_ptr() if h.numel() else None for h in hashes])
+        ns = _u64arr([h.numel() for h in hashes])
+        counts = (C.c_uint64 * (world * n_asm))()
+        h, send = C.c_void_p(), C.c_void_p()
+        check(self._lib, self._lib.mxe_a2a_partition(self._e._h, hp, ns, n_asm, int(rank), int(world), C.byref(h), counts, C.byref(send)))
+        total = sum(int(x.numel()) for x in hashes)
+        cnt = np.frombuffer(counts, dtype=np.uint64).astype(np.int64).reshape(world, n_asm)
+        return h, cnt, self._view(send.value, total, torch.int64)
+
+    def mark(self, handle, recv_keys, recv_counts, ret_marks):
+        nv = C.c_uint64()
+        check(self._lib, self._lib.mxe_a2a_mark(handle, C.c_void_p(recv_keys.data_ptr() if recv_keys.numel() else None),
+                                                _u64arr(np.asarray(recv_counts).reshape(-1)),
+                                                C.c_void_p(ret_marks.data_ptr() if ret_marks.numel() else None), C.byref(nv)))
+        return nv.value
+
+    def sightings(self, handle, marks, contigs, goff, world):
+        import torch
+        n = len(contigs)
+        cp = (C.c_void_p * n)(*[c.data_ptr() if c.numel() else None for c in contigs])
+        rc = (C.c_uint64 * world)()
+        send = C.c_void_p()
+        check(self._lib, self._lib.mxe_a2a_sightings(handle, C.c_void_p(marks.data_ptr() if marks.numel() else None), cp, _u64arr(goff),
+                                                     rc, C.byref(send)))
+        cnt = np.frombuffer(rc, dtype=np.uint64).astype(np.int64)
+        return cnt, self._view(send.value, 3 * int(cnt.sum()), torch.int64)
+
+    def finish(self, handle, recv_records, n_records, n_global, weights):
+        n = len(weights)
+        ws = (C.c_double * n)(*[float(x) for x in weights])
+        out = C.c_void_p()
+        try:
+            check(self._lib, self._lib.mxe_a2a_finish(handle, C.c_void_p(recv_records.data_ptr() if recv_records.numel() else None),
+                                                      int(n_records), int(n_global), ws, C.byref(out)))
+        finally:
+            self._lib.mxe_a2a_free(handle)
+        return FilterResult(self._e, out, n)
+
+    def abort(self, handle):
+        self._lib.mxe_a2a_free(handle)

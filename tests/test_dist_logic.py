@@ -10,7 +10,9 @@ import torch
 from ntjoin_b200 import synth
 from ntjoin_b200.dist import Layout, merge_shards, run_lockstep, shard_ranges
 
-from dist_ref_stages import NumpyDistStages
+from dist_ref_stages import NumpyA2AStages, NumpyDistStages
+
+STAGES = {"allreduce": NumpyDistStages, "alltoall": NumpyA2AStages}
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 WEIGHTS3 = [2.0, 2.0, 1.0]
@@ -60,17 +62,19 @@ def test_layout_offsets():
     assert lay.goff.tolist() == [[0, 5], [3, 5], [5, 10]]
 
 
+@pytest.mark.parametrize("mode", ["alltoall", "allreduce"])
 @pytest.mark.parametrize("world", [1, 2, 3, 5])
-def test_lockstep_matches_oracle(oracle, world):
+def test_lockstep_matches_oracle(oracle, world, mode):
     asms, full = make_case(oracle)
     want = oracle.filter_and_edges([f["out_hash"] for f in full], [f["contig"] for f in full], WEIGHTS3)
     assert len(want["edges"]) > 100
     hashes, contigs = shard_case(oracle, asms, world)
-    shards = run_lockstep([NumpyDistStages() for _ in range(world)], hashes, contigs, WEIGHTS3, torch.device("cpu"))
+    shards = run_lockstep([STAGES[mode]() for _ in range(world)], hashes, contigs, WEIGHTS3, torch.device("cpu"))
     check_merged(merge_shards([s.fetch() for s in shards]), want)
 
 
-def test_lockstep_empty_rank_and_no_survivors(oracle):
+@pytest.mark.parametrize("mode", ["alltoall", "allreduce"])
+def test_lockstep_empty_rank_and_no_survivors(oracle, mode):
     """more ranks than records on one side, and assemblies with nothing in common"""
     a = synth.make_reference(60_000, n_chrom=2, seed=3)
     b = synth.make_reference(60_000, n_chrom=2, seed=4)
@@ -79,11 +83,11 @@ def test_lockstep_empty_rank_and_no_survivors(oracle):
     want = oracle.filter_and_edges([f["out_hash"] for f in full], [f["contig"] for f in full], [1.0, 1.0])
     assert len(want["vertices"]) == 0
     hashes, contigs = shard_case(oracle, asms, 6, w=50)
-    shards = run_lockstep([NumpyDistStages() for _ in range(6)], hashes, contigs, [1.0, 1.0], torch.device("cpu"))
+    shards = run_lockstep([STAGES[mode]() for _ in range(6)], hashes, contigs, [1.0, 1.0], torch.device("cpu"))
     check_merged(merge_shards([s.fetch() for s in shards]), want)
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, mode):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -94,7 +98,7 @@ def _worker(rank, world, port, q):
     orc = oracle_lib.Oracle()
     asms, full = make_case(orc)
     hashes, contigs = shard_case(orc, asms, world)
-    shard = distributed_filter_and_edges(NumpyDistStages(), hashes[rank], contigs[rank], WEIGHTS3, TorchComm(torch.device("cpu")))
+    shard = distributed_filter_and_edges(STAGES[mode](), hashes[rank], contigs[rank], WEIGHTS3, TorchComm(torch.device("cpu")))
     gathered = [None] * world
     dist.all_gather_object(gathered, shard.fetch())
     ok = True
@@ -108,13 +112,14 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_two_rank_gloo_distributed_filter():
-    """world_size 2 over gloo: all-gather + three all-reduces reproduce the single-process steps 2-3"""
+@pytest.mark.parametrize("mode", ["alltoall", "allreduce"])
+def test_two_rank_gloo_distributed_filter(mode):
+    """world_size 2 over gloo: the exchanges of either formulation reproduce the single-process steps 2-3"""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 31500 + os.getpid() % 2000
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port + (7 if mode == "alltoall" else 0), q, mode)) for r in range(2)]
     for p in procs:
         p.start()
     out = [q.get(timeout=240) for _ in procs]

@@ -64,8 +64,13 @@ def torch_stream_engine(engine):
         engine.set_stream(None)
 
 
+def _stages(eng, mode):
+    return eng.a2a_stages() if mode == "alltoall" else eng.dist_stages()
+
+
+@pytest.mark.parametrize("mode", ["alltoall", "allreduce"])
 @pytest.mark.parametrize("world,n_ref,w", [(2, 1, 250), (3, 2, 100), (8, 1, 1000), (5, 3, 500)])
-def test_lockstep_device_stages(torch_stream_engine, oracle, world, n_ref, w):
+def test_lockstep_device_stages(torch_stream_engine, oracle, world, n_ref, w, mode):
     eng = torch_stream_engine
     dev = torch.device("cuda", 0)
     asms = _case(n_ref, 3_000_000)
@@ -78,7 +83,7 @@ def test_lockstep_device_stages(torch_stream_engine, oracle, world, n_ref, w):
     for a in range(len(asms)):
         cat = torch.cat([hashes[r][a] for r in range(world)]).cpu().numpy().view(np.uint64)
         np.testing.assert_array_equal(cat, full[a].out_hash)
-    shards = run_lockstep([eng.dist_stages() for _ in range(world)], hashes, contigs, weights, dev)
+    shards = run_lockstep([_stages(eng, mode) for _ in range(world)], hashes, contigs, weights, dev)
     merged = merge_shards([s.fetch() for s in shards])
     _check(merged, want)
     single = eng.filter_and_edges(full, weights)
@@ -89,20 +94,21 @@ def test_lockstep_device_stages(torch_stream_engine, oracle, world, n_ref, w):
         s.close()
 
 
-def test_lockstep_nothing_shared(torch_stream_engine, oracle):
+@pytest.mark.parametrize("mode", ["alltoall", "allreduce"])
+def test_lockstep_nothing_shared(torch_stream_engine, oracle, mode):
     eng = torch_stream_engine
     dev = torch.device("cuda", 0)
     a = synth.make_reference(400_000, n_chrom=3, seed=5)
     b = synth.make_reference(400_000, n_chrom=2, seed=6)
     asms = [(a[0], a[1]), (b[0], b[1])]
     hashes, contigs, keep = _rank_inputs(eng, asms, 4, 32, 100, dev)
-    shards = run_lockstep([eng.dist_stages() for _ in range(4)], hashes, contigs, [1.0, 1.0], dev)
+    shards = run_lockstep([_stages(eng, mode) for _ in range(4)], hashes, contigs, [1.0, 1.0], dev)
     merged = merge_shards([s.fetch() for s in shards])
     assert len(merged["vertices"]) == 0 and len(merged["edge_u"]) == 0
     assert not any(k.any() for k in merged["keep"])
 
 
-def _nccl_worker(rank, world, port, q):
+def _nccl_worker(rank, world, port, q, mode):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -120,7 +126,7 @@ def _nccl_worker(rank, world, port, q):
     asms = _case(1, 4_000_000)
     weights = [2.0, 1.0]
     hashes, contigs, keep = _rank_inputs(eng, asms, world, 32, 500, dev)
-    shard = distributed_filter_and_edges(eng.dist_stages(), hashes[rank], contigs[rank], weights, TorchComm(dev))
+    shard = distributed_filter_and_edges(_stages(eng, mode), hashes[rank], contigs[rank], weights, TorchComm(dev))
     gathered = [None] * world
     dist.all_gather_object(gathered, shard.fetch())
     ok = True
@@ -141,12 +147,13 @@ def _nccl_worker(rank, world, port, q):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-def test_two_process_nccl():
+@pytest.mark.parametrize("mode", ["alltoall", "allreduce"])
+def test_two_process_nccl(mode):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 32500 + os.getpid() % 2000
-    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port + (11 if mode == "alltoall" else 0), q, mode)) for r in range(2)]
     for p in procs:
         p.start()
     out = [q.get(timeout=600) for _ in procs]
