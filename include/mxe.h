@@ -153,8 +153,8 @@ void mxe_result_free(mxe_result_t* r);
  * GLOBALLY indexed device arrays, each rank doing 1/world of the single-GPU work:
  *
  *   all-gather(hashes)   -> mxe_dist_mark       (owned hash range: unique / found-in-all / vertex ids)
- *   all-reduce(sum, mk)  -> mxe_dist_adjacency  (own records: survivors, adjacent pairs -> succ/pred)
- *   all-reduce(sum, s/p) -> mxe_dist_edges      (support masks, edge ownership, first-source table)
+ *   all-reduce(sum, mk)  -> mxe_dist_adjacency  (own records: survivors, adjacent pairs -> successor table)
+ *   all-reduce(sum, suc) -> mxe_dist_edges      (support masks, edge ownership, first-source table)
  *   all-reduce(min, src) -> mxe_dist_finish     (local edge shard with global order keys)
  *
  * Global index space: assemblies in order (references ..., target last); inside an assembly the
@@ -170,15 +170,16 @@ int mxe_dist_mark(mxe_t* e, const void* d_keys, const uint64_t* asm_off, int n_a
 
 /* d_mk: summed over ranks.  vbase: world+1 exclusive prefix of the per-rank vertex counts.
  * loc_off[a] / loc_n[a]: this rank's slice of assembly a in the global index space;
- * d_contig[a]: its loc_n[a] uint32 record ids.  d_succ / d_pred (out): n_asm * nV uint32 each,
- * entries 1 + global vertex id of the successor / predecessor of a vertex in an assembly, zero
- * outside this rank's sightings (so the tables of all ranks combine by summation). */
+ * d_contig[a]: its loc_n[a] uint32 record ids.  d_succ (out): n_asm * nV uint32, entry [a * nV + v] =
+ * 1 + global vertex id of the successor of vertex v in assembly a, zero outside this rank's
+ * sightings (so the tables of all ranks combine by summation; the predecessor of v is x exactly
+ * when the successor of x is v, so one table serves both directions). */
 int mxe_dist_adjacency(mxe_dist_t* d, const void* d_mk, const uint64_t* vbase, const uint64_t* loc_off,
-                       const uint64_t* loc_n, const void* const* d_contig, void* d_succ, void* d_pred);
+                       const uint64_t* loc_n, const void* const* d_contig, void* d_succ);
 
-/* d_succ / d_pred: summed over ranks.  d_srcmin (out): nV uint32, for every vertex the creation
+/* d_succ: summed over ranks.  d_srcmin (out): nV uint32, for every vertex the creation
  * index of the first edge this rank owns with that vertex as source (0x7f7f7f7f = none). */
-int mxe_dist_edges(mxe_dist_t* d, const void* d_succ, const void* d_pred, void* d_srcmin, uint64_t* n_edges_local);
+int mxe_dist_edges(mxe_dist_t* d, const void* d_succ, void* d_srcmin, uint64_t* n_edges_local);
 
 /* d_srcmin: minimum over ranks.  The result is this rank's SHARD: flags of its own slices
  * (mxe_result_flags), its vertices (owned hash range, ascending), its edges ordered by
@@ -187,7 +188,7 @@ int mxe_dist_edges(mxe_dist_t* d, const void* d_succ, const void* d_pred, void* 
 int mxe_dist_finish(mxe_dist_t* d, const void* d_srcmin, const double* weights, mxe_result_t** out);
 void mxe_dist_free(mxe_dist_t* d);
 
-/* ---- the same across GPUs with all-to-all exchanges (production path) ----------------------
+/* ---- the same across GPUs with all-to-all exchanges (work and traffic ~ 1/world) -------------
  *
  * Every item travels once, to the rank that needs it (NVSwitch: uniform all-to-all bandwidth):
  *

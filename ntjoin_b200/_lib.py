@@ -68,8 +68,8 @@ def load_library():
     lib.mxe_result_free.argtypes = [vp]
     lib.mxe_result_free.restype = None
     lib.mxe_dist_mark.argtypes = [vp, vp, u64p, C.c_int, C.c_int, C.c_int, vp, pp, u64p]
-    lib.mxe_dist_adjacency.argtypes = [vp, vp, u64p, u64p, u64p, pp, vp, vp]
-    lib.mxe_dist_edges.argtypes = [vp, vp, vp, vp, u64p]
+    lib.mxe_dist_adjacency.argtypes = [vp, vp, u64p, u64p, u64p, pp, vp]
+    lib.mxe_dist_edges.argtypes = [vp, vp, vp, u64p]
     lib.mxe_dist_finish.argtypes = [vp, vp, C.POINTER(C.c_double), pp]
     lib.mxe_dist_free.argtypes = [vp]
     lib.mxe_dist_free.restype = None

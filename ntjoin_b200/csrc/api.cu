@@ -660,20 +660,20 @@ int mxe_dist_mark(mxe_t* e, const void* d_keys, const uint64_t* asm_off, int n_a
 }
 
 int mxe_dist_adjacency(mxe_dist_t* X, const void* d_mk, const uint64_t* vbase, const uint64_t* loc_off, const uint64_t* loc_n,
-                       const void* const* d_contig, void* d_succ, void* d_pred)
+                       const void* const* d_contig, void* d_succ)
 {
-    if (!X || !d_mk || !vbase || !loc_off || !loc_n || !d_contig || !d_succ || !d_pred) { set_error("null argument"); return MXE_ERR_ARG; }
+    if (!X || !d_mk || !vbase || !loc_off || !loc_n || !d_contig || !d_succ) { set_error("null argument"); return MXE_ERR_ARG; }
     MXE_CUDA(cudaSetDevice(X->eng->device));
     ArenaScope scope(X->eng);
-    return dist_adjacency_impl(X, (const uint32_t*)d_mk, vbase, loc_off, loc_n, (const uint32_t* const*)d_contig, (uint32_t*)d_succ, (uint32_t*)d_pred);
+    return dist_adjacency_impl(X, (const uint32_t*)d_mk, vbase, loc_off, loc_n, (const uint32_t* const*)d_contig, (uint32_t*)d_succ);
 }
 
-int mxe_dist_edges(mxe_dist_t* X, const void* d_succ, const void* d_pred, void* d_srcmin, uint64_t* n_edges_local)
+int mxe_dist_edges(mxe_dist_t* X, const void* d_succ, void* d_srcmin, uint64_t* n_edges_local)
 {
-    if (!X || !d_succ || !d_pred || !d_srcmin || !n_edges_local) { set_error("null argument"); return MXE_ERR_ARG; }
+    if (!X || !d_succ || !d_srcmin || !n_edges_local) { set_error("null argument"); return MXE_ERR_ARG; }
     MXE_CUDA(cudaSetDevice(X->eng->device));
     ArenaScope scope(X->eng);
-    return dist_edges_impl(X, (const uint32_t*)d_succ, (const uint32_t*)d_pred, (uint32_t*)d_srcmin, n_edges_local);
+    return dist_edges_impl(X, (const uint32_t*)d_succ, (uint32_t*)d_srcmin, n_edges_local);
 }
 
 int mxe_dist_finish(mxe_dist_t* X, const void* d_srcmin, const double* weights, mxe_result_t** out)

@@ -132,7 +132,7 @@ int filter_and_edges_impl(mxe_engine* e, const uint64_t* const* d_hash, const ui
 int dist_mark_impl(mxe_engine* e, const uint64_t* d_keys, const uint64_t* asm_off, int n_asm, int rank, int world,
                    uint32_t* d_mk, mxe_dist* X, uint64_t* nv_local);
 int dist_adjacency_impl(mxe_dist* X, const uint32_t* d_mk, const uint64_t* vbase, const uint64_t* loc_off, const uint64_t* loc_n,
-                        const uint32_t* const* d_contig, uint32_t* d_succ, uint32_t* d_pred);
-int dist_edges_impl(mxe_dist* X, const uint32_t* d_succ, const uint32_t* d_pred, uint32_t* d_srcmin, uint64_t* n_edges_local);
+                        const uint32_t* const* d_contig, uint32_t* d_succ);
+int dist_edges_impl(mxe_dist* X, const uint32_t* d_succ, uint32_t* d_srcmin, uint64_t* n_edges_local);
 int dist_finish_impl(mxe_dist* X, const uint32_t* d_srcmin, const double* weights, mxe_result* out);
 }

@@ -149,24 +149,23 @@ __global__ void __launch_bounds__(256) pair_flag_kernel(const uint32_t* __restri
 }
 
 // Edge de-duplication without sorting.  Every surviving hash occurs exactly once per assembly, so a vertex has at
-// most one successor and one predecessor per assembly.  The sightings (v -> x) of the undirected edge {v,x} are found
-// by looking v up in every assembly's succ/pred table; the sighting in the first supporting assembly owns the edge
+// most one successor per assembly.  Assembly b supports the undirected edge {v,x} iff succ_b[v] == x or succ_b[x] == v
+// (one table per assembly: the predecessor of v is x exactly when the successor of x is v); the sighting in the first supporting assembly owns the edge
 // (that is the reference's first-seen orientation, bin/ntjoin_utils.py:101-108), so ordered compaction of the owning
 // sightings yields the distinct edges already in first-seen order.
 __global__ void __launch_bounds__(256) adjacency_kernel(const uint32_t* __restrict__ cvid, const uint32_t* __restrict__ cidx,
                                                          const uint32_t* __restrict__ eflag, uint64_t n_keep, AsmOffsets A, uint64_t nV,
-                                                         uint32_t* __restrict__ succ, uint32_t* __restrict__ pred)
+                                                         uint32_t* __restrict__ succ)
 {
     uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_keep || !eflag[j]) return;
     const uint64_t a = (uint64_t)asm_of(A, cidx[j]);
     succ[a * nV + cvid[j]] = cvid[j + 1];
-    pred[a * nV + cvid[j + 1]] = cvid[j];
 }
 
 __global__ void __launch_bounds__(256) edge_owner_kernel(const uint32_t* __restrict__ cvid, const uint32_t* __restrict__ cidx,
                                                           const uint32_t* __restrict__ eflag, uint64_t n_keep, AsmOffsets A, uint64_t nV,
-                                                          const uint32_t* __restrict__ succ, const uint32_t* __restrict__ pred,
+                                                          const uint32_t* __restrict__ succ,
                                                           uint32_t* __restrict__ own, uint32_t* __restrict__ mask_out)
 {
     uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -177,7 +176,7 @@ __global__ void __launch_bounds__(256) edge_owner_kernel(const uint32_t* __restr
         const uint32_t v = cvid[j], x = cvid[j + 1];
         uint32_t mask = 0;
         for (int b = 0; b < A.n; b++)
-            if (succ[(uint64_t)b * nV + v] == x || pred[(uint64_t)b * nV + v] == x) mask |= 1u << b;
+            if (succ[(uint64_t)b * nV + v] == x || succ[(uint64_t)b * nV + x] == v) mask |= 1u << b;
         is_owner = (__ffs(mask) - 1) == a;
         mask_out[j] = mask;
     }
@@ -303,16 +302,15 @@ int filter_and_edges_impl(mxe_engine* e, const uint64_t* const* d_hash, const ui
     MXE_CUDA(cudaStreamSynchronize(st));
     if (n_pairs == 0) { R->d_vertices = vertices.detach(); return MXE_OK; }
 
-    DBuf<uint32_t> succ, pred, own, emask_j, srcmin;
+    DBuf<uint32_t> succ, own, emask_j, srcmin;
     DBuf<uint64_t> uprefix;
-    MXE_TRY(succ.alloc((uint64_t)n_asm * nV, st)); MXE_TRY(pred.alloc((uint64_t)n_asm * nV, st));
+    MXE_TRY(succ.alloc((uint64_t)n_asm * nV, st));
     MXE_TRY(own.alloc(n_keep, st)); MXE_TRY(emask_j.alloc(n_keep, st)); MXE_TRY(uprefix.alloc(n_keep + 1, st));
     MXE_TRY(srcmin.alloc(nV, st));
     MXE_CUDA(cudaMemsetAsync(succ.p, 0xFF, (uint64_t)n_asm * nV * sizeof(uint32_t), st));
-    MXE_CUDA(cudaMemsetAsync(pred.p, 0xFF, (uint64_t)n_asm * nV * sizeof(uint32_t), st));
     MXE_CUDA(cudaMemsetAsync(srcmin.p, 0xFF, nV * sizeof(uint32_t), st));
-    MXE_LAUNCH(e, adjacency_kernel, gridf(n_keep), 256, 0, cvid.p, cidx.p, eflag.p, n_keep, A, nV, succ.p, pred.p);
-    MXE_LAUNCH(e, edge_owner_kernel, gridf(n_keep), 256, 0, cvid.p, cidx.p, eflag.p, n_keep, A, nV, succ.p, pred.p, own.p, emask_j.p);
+    MXE_LAUNCH(e, adjacency_kernel, gridf(n_keep), 256, 0, cvid.p, cidx.p, eflag.p, n_keep, A, nV, succ.p);
+    MXE_LAUNCH(e, edge_owner_kernel, gridf(n_keep), 256, 0, cvid.p, cidx.p, eflag.p, n_keep, A, nV, succ.p, own.p, emask_j.p);
     MXE_TRY(exclusive_scan_u32_u64(e, own.p, uprefix.p, n_keep));
     uint64_t nE = 0;
     MXE_CUDA(cudaMemcpyAsync(&nE, uprefix.p + n_keep, 8, cudaMemcpyDeviceToHost, st));
@@ -347,8 +345,8 @@ int filter_and_edges_impl(mxe_engine* e, const uint64_t* const* d_hash, const ui
 //                         so per-rank vertex lists concatenate to the ascending single-GPU order)
 //   stage 1 mark        : uniqueness / found-in-all / local vertex ids for the owned hash range -> mk[N]
 //                         (zero outside the owned entries)                        -> all-reduce(sum) mk
-//   stage 2 adjacency   : this rank's survivors (its own records) -> succ/pred tables indexed by
-//                         GLOBAL vertex id (zero outside own sightings)           -> all-reduce(sum)
+//   stage 2 adjacency   : this rank's survivors (its own records) -> successor table indexed by
+//                         (assembly, GLOBAL vertex id), zero outside own sightings -> all-reduce(sum)
 //   stage 3 edges       : support mask + ownership of the local sightings, srcmin -> all-reduce(min)
 //   stage 4 finish      : local edge shard ordered by (first-creation index of the source, creation
 //                         index); merging the shards by that key reproduces formatted_edges order.
@@ -429,21 +427,20 @@ __global__ void __launch_bounds__(256) local_pair_flag_kernel(const uint32_t* __
     eflag[j] = f;
 }
 
-// succ/pred entries are 1 + vertex id (0 = none) so that the tables of all ranks combine by summation
+// successor entries are 1 + vertex id (0 = none) so that the tables of all ranks combine by summation
 __global__ void __launch_bounds__(256) dist_adjacency_kernel(const uint32_t* __restrict__ cvid, const uint32_t* __restrict__ cidx,
                                                               const uint32_t* __restrict__ eflag, uint64_t n_keep, AsmOffsets A, uint64_t nV,
-                                                              uint32_t* __restrict__ succ, uint32_t* __restrict__ pred)
+                                                              uint32_t* __restrict__ succ)
 {
     uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_keep || !eflag[j]) return;
     const uint64_t a = (uint64_t)asm_of(A, cidx[j]);
     succ[a * nV + cvid[j]] = cvid[j + 1] + 1u;
-    pred[a * nV + cvid[j + 1]] = cvid[j] + 1u;
 }
 
 __global__ void __launch_bounds__(256) dist_edge_owner_kernel(const uint32_t* __restrict__ cvid, const uint32_t* __restrict__ cidx,
                                                                const uint32_t* __restrict__ eflag, uint64_t n_keep, AsmOffsets A, uint64_t nV,
-                                                               const uint32_t* __restrict__ succ, const uint32_t* __restrict__ pred,
+                                                               const uint32_t* __restrict__ succ,
                                                                uint32_t* __restrict__ own, uint32_t* __restrict__ mask_out)
 {
     uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -451,10 +448,10 @@ __global__ void __launch_bounds__(256) dist_edge_owner_kernel(const uint32_t* __
     uint32_t is_owner = 0;
     if (eflag[j]) {
         const int a = asm_of(A, cidx[j]);
-        const uint32_t v = cvid[j], x1 = cvid[j + 1] + 1u;
+        const uint32_t v = cvid[j], x = cvid[j + 1];
         uint32_t mask = 0;
         for (int b = 0; b < A.n; b++)
-            if (succ[(uint64_t)b * nV + v] == x1 || pred[(uint64_t)b * nV + v] == x1) mask |= 1u << b;
+            if (succ[(uint64_t)b * nV + v] == x + 1u || succ[(uint64_t)b * nV + x] == v + 1u) mask |= 1u << b;
         is_owner = (__ffs(mask) - 1) == a;
         mask_out[j] = mask;
     }
@@ -566,7 +563,7 @@ int dist_mark_impl(mxe_engine* e, const uint64_t* d_keys, const uint64_t* asm_of
 }
 
 int dist_adjacency_impl(mxe_dist* X, const uint32_t* d_mk, const uint64_t* vbase, const uint64_t* loc_off, const uint64_t* loc_n,
-                        const uint32_t* const* d_contig, uint32_t* d_succ, uint32_t* d_pred)
+                        const uint32_t* const* d_contig, uint32_t* d_succ)
 {
     mxe_engine* e = X->eng;
     cudaStream_t st = e->stream;
@@ -587,7 +584,6 @@ int dist_adjacency_impl(mxe_dist* X, const uint32_t* d_mk, const uint64_t* vbase
     X->nV = nV;
     if (nV >= 0x7FFFFFFFULL) { set_error("too many vertices"); return MXE_ERR_ARG; }
     MXE_CUDA(cudaMemsetAsync(d_succ, 0, (size_t)n_asm * (nV ? nV : 1) * sizeof(uint32_t), st));
-    MXE_CUDA(cudaMemsetAsync(d_pred, 0, (size_t)n_asm * (nV ? nV : 1) * sizeof(uint32_t), st));
     MXE_TRY(X->alloc(&X->luniq, L)); MXE_TRY(X->alloc(&X->lkeep, L));
     X->n_keep = 0;
     if (L == 0) return MXE_OK;
@@ -608,12 +604,12 @@ int dist_adjacency_impl(mxe_dist* X, const uint32_t* d_mk, const uint64_t* vbase
     if (n_keep == 0) return MXE_OK;
     MXE_LAUNCH(e, local_compact_kernel, gridf(L), 256, 0, d_mk, X->d_keys, S, L, kflag.p, kprefix.p, X->D, X->cvid, X->cidx, X->cloc);
     MXE_LAUNCH(e, local_pair_flag_kernel, gridf(n_keep), 256, 0, X->cloc, n_keep, S, lcontig.p, X->eflag);
-    MXE_LAUNCH(e, dist_adjacency_kernel, gridf(n_keep), 256, 0, X->cvid, X->cidx, X->eflag, n_keep, X->A, nV, d_succ, d_pred);
+    MXE_LAUNCH(e, dist_adjacency_kernel, gridf(n_keep), 256, 0, X->cvid, X->cidx, X->eflag, n_keep, X->A, nV, d_succ);
     MXE_CUDA(cudaGetLastError());
     return MXE_OK;
 }
 
-int dist_edges_impl(mxe_dist* X, const uint32_t* d_succ, const uint32_t* d_pred, uint32_t* d_srcmin, uint64_t* n_edges_local)
+int dist_edges_impl(mxe_dist* X, const uint32_t* d_succ, uint32_t* d_srcmin, uint64_t* n_edges_local)
 {
     mxe_engine* e = X->eng;
     cudaStream_t st = e->stream;
@@ -627,7 +623,7 @@ int dist_edges_impl(mxe_dist* X, const uint32_t* d_succ, const uint32_t* d_pred,
     DBuf<uint32_t> own, emask_j;
     DBuf<uint64_t> uprefix;
     MXE_TRY(own.alloc(n_keep, st)); MXE_TRY(emask_j.alloc(n_keep, st)); MXE_TRY(uprefix.alloc(n_keep + 1, st));
-    MXE_LAUNCH(e, dist_edge_owner_kernel, gridf(n_keep), 256, 0, X->cvid, X->cidx, X->eflag, n_keep, X->A, nV, d_succ, d_pred, own.p, emask_j.p);
+    MXE_LAUNCH(e, dist_edge_owner_kernel, gridf(n_keep), 256, 0, X->cvid, X->cidx, X->eflag, n_keep, X->A, nV, d_succ, own.p, emask_j.p);
     MXE_TRY(exclusive_scan_u32_u64(e, own.p, uprefix.p, n_keep));
     uint64_t nE = 0;
     MXE_CUDA(cudaMemcpyAsync(&nE, uprefix.p + n_keep, 8, cudaMemcpyDeviceToHost, st));
@@ -672,8 +668,9 @@ int dist_finish_impl(mxe_dist* X, const uint32_t* d_srcmin, const double* weight
 
 
 // ====================================================================================================
-// Multi-GPU steps 2-3, all-to-all formulation (the production path; the all-reduce formulation above is
-// kept as a cross-check).  Every exchange moves each item exactly once, to the rank that needs it:
+// Multi-GPU steps 2-3, all-to-all formulation: per-rank work and traffic shrink with 1/world (the all-reduce
+// formulation above keeps O(N) arrays on every rank and is the faster one while a step is latency-bound, i.e. at
+// BASELINE configs[2] scale on 2-8 GPUs).  Every exchange moves each item exactly once, to the rank that needs it:
 //
 //   A partition   (source)   own minimizers grouped by HASH OWNER            -> all-to-all(keys, 8 B each)
 //   B mark        (owner)    unique / found-in-all / vertex ids of the range  -> all-to-all(marks, 4 B, same order back)

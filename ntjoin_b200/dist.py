@@ -11,9 +11,9 @@ every rank doing 1/world of the work on globally indexed arrays:
 
     all-gather(hashes)      FULL per-rank lists (the multiset, not the locally-unique sets)
     stage mark              rank r owns the hash range r: unique / found-in-all / vertex ids
-    all-reduce(sum, mk)     N x u32 marks, zero outside the owned entries
-    stage adjacency         own records: ordered survivors, adjacent pairs -> succ/pred tables
-    all-reduce(sum, s/p)    n_asm x nV x u32 x 2, zero outside own sightings
+    all-reduce(sum, mk)     N x u32 marks, zero outside the owned entries (+ the per-rank vertex counts)
+    stage adjacency         own records: ordered survivors, adjacent pairs -> successor table
+    all-reduce(sum, succ)   n_asm x nV x u32, zero outside own sightings
     stage edges             support masks + ownership of the local sightings, first-source table
     all-reduce(min, srcmin) nV x u32
     stage finish            local edge shard with global order keys
@@ -119,29 +119,30 @@ def _filter_steps(stages, hashes, contigs, weights, rank, world, device):
     counts = yield ("counts", [int(h.numel()) for h in hashes])
     lay = Layout(counts)
     keys = yield ("keys", (hashes, lay))                         # int64[N] in the global layout
-    mk = torch.empty(max(1, lay.N), dtype=torch.int32, device=device)
+    mk = torch.empty(lay.N + world, dtype=torch.int32, device=device)   # marks + one slot per rank for its vertex count
     handle, nv_local = stages.mark(keys, lay.asm_off, rank, world, mk)
     try:
-        nvs = yield ("counts", [int(nv_local)])
-        vbase = np.concatenate([[0], np.cumsum(nvs[:, 0])]).astype(np.int64)
+        mk[lay.N:].zero_()
+        mk[lay.N + rank] = int(nv_local)
+        yield ("sum", mk)                                          # the vertex counts ride along with the marks
+        nvs = mk[lay.N:].cpu().numpy().astype(np.int64)
+        vbase = np.concatenate([[0], np.cumsum(nvs)]).astype(np.int64)
         n_v = int(vbase[-1])
-        yield ("sum", mk)
-        table = torch.empty(2 * n_asm * max(1, n_v), dtype=torch.int32, device=device)
-        succ, pred = table[:n_asm * max(1, n_v)], table[n_asm * max(1, n_v):]
-        stages.adjacency(handle, mk, vbase, lay.goff[rank], lay.counts[rank], contigs, succ, pred)
-        yield ("sum", table)
+        succ = torch.empty(n_asm * max(1, n_v), dtype=torch.int32, device=device)
+        stages.adjacency(handle, mk, vbase, lay.goff[rank], lay.counts[rank], contigs, succ)
+        yield ("sum", succ)
         srcmin = torch.empty(max(1, n_v), dtype=torch.int32, device=device)
-        n_e_local = stages.edges(handle, succ, pred, srcmin)
+        n_e_local = stages.edges(handle, succ, srcmin)
         yield ("min", srcmin)
     except BaseException:
         stages.abort(handle)
         raise
     shard = stages.finish(handle, srcmin, weights)
-    return DistShard(shard, lay, rank, vbase, int(n_e_local), keep=(keys, mk, table, srcmin))
+    return DistShard(shard, lay, rank, vbase, int(n_e_local), keep=(keys, mk, succ, srcmin))
 
 
 def _a2a_steps(stages, hashes, contigs, weights, rank, world, device):
-    """All-to-all formulation (production).  Same inputs and result as `_filter_steps`; every item travels once:
+    """All-to-all formulation (traffic and work shrink with 1/world).  Same inputs and result as `_filter_steps`; every item travels once:
     keys to their hash owner, marks back, sightings to the owners of their two vertices."""
     import torch
     n_asm = len(hashes)
@@ -295,8 +296,8 @@ class TorchComm:
 
 def distributed_filter_and_edges(stages, hashes, contigs, weights, comm):
     """Steps 2-3 across the ranks of `comm` (a TorchComm).  Returns this rank's DistShard.
-    `stages` selects the formulation: Engine.a2a_stages() (all-to-all, production) or Engine.dist_stages()
-    (all-reduce cross-check).  The engine must run on torch's current stream (Engine.set_stream)."""
+    `stages` selects the formulation: Engine.dist_stages() (all-reduce; default, faster while a step is latency-bound)
+    or Engine.a2a_stages() (all-to-all; per-rank work and traffic shrink with 1/world).  The engine must run on torch's current stream (Engine.set_stream)."""
     steps = _a2a_steps if hasattr(stages, "partition") else _filter_steps
     gen = steps(stages, hashes, contigs, weights, comm.rank, comm.world, comm.device)
     try:

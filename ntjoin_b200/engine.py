@@ -306,11 +306,11 @@ class Engine:
         return FilterResult(self, out, n)
 
     def dist_stages(self):
-        """Engine-backed stages of the multi-GPU steps 2-3, all-reduce formulation (ntjoin_b200.dist, cross-check)."""
+        """Engine-backed stages of the multi-GPU steps 2-3, all-reduce formulation (ntjoin_b200.dist; default)."""
         return EngineDistStages(self)
 
     def a2a_stages(self):
-        """Engine-backed stages of the multi-GPU steps 2-3, all-to-all formulation (ntjoin_b200.dist, production)."""
+        """Engine-backed stages of the multi-GPU steps 2-3, all-to-all formulation (ntjoin_b200.dist; work ~ 1/world)."""
         return EngineA2AStages(self)
 
     def timing(self, name):
@@ -358,16 +358,15 @@ class EngineDistStages:
                                                  int(rank), int(world), C.c_void_p(mk.data_ptr()), C.byref(h), C.byref(nv)))
         return h, nv.value
 
-    def adjacency(self, handle, mk, vbase, loc_off, loc_n, contigs, succ, pred):
+    def adjacency(self, handle, mk, vbase, loc_off, loc_n, contigs, succ):
         n = len(contigs)
         cp = (C.c_void_p * n)(*[c.data_ptr() if c.numel() else None for c in contigs])
         check(self._lib, self._lib.mxe_dist_adjacency(handle, C.c_void_p(mk.data_ptr()), _u64arr(vbase), _u64arr(loc_off), _u64arr(loc_n),
-                                                      cp, C.c_void_p(succ.data_ptr()), C.c_void_p(pred.data_ptr())))
+                                                      cp, C.c_void_p(succ.data_ptr())))
 
-    def edges(self, handle, succ, pred, srcmin):
+    def edges(self, handle, succ, srcmin):
         ne = C.c_uint64()
-        check(self._lib, self._lib.mxe_dist_edges(handle, C.c_void_p(succ.data_ptr()), C.c_void_p(pred.data_ptr()),
-                                                  C.c_void_p(srcmin.data_ptr()), C.byref(ne)))
+        check(self._lib, self._lib.mxe_dist_edges(handle, C.c_void_p(succ.data_ptr()), C.c_void_p(srcmin.data_ptr()), C.byref(ne)))
         return ne.value
 
     def finish(self, handle, srcmin, weights):

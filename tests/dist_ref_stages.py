@@ -61,11 +61,10 @@ class NumpyDistStages:
             st.vertices = hu[keep_h]
         return st, len(st.vertices)
 
-    def adjacency(self, st, mk, vbase, loc_off, loc_n, contigs, succ, pred):
+    def adjacency(self, st, mk, vbase, loc_off, loc_n, contigs, succ):
         m = _u32(mk)
-        s, p = _u32(succ), _u32(pred)
+        s = _u32(succ)
         s[:] = 0
-        p[:] = 0
         vbase = np.asarray(vbase, dtype=np.int64)
         st.nV = int(vbase[-1])
         st.luniq, st.lkeep, sight = [], [], []
@@ -87,17 +86,16 @@ class NumpyDistStages:
             st.eflag[:-1] = (st.casm[:-1] == st.casm[1:]) & (ctg[:-1] == ctg[1:])
         j = np.nonzero(st.eflag)[0]
         s[st.casm[j] * st.nV + st.cvid[j]] = (st.cvid[j + 1] + 1).astype(np.uint32)
-        p[st.casm[j] * st.nV + st.cvid[j + 1]] = (st.cvid[j] + 1).astype(np.uint32)
 
-    def edges(self, st, succ, pred, srcmin):
-        s, p = _u32(succ), _u32(pred)
+    def edges(self, st, succ, srcmin):
+        s = _u32(succ)
         sm = _u32(srcmin)
         sm[:] = 0x7F7F7F7F
         j = np.nonzero(st.eflag)[0]
-        v, x1 = st.cvid[j], (st.cvid[j + 1] + 1).astype(np.uint32)
+        v, x = st.cvid[j], st.cvid[j + 1]
         mask = np.zeros(len(j), dtype=np.uint32)
         for b in range(st.n_asm):
-            hit = (s[b * st.nV + v] == x1) | (p[b * st.nV + v] == x1)
+            hit = (s[b * st.nV + v] == (x + 1).astype(np.uint32)) | (s[b * st.nV + x] == (v + 1).astype(np.uint32))
             mask |= hit.astype(np.uint32) << np.uint32(b)
         first = np.array([(int(mm) & -int(mm)).bit_length() - 1 for mm in mask], dtype=np.int64)
         own = first == st.casm[j]
