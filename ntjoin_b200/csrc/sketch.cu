@@ -241,6 +241,10 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
     uint32_t* s_ctg = cctg.p;
     DBuf<uint64_t> cpos2, cord2, pprefix;
     DBuf<uint32_t> cctg2, klo, khi, pflag;
+    DBuf<uint64_t> PF, PR;                 // position-specific hash tables (k/4 groups x 256), shared by the exact-hash kernels
+    const int G4 = k / 4;
+    const bool pos_tables = G4 >= 1 && G4 <= HASHPOS_MAX_GROUPS;
+    const size_t hsm = (size_t)2 * G4 * 256 * sizeof(uint64_t);
     {
         Span sp(e, "eval");
         if (n_cand) {
@@ -260,13 +264,10 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
                 s_pos = cpos2.p; s_ord = cord2.p; s_ctg = cctg2.p;
             }
             if (n_sel) {
-                const int G = k / 4;
-                if (G >= 1 && G <= HASHPOS_MAX_GROUPS) {
+                if (pos_tables) {
                     // position-specific tables (built once per sketch) -> no rotations per candidate
-                    DBuf<uint64_t> PF, PR;
-                    MXE_TRY(PF.alloc((size_t)G * 256, st)); MXE_TRY(PR.alloc((size_t)G * 256, st));
-                    MXE_LAUNCH(e, hash_pos_tables_kernel, G, 256, 0, Tb, k, PF.p, PR.p);
-                    const size_t hsm = (size_t)2 * G * 256 * sizeof(uint64_t);
+                    MXE_TRY(PF.alloc((size_t)G4 * 256, st)); MXE_TRY(PR.alloc((size_t)G4 * 256, st));
+                    MXE_LAUNCH(e, hash_pos_tables_kernel, G4, 256, 0, Tb, k, PF.p, PR.p);
                     MXE_CUDA(cudaFuncSetAttribute(cand_hash_pos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
                     const unsigned grid = (unsigned)std::min<uint64_t>(grid_for(n_sel, 256), (uint64_t)e->sm_count * 5);
                     MXE_LAUNCH(e, cand_hash_pos_kernel, grid, 256, hsm, s_pos, n_sel, pk.p, P, Tb, PF.p, PR.p, ch0.p);
@@ -325,6 +326,7 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
         DBuf<uint64_t> mpos;
         MXE_TRY(mpos.alloc(n_mx, st));
         MXE_TRY(bitmap_extract(e, M.p, nW, mprefix.p, mpos.p));
+        // (the position-specific tables of the candidate stage do not pay here: 6 M items cannot amortise staging 32 KB per CTA)
         MXE_LAUNCH(e, final_eval_kernel, grid_for(n_mx, 256), 256, 0, mpos.p, n_mx, pk.p, d_offsets.p, n_contigs, P, Tb,
                    S->d_out_hash, S->d_min_hash, S->d_pos, S->d_contig, S->d_forward);
     }

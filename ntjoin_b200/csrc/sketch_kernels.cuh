@@ -685,6 +685,53 @@ __global__ void __launch_bounds__(256) hash_pos_tables_kernel(SketchTables Tb, i
     }
 }
 
+// exact base hashes of the k-mer at p from the position-specific tables staged in shared memory (pf, pr: G x 256)
+__device__ __forceinline__ void kmer_hash64_pos(const uint32_t* __restrict__ pk, uint64_t p, int k, const uint64_t* pf, const uint64_t* pr,
+                                                const uint64_t* s1, uint64_t& fwd, uint64_t& rev)
+{
+    const uint64_t q = p >> 4;
+    const uint32_t sh = ((uint32_t)p & 15u) * 2u;
+    uint64_t f = 0, r = 0;
+    uint32_t cur = pk_to_natural(__ldg(pk + q));
+    int g = 0, left = k;
+    for (int m = 0; left > 0; m++) {
+        const uint32_t nxt = pk_to_natural(__ldg(pk + q + m + 1));
+        uint32_t N = __funnelshift_r(cur, nxt, sh);          // 16 bases starting at p + 16 m, natural order
+        cur = nxt;
+        int nb = left < 16 ? left : 16;
+        left -= nb;
+        for (; nb >= 4; nb -= 4, g++) {
+            const uint32_t v = N & 0xFFu;
+            N >>= 8;
+            f ^= pf[g * 256 + v];
+            r ^= pr[g * 256 + v];
+        }
+        for (; nb > 0; nb--) {                               // k % 4 trailing bases (last word only)
+            const uint32_t c = N & 3u;
+            N >>= 2;
+            f = srol1(f) ^ s1[c];
+            r = sror1(r) ^ s1[4 + c];
+        }
+    }
+    fwd = f;
+    rev = r;
+}
+
+// stage the position-specific tables (and the single-base terms for k % 4 trailing bases) in shared memory
+__device__ __forceinline__ void stage_pos_tables(const SketchTables& Tb, int k, const uint64_t* __restrict__ PF, const uint64_t* __restrict__ PR,
+                                                 uint64_t* pf, uint64_t* pr, uint64_t* s1)
+{
+    const int G = k / 4;
+    for (int i = threadIdx.x; i < G * 256; i += blockDim.x) { pf[i] = PF[i]; pr[i] = PR[i]; }
+    if (threadIdx.x < 4) {
+        s1[threadIdx.x] = Tb.seed[threadIdx.x];
+        uint64_t sc = Tb.seed[threadIdx.x ^ 2];
+        for (int q = 0; q < k - 1; q++) sc = srol1(sc);
+        s1[4 + threadIdx.x] = sc;
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(256) cand_hash_pos_kernel(const uint64_t* __restrict__ cpos, uint64_t n_cand, const uint32_t* __restrict__ pk,
                                                              SketchParams P, SketchTables Tb, const uint64_t* __restrict__ PF,
                                                              const uint64_t* __restrict__ PR, uint64_t* __restrict__ h0)
@@ -694,40 +741,10 @@ __global__ void __launch_bounds__(256) cand_hash_pos_kernel(const uint64_t* __re
     uint64_t* pf = hp;
     uint64_t* pr = hp + G * 256;
     __shared__ uint64_t s1[8];
-    for (int i = threadIdx.x; i < G * 256; i += blockDim.x) { pf[i] = PF[i]; pr[i] = PR[i]; }
-    if (threadIdx.x < 4) {
-        s1[threadIdx.x] = Tb.seed[threadIdx.x];
-        uint64_t sc = Tb.seed[threadIdx.x ^ 2];
-        for (int q = 0; q < P.k - 1; q++) sc = srol1(sc);
-        s1[4 + threadIdx.x] = sc;
-    }
-    __syncthreads();
+    stage_pos_tables(Tb, P.k, PF, PR, pf, pr, s1);
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cand; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t p = cpos[i];
-        const uint64_t q = p >> 4;
-        const uint32_t sh = ((uint32_t)p & 15u) * 2u;
-        uint64_t f = 0, r = 0;
-        uint32_t cur = pk_to_natural(__ldg(pk + q));
-        int g = 0, left = P.k;
-        for (int m = 0; left > 0; m++) {
-            const uint32_t nxt = pk_to_natural(__ldg(pk + q + m + 1));
-            uint32_t N = __funnelshift_r(cur, nxt, sh);          // 16 bases starting at p + 16 m, natural order
-            cur = nxt;
-            int nb = left < 16 ? left : 16;
-            left -= nb;
-            for (; nb >= 4; nb -= 4, g++) {
-                const uint32_t v = N & 0xFFu;
-                N >>= 8;
-                f ^= pf[g * 256 + v];
-                r ^= pr[g * 256 + v];
-            }
-            for (; nb > 0; nb--) {                               // k % 4 trailing bases (last word only)
-                const uint32_t c = N & 3u;
-                N >>= 2;
-                f = srol1(f) ^ s1[c];
-                r = sror1(r) ^ s1[4 + c];
-            }
-        }
+        uint64_t f, r;
+        kmer_hash64_pos(pk, cpos[i], P.k, pf, pr, s1, f, r);
         h0[i] = canon(f, r, P.canon_min);
     }
 }
@@ -1021,6 +1038,20 @@ __global__ void __launch_bounds__(256) gap_kernel(const Gap* __restrict__ gaps, 
 }
 
 // ---------------------------------------------------------------- final_eval: one thread per minimizer
+__device__ __forceinline__ void emit_minimizer(uint64_t i, uint64_t p, uint64_t f, uint64_t r, const uint64_t* __restrict__ offsets,
+                                               uint32_t n_contigs, const SketchParams& P, uint64_t* __restrict__ out_hash,
+                                               uint64_t* __restrict__ min_hash, uint32_t* __restrict__ pos, uint32_t* __restrict__ contig,
+                                               uint8_t* __restrict__ forward)
+{
+    const uint64_t h0 = canon(f, r, P.canon_min);
+    const uint32_t c = contig_of(offsets, n_contigs, p);
+    out_hash[i] = mix_out_hash(h0, P.k);
+    min_hash[i] = h0;
+    pos[i] = (uint32_t)(p - offsets[c]);
+    contig[i] = c;
+    forward[i] = f <= r;
+}
+
 __global__ void __launch_bounds__(256) final_eval_kernel(const uint64_t* __restrict__ mpos, uint64_t n_mx,
                                                           const uint32_t* __restrict__ pk,
                                                           const uint64_t* __restrict__ offsets, uint32_t n_contigs,
@@ -1036,13 +1067,7 @@ __global__ void __launch_bounds__(256) final_eval_kernel(const uint64_t* __restr
     const uint64_t p = mpos[i];
     uint64_t f, r;
     kmer_hash64_tab(pk, p, P.k, &H, f, r);
-    const uint64_t h0 = canon(f, r, P.canon_min);
-    const uint32_t c = contig_of(offsets, n_contigs, p);
-    out_hash[i] = mix_out_hash(h0, P.k);
-    min_hash[i] = h0;
-    pos[i] = (uint32_t)(p - offsets[c]);
-    contig[i] = c;
-    forward[i] = f <= r;
+    emit_minimizer(i, p, f, r, offsets, n_contigs, P, out_hash, min_hash, pos, contig, forward);
 }
 
 }  // namespace mxe
