@@ -32,8 +32,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-K, W = 32, 1000
-WEIGHTS = [2.0, 1.0]          # reference_weights='2', target_weight=1 (tests/ntjoin_test.py:22)
+K, W = 32, 1000               # overridden per run from the workload / -k / -w
+WEIGHTS = [2.0, 1.0]          # reference_weights='2', target_weight=1 (tests/ntjoin_test.py:22); one 2.0 per reference
 GRCH38_MBP = [248, 242, 198, 190, 182, 171, 159, 145, 138, 134, 135, 133, 114, 107, 102, 90, 83, 80, 59, 64, 47, 51, 156, 57]
 
 
@@ -43,8 +43,14 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c2", "c3"],
-                    help="c3: BASELINE configs[2] 3 Gbp target + 3 Gbp reference (default); c2: configs[1] 100 Mbp + 100 Mbp")
+    ap.add_argument("--workload", default="c3", choices=["c2", "c3", "c4"],
+                    help="c3: BASELINE configs[2] 3 Gbp target + 3 Gbp reference (default); c2: configs[1] 100 Mbp + 100 Mbp; "
+                         "c4: configs[3] 3 Gbp target + 3 references, w=500 (multi-way intersection)")
+    ap.add_argument("-k", type=int, default=0, help="k-mer size (default: the workload's, 32)")
+    ap.add_argument("-w", type=int, default=0, help="window size (default: the workload's)")
+    ap.add_argument("--sweep", action="store_true",
+                    help="configs[4]: k in {24,32,40} x w in {250,500,1000,5000} on the workload's data, device-resident timing and "
+                         "roofline fraction per point (one JSON line with a 'sweep' list; single GPU)")
     ap.add_argument("--bases", type=float, default=0, help="override bases per assembly")
     ap.add_argument("--with-n", action="store_true", help="put 0.5%% of the reference in N runs (default: N-free headline variant)")
     ap.add_argument("--cpu-sample", type=float, default=0, help="bases per assembly for the CPU baseline sample (0 = auto)")
@@ -53,16 +59,21 @@ def parse_args():
 
 
 def workload_spec(args):
+    n_refs, w = 1, 1000
     if args.workload == "c2":
         g, nchr, prop, lo, hi, dup = 100e6, 10, None, 20_000, 2_000_000, 0.0
         name = "configs[1]: synthetic 100 Mbp target + 100 Mbp reference"
+    elif args.workload == "c4":
+        g, nchr, prop, lo, hi, dup = 3e9, 24, GRCH38_MBP, 50_000, 20_000_000, 0.02
+        n_refs, w = 3, 500
+        name = "configs[3]: synthetic 3 Gbp target + 3 references (multi-way intersection)"
     else:
         g, nchr, prop, lo, hi, dup = 3e9, 24, GRCH38_MBP, 50_000, 20_000_000, 0.02
         name = "configs[2]: synthetic 3 Gbp human-scale target + 1 reference"
     if args.bases:
         g = args.bases
         name += f" (scaled to {g:.3g} bp per assembly)"
-    return dict(G=int(g), n_chrom=nchr, prop=prop, lo=lo, hi=hi, dup=dup, name=name)
+    return dict(G=int(g), n_chrom=nchr, prop=prop, lo=lo, hi=hi, dup=dup, name=name, n_refs=n_refs, w=w)
 
 
 # ------------------------------------------------------------------------------------ data (GPU)
@@ -127,7 +138,16 @@ def gen_assemblies_gpu(spec, with_n, device):
     sub = lut[torch.randint(0, 4, (idx.numel(),), dtype=torch.uint8, device=device, generator=g).long()]
     keep = tgt[idx] != ord("N")
     tgt[idx[keep]] = sub[keep]
-    return [(ref, roffs), (tgt, toffs)]     # assembly order: reference(s) first, target last
+    refs = [(ref, roffs)]
+    for r in range(1, spec.get("n_refs", 1)):       # further references: the ancestor with 0.1-0.5 % independent substitutions
+        other = ref.clone()
+        n_s = int(G * 0.001 * (r + 1))
+        ix = torch.unique(torch.randint(0, G, (n_s,), device=device, generator=g))
+        sb = lut[torch.randint(0, 4, (ix.numel(),), dtype=torch.uint8, device=device, generator=g).long()]
+        ok = other[ix] != ord("N")
+        other[ix[ok]] = sb[ok]
+        refs.append((other, roffs))
+    return refs + [(tgt, toffs)]     # assembly order: reference(s) first, target last
 
 
 # ------------------------------------------------------------------------------------ clocks
@@ -212,7 +232,7 @@ def cpu_reference_run(spec, args, steps, warmup, sample_bases=None):
     n_chrom = max(spec["n_chrom"], cores)         # enough records to keep every thread busy
     rseq, roffs, _ = synth.make_reference(sample_bases, n_chrom=n_chrom, dup_frac=spec["dup"])
     tseq, toffs, _ = synth.derive_target(rseq, roffs, min_len=spec["lo"], max_len=min(spec["hi"], max(spec["lo"] * 2, sample_bases // cores)))
-    asms = [(rseq, roffs), (tseq, toffs)]
+    asms = [(rseq, roffs)] * spec.get("n_refs", 1) + [(tseq, toffs)]
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
@@ -221,7 +241,7 @@ def cpu_reference_run(spec, args, steps, warmup, sample_bases=None):
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
-    total = 2 * sample_bases
+    total = len(asms) * sample_bases
     sec = float(np.mean(times))
     return {"value": total / sec / 1e9, "unit": "Gbases/s", "cores": cores, "kind": "port",
             "sample": f"{sample_bases} bp reference + derived target (same generator as the workload), k={K} w={W}, "
@@ -235,7 +255,7 @@ def run_reference_arm(args, spec):
     warm = max(1, min(args.warmup, 1))
     steps = max(1, min(args.steps, 3))
     cb, sec = cpu_reference_run(spec, args, steps, warm)
-    line = {"metric": "Gbases/s sketched+filtered at k=32 w=1000", "value": cb["value"], "unit": "Gbases/s", "impl": "reference",
+    line = {"metric": f"Gbases/s sketched+filtered at k={K} w={W}", "value": cb["value"], "unit": "Gbases/s", "impl": "reference",
             "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": spec["name"], "k": K, "w": W, "note": "bounded sample on host cores"},
@@ -244,10 +264,55 @@ def run_reference_arm(args, spec):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------ k x w sweep (configs[4])
+def run_sweep(args, spec, eng, shards, total_bases):
+    """Device-resident step time and roofline fraction of the dominant sketch kernel per (k, w) point."""
+    import torch
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = peaks.get("hbm_gbs", 6650.0)
+    points = []
+    for k in (24, 32, 40):
+        for w in (250, 500, 1000, 5000):
+            def step():
+                sks = [eng.sketch_device(s.data_ptr(), o, k, w) for s, o, _ in shards]
+                res = eng.filter_and_edges(sks, WEIGHTS)
+                out = ([sk.n for sk in sks],) + tuple(res.counts())
+                for sk in sks:
+                    sk.close()
+                res.close()
+                return out
+            for _ in range(max(1, min(args.warmup, 2))):
+                step()
+            eng.timing_reset()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                n_mx, _n, n_v, n_e = step()
+            torch.cuda.synchronize()
+            sec = (time.perf_counter() - t0) / args.steps
+            t_cand, n_cand = eng.timing("cand")
+            cand_ms = t_cand / max(1, n_cand)
+            per_launch = (total_bases + 16.0 * sum(n_mx)) / len(shards)
+            achieved = per_launch / (cand_ms * 1e-3) / 1e9
+            points.append({"k": k, "w": w, "value": total_bases / sec / 1e9, "ms_per_step": sec * 1e3, "cand_ms": cand_ms,
+                           "roofline_frac": achieved / peak, "minimizers": n_mx, "vertices": n_v, "edges": n_e,
+                           "sketch_ms": eng.timing("sketch")[0] / args.steps, "filter_ms": eng.timing("filter")[0] / args.steps})
+    print(json.dumps({"metric": "Gbases/s sketched+filtered, k x w sweep", "unit": "Gbases/s", "n_gpus": 1, "steps": args.steps,
+                      "config": {"workload": spec["name"], "bases_per_step": total_bases}, "roofline_peak_gbs": peak,
+                      "roofline_kernel": "cand31_kernel (k % 4 == 0: all three k)", "sweep": points}), flush=True)
+
+
 # ------------------------------------------------------------------------------------ GPU arm
 def main():
+    global K, W, WEIGHTS
     args = parse_args()
     spec = workload_spec(args)
+    K, W = args.k or 32, args.w or spec["w"]
+    WEIGHTS = [2.0] * spec["n_refs"] + [1.0]
     if args.impl == "reference":
         run_reference_arm(args, spec)
         return
@@ -285,7 +350,7 @@ def main():
     if world > 1:
         torch.cuda.empty_cache()
     my_bases = sum(int(o[-1]) for _, o, _ in shards)
-    total_bases = spec["G"] * 2
+    total_bases = spec["G"] * len(shards)
     host = [torch.empty(s.numel(), dtype=torch.uint8).pin_memory() for s, _, _ in shards]
     for h, (s, _, _) in zip(host, shards):
         h.copy_(s)
@@ -293,6 +358,11 @@ def main():
 
     n_asm = len(shards)
     stats = {}
+
+    if args.sweep:
+        run_sweep(args, spec, eng, shards, total_bases)
+        eng.close()
+        return
 
     def gather_and_filter(sks):
         if world == 1:
@@ -398,7 +468,7 @@ def main():
         achieved = algo_bytes_per_launch / (cand_ms * 1e-3) / 1e9 if cand_ms > 0 else 0.0
         value = total_bases * args.steps / sec / 1e9
         line = {
-            "metric": "Gbases/s sketched+filtered at k=32 w=1000", "value": value, "unit": "Gbases/s",
+            "metric": f"Gbases/s sketched+filtered at k={K} w={W}", "value": value, "unit": "Gbases/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec / args.steps * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": spec["name"], "k": K, "w": W, "bases_per_step": total_bases, "n_free": not args.with_n,

@@ -518,19 +518,12 @@ __global__ void __launch_bounds__(CAND_THREADS) cand31_kernel(const uint32_t* __
 
     const uint64_t p0 = cta_p0 + (uint64_t)threadIdx.x * P.chunk;
     if (p0 < P.n) {
-        uint32_t F, R;
-        int g = 0;
-        if (ks == 0) {
-            // warm-up by rolling: start from the all-A k-mer and roll k steps with out = A, in = first k bases
-            F = Tb.f0; R = Tb.r0; g = -kq;
-        } else {
-            F = 0; R = 0;
-            for (int i = 0; i < k; i++) {
-                uint32_t cf = pk_code(pk, p0 + i), cr = pk_code(pk, p0 + k - 1 - i) ^ 2u;
-                F = rol31(F) ^ Tb.shi[cf];
-                R = rol31(R) ^ Tb.shi[cr];
-            }
-        }
+        // warm-up by rolling, without a special case: start from the all-A k-mer and roll ceil(k/16) groups with out = A;
+        // when k is not a multiple of 16 the first group is fed 16 - k % 16 further A's in front of the first real bases
+        // (rolling A in and A out leaves the all-A k-mer unchanged)
+        const int kqc = kq + (ks ? 1 : 0);
+        uint32_t F = Tb.f0, R = Tb.r0;
+        int g = -kqc;
         R <<= 1;
         const uint32_t lowmask = ks == 1 ? 0x3F3F3F3Fu : ks == 2 ? 0x0F0F0F0Fu : 0x03030303u;
         const char* tb = reinterpret_cast<const char*>(tab);
@@ -543,10 +536,13 @@ __global__ void __launch_bounds__(CAND_THREADS) cand31_kernel(const uint32_t* __
         for (; g < n_g; g++) {
             const uint32_t io = row + g, ii = row + g + kq;
             uint32_t o = g < 0 ? 0u : pkS[io + (io >> lw)];
-            uint32_t in = pkS[ii + (ii >> lw)];
+            uint32_t in;
             if (ks) {
-                uint32_t b2 = pkS[ii + 1 + ((ii + 1) >> lw)];
-                in = ((in >> (2 * ks)) & lowmask) | ((b2 << (8 - 2 * ks)) & ~lowmask);
+                const uint32_t lo = g == -kqc ? 0u : pkS[ii + (ii >> lw)];      // first warm-up group: the padding A's
+                const uint32_t b2 = pkS[ii + 1 + ((ii + 1) >> lw)];
+                in = ((lo >> (2 * ks)) & lowmask) | ((b2 << (8 - 2 * ks)) & ~lowmask);
+            } else {
+                in = pkS[ii + (ii >> lw)];
             }
             // table byte offsets (idx << 3), one per byte: zq[j] serves positions 4j..4j+3 of the group
             uint32_t z1 = ((o << 2) & 0xCCCCCCCCu) | (in & 0x33333333u);
