@@ -135,6 +135,7 @@ int mxe_create(int device, mxe_t** out)
     if (const char* s = getenv("MXE_PRUNE")) e->prune = atoi(s) != 0;
     if (const char* s = getenv("MXE_SORT_BITS")) e->sort_bits = atoi(s);
     if (const char* s = getenv("MXE_FMA_OFFLOAD")) e->fma_offload = atoi(s) != 0;
+    if (const char* s = getenv("MXE_SELECT_NARROW")) e->select_narrow = atoi(s) != 0;
     *out = e;
     return MXE_OK;
 }
@@ -176,6 +177,7 @@ int mxe_set_option(mxe_t* e, const char* name, double value)
     else if (!strcmp(name, "prune")) e->prune = value != 0;
     else if (!strcmp(name, "sort_bits")) e->sort_bits = (int)value;
     else if (!strcmp(name, "fma_offload")) e->fma_offload = value != 0;
+    else if (!strcmp(name, "select_narrow")) e->select_narrow = value != 0;
     else if (!strcmp(name, "timing")) e->timing = value != 0;
     else { set_error("unknown option %s", name); return MXE_ERR_ARG; }
     return MXE_OK;

@@ -69,6 +69,7 @@ struct Engine {
     int cand_variant = 1;    // 0 = generic 64-bit, 1 = 31-bit lane prefilter
     bool prune = false;      // drop dominated candidates on 31-bit bounds before the exact stages
     bool fma_offload = true; // cand31: additions of the threshold test as IMADs on the FMA pipe
+    bool select_narrow = true;   // window selection in 32-bit arithmetic when the ordinals allow it
     int sort_bits = 0;       // steps 2-3: top hash bits covered by the radix sort (24/32/40; 0 = by size), rest by the fix-up
     bool timing = false;
     // accounting

@@ -283,8 +283,13 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
             MXE_TRY(gaps.alloc(gap_cap, st));
             MXE_CUDA(cudaMemsetAsync(gcount.p, 0, 2 * sizeof(unsigned long long), st));
             GapList G{gaps.p, gcount.p, gcount.p + 1, gap_cap};
-            if (n_sel)
-                MXE_LAUNCH(e, select_kernel, grid_for(n_sel, 256), 256, 0, s_pos, ch0.p, s_ord, s_ctg, n_sel, ostart.p, P, M.p, G);
+            // 32-bit window arithmetic whenever every padded ordinal (+ 2w) fits (see select_kernel)
+            const bool narrow = e->select_narrow && n_sel < 0xFFFFFFFFULL &&
+                                n_valid + ((uint64_t)n_contigs + 2) * (uint64_t)w < 0xFFFFFFFFULL;
+            if (n_sel && narrow)
+                MXE_LAUNCH(e, select_kernel<true>, grid_for(n_sel, 256), 256, 0, s_pos, ch0.p, s_ord, s_ctg, n_sel, ostart.p, P, M.p, G);
+            else if (n_sel)
+                MXE_LAUNCH(e, select_kernel<false>, grid_for(n_sel, 256), 256, 0, s_pos, ch0.p, s_ord, s_ctg, n_sel, ostart.p, P, M.p, G);
             MXE_LAUNCH(e, empty_contig_gap_kernel, grid_for(n_contigs, 128), 128, 0, s_pos, n_sel, d_offsets.p, n_contigs, ostart.p, P, G);
             MXE_CUDA(cudaMemcpyAsync(gc, gcount.p, sizeof(gc), cudaMemcpyDeviceToHost, st));
             MXE_CUDA(cudaStreamSynchronize(st));

@@ -18,6 +18,7 @@
 // other window is re-evaluated densely.  Ties on hash0 resolve to the rightmost k-mer (btllib `<=`).
 #pragma once
 #include "common.cuh"
+#include <type_traits>
 
 namespace mxe {
 
@@ -630,7 +631,8 @@ __global__ void __launch_bounds__(256) cand_extract_kernel(const uint32_t* __res
     uint32_t c = contig_of_warp(offsets, n_contigs, sb * (uint64_t)(32 * XW * 32), lane);
     if (cc == 0) return;                              // after the collectives
     uint64_t o = c_base + (cx - cc);
-    uint64_t vb = vprefix[blk0] + (vx - vc);
+    uint64_t nextb = c + 1 < n_contigs ? offsets[c + 1] : ~0ULL;     // start of the next record
+    uint64_t vb = vprefix[blk0] + (vx - vc) + (uint64_t)c * w;       // padded ordinal base (see select_kernel)
 #pragma unroll
     for (int j = 0; j < XW; j++) {
         uint32_t wv = cw[j];
@@ -639,9 +641,9 @@ __global__ void __launch_bounds__(256) cand_extract_kernel(const uint32_t* __res
             const int b = __ffs(wv) - 1;
             wv &= wv - 1;
             const uint64_t p = base + b;
-            while (c + 1 < n_contigs && offsets[c + 1] <= p) c++;
+            while (p >= nextb) { c++; vb += w; nextb = c + 1 < n_contigs ? offsets[c + 1] : ~0ULL; }
             cpos[o] = p;
-            cord[o] = vb + __popc(vw[j] & ((1u << b) - 1u)) + (uint64_t)c * w;     // padded ordinal (see select_kernel)
+            cord[o] = vb + __popc(vw[j] & ((1u << b) - 1u));
             cctg[o] = c;
             o++;
         }
@@ -885,52 +887,65 @@ __device__ __forceinline__ void push_gap(const GapList& G, uint64_t ja, uint64_t
 
 // gord holds PADDED ordinals (ordinal + record * w): two candidates of different records are at least w apart, so the
 // window scans stop at record boundaries by themselves and only the candidate's own record id is looked up.
+// The kernel is instruction bound (ALU pipe 75 %), so when every padded ordinal (+ 2w) fits 32 bits -- any input below
+// ~4 G valid k-mers -- the NARROW variant reads only the low halves of the ordinals and does all window arithmetic and
+// indexing in 32 bits.
+template <bool NARROW>
 __global__ void __launch_bounds__(256) select_kernel(const uint64_t* __restrict__ cpos, const uint64_t* __restrict__ h0,
                                                       const uint64_t* __restrict__ gord, const uint32_t* __restrict__ ctg,
                                                       uint64_t n_cand, const uint64_t* __restrict__ ostart,
                                                       SketchParams P, uint32_t* __restrict__ M, GapList G)
 {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_cand) return;
+    typedef typename std::conditional<NARROW, uint32_t, uint64_t>::type ord_t;   // ordinals
+    typedef typename std::conditional<NARROW, uint32_t, uint64_t>::type idx_t;   // candidate indices
+    const idx_t i = (idx_t)((uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+    const idx_t n = (idx_t)n_cand;
+    if ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x >= n_cand) return;
+    auto ord = [&](idx_t j) -> ord_t {
+        if (NARROW) return (ord_t) reinterpret_cast<const uint32_t*>(gord)[2 * (size_t)j];   // low half (little endian)
+        return (ord_t)gord[j];
+    };
     const uint32_t c = ctg[i];
-    const uint64_t w = (uint64_t)P.w, pad = (uint64_t)c * w;
-    const uint64_t os = ostart[c] + pad, oe = ostart[c + 1] + pad;
-    if (oe - os < w) return;                      // record has fewer than w valid k-mers: no window
-    const uint64_t o = gord[i], h = h0[i];
-    const uint64_t jmin = os + w - 1, jmax = oe - 1;
+    const uint64_t pad64 = (uint64_t)c * (uint64_t)P.w;
+    const ord_t w = (ord_t)P.w, pad = (ord_t)pad64;
+    const ord_t os = (ord_t)(ostart[c] + pad64), oe = (ord_t)(ostart[c + 1] + pad64);
+    if ((ord_t)(oe - os) < w) return;             // record has fewer than w valid k-mers: no window
+    const ord_t o = ord(i);
+    const uint64_t h = h0[i];
+    const ord_t jmin = os + w - 1, jmax = oe - 1;
 
-    uint64_t jlo = o > jmin ? o : jmin;
-    uint64_t jhi = o + w - 1 < jmax ? o + w - 1 : jmax;
+    ord_t jlo = o > jmin ? o : jmin;
+    ord_t jhi = o + w - 1 < jmax ? o + w - 1 : jmax;
     // nearest strictly smaller to the left within the window span
-    for (uint64_t j = i; j-- > 0;) {
-        const uint64_t oj = gord[j];
+    for (idx_t j = i; j-- > 0;) {
+        const ord_t oj = ord(j);
         if (oj + w <= o) break;
-        if (h0[j] < h) { uint64_t b = oj + w; if (b > jlo) jlo = b; break; }
+        if (h0[j] < h) { const ord_t b = oj + w; if (b > jlo) jlo = b; break; }
     }
     // nearest smaller-or-equal to the right (rightmost wins ties)
-    const uint64_t o_next = i + 1 < n_cand ? gord[i + 1] : ~0ULL;
-    for (uint64_t j = i + 1; j < n_cand; j++) {
-        const uint64_t oj = j == i + 1 ? o_next : gord[j];
+    const ord_t o_next = i + 1 < n ? ord(i + 1) : (ord_t)~(ord_t)0;
+    for (idx_t j = i + 1; j < n; j++) {
+        const ord_t oj = ord(j);
         if (oj >= o + w) break;
-        if (h0[j] <= h) { uint64_t b = oj - 1; if (b < jhi) jhi = b; break; }
+        if (h0[j] <= h) { const ord_t b = oj - 1; if (b < jhi) jhi = b; break; }
     }
     if (jlo <= jhi) {
         if ((uint32_t)(h >> 33) <= P.T && h != ~0ULL) {
-            uint64_t p = cpos[i];
+            const uint64_t p = cpos[i];
             atomicOr(&M[p >> 5], 1u << (p & 31));
         } else {
-            push_gap(G, jlo - pad, jhi - pad);
+            push_gap(G, (uint64_t)(ord_t)(jlo - pad), (uint64_t)(ord_t)(jhi - pad));
         }
     }
     // candidate-free windows to the right of this candidate (a candidate of the next record lies beyond jmax)
     {
-        uint64_t ga = o + w > jmin ? o + w : jmin;
-        uint64_t gb = o_next - 1 < jmax ? o_next - 1 : jmax;
-        if (ga <= gb) push_gap(G, ga - pad, gb - pad);
+        const ord_t ga = o + w > jmin ? o + w : jmin;
+        const ord_t gb = (ord_t)(o_next - 1) < jmax ? (ord_t)(o_next - 1) : jmax;
+        if (ga <= gb) push_gap(G, (uint64_t)(ord_t)(ga - pad), (uint64_t)(ord_t)(gb - pad));
     }
     // ... and to the left of the first candidate of the record (the previous candidate lies before os)
-    if (i == 0 || gord[i - 1] < os) {
-        if (o > jmin) push_gap(G, jmin - pad, ((o - 1 < jmax) ? o - 1 : jmax) - pad);
+    if (i == 0 || ord(i - 1) < os) {
+        if (o > jmin) push_gap(G, (uint64_t)(ord_t)(jmin - pad), (uint64_t)(ord_t)(((ord_t)(o - 1) < jmax ? (ord_t)(o - 1) : jmax) - pad));
     }
 }
 
