@@ -124,7 +124,6 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
     MXE_TRY(ostart.alloc(n_contigs + 1, st));
     MXE_CUDA(cudaMemcpyAsync(d_offsets.p, offsets, (n_contigs + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     MXE_CUDA(cudaMemsetAsync(pk.p + 2 * nW, 0, (pk_words - 2 * nW) * sizeof(uint32_t), st));
-    MXE_CUDA(cudaMemsetAsync(C.p, 0, nW * sizeof(uint32_t), st));
     MXE_CUDA(cudaMemsetAsync(M.p, 0, nW * sizeof(uint32_t), st));
 
     // ---- pack + validity
@@ -170,6 +169,7 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
                       (e->cand_variant >= 3 || n >= ((uint64_t)1 << 29));
         if (sliced) {
             // bit-sliced kernel: transpose pk into bit planes, run 32 streams per thread, then C &= V with counts
+            MXE_CUDA(cudaMemsetAsync(C.p, 0, nW * sizeof(uint32_t), st));      // it sets candidate bits with atomics; the others write whole words
             BsParams BP;
             BP.n = n; BP.k = k; BP.iters = bs_iters(k); BP.rows = bs_rows(k);
             BP.n_tiles = (n + BS_TILE - 1) / BS_TILE;

@@ -683,19 +683,26 @@ __global__ void __launch_bounds__(256) hash_pos_tables_kernel(SketchTables Tb, i
     }
 }
 
-// exact base hashes of the k-mer at p from the position-specific tables staged in shared memory (pf, pr: G x 256)
+// exact base hashes of the k-mer at p from the position-specific tables staged in shared memory (pf, pr: G x 256).
+// k <= 4 * HASHPOS_MAX_GROUPS + 3 = 43: the k-mer spans at most four pk words, which are all requested up front so that
+// the (scattered) loads of one candidate overlap instead of following each other.
 __device__ __forceinline__ void kmer_hash64_pos(const uint32_t* __restrict__ pk, uint64_t p, int k, const uint64_t* pf, const uint64_t* pr,
                                                 const uint64_t* s1, uint64_t& fwd, uint64_t& rev)
 {
     const uint64_t q = p >> 4;
     const uint32_t sh = ((uint32_t)p & 15u) * 2u;
+    const int nw = ((k + 15) >> 4) + 1;
+    uint32_t wd[4];
+#pragma unroll
+    for (int m = 0; m < 4; m++) wd[m] = m < nw ? __ldg(pk + q + m) : 0u;
+#pragma unroll
+    for (int m = 0; m < 4; m++) wd[m] = pk_to_natural(wd[m]);
     uint64_t f = 0, r = 0;
-    uint32_t cur = pk_to_natural(__ldg(pk + q));
     int g = 0, left = k;
-    for (int m = 0; left > 0; m++) {
-        const uint32_t nxt = pk_to_natural(__ldg(pk + q + m + 1));
-        uint32_t N = __funnelshift_r(cur, nxt, sh);          // 16 bases starting at p + 16 m, natural order
-        cur = nxt;
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+        if (left <= 0) break;
+        uint32_t N = __funnelshift_r(wd[m], wd[m + 1], sh);      // 16 bases starting at p + 16 m, natural order
         int nb = left < 16 ? left : 16;
         left -= nb;
         for (; nb >= 4; nb -= 4, g++) {
