@@ -61,33 +61,6 @@ def shard_ranges(offsets_per_asm, world):
     return [[(cuts[a][r], cuts[a][r + 1]) for a in range(n_asm)] for r in range(world)]
 
 
-def all_gather_minimizers(hashes, contigs, first_record, group=None):
-    """hashes: int64 tensor (bit pattern of the uint64 out_hash), contigs: int32 tensor of LOCAL record
-    ids, both in (record, pos) order on this rank; first_record: global id of this rank's first record.
-    Returns (all_hashes, all_contigs) with GLOBAL record ids, identical on every rank."""
-    import torch
-    import torch.distributed as dist
-    world = dist.get_world_size(group)
-    dev = hashes.device
-    n = hashes.numel()
-    counts = torch.empty(world, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(counts, torch.tensor([n], dtype=torch.int64, device=dev), group=group)
-    counts = counts.cpu().numpy()
-    mx = max(1, int(counts.max()))
-    hbuf = torch.zeros(mx, dtype=torch.int64, device=dev)
-    cbuf = torch.zeros(mx, dtype=torch.int32, device=dev)
-    if n:
-        hbuf[:n] = hashes
-        cbuf[:n] = contigs + int(first_record)
-    gh = torch.empty(world * mx, dtype=torch.int64, device=dev)
-    gc = torch.empty(world * mx, dtype=torch.int32, device=dev)
-    dist.all_gather_into_tensor(gh, hbuf, group=group)
-    dist.all_gather_into_tensor(gc, cbuf, group=group)
-    hh = torch.cat([gh[r * mx:r * mx + int(counts[r])] for r in range(world)])
-    cc = torch.cat([gc[r * mx:r * mx + int(counts[r])] for r in range(world)])
-    return hh, cc
-
-
 class DeviceArray:
     """Zero-copy view of an engine-owned device array for torch.as_tensor (__cuda_array_interface__)."""
 

@@ -118,3 +118,23 @@ def test_config4_four_way(engine, oracle):
     assert 15 in masks and len(masks) >= 4 and set(np.unique(res.weight)) >= {7.0}
     # n=2 filtering downstream (bin/ntjoin.py:80-89) keeps edges with weight >= 2: every edge seen only in the target is dropped
     assert (res.weight[res.support == 8] == 1.0).all()
+
+
+@pytest.mark.parametrize("bits", [24, 32, 40])
+def test_sort_width_independence(engine, oracle, bits):
+    """the radix sort covers the top 24/32/40 hash bits and the fix-up the rest: same result for every split"""
+    rseq, roffs, _ = synth.make_reference(2_000_000, n_chrom=4, dup_frac=0.05)
+    asms = [(rseq, roffs), synth.derive_target(rseq, roffs, seed=5, min_len=4000, max_len=100_000)[:2]]
+    sks = [engine.sketch_buffers(s, o, 32, 50) for s, o in asms]
+    want = oracle.filter_and_edges([s.out_hash for s in sks], [s.contig for s in sks], [2.0, 1.0])
+    engine.set_option("sort_bits", bits)
+    try:
+        res = engine.filter_and_edges(sks, [2.0, 1.0])
+        np.testing.assert_array_equal(res.vertices, want["vertices"])
+        np.testing.assert_array_equal(res.edge_u, want["edges"]["u"])
+        np.testing.assert_array_equal(res.edge_v, want["edges"]["v"])
+        np.testing.assert_array_equal(res.support, want["edges"]["support_mask"])
+        for a in range(2):
+            np.testing.assert_array_equal(res.uniq[a], want["uniq"][a])
+    finally:
+        engine.set_option("sort_bits", 0)

@@ -79,7 +79,21 @@ def test_messy_synthetic(engine, oracle, canonical, variant):
         sk = engine.sketch_buffers(seq, offs, k, w, canonical=canonical)
         assert_same(sk, ref)
     engine.set_option("cand_variant", 1)
-    engine.set_option("prune", 1)
+    engine.set_option("prune", 0)
+
+
+@pytest.mark.parametrize("option", ["select_narrow", "fma_offload"])
+def test_kernel_variants_behind_options(engine, oracle, option):
+    """the 64-bit window selection (inputs beyond 4 G valid k-mers) and the all-ALU threshold test of cand31 are only
+    reachable through their options at test sizes: both must give the same sketch as the defaults"""
+    seq, offs = _messy(1_200_000, 23)
+    engine.set_option(option, 0)
+    try:
+        for k, w, canonical in [(32, 1000, "sum"), (32, 100, "sum"), (24, 250, "sum"), (40, 500, "min"), (16, 10, "sum")]:
+            ref = oracle.sketch(seq, offs, k, w, canonical=canonical)
+            assert_same(engine.sketch_buffers(seq, offs, k, w, canonical=canonical), ref)
+    finally:
+        engine.set_option(option, 1)
 
 
 @pytest.mark.parametrize("tau", [0.5, 3.0, 10.0, 1e9])
