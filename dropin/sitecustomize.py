@@ -2,7 +2,8 @@
 
 Usage:  PYTHONPATH=<repo>/dropin:<repo>  NTJOIN_B200=1  ntJoin assemble ...
 Python imports `sitecustomize` at start-up; this one registers an import hook that patches the
-reference's `ntjoin_utils` right after it is loaded (see ntjoin_b200/dropin.py).
+reference's `ntjoin_utils` (and `Ntjoin.print_graph` in `ntjoin`) right after they are loaded (see
+ntjoin_b200/dropin.py).
 """
 import importlib.abc
 import importlib.util
@@ -12,7 +13,7 @@ import sys
 if os.environ.get("NTJOIN_B200", "0") not in ("", "0"):
     class _Patch(importlib.abc.MetaPathFinder):
         def find_spec(self, name, path, target=None):
-            if name != "ntjoin_utils":
+            if name not in ("ntjoin_utils", "ntjoin"):
                 return None
             sys.meta_path.remove(self)
             try:
@@ -27,7 +28,10 @@ if os.environ.get("NTJOIN_B200", "0") not in ("", "0"):
             def exec_module(module):
                 orig_exec(module)
                 from ntjoin_b200 import dropin
-                dropin.install(module)
+                if name == "ntjoin_utils":
+                    dropin.install(module)
+                else:
+                    dropin.install_print_graph(module)      # Ntjoin.print_graph -> .mx.dot from arrays
 
             loader.exec_module = exec_module
             return spec

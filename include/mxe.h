@@ -145,6 +145,17 @@ int mxe_result_graph(mxe_result_t* r, uint64_t* n_vertices, const uint64_t** ver
 
 void mxe_result_free(mxe_result_t* r);
 
+/* `<prefix>.mx.dot` exactly as Ntjoin.print_graph writes it (bin/ntjoin.py:25-67), from arrays instead of a
+ * walk over igraph objects.  Host only (no engine, no GPU).  vertices: n_v hashes in graph.vs order; the label
+ * of vertex i carries one line "<asm_keys[a]>_(<ctg_reprs[a][v_ctg[a][i]]>, <v_pos[a][i]>)" per assembly (the
+ * caller passes Python's repr() of every record name); edge t joins vertices[e_src[t]] -- vertices[e_dst[t]]
+ * (indices, as igraph reports source/target) and ends with attr_text[e_attr[t]], e.g.
+ * " [weight=3.0 color=lightgrey]\n" (one text per distinct support set: float formatting stays Python's). */
+int mxe_write_dot(const char* path, uint64_t n_v, const uint64_t* vertices, int n_asm, const char* const* asm_keys,
+                  const char* const* const* ctg_reprs, const uint32_t* const* v_ctg, const uint32_t* const* v_pos,
+                  uint64_t n_e, const uint32_t* e_src, const uint32_t* e_dst, const uint32_t* e_attr,
+                  const char* const* attr_text);
+
 /* ---- steps 2-3 across GPUs (one process per GPU) ------------------------------------------
  *
  * Uniqueness is per ASSEMBLY, not per GPU (bin/ntjoin_utils.py:182-187), and the intersection is

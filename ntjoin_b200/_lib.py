@@ -11,7 +11,7 @@ SYMBOLS = [
     "mxe_sketch_file", "mxe_sketch_buffers", "mxe_prefetch_buffers", "mxe_sketch_device", "mxe_sketch_load_tsv", "mxe_sketch_view",
     "mxe_sketch_device_view", "mxe_sketch_contig_name", "mxe_sketch_counts", "mxe_write_tsv", "mxe_sketch_free",
     "mxe_filter_and_edges", "mxe_filter_and_edges_device", "mxe_result_counts", "mxe_result_flags", "mxe_result_graph",
-    "mxe_result_free", "mxe_timing", "mxe_timing_reset", "mxe_kernel_launches",
+    "mxe_result_free", "mxe_write_dot", "mxe_timing", "mxe_timing_reset", "mxe_kernel_launches",
     "mxe_dist_mark", "mxe_dist_adjacency", "mxe_dist_edges", "mxe_dist_finish", "mxe_dist_free", "mxe_result_edge_keys",
     "mxe_a2a_partition", "mxe_a2a_mark", "mxe_a2a_sightings", "mxe_a2a_finish", "mxe_a2a_free",
 ]
@@ -80,6 +80,8 @@ def load_library():
     lib.mxe_a2a_finish.argtypes = [vp, vp, C.c_uint64, C.c_uint64, C.POINTER(C.c_double), pp]
     lib.mxe_a2a_free.argtypes = [vp]
     lib.mxe_a2a_free.restype = None
+    lib.mxe_write_dot.argtypes = [C.c_char_p, C.c_uint64, vp, C.c_int, C.POINTER(C.c_char_p), pp, pp, pp,
+                                  C.c_uint64, vp, vp, vp, C.POINTER(C.c_char_p)]
     lib.mxe_timing.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), u64p]
     lib.mxe_timing_reset.argtypes = [vp]
     lib.mxe_kernel_launches.argtypes = [vp]

@@ -521,6 +521,59 @@ void mxe_sketch_free(mxe_sketch_t* S)
     delete S;
 }
 
+// ------------------------------------------------------------------ .mx.dot from arrays (host only)
+// Text format of Ntjoin.print_graph (bin/ntjoin.py:25-67):
+//   graph G {
+//   "<mx>" [label="<mx>\n<asm key>_<(ctg, pos)>\n..."]         one label line per assembly, literal newlines
+//   "<u>" --"<v>" [weight=<float> color=<colour>]
+//   }
+int mxe_write_dot(const char* path, uint64_t n_v, const uint64_t* vertices, int n_asm, const char* const* asm_keys,
+                  const char* const* const* ctg_reprs, const uint32_t* const* v_ctg, const uint32_t* const* v_pos,
+                  uint64_t n_e, const uint32_t* e_src, const uint32_t* e_dst, const uint32_t* e_attr,
+                  const char* const* attr_text)
+{
+    if (!path || (n_v && !vertices) || n_asm < 0 || (n_asm && (!asm_keys || !ctg_reprs || !v_ctg || !v_pos)) ||
+        (n_e && (!e_src || !e_dst || !e_attr || !attr_text))) { set_error("null argument"); return MXE_ERR_ARG; }
+    FILE* f = fopen(path, "wb");
+    if (!f) { set_error("cannot open %s: %s", path, strerror(errno)); return MXE_ERR_IO; }
+    std::vector<char> buf(1 << 22);
+    char* p = buf.data();
+    bool ok = true;
+    auto flush = [&]() { ok = ok && fwrite(buf.data(), 1, p - buf.data(), f) == (size_t)(p - buf.data()); p = buf.data(); };
+    auto put_str = [&](const char* t) {
+        size_t len = strlen(t);
+        if (len > buf.size() / 2) { flush(); ok = ok && fwrite(t, 1, len, f) == len; return; }
+        if ((size_t)(buf.data() + buf.size() - p) < len + 64) flush();
+        memcpy(p, t, len); p += len;
+    };
+    put_str("graph G {\n");
+    std::vector<size_t> key_len(n_asm);
+    for (uint64_t i = 0; i < n_v && ok; i++) {
+        if ((size_t)(buf.data() + buf.size() - p) < 128) flush();
+        *p++ = '"'; p = put_u64(p, vertices[i]); memcpy(p, "\" [label=\"", 10); p += 10; p = put_u64(p, vertices[i]);
+        for (int a = 0; a < n_asm; a++) {
+            *p++ = '\n';
+            put_str(asm_keys[a]);
+            *p++ = '_'; *p++ = '(';
+            put_str(ctg_reprs[a][v_ctg[a][i]]);
+            if ((size_t)(buf.data() + buf.size() - p) < 64) flush();
+            *p++ = ','; *p++ = ' '; p = put_u64(p, v_pos[a][i]); *p++ = ')';
+        }
+        *p++ = '"'; *p++ = ']'; *p++ = '\n';
+    }
+    for (uint64_t t = 0; t < n_e && ok; t++) {
+        if ((size_t)(buf.data() + buf.size() - p) < 128) flush();
+        if (e_src[t] >= n_v || e_dst[t] >= n_v) { ok = false; set_error("edge %llu refers to a vertex out of range", (unsigned long long)t); fclose(f); return MXE_ERR_ARG; }
+        *p++ = '"'; p = put_u64(p, vertices[e_src[t]]); memcpy(p, "\" --\"", 5); p += 5; p = put_u64(p, vertices[e_dst[t]]); *p++ = '"';
+        put_str(attr_text[e_attr[t]]);
+    }
+    put_str("}\n");
+    flush();
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) { set_error("write to %s failed", path); return MXE_ERR_IO; }
+    return MXE_OK;
+}
+
 // ------------------------------------------------------------------ steps 2-3
 int mxe_filter_and_edges_device(mxe_t* e, const void* const* d_hash, const void* const* d_contig,
                                 const uint64_t* n, int n_asm, const double* weights, mxe_result_t** out)

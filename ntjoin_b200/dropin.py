@@ -6,7 +6,8 @@ Reference signatures (bin/ntjoin_utils.py):
     build_graph(list_mxs, weights, graph=None, black_list=None) -> igraph.Graph (vs['name'], es['support'],
                                                                                es['weight'])                 :83-141
 
-`install(ntjoin_utils_module)` swaps them in.  Return types and contents are identical to the
+`install(ntjoin_utils_module)` swaps them in; `install_print_graph(ntjoin_module)` does the same for
+Ntjoin.print_graph (bin/ntjoin.py:25-67), which then writes `<prefix>.mx.dot` from the engine's arrays.  Return types and contents are identical to the
 reference's; the arithmetic (uniqueness counting, intersection, adjacent-pair edge reduction, weights)
 runs on the GPU through the C ABI.  The lists returned by read_minimizers / filter_minimizers carry a
 hidden handle to the device-resident arrays so the next stage does not re-parse strings.  Calls the
@@ -104,10 +105,75 @@ def make_build_graph(original, ig):
         n_asm = len(keys)
         g.es["support"] = [[keys[a] for a in range(n_asm) if m >> a & 1] for m in res.support.tolist()]
         g.es["weight"] = res.weight.tolist()
+        _attach_dot_payload(g, keys, vals, weights, vs, eu, ev, res)
         res.close()
         return g
     build_graph.__doc__ = original.__doc__
     return build_graph
+
+
+class _DotPayload:
+    """arrays behind a graph built by the engine-backed build_graph: lets print_graph write `.mx.dot` without
+    walking igraph objects"""
+    pass
+
+
+def _attach_dot_payload(g, keys, vals, weights, vs, eu, ev, res):
+    p = _DotPayload()
+    p.keys, p.vertices, p.weights = list(keys), vs, [weights[k] for k in keys]
+    p.e_src, p.e_dst = np.minimum(eu, ev).astype(np.uint32), np.maximum(eu, ev).astype(np.uint32)   # igraph: source = lower id
+    p.masks = res.support.copy()
+    p.names, p.v_ctg, p.v_pos = [], [], []
+    for a, v in enumerate(vals):
+        sk, keep = v._sketch, res.keep[a]
+        order = np.argsort(sk.out_hash[keep], kind="stable")          # survivors of assembly a in vertex (ascending hash) order
+        p.names.append(list(sk.names))
+        p.v_ctg.append(sk.contig[keep][order])
+        p.v_pos.append(sk.pos[keep][order])
+    try:
+        g["_mxe_dot"] = p            # python-igraph: graph attribute
+    except TypeError:
+        g._mxe_dot = p               # stand-ins without graph attributes
+
+
+def _dot_payload(graph):
+    try:
+        return graph["_mxe_dot"]
+    except (KeyError, TypeError, IndexError):
+        return getattr(graph, "_mxe_dot", None)
+
+
+def make_print_graph(original):
+    """Ntjoin.print_graph (bin/ntjoin.py:25-67) with the per-vertex / per-edge text written from arrays."""
+    def print_graph(self, graph, out_prefix=None):
+        import datetime
+        import sys
+        from .dot import COLOURS, write_mx_dot
+        p = _dot_payload(graph)
+        count = lambda seq: seq() if callable(seq) else seq      # noqa: E731
+        if p is None or list(self.list_mx_info.keys()) != p.keys or \
+                len(count(graph.vs)) != len(p.vertices) or len(count(graph.es)) != len(p.e_src):
+            return original(self, graph, out_prefix)
+        out_graph = self.args.p + ".mx.dot" if out_prefix is None else out_prefix + "mx.dot"
+        print(datetime.datetime.today(), ": Printing graph", out_graph, sep=" ", file=sys.stdout)
+        write_mx_dot(out_graph, p.vertices, p.keys, p.names, p.v_ctg, p.v_pos, p.e_src, p.e_dst, p.masks, p.weights)
+        colours = COLOURS if len(p.keys) <= len(COLOURS) else ["red"] * len(p.keys)
+        print("\nfile_name\tnumber\tcolour")
+        for i, filename in enumerate(p.keys):
+            print(filename, i, colours[i], sep="\t")
+        print("", flush=True)
+    print_graph.__doc__ = original.__doc__
+    return print_graph
+
+
+def install_print_graph(module):
+    """Patch a loaded `ntjoin` module (bin/ntjoin.py) in place (idempotent)."""
+    cls = getattr(module, "Ntjoin", None)
+    if cls is None or getattr(cls, "_mxe_print_graph", False):
+        return module
+    cls.print_graph = make_print_graph(cls.print_graph)
+    cls._mxe_print_graph = True
+    return module
 
 
 def install(module):

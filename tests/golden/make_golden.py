@@ -7,6 +7,9 @@ Run in the build container only (needs /root/reference; the GPU box never runs t
 What it records
   inputs/*.fa            small FASTA fixtures of the reference's own test-suite (tests/*.fa), verbatim
   expected/*.tsv,*.dot   the reference's shipped golden outputs (tests/expected_outputs/)
+  expected/print_graph_*.mx.dot   the reference's OWN Ntjoin.print_graph (bin/ntjoin.py:25-67) run on the graph of
+                         each steps23 case (vertices in ascending-hash order, edge endpoints as igraph reports them:
+                         lower vertex id first), with the assembly keys "<i>.<fasta>.k<k>.w<w>.tsv"
   steps23_*.json         outputs of the reference's OWN Python functions read_minimizers,
                          filter_minimizers and build_graph (bin/ntjoin_utils.py, imported unmodified
                          from /root/reference/bin with a recording stand-in for python-igraph), run on
@@ -84,6 +87,38 @@ class FakeGraph:
         return _Seq([{"name": n} for n in self.vnames], {})
 
 
+class DotGraph:
+    """What Ntjoin.print_graph reads from python-igraph: vs() / vs[i]['name'], es() with source / target (an
+    undirected igraph edge reports the lower vertex id as its source) and the weight / support attributes."""
+
+    class _Edge(dict):
+        pass
+
+    class _VS(list):
+        def __call__(self):
+            return self
+
+    def __init__(self, names, edges, support, weight):
+        index = {n: i for i, n in enumerate(names)}
+        self.vs = DotGraph._VS({"name": n} for n in names)
+        self._es = []
+        for (s, t), sup, w in zip(edges, support, weight):
+            e = DotGraph._Edge(weight=w, support=sup)
+            e.source, e.target = sorted((index[s], index[t]))
+            self._es.append(e)
+
+    def es(self):
+        return self._es
+
+
+def reference_print_graph(ntjoin_mod, utils, names, edges, support, weight, list_mx_info, out_path):
+    obj = ntjoin_mod.Ntjoin.__new__(ntjoin_mod.Ntjoin)
+    obj.list_mx_info = list_mx_info
+    obj.args = types.SimpleNamespace(p=out_path[:-len(".mx.dot")])
+    with utils.HiddenPrints():
+        obj.print_graph(DotGraph(names, edges, support, weight))
+
+
 def load_reference_utils():
     ig = types.ModuleType("igraph")
     ig.Graph = FakeGraph
@@ -103,6 +138,7 @@ def main():
         shutil.copyfile(os.path.join(REF, "tests", "expected_outputs", f), os.path.join(HERE, "expected", f))
 
     utils = load_reference_utils()
+    import ntjoin as ntjoin_mod            # the reference's bin/ntjoin.py (igraph is the recording stand-in)
     for name, refs, target, k, w, weights in CASES:
         with tempfile.TemporaryDirectory() as tmp:
             files = refs + [target]          # assembly order: references, then target (ntjoin_assemble.py:804-807)
@@ -133,6 +169,11 @@ def main():
             }
             with open(os.path.join(HERE, f"steps23_{name}.json"), "w") as fh:
                 json.dump(out, fh, indent=0, sort_keys=True)
+            base = {t: os.path.basename(t) for t in tsvs}
+            reference_print_graph(ntjoin_mod, utils, out["vertices"], graph.edges,
+                                  [[base[f] for f in sup] for sup in graph.eattr["support"]], graph.eattr["weight"],
+                                  {base[t]: list_mx_info[t] for t in tsvs},
+                                  os.path.join(HERE, "expected", f"print_graph_{name}.mx.dot"))
             print(name, "vertices", len(out["vertices"]), "edges", len(out["edges"]))
 
     # sketch digests on the large reference fixture (not copied: 13.8 MB)

@@ -45,9 +45,16 @@ class RecordingGraph:
         def __iter__(self):
             return iter(())
 
+        def __len__(self):
+            return len(self.g.edges)
+
     @property
     def es(self):
         return RecordingGraph._ES(self)
+
+    @property
+    def vs(self):
+        return [{"name": n} for n in self.vnames]
 
 
 def read_minimizers(tsv_filename, repeat_bf=False):

@@ -59,6 +59,40 @@ def test_dropin_functions_vs_golden(golden_dir, tmp_path):
         assert gr.eattr["weight"] == g["weight"], path
 
 
+def test_dropin_print_graph_bytes(golden_dir, tmp_path, monkeypatch):
+    """Ntjoin.print_graph replaced by the array writer: same bytes as the reference's own print_graph wrote for the
+    same graph (tests/golden/expected/print_graph_*.mx.dot), and the original runs when the graph is not ours"""
+    import types
+    from ntjoin_b200 import dropin
+    mod = dropin.install(ref_py.as_module())
+    calls = []
+
+    class Ntjoin:                                        # shaped like bin/ntjoin.py's class: list_mx_info, args.p
+        def print_graph(self, graph, out_prefix=None):
+            calls.append(graph)
+
+    nt = dropin.install_print_graph(types.SimpleNamespace(Ntjoin=Ntjoin))
+    monkeypatch.chdir(tmp_path)
+    for name in ("config1_ff_w500", "three_way_w1000", "misassembled_frrf_w500", "selfdup_w250"):
+        g = json.load(open(os.path.join(golden_dir, f"steps23_{name}.json")))
+        obj = nt.Ntjoin()
+        obj.list_mx_info, list_mxs, weights = {}, {}, {}
+        for i, f in enumerate(g["files"]):
+            tsv = f"{i}.{f}.k{g['k']}.w{g['w']}.tsv"     # relative names = the assembly keys of the golden file
+            subprocess.check_call([sys.executable, INDEXLR, "--seq", "--long", "--pos", "-k", str(g["k"]), "-w", str(g["w"]),
+                                   os.path.join(golden_dir, "inputs", f), "-o", tsv])
+            obj.list_mx_info[tsv], list_mxs[tsv] = mod.read_minimizers(tsv)
+            weights[tsv] = g["weights"][i]
+        gr = mod.build_graph(mod.filter_minimizers(list_mxs), weights)
+        obj.args = types.SimpleNamespace(p=f"out_{name}")
+        obj.print_graph(gr)
+        want = open(os.path.join(golden_dir, "expected", f"print_graph_{name}.mx.dot"), "rb").read()
+        assert open(f"out_{name}.mx.dot", "rb").read() == want, name
+    assert not calls
+    obj.print_graph(types.SimpleNamespace(vs=[], es=[]))     # not built by the engine: the original must run
+    assert len(calls) == 1
+
+
 def test_dropin_falls_through_for_plain_lists():
     """callers like bin/ntjoin_overlap.py:25-28 pass plain lists keyed by ints: the originals must run"""
     from ntjoin_b200 import dropin
