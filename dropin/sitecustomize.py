@@ -13,7 +13,7 @@ import sys
 if os.environ.get("NTJOIN_B200", "0") not in ("", "0"):
     class _Patch(importlib.abc.MetaPathFinder):
         def find_spec(self, name, path, target=None):
-            if name not in ("ntjoin_utils", "ntjoin"):
+            if name not in ("ntjoin_utils", "ntjoin", "ntjoin_assemble"):
                 return None
             sys.meta_path.remove(self)
             try:
@@ -30,8 +30,10 @@ if os.environ.get("NTJOIN_B200", "0") not in ("", "0"):
                 from ntjoin_b200 import dropin
                 if name == "ntjoin_utils":
                     dropin.install(module)
-                else:
+                elif name == "ntjoin":
                     dropin.install_print_graph(module)      # Ntjoin.print_graph -> .mx.dot from arrays
+                else:
+                    dropin.install_scaffolder(module)       # NtjoinScaffolder.find_mx_min_max from arrays
 
             loader.exec_module = exec_module
             return spec

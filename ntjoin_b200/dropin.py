@@ -166,6 +166,40 @@ def make_print_graph(original):
     return print_graph
 
 
+def make_find_mx_min_max(original):
+    """NtjoinScaffolder.find_mx_min_max (bin/ntjoin_assemble.py:688-702): per record of the target, the smallest and
+    largest position of a minimizer that is a graph vertex -- from the arrays instead of one igraph name lookup per
+    unique minimizer of the target."""
+    def find_mx_min_max(self, target):
+        p = _dot_payload(self.graph) if self.graph is not None else None
+        count = lambda seq: seq() if callable(seq) else seq      # noqa: E731
+        if p is None or target not in p.keys or len(count(self.graph.vs)) != len(p.vertices):
+            return original(self, target)
+        a = p.keys.index(target)
+        ctg, pos = np.asarray(p.v_ctg[a], dtype=np.int64), np.asarray(p.v_pos[a], dtype=np.int64)
+        if not len(ctg):
+            return {}
+        order = np.argsort(ctg, kind="stable")
+        ctg, pos = ctg[order], pos[order]
+        starts = np.flatnonzero(np.concatenate([[True], ctg[1:] != ctg[:-1]]))
+        lo, hi = np.minimum.reduceat(pos, starts), np.maximum.reduceat(pos, starts)
+        names = p.names[a]
+        # the reference's dict is filled in (record, position) order of the target's minimizers: records ascending
+        return {names[int(c)]: (int(l), int(h)) for c, l, h in zip(ctg[starts], lo, hi)}
+    find_mx_min_max.__doc__ = original.__doc__
+    return find_mx_min_max
+
+
+def install_scaffolder(module):
+    """Patch a loaded `ntjoin_assemble` module (bin/ntjoin_assemble.py) in place (idempotent)."""
+    cls = getattr(module, "NtjoinScaffolder", None)
+    if cls is None or getattr(cls, "_mxe_min_max", False):
+        return module
+    cls.find_mx_min_max = make_find_mx_min_max(cls.find_mx_min_max)
+    cls._mxe_min_max = True
+    return module
+
+
 def install_print_graph(module):
     """Patch a loaded `ntjoin` module (bin/ntjoin.py) in place (idempotent)."""
     cls = getattr(module, "Ntjoin", None)

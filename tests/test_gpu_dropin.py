@@ -93,6 +93,42 @@ def test_dropin_print_graph_bytes(golden_dir, tmp_path, monkeypatch):
     assert len(calls) == 1
 
 
+def test_dropin_find_mx_min_max(golden_dir, tmp_path, monkeypatch):
+    """NtjoinScaffolder.find_mx_min_max from arrays == the reference loop (bin/ntjoin_assemble.py:688-702), incl. dict order"""
+    import types
+    from ntjoin_b200 import dropin
+    mod = dropin.install(ref_py.as_module())
+
+    class NtjoinScaffolder:
+        def find_mx_min_max(self, target):               # the reference's loop, vertex lookup by name
+            vertices = {v["name"] for v in self.graph.vs}
+            out = {}
+            for mx, (ctg, pos) in self.list_mx_info[target].items():
+                if mx in vertices:
+                    out[ctg] = (min(out[ctg][0], pos), max(out[ctg][1], pos)) if ctg in out else (pos, pos)
+            return out
+
+    original = NtjoinScaffolder.find_mx_min_max
+    sc = dropin.install_scaffolder(types.SimpleNamespace(NtjoinScaffolder=NtjoinScaffolder)).NtjoinScaffolder
+    monkeypatch.chdir(tmp_path)
+    for name in ("multiple_w500", "misassembled_ffrr_w500", "selfdup_w250", "overlap_k15_w10"):
+        g = json.load(open(os.path.join(golden_dir, f"steps23_{name}.json")))
+        obj = sc()
+        obj.list_mx_info, list_mxs, weights = {}, {}, {}
+        for i, f in enumerate(g["files"]):
+            tsv = f"{i}.{f}.k{g['k']}.w{g['w']}.tsv"
+            subprocess.check_call([sys.executable, INDEXLR, "--seq", "--long", "--pos", "-k", str(g["k"]), "-w", str(g["w"]),
+                                   os.path.join(golden_dir, "inputs", f), "-o", tsv])
+            obj.list_mx_info[tsv], list_mxs[tsv] = mod.read_minimizers(tsv)
+            weights[tsv] = g["weights"][i]
+        obj.graph = mod.build_graph(mod.filter_minimizers(list_mxs), weights)
+        for target in list_mxs:
+            got, want = obj.find_mx_min_max(target), original(obj, target)
+            assert got == want and list(got) == list(want), (name, target)
+            assert all(type(v[0]) is int and type(v[1]) is int for v in got.values())
+        assert len(want) > 0
+
+
 def test_dropin_falls_through_for_plain_lists():
     """callers like bin/ntjoin_overlap.py:25-28 pass plain lists keyed by ints: the originals must run"""
     from ntjoin_b200 import dropin
