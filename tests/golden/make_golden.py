@@ -47,6 +47,12 @@ CASES = [
     ("termN_w1000", ["ref.fa"], "scaf.f-f.termN.unassigned.fa", 32, 1000, [2.0, 1.0]),
     ("selfdup_w250", ["scaf.more_seqs.fa"], "scaf.more_seqs.fa", 32, 250, [2.0, 1.0]),
     ("overlap_k15_w10", ["ref.fa"], "scaf.f-f.overlapping.fa", 15, 10, [1.0, 1.0]),
+    ("rr_w500", ["ref.fa"], "scaf.r-r.fa", 32, 500, [2.0, 1.0]),
+    ("fr_w1000", ["ref.fa"], "scaf.f-r.fa", 32, 1000, [2.0, 1.0]),
+    ("four_way_w500", ["ref.fa", "scaf.f-f.copy.fa", "scaf.r-f.fa"], "scaf.f-f.fa", 32, 500, [2.0, 2.0, 1.5, 1.0]),
+    ("multiple_k24_w250", ["ref.multiple.fa"], "scaf.multiple.fa", 24, 250, [2.0, 1.0]),
+    ("termN_k40_w500", ["ref.fa"], "scaf.f-f.termN.fa", 40, 500, [3.0, 1.0]),
+    ("more_seqs_vs_misassembled_k20_w50", ["scaf.more_seqs.fa"], "scaf.misassembled.f-f.r-r.fa", 20, 50, [1.0, 1.0]),
 ]
 
 
