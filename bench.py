@@ -264,6 +264,31 @@ def run_reference_arm(args, spec):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------ the bound that actually binds
+ALU_OPS_PER_BASE = 9.3       # ALU-pipe instructions per base of cand31_kernel<0,1>, counted in its SASS
+
+
+def alu_roofline(bases_per_launch, launch_ms):
+    """cand31_kernel against the INT32 ALU pipe (LOP3/SHF/IADD3/ISETP/PRMT): the secondary roofline of SURVEY.md 8(d).
+    Peak = LOP3 rate measured on this GPU type by tools/alu_peak.cu (profiles/r01_l_alu_peak_microbench.jsonl), else the
+    nominal 148 SMs x 64 lanes x 1.965 GHz."""
+    try:
+        peak, source = 148 * 64 * 1.965e9 / 1e12, "nominal 148 SM x 64 lanes x 1.965 GHz"
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_l_alu_peak_microbench.jsonl")) as fh:
+                for row in fh:
+                    r = json.loads(row)
+                    if str(r.get("op", "")).startswith("LOP3"):
+                        peak, source = float(r["tera_thread_ops_per_s"]), "tools/alu_peak.cu LOP3 rate (profiles/r01_l_alu_peak_microbench.jsonl)"
+        except (OSError, ValueError, KeyError):
+            pass
+        achieved = ALU_OPS_PER_BASE * bases_per_launch / (launch_ms * 1e-3) / 1e12 if launch_ms > 0 else 0.0
+        return {"bound": "int32 alu pipe", "ops_per_base": ALU_OPS_PER_BASE, "achieved": achieved, "peak": peak, "unit": "Tops/s",
+                "frac": achieved / peak if peak else None, "peak_source": source}
+    except Exception as exc:           # reporting only: never lose the bench line over it
+        return {"error": str(exc)}
+
+
 # ------------------------------------------------------------------------------------ k x w sweep (configs[4])
 def run_sweep(args, spec, eng, shards, total_bases):
     """Device-resident step time and roofline fraction of the dominant sketch kernel per (k, w) point."""
@@ -486,6 +511,7 @@ def main():
                          "phase_ms_per_step": phases},
             "clocks": clocks,
         }
+        line["roofline"]["alu"] = alu_roofline(my_bases / n_asm, cand_ms)
         if not args.no_cpu_baseline:
             cb, _ = cpu_reference_run(spec, args, 1, 1)
             line["cpu_baseline"] = cb
