@@ -22,6 +22,10 @@ __global__ void __launch_bounds__(256) rate_kernel(uint32_t* out, uint32_t a, ui
                 if (MODE == 0) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[j]) : "r"(x[(j + 1) % CHAINS]), "r"(a));
                 if (MODE == 1) asm volatile("shf.l.wrap.b32 %0, %0, %1, %2;" : "+r"(x[j]) : "r"(x[(j + 1) % CHAINS]), "r"(b));
                 if (MODE == 2) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[j]) : "r"(a), "r"(x[(j + 1) % CHAINS]));
+                if (MODE == 4) asm volatile("xor.b32 %0, %0, %1;" : "+r"(x[j]) : "r"(x[(j + 1) % CHAINS]));                    // two register sources
+                if (MODE == 5) asm volatile("lop3.b32 %0, %0, %1, 0x5bd1e995, 0x96;" : "+r"(x[j]) : "r"(x[(j + 1) % CHAINS]));  // two registers + immediate
+                if (MODE == 6) asm volatile("shf.l.wrap.b32 %0, %0, %1, 7;" : "+r"(x[j]) : "r"(x[(j + 1) % CHAINS]));           // immediate shift
+                if (MODE == 7) asm volatile("mad.lo.u32 %0, %0, 3, %1;" : "+r"(x[j]) : "r"(x[(j + 1) % CHAINS]));               // immediate multiplier
                 if (MODE == 3) {
                     if (j % 3 == 2) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[j]) : "r"(a), "r"(x[(j + 1) % CHAINS]));
                     else asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[j]) : "r"(x[(j + 1) % CHAINS]), "r"(a));
@@ -73,5 +77,12 @@ int main()
     run<1>("SHF funnel (ALU pipe)", p.multiProcessorCount, ghz);
     run<2>("IMAD (FMA pipe)", p.multiProcessorCount, ghz);
     run<3>("3 LOP3 : 1 IMAD (both pipes)", p.multiProcessorCount, ghz);
+    // operand-bandwidth question left open by the four lines above (all three-register forms): do forms with two
+    // register sources issue faster?  (Not yet run on a GPU.  ptxas fuses pairs of the two-source XORs into LOP3s --
+    // check the instruction count with cuobjdump before trusting that line.)
+    run<4>("XOR, two register sources", p.multiProcessorCount, ghz);
+    run<5>("LOP3, two registers + immediate", p.multiProcessorCount, ghz);
+    run<6>("SHF funnel, immediate shift", p.multiProcessorCount, ghz);
+    run<7>("IMAD, immediate multiplier", p.multiProcessorCount, ghz);
     return 0;
 }
