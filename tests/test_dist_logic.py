@@ -87,6 +87,27 @@ def test_lockstep_empty_rank_and_no_survivors(oracle, mode):
     check_merged(merge_shards([s.fetch() for s in shards]), want)
 
 
+@pytest.mark.parametrize("mode", ["alltoall", "allreduce"])
+def test_lockstep_single_assembly_and_heavy_duplicates(oracle, mode):
+    """n_asm = 1 (every unique hash survives; edges come from one assembly) and an assembly full of repeated segments"""
+    rseq, roffs, _ = synth.make_reference(250_000, n_chrom=7, dup_frac=0.4, seed=21)
+    one = [(rseq, roffs)]
+    full = [oracle.sketch(rseq, roffs, 32, 40)]
+    want = oracle.filter_and_edges([full[0]["out_hash"]], [full[0]["contig"]], [1.5])
+    assert 0 < want["uniq"][0].sum() < len(full[0])          # duplicates were dropped
+    for world in (2, 3):
+        hashes, contigs = shard_case(oracle, one, world, w=40)
+        shards = run_lockstep([STAGES[mode]() for _ in range(world)], hashes, contigs, [1.5], torch.device("cpu"))
+        check_merged(merge_shards([s.fetch() for s in shards]), want)
+    tseq, toffs, _ = synth.derive_target(rseq, roffs, min_len=2000, max_len=30000, seed=22)
+    two = [(rseq, roffs), (tseq, toffs)]
+    full = [oracle.sketch(s, o, 32, 40) for s, o in two]
+    want = oracle.filter_and_edges([f["out_hash"] for f in full], [f["contig"] for f in full], [2.0, 1.0])
+    hashes, contigs = shard_case(oracle, two, 4, w=40)
+    shards = run_lockstep([STAGES[mode]() for _ in range(4)], hashes, contigs, [2.0, 1.0], torch.device("cpu"))
+    check_merged(merge_shards([s.fetch() for s in shards]), want)
+
+
 def _worker(rank, world, port, q, mode):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     sys.path.insert(0, ROOT)
