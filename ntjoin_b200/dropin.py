@@ -19,6 +19,15 @@ import numpy as np
 _ENGINE = None
 
 
+def _trace(what):
+    """MXE_DROPIN_TRACE=<file>: one line per seam call, saying whether the engine served it or the original ran"""
+    import os
+    path = os.environ.get("MXE_DROPIN_TRACE")
+    if path:
+        with open(path, "a", encoding="utf-8") as fh:
+            fh.write(what + "\n")
+
+
 def _engine():
     global _ENGINE
     if _ENGINE is None:
@@ -52,7 +61,9 @@ def _lists_from(sk, mask):
 def make_read_minimizers(original):
     def read_minimizers(tsv_filename, repeat_bf=False):
         if repeat_bf:
+            _trace("read_minimizers original")
             return original(tsv_filename, repeat_bf)
+        _trace("read_minimizers engine")
         eng = _engine()
         sk = eng.load_tsv(tsv_filename)
         res = eng.filter_and_edges([sk], [1.0])
@@ -72,7 +83,9 @@ def make_filter_minimizers(original):
     def filter_minimizers(list_mxs):
         vals = list(list_mxs.values())
         if not vals or not all(isinstance(v, MxLists) and v._sketch is not None for v in vals):
+            _trace("filter_minimizers original")
             return original(list_mxs)
+        _trace("filter_minimizers engine")
         eng = _engine()
         sks = [v._sketch for v in vals]
         res = eng.filter_and_edges(sks, [1.0] * len(sks))
@@ -92,7 +105,9 @@ def make_build_graph(original, ig):
         vals = list(list_mxs.values())
         if graph is not None or black_list is not None or not vals or \
                 not all(isinstance(v, MxLists) and v._sketch is not None and v._asm_index is not None for v in vals):
+            _trace("build_graph original")
             return original(list_mxs, weights, graph, black_list)
+        _trace("build_graph engine")
         eng = _engine()
         keys = list(list_mxs.keys())
         res = eng.filter_and_edges([v._sketch for v in vals], [weights[k] for k in keys])
@@ -153,7 +168,9 @@ def make_print_graph(original):
         count = lambda seq: seq() if callable(seq) else seq      # noqa: E731
         if p is None or list(self.list_mx_info.keys()) != p.keys or \
                 len(count(graph.vs)) != len(p.vertices) or len(count(graph.es)) != len(p.e_src):
+            _trace("print_graph original")
             return original(self, graph, out_prefix)
+        _trace("print_graph engine")
         out_graph = self.args.p + ".mx.dot" if out_prefix is None else out_prefix + "mx.dot"
         print(datetime.datetime.today(), ": Printing graph", out_graph, sep=" ", file=sys.stdout)
         write_mx_dot(out_graph, p.vertices, p.keys, p.names, p.v_ctg, p.v_pos, p.e_src, p.e_dst, p.masks, p.weights)
@@ -174,7 +191,9 @@ def make_find_mx_min_max(original):
         p = _dot_payload(self.graph) if self.graph is not None else None
         count = lambda seq: seq() if callable(seq) else seq      # noqa: E731
         if p is None or target not in p.keys or len(count(self.graph.vs)) != len(p.vertices):
+            _trace("find_mx_min_max original")
             return original(self, target)
+        _trace("find_mx_min_max engine")
         a = p.keys.index(target)
         ctg, pos = np.asarray(p.v_ctg[a], dtype=np.int64), np.asarray(p.v_pos[a], dtype=np.int64)
         if not len(ctg):

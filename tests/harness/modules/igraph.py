@@ -102,7 +102,17 @@ class Graph:
         self._vattr = {"name": []}
         self._edges = []             # (u, v) vertex ids as given
         self._eattr = {}
+        self._gattr = {}             # graph attributes: g["key"] = value, kept by copy() and subgraph()
         self._cache = {}
+
+    def __setitem__(self, key, value):
+        self._gattr[key] = value
+
+    def __getitem__(self, key):
+        return self._gattr[key]
+
+    def attributes(self):
+        return list(self._gattr)
 
     # ---- internals
     def _touch(self):
@@ -152,6 +162,7 @@ class Graph:
         g._vattr = {k: list(v) for k, v in self._vattr.items()}
         g._edges = list(self._edges)
         g._eattr = {k: list(v) for k, v in self._eattr.items()}
+        g._gattr = dict(self._gattr)
         return g
 
     def delete_edges(self, ids):
@@ -212,6 +223,7 @@ class Graph:
         keep = [i for i, (u, v) in enumerate(self._edges) if u in new and v in new]
         g._edges = [(new[self._edges[i][0]], new[self._edges[i][1]]) for i in keep]
         g._eattr = {k: [v[i] for i in keep] for k, v in self._eattr.items()}
+        g._gattr = dict(self._gattr)
         return g
 
     def get_shortest_paths(self, v, to=None, output="vpath", **_kw):

@@ -20,7 +20,7 @@ needs_reference = pytest.mark.skipif(not os.path.exists(os.path.join(REF, "tests
                                      reason="reference checkout not on this box")
 
 
-def run_suite(tmp_path, canonical=None, extra=()):
+def run_suite(tmp_path, canonical=None, extra=(), dropin=False):
     oracle_lib.build()
     work = tmp_path / "ntJoin"
     shutil.copytree(REF, work, symlinks=True, ignore=shutil.ignore_patterns(".git"))
@@ -32,6 +32,11 @@ def run_suite(tmp_path, canonical=None, extra=()):
     env.pop("MXO_CANONICAL", None)
     if canonical:
         env["MXO_CANONICAL"] = canonical
+    if dropin:      # the product's drop-in layer on, its two engine calls served by the oracle (tests/harness/fake_engine.py)
+        env["NTJOIN_B200"] = "1"
+        env["MXE_REPO_ROOT"] = os.path.dirname(HERE)
+        env["PYTHONPATH"] = os.path.join(HERE, "harness", "dropin_site") + os.pathsep + env["PYTHONPATH"]
+        env["MXE_DROPIN_TRACE"] = str(tmp_path / "dropin_trace.txt")
     r = subprocess.run([sys.executable, "-m", "pytest", "ntjoin_test.py", "-q", "-p", "no:cacheprovider", *extra],
                        cwd=work / "tests", env=env, capture_output=True, text=True)
     return r, (r.stdout + r.stderr)[-3000:]
@@ -53,3 +58,27 @@ def test_reference_suite_rejects_legacy_min_combiner(tmp_path):
     r, tail = run_suite(tmp_path, canonical="min")
     assert r.returncode != 0 and " failed" in r.stdout, tail
     assert "test_regions_ff_rr" in r.stdout and "overlap" in r.stdout, tail
+
+
+@needs_reference
+@pytest.mark.timeout(1500)
+def test_reference_suite_with_dropin_layer(tmp_path):
+    """the reference's 20 tests with the PRODUCT's seam-S3 layer switched on through its own import hook:
+    read_minimizers / filter_minimizers / build_graph rebuilt from arrays, Ntjoin.print_graph through mxe_write_dot,
+    NtjoinScaffolder.find_mx_min_max from arrays, plain-list callers (ntjoin_overlap) falling through -- only the two
+    engine calls underneath are served by the oracle here, because this container has no GPU"""
+    r, tail = run_suite(tmp_path, extra=("-x",), dropin=True)
+    assert r.returncode == 0, tail
+    assert "20 passed" in r.stdout, tail
+    # the hooks really ran: every seam function was served through the drop-in layer in every run, and the plain-list
+    # callers of the overlap code (bin/ntjoin_overlap.py:25-28,132) fell through to the reference's originals
+    trace = (tmp_path / "dropin_trace.txt").read_text().split("\n")
+    for fn in ("read_minimizers", "filter_minimizers", "build_graph", "print_graph", "find_mx_min_max"):
+        assert trace.count(fn + " engine") >= 20, (fn, trace.count(fn + " engine"))
+    assert trace.count("build_graph original") > 0 and trace.count("filter_minimizers original") > 0
+    assert trace.count("print_graph original") == 0 and trace.count("find_mx_min_max original") == 0
+    dots = sorted((tmp_path / "ntJoin" / "tests").glob("*.mx.dot"))
+    assert dots
+    for d in dots:      # written by the array writer from the engine-built graph: vertices in ascending hash order
+        names = [int(line.split('"')[1]) for line in d.read_text().splitlines() if "[label=" in line]
+        assert names == sorted(names), d
