@@ -32,6 +32,7 @@ typedef struct mxe_sketch mxe_sketch_t;
 typedef struct mxe_result mxe_result_t;
 typedef struct mxe_dist mxe_dist_t;
 typedef struct mxe_a2a mxe_a2a_t;
+typedef struct mxe_fasta mxe_fasta_t;
 
 enum {
     MXE_OK = 0,
@@ -69,6 +70,14 @@ int  mxe_set_option(mxe_t* e, const char* name, double value);
 /* FASTA file (multi-line records, '>' headers; id = header up to first whitespace).
  * Replaces: indexlr subprocess, ntJoin:204-205. */
 int mxe_sketch_file(mxe_t* e, const char* fasta_path, int k, int w, int flags, mxe_sketch_t** out);
+
+/* The same reader on its own, host only (no engine, no GPU): what btllib.SeqReader gives ntJoin
+ * (bin/ntjoin_assemble.py:313-316).  FASTA or FASTQ; record id = header up to the first blank; sequence lines
+ * joined and upper-cased.  `seq` holds all records back to back (offsets has n_records + 1 entries). */
+int mxe_fasta_read(const char* path, mxe_fasta_t** out);
+int mxe_fasta_view(mxe_fasta_t* f, uint32_t* n_records, const uint64_t** offsets, const char** seq);
+int mxe_fasta_name(mxe_fasta_t* f, uint32_t idx, const char** name);
+void mxe_fasta_free(mxe_fasta_t* f);
 
 /* Host buffers: `seq` = all records concatenated (ASCII, either case, no separators),
  * `offsets` = n_contigs+1 starts, `names` may be NULL.  Host->device copy is inside the call. */

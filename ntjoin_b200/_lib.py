@@ -8,6 +8,7 @@ _LIB = None
 # every symbol declared in include/mxe.h (tests check the library exports each one)
 SYMBOLS = [
     "mxe_version", "mxe_last_error", "mxe_create", "mxe_destroy", "mxe_set_stream", "mxe_set_option",
+    "mxe_fasta_read", "mxe_fasta_view", "mxe_fasta_name", "mxe_fasta_free",
     "mxe_sketch_file", "mxe_sketch_buffers", "mxe_prefetch_buffers", "mxe_sketch_device", "mxe_sketch_load_tsv", "mxe_sketch_view",
     "mxe_sketch_device_view", "mxe_sketch_contig_name", "mxe_sketch_counts", "mxe_write_tsv", "mxe_sketch_free",
     "mxe_filter_and_edges", "mxe_filter_and_edges_device", "mxe_result_counts", "mxe_result_flags", "mxe_result_graph",
@@ -50,6 +51,11 @@ def load_library():
     lib.mxe_set_option.argtypes = [vp, C.c_char_p, C.c_double]
     lib.mxe_sketch_file.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_int, pp]
     lib.mxe_sketch_buffers.argtypes = [vp, vp, u64p, C.c_uint32, C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_int, pp]
+    lib.mxe_fasta_read.argtypes = [C.c_char_p, pp]
+    lib.mxe_fasta_view.argtypes = [vp, u32p, pp, pp]
+    lib.mxe_fasta_name.argtypes = [vp, C.c_uint32, C.POINTER(C.c_char_p)]
+    lib.mxe_fasta_free.argtypes = [vp]
+    lib.mxe_fasta_free.restype = None
     lib.mxe_prefetch_buffers.argtypes = [vp, vp, C.c_uint64]
     lib.mxe_sketch_device.argtypes = [vp, vp, u64p, C.c_uint32, C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_int, pp]
     lib.mxe_sketch_load_tsv.argtypes = [vp, C.c_char_p, pp]

@@ -87,10 +87,30 @@ class SeqReader:
         pass
 
     def __iter__(self):
+        if str(self._path).endswith(".gz"):
+            yield from self._iter_python()
+            return
+        # the engine's own reader (host only: mxe_fasta_read), the one mxe_sketch_file sketches from
+        import ctypes as C
+        from ._lib import check, load_library
+        lib = load_library()
+        h = C.c_void_p()
+        check(lib, lib.mxe_fasta_read(str(self._path).encode(), C.byref(h)))
+        try:
+            n, offs, seq, nm = C.c_uint32(), C.c_void_p(), C.c_void_p(), C.c_char_p()
+            check(lib, lib.mxe_fasta_view(h, C.byref(n), C.byref(offs), C.byref(seq)))
+            offsets = C.cast(offs, C.POINTER(C.c_uint64))
+            for i in range(n.value):
+                check(lib, lib.mxe_fasta_name(h, i, C.byref(nm)))
+                a, b = offsets[i], offsets[i + 1]
+                yield SeqRecord(i, nm.value.decode("utf-8", "replace"), "", C.string_at(seq.value + a, b - a).decode("ascii", "replace"), "")
+        finally:
+            lib.mxe_fasta_free(h)
+
+    def _iter_python(self):
         import gzip
-        op = gzip.open if str(self._path).endswith(".gz") else open
         num, name, comment, parts = 0, None, "", []
-        with op(self._path, "rt") as fh:
+        with gzip.open(self._path, "rt") as fh:
             first = fh.read(1)
             fh.seek(0)
             if first == "@":

@@ -306,6 +306,41 @@ static int read_fasta(const char* path, std::vector<char>& seq, std::vector<uint
     return MXE_OK;
 }
 
+// host-only face of the reader (no engine, no GPU): what btllib.SeqReader gives ntJoin (bin/ntjoin_assemble.py:313-316)
+struct mxe_fasta {
+    std::vector<char> seq;
+    std::vector<uint64_t> offsets;
+    std::vector<std::string> names;
+};
+
+int mxe_fasta_read(const char* path, mxe_fasta_t** out)
+{
+    if (!path || !out) { set_error("null argument"); return MXE_ERR_ARG; }
+    mxe_fasta* F = new mxe_fasta();
+    int rc = read_fasta(path, F->seq, F->offsets, F->names);
+    if (rc != MXE_OK) { delete F; return rc; }
+    *out = F;
+    return MXE_OK;
+}
+
+int mxe_fasta_view(mxe_fasta_t* F, uint32_t* n_records, const uint64_t** offsets, const char** seq)
+{
+    if (!F) { set_error("null argument"); return MXE_ERR_ARG; }
+    if (n_records) *n_records = (uint32_t)F->names.size();
+    if (offsets) *offsets = F->offsets.data();
+    if (seq) *seq = F->seq.data();
+    return MXE_OK;
+}
+
+int mxe_fasta_name(mxe_fasta_t* F, uint32_t idx, const char** name)
+{
+    if (!F || !name || idx >= F->names.size()) { set_error("bad record index"); return MXE_ERR_ARG; }
+    *name = F->names[idx].c_str();
+    return MXE_OK;
+}
+
+void mxe_fasta_free(mxe_fasta_t* F) { delete F; }
+
 int mxe_sketch_file(mxe_t* e, const char* fasta_path, int k, int w, int flags, mxe_sketch_t** out)
 {
     if (!e || !out || !fasta_path) { set_error("null argument"); return MXE_ERR_ARG; }

@@ -66,3 +66,10 @@ class Indexlr(_Ctx):
                 mxs.append(Minimizer(int(m["min_hash"][at]), int(m["out_hash"][at]), int(m["pos"][at]), bool(m["forward"][at]), ""))
                 at += 1
             yield IndexlrRecord(i, name, "", int(offs[i + 1] - offs[i]), mxs)
+
+
+if os.environ.get("NTJOIN_B200", "0") not in ("", "0") and os.environ.get("MXE_REPO_ROOT"):
+    # drop-in run: the PRODUCT's SeqReader (host-only C reader, mxe_fasta_read) serves bin/ntjoin_assemble.py:313-316
+    if os.environ["MXE_REPO_ROOT"] not in sys.path:
+        sys.path.insert(0, os.environ["MXE_REPO_ROOT"])
+    from ntjoin_b200.btllib_compat import SeqReader, SeqReaderFlag  # noqa: E402,F401,F811
