@@ -113,3 +113,56 @@ def as_module():
     m.ig = ig
     m.read_minimizers, m.filter_minimizers, m.build_graph = read_minimizers, filter_minimizers, build_graph
     return m
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Step 1 in plain Python integers, written independently of oracle/mxo.c: no rolling, no
+# deque -- every valid k-mer is hashed from scratch and every window is scanned.  Small inputs only.
+# ---------------------------------------------------------------------------------------------------------
+_M64 = (1 << 64) - 1
+_SEED = {"A": 0x3c8bfbb395c60474, "C": 0x3193c18562a02b4c, "G": 0x20323ed082572324, "T": 0x295549f54be24456}
+_COMP = {"A": "T", "C": "G", "G": "C", "T": "A"}
+
+
+def _srol(x, n=1):
+    """rotate the 33-bit group (bits 32:0) and the 31-bit group (bits 63:33) left by n, independently"""
+    lo, hi = x & ((1 << 33) - 1), x >> 33
+    a, b = n % 33, n % 31
+    lo = ((lo << a) | (lo >> (33 - a))) & ((1 << 33) - 1) if a else lo
+    hi = ((hi << b) | (hi >> (31 - b))) & ((1 << 31) - 1) if b else hi
+    return (hi << 33) | lo
+
+
+def kmer_hashes_py(kmer, canonical="sum"):
+    """(fwd, rev, hash0, hash1, forward) of one k-mer of ACGT"""
+    k = len(kmer)
+    fwd = rev = 0
+    for i, ch in enumerate(kmer):
+        fwd ^= _srol(_SEED[ch], k - 1 - i)
+        rev ^= _srol(_SEED[_COMP[ch]], i)
+    h0 = (fwd + rev) & _M64 if canonical == "sum" else min(fwd, rev)
+    t = (h0 * (1 ^ ((k * 0x90b45d39fb6da1fa) & _M64))) & _M64
+    return fwd, rev, h0, t ^ (t >> 27), fwd <= rev
+
+
+def sketch_py(seq, offsets, k, w, canonical="sum"):
+    """[(record, pos, out_hash, min_hash, forward)] -- windows over VALID k-mers, rightmost minimum, emitted when it moves"""
+    text = bytes(seq).decode("latin-1").upper()
+    out = []
+    for c in range(len(offsets) - 1):
+        rec = text[int(offsets[c]):int(offsets[c + 1])]
+        valid = []                                   # (pos, hash0, hash1, forward) of every k-mer made of ACGT only
+        for p in range(len(rec) - k + 1):
+            km = rec[p:p + k]
+            if all(ch in _SEED for ch in km):
+                _, _, h0, h1, fw = kmer_hashes_py(km, canonical)
+                valid.append((p, h0, h1, fw))
+        last = -1
+        for j in range(w - 1, len(valid)):
+            win = valid[j - w + 1:j + 1]
+            best = min(x[1] for x in win)
+            p, h0, h1, fw = [x for x in win if x[1] == best][-1]      # ties: the rightmost
+            if p > last and h0 != _M64:
+                out.append((c, p, h1, h0, fw))
+                last = p
+    return out
