@@ -265,7 +265,7 @@ def run_reference_arm(args, spec):
 
 
 # ------------------------------------------------------------------------------------ the bound that actually binds
-ALU_OPS_PER_BASE = 9.3       # ALU-pipe instructions per base of cand31_kernel<0,1>, counted in its SASS
+ALU_OPS_PER_BASE = 9.1       # ALU-pipe instructions per base of cand31_kernel<0,1>, counted in its SASS
 
 
 def alu_roofline(bases_per_launch, launch_ms):

@@ -1,0 +1,57 @@
+"""CPU: the per-base instruction counts DESIGN.md 3.3 and bench.py (roofline.alu, ALU_OPS_PER_BASE) quote for
+cand31_kernel are read off the SASS of the library that ships -- this test re-derives them with cuobjdump so the quoted
+figures cannot drift from the binary."""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+import ntjoin_b200
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ALU = ("LOP3", "SHF", "PRMT", "ISETP", "IADD3", "VIADD", "LEA", "SEL", "VIMNMX", "VIADDMNMX", "POPC", "FLO", "BREV", "IABS")
+FMA = ("IMAD", "FFMA", "FMUL")
+LSU = ("LDS", "STS", "LDG", "STG", "LD", "ST", "ATOMS", "RED")
+
+
+def main_loop(sass):
+    """instructions of the innermost loop that holds the sixteen LDS.64 table lookups (one group of 16 bases)"""
+    ins = []
+    for line in sass.splitlines():
+        m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", line)
+        if m:
+            ins.append((int(m.group(1), 16), m.group(2).strip()))
+    best = None
+    for addr, text in ins:
+        m = re.search(r"BRA\s+(?:`\(\S+\)|0x([0-9a-f]+))", text)
+        if m and m.group(1) and int(m.group(1), 16) < addr:
+            body = [t for a, t in ins if int(m.group(1), 16) <= a <= addr]
+            if sum("LDS.64" in t for t in body) == 16 and (best is None or len(body) < len(best)):
+                best = body
+    return best
+
+
+@pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump not on PATH")
+def test_cand31_instruction_mix_per_base():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    out = subprocess.run(["cuobjdump", "-sass", ntjoin_b200.library_path()], capture_output=True, text=True, check=True).stdout
+    chunks = out.split("Function : ")
+    fn = [c for c in chunks if c.startswith("_ZN3mxe13cand31_kernelILi0ELi1E")]
+    assert len(fn) == 1, "cand31_kernel<0, 1> (sum combiner, FMA-offloaded test) not found in libmxe.so"
+    body = main_loop(fn[0])
+    assert body is not None, "main loop with 16 LDS.64 not found"
+    op = lambda t: re.sub(r"^@!?U?P\d+\s+", "", t).split()[0].split(".")[0]      # noqa: E731
+    ops = [op(t) for t in body]
+    alu = sum(o in ALU for o in ops) / 16.0
+    fma = sum(o in FMA for o in ops) / 16.0
+    lsu = sum(o in LSU for o in ops) / 16.0
+    # 16 bases per trip: the roll is 5 ALU ops per base (2 rotations x 2 + ... ), test + accumulate on the FMA pipe
+    assert sum(t.startswith("LDS.64") or " LDS.64" in t for t in body) == 16
+    assert abs(alu - bench.ALU_OPS_PER_BASE) <= 0.25, (alu, fma, lsu)
+    assert 4.0 <= fma <= 6.0 and 1.0 <= lsu <= 2.0, (alu, fma, lsu)
+    assert len(ops) / 16.0 < 17.5            # whole trip, including loop overhead
