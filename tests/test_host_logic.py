@@ -47,3 +47,30 @@ def test_shard_ranges_compensates_coarse_assembly():
         rr = shard_ranges([big, small], world)
         loads = [int(big[rr[r][0][1]] - big[rr[r][0][0]]) + int(small[rr[r][1][1]] - small[rr[r][1][0]]) for r in range(world)]
         assert sum(loads) == total and max(loads) <= total / world * 1.02
+
+
+def _indexlr_module():
+    import importlib.machinery
+    import importlib.util
+    path = os.path.join(ROOT, "bin", "indexlr")
+    loader = importlib.machinery.SourceFileLoader("indexlr_cli", path)
+    spec = importlib.util.spec_from_loader("indexlr_cli", loader)
+    mod = importlib.util.module_from_spec(spec)
+    loader.exec_module(mod)
+    return mod
+
+
+def test_indexlr_cli_argv_forms():
+    """bin/indexlr parses both argv forms the reference uses (ntJoin:205, bin/ntjoin_utils.py:197-198) and rejects the rest"""
+    cli = _indexlr_module()
+    a = cli.parse("--seq --long --pos -k 32 -w 1000 -t 4 asm.fa".split())
+    b = cli.parse("asm.fa --seq --long --pos -k32 -w1000 -t4 -o asm.fa.k32.w1000.tsv".split())
+    for o in (a, b):
+        assert (o["k"], o["w"], o["t"], o["pos"], o["seq"], o["strand"], o["files"]) == (32, 1000, 4, True, True, False, ["asm.fa"])
+    assert a["out"] == "-" and b["out"] == "asm.fa.k32.w1000.tsv" and a["canonical"] == "sum"
+    assert cli.parse("-k 15 -w 10 --canonical min x.fa y.fa".split())["files"] == ["x.fa", "y.fa"]
+    for bad in (["-k", "32", "x.fa"], ["-k", "32", "-w", "10"], ["-k", "0", "-w", "5", "x.fa"], ["--frobnicate", "-k", "3", "-w", "3", "x.fa"],
+                ["-k"]):
+        with pytest.raises(SystemExit) as ei:
+            cli.parse(bad)
+        assert ei.value.code not in (0, None)
