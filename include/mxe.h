@@ -94,6 +94,14 @@ int mxe_prefetch_buffers(mxe_t* e, const uint8_t* seq, uint64_t n);
 int mxe_sketch_device(mxe_t* e, const void* d_seq, const uint64_t* offsets, uint32_t n_contigs,
                       const char* const* names, int k, int w, int flags, mxe_sketch_t** out);
 
+/* Host only (no engine): a sketch object over caller-provided arrays (copied) -- e.g. the minimizers of one assembly
+ * gathered from several GPUs -- so that mxe_write_tsv / mxe_sketch_view serve them like a sketch computed here.
+ * contig[] ascending; min_hash / forward may be NULL; offsets (n_contigs + 1 record starts in `seq`) and `seq`
+ * (borrowed, must outlive the object) are only needed for --seq output. */
+int mxe_sketch_from_arrays(const uint64_t* out_hash, const uint64_t* min_hash, const uint32_t* pos, const uint32_t* contig,
+                           const uint8_t* forward, uint64_t n, const char* const* names, const uint64_t* offsets,
+                           uint32_t n_contigs, int k, const uint8_t* seq, mxe_sketch_t** out);
+
 /* Load a sketch back from an `indexlr` TSV written earlier (make's resume path: ntJoin keeps
  * <fasta>.k<k>.w<w>.tsv as .SECONDARY, ntJoin:202).  Parses id \t hash[:pos[:...]] ... exactly as
  * bin/ntjoin_utils.py:173-185 does; the arrays are uploaded for mxe_filter_and_edges. */

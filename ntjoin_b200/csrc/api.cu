@@ -250,65 +250,9 @@ int mxe_sketch_device(mxe_t* e, const void* d_seq, const uint64_t* offsets, uint
     return MXE_OK;
 }
 
-// FASTA / FASTQ ingest (reference: btllib SeqReader behind indexlr): id = header up to the
-// first whitespace, multi-line sequences concatenated, input order kept, sequence upper-cased.
-static int read_fasta(const char* path, std::vector<char>& seq, std::vector<uint64_t>& offsets, std::vector<std::string>& names)
-{
-    FILE* f = fopen(path, "rb");
-    if (!f) { set_error("cannot open %s: %s", path, strerror(errno)); return MXE_ERR_IO; }
-    fseek(f, 0, SEEK_END);
-    long long sz = ftell(f);
-    fseek(f, 0, SEEK_SET);
-    std::vector<char> buf((size_t)sz + 1);
-    if (sz && fread(buf.data(), 1, (size_t)sz, f) != (size_t)sz) { fclose(f); set_error("short read on %s", path); return MXE_ERR_IO; }
-    fclose(f);
-    buf[sz] = '\n';
-    seq.resize((size_t)sz + 64);
-    offsets.clear(); names.clear();
-    size_t at = 0;
-    const char* p = buf.data();
-    const char* end = p + sz;
-    if (p < end && *p == '@') {   // FASTQ: 4-line records
-        while (p < end) {
-            const char* nl = (const char*)memchr(p, '\n', end - p); if (!nl) nl = end;
-            const char* s = p + 1; const char* q = s;
-            while (q < nl && *q != ' ' && *q != '\t' && *q != '\r') q++;
-            names.emplace_back(s, q - s);
-            offsets.push_back(at);
-            p = nl + 1;
-            nl = (const char*)memchr(p, '\n', end > p ? end - p : 0); if (!nl) nl = end;
-            size_t len = nl - p; if (len && p[len - 1] == '\r') len--;
-            memcpy(&seq[at], p, len); at += len;
-            p = nl + 1;
-            for (int i = 0; i < 2 && p < end; i++) { nl = (const char*)memchr(p, '\n', end - p); p = nl ? nl + 1 : end; }
-        }
-    } else {
-        bool have = false;
-        while (p < end) {
-            const char* nl = (const char*)memchr(p, '\n', end - p + 1);
-            if (*p == '>') {
-                const char* s = p + 1; const char* q = s;
-                while (q < nl && *q != ' ' && *q != '\t' && *q != '\r') q++;
-                names.emplace_back(s, q - s);
-                offsets.push_back(at);
-                have = true;
-            } else if (have) {
-                size_t len = nl - p; if (len && p[len - 1] == '\r') len--;
-                memcpy(&seq[at], p, len); at += len;
-            }
-            p = nl + 1;
-        }
-    }
-    offsets.push_back(at);
-    for (size_t i = 0; i < at; i++) { char c = seq[i]; if (c >= 'a' && c <= 'z') seq[i] = (char)(c - 32); }
-    memset(&seq[at], 0, 64);
-    seq.resize(at + 64);
-    return MXE_OK;
-}
-
 // host-only face of the reader (no engine, no GPU): what btllib.SeqReader gives ntJoin (bin/ntjoin_assemble.py:313-316)
 struct mxe_fasta {
-    std::vector<char> seq;
+    mxe::HostText seq;
     std::vector<uint64_t> offsets;
     std::vector<std::string> names;
 };
@@ -489,15 +433,6 @@ int mxe_sketch_counts(mxe_sketch_t* S, uint64_t* n_bases, uint64_t* n_valid_kmer
     return MXE_OK;
 }
 
-static inline char* put_u64(char* p, uint64_t v)
-{
-    char tmp[24];
-    int n = 0;
-    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
-    while (n) *p++ = tmp[--n];
-    return p;
-}
-
 int mxe_write_tsv(mxe_sketch_t* S, const char* path, int with_pos, int with_strand, int with_seq)
 {
     if (!S || !path) { set_error("null argument"); return MXE_ERR_ARG; }
@@ -506,37 +441,44 @@ int mxe_write_tsv(mxe_sketch_t* S, const char* path, int with_pos, int with_stra
     if (with_seq && !text && S->n) { set_error("sequence text not available for --seq output"); return MXE_ERR_ARG; }
     FILE* f = (path[0] == '-' && !path[1]) ? stdout : fopen(path, "wb");
     if (!f) { set_error("cannot open %s: %s", path, strerror(errno)); return MXE_ERR_IO; }
-    std::vector<char> buf(1 << 22);
-    char* p = buf.data();
-    char* lim = buf.data() + buf.size() - (64 + (size_t)S->k + 8);
-    size_t i = 0;
-    bool ok = true;
-    for (uint32_t c = 0; c < S->n_contigs && ok; c++) {
-        const std::string& nm = S->names[c];
-        if ((size_t)(lim - p) < nm.size() + 2) { ok = fwrite(buf.data(), 1, p - buf.data(), f) == (size_t)(p - buf.data()); p = buf.data(); }
-        if (nm.size() + 2 > buf.size() / 2) { ok = ok && fwrite(nm.data(), 1, nm.size(), f) == nm.size(); }
-        else { memcpy(p, nm.data(), nm.size()); p += nm.size(); }
-        *p++ = '\t';
-        bool first = true;
-        while (i < S->n && S->h_contig[i] == c) {
-            if (p > lim) { ok = ok && fwrite(buf.data(), 1, p - buf.data(), f) == (size_t)(p - buf.data()); p = buf.data(); }
-            if (!first) *p++ = ' ';
-            first = false;
-            p = put_u64(p, S->h_out_hash[i]);
-            if (with_pos) { *p++ = ':'; p = put_u64(p, S->h_pos[i]); }
-            if (with_strand) { *p++ = ':'; *p++ = S->h_forward[i] ? '+' : '-'; }
-            if (with_seq) {
-                *p++ = ':';
-                const char* km = text + S->offsets[c] + S->h_pos[i];
-                for (int j = 0; j < S->k; j++) { char ch = km[j]; *p++ = (ch >= 'a' && ch <= 'z') ? (char)(ch - 32) : ch; }
-            }
-            i++;
-        }
-        *p++ = '\n';
-    }
-    ok = ok && fwrite(buf.data(), 1, p - buf.data(), f) == (size_t)(p - buf.data());
+    int rc = write_tsv_text(S, text, f, with_pos, with_strand, with_seq);
+    bool ok = rc == MXE_OK;
     if (f != stdout) ok = (fclose(f) == 0) && ok; else fflush(f);
     if (!ok) { set_error("write to %s failed", path); return MXE_ERR_IO; }
+    return MXE_OK;
+}
+
+// Host only: a sketch object over caller-provided arrays (copied), e.g. the minimizers of one assembly gathered from
+// several GPUs, so that mxe_write_tsv / mxe_sketch_view serve them like a sketch computed here.
+int mxe_sketch_from_arrays(const uint64_t* out_hash, const uint64_t* min_hash, const uint32_t* pos, const uint32_t* contig,
+                           const uint8_t* forward, uint64_t n, const char* const* names, const uint64_t* offsets,
+                           uint32_t n_contigs, int k, const uint8_t* seq, mxe_sketch_t** out)
+{
+    if (!out || (n && (!out_hash || !pos || !contig)) || (n_contigs && !names)) { set_error("null argument"); return MXE_ERR_ARG; }
+    for (uint64_t i = 0; i < n; i++)
+        if (contig[i] >= n_contigs || (i && contig[i] < contig[i - 1])) { set_error("record indices must be ascending and below n_contigs"); return MXE_ERR_ARG; }
+    mxe_sketch* S = new mxe_sketch();
+    S->k = k; S->n = n; S->n_contigs = n_contigs;
+    S->names.assign(names, names + n_contigs);
+    if (offsets) S->offsets.assign(offsets, offsets + n_contigs + 1); else S->offsets.assign((size_t)n_contigs + 1, 0);
+    S->seq_borrowed = offsets ? seq : nullptr;
+    const size_t bytes = n * (8 + 8 + 4 + 4 + 1) + 64;
+    char* blk = (char*)malloc(bytes);
+    if (!blk) { delete S; set_error("host allocation of %zu bytes failed", bytes); return MXE_ERR_NOMEM; }
+    S->h_block = blk; S->h_bytes = bytes;
+    S->h_out_hash = (uint64_t*)blk;
+    S->h_min_hash = (uint64_t*)(blk + 8 * n);
+    S->h_pos = (uint32_t*)(blk + 16 * n);
+    S->h_contig = (uint32_t*)(blk + 20 * n);
+    S->h_forward = (uint8_t*)(blk + 24 * n);
+    if (n) {
+        memcpy(S->h_out_hash, out_hash, 8 * n);
+        if (min_hash) memcpy(S->h_min_hash, min_hash, 8 * n); else memset(S->h_min_hash, 0, 8 * n);
+        memcpy(S->h_pos, pos, 4 * n);
+        memcpy(S->h_contig, contig, 4 * n);
+        if (forward) memcpy(S->h_forward, forward, n); else memset(S->h_forward, 0, n);
+    }
+    *out = S;
     return MXE_OK;
 }
 
@@ -552,6 +494,8 @@ void mxe_sketch_free(mxe_sketch_t* S)
         if (S->d_contig) cudaFreeAsync(S->d_contig, st);
         if (S->d_forward) cudaFreeAsync(S->d_forward, st);
         S->eng->pinned_release(S->h_block, S->h_bytes);
+    } else {
+        free(S->h_block);              // mxe_sketch_from_arrays
     }
     delete S;
 }

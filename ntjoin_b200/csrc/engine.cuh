@@ -1,6 +1,27 @@
 // engine.cuh -- object definitions behind the opaque C handles.
 #pragma once
 #include "common.cuh"
+#include <memory>
+
+namespace mxe {
+// allocator that leaves new elements uninitialised: a 3 GB text buffer is not zero-filled before it is overwritten
+template <typename T>
+struct DefaultInit : std::allocator<T> {
+    template <typename U> struct rebind { using other = DefaultInit<U>; };
+    template <typename U> void construct(U* p) noexcept { ::new ((void*)p) U; }
+    template <typename U, typename... A> void construct(U* p, A&&... a) { ::new ((void*)p) U(std::forward<A>(a)...); }
+};
+typedef std::vector<char, DefaultInit<char>> HostText;
+
+inline char* put_u64(char* p, uint64_t v)      // decimal digits, returns the end
+{
+    char tmp[24];
+    int n = 0;
+    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (n) *p++ = tmp[--n];
+    return p;
+}
+}
 
 // Host-input path: a host buffer is copied in chunks on two copy streams into an engine-owned staging slot; the pack
 // kernel of each chunk waits for that chunk's arrival event only.  Two slots, so that the copy of the next assembly
@@ -44,7 +65,7 @@ struct mxe_sketch {
     uint64_t* h_out_hash = nullptr; uint64_t* h_min_hash = nullptr;
     uint32_t* h_pos = nullptr; uint32_t* h_contig = nullptr; uint8_t* h_forward = nullptr;
     // sequence text for --seq output: either an owned copy of the whole input or nothing
-    std::vector<char> seq_text;       // upper-cased concatenated sequence (mxe_sketch_file)
+    mxe::HostText seq_text;           // upper-cased concatenated sequence (mxe_sketch_file)
     const uint8_t* seq_borrowed = nullptr;   // caller buffer (mxe_sketch_buffers), valid while caller keeps it
 };
 
@@ -127,6 +148,10 @@ int a2a_finish_impl(mxe_a2a* X, const uint64_t* d_rec, uint64_t n_rec, uint64_t 
 int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const uint64_t* offsets, uint32_t n_contigs,
                        int k, int w, int flags, mxe_sketch* out, H2DSlot* staged = nullptr);
 int h2d_issue(mxe_engine* e, H2DSlot& s, const uint8_t* h, uint64_t n);
+// host side of the file seam (hostio.cu): multi-threaded FASTA/FASTQ ingest and TSV text
+int host_threads();
+int read_fasta(const char* path, HostText& seq, std::vector<uint64_t>& offsets, std::vector<std::string>& names);
+int write_tsv_text(const mxe_sketch* S, const char* text, FILE* f, int with_pos, int with_strand, int with_seq);
 int filter_and_edges_impl(mxe_engine* e, const uint64_t* const* d_hash, const uint32_t* const* d_contig,
                           const uint64_t* n, int n_asm, const double* weights, mxe_result* out);
 int dist_mark_impl(mxe_engine* e, const uint64_t* d_keys, const uint64_t* asm_off, int n_asm, int rank, int world,

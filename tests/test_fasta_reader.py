@@ -41,3 +41,55 @@ def test_fastq_and_gz(tmp_path):
 def test_missing_file_raises(tmp_path):
     with pytest.raises(FileNotFoundError):
         btllib.SeqReader(str(tmp_path / "nope.fa"), btllib.SeqReaderFlag.LONG_MODE, 1)
+
+
+def _big_messy_fasta(path, seed=3, n_records=40):
+    """about 28 MB, four 8 MB chunks: multi-line records of mixed line widths, CRLF stretches, lower case, blank lines,
+    headers with descriptions, empty records, junk before the first header, no newline at the end"""
+    import numpy as np
+    rng = np.random.Generator(np.random.PCG64(seed))
+    alphabet = np.frombuffer(b"ACGTacgtNnRY", dtype=np.uint8)
+    want, out = [], [b"this line and the next come before any header\nACGT\n"]
+    for r in range(n_records):
+        name = f"rec{r}|x"
+        n = int(rng.choice([0, 1, 59, 60, 61, 5_000, 300_000, 3_000_000]))
+        seq = alphabet[rng.integers(0, len(alphabet), n)].tobytes()
+        want.append((name, seq.decode().upper()))
+        out.append(f">{name} description {r}\tmore".encode() + (b"\r\n" if r % 3 == 0 else b"\n"))
+        width = int(rng.choice([60, 61, 80, 1000, 10_000_000]))
+        eol = b"\r\n" if r % 3 == 0 else b"\n"
+        for i in range(0, n, width):
+            out.append(seq[i:i + width] + eol)
+            if r % 7 == 0 and i == 0:
+                out.append(eol)                      # a blank line inside a record
+    data = b"".join(out)
+    data = data[:-1] if data.endswith(b"\n") and not data.endswith(b"\r\n") else data
+    with open(path, "wb") as fh:
+        fh.write(data)
+    return want
+
+
+@pytest.mark.parametrize("threads", ["1", "2", "3", "7", "16"])
+def test_parallel_reader_is_thread_count_independent(tmp_path, monkeypatch, threads):
+    p = tmp_path / "big.fa"
+    want = _big_messy_fasta(p)
+    assert os.path.getsize(p) > 24 << 20          # at least four 8 MB chunks
+    monkeypatch.setenv("MXE_HOST_THREADS", threads)
+    got = _records(p)
+    assert [g[0] for g in got] == [w[0] for w in want]
+    assert all(g[1] == w[1] for g, w in zip(got, want))
+
+
+def test_reader_edge_files(tmp_path):
+    cases = {
+        "empty.fa": (b"", []),
+        "only_junk.fa": (b"no header here\nACGT\n", []),
+        "header_only.fa": (b">x", [("x", "")]),
+        "one_line_no_nl.fa": (b">x y\nacgt", [("x", "ACGT")]),
+        "crlf_end.fa": (b">a\r\nAC\r\n>b\r\n\r\nGT\r\n", [("a", "AC"), ("b", "GT")]),
+        "gt_inside.fa": (b">a\nAC>GT\n", [("a", "AC>GT")]),
+    }
+    for name, (data, want) in cases.items():
+        p = tmp_path / name
+        p.write_bytes(data)
+        assert _records(p) == want, name
