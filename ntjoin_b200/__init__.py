@@ -6,7 +6,7 @@ importing works anywhere, creating an Engine without a CUDA device or without th
 raises.
 """
 from ._lib import MxeError, load_library, library_path  # noqa: F401
-from .engine import Engine, Sketch, FilterResult  # noqa: F401
+from .engine import Engine, Sketch, FilterResult, HostSketch  # noqa: F401
 
-__all__ = ["Engine", "Sketch", "FilterResult", "MxeError", "load_library", "library_path"]
+__all__ = ["Engine", "Sketch", "FilterResult", "HostSketch", "MxeError", "load_library", "library_path"]
 __version__ = "0.1.0"

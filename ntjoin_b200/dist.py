@@ -61,6 +61,48 @@ def shard_ranges(offsets_per_asm, world):
     return [[(cuts[a][r], cuts[a][r + 1]) for a in range(n_asm)] for r in range(world)]
 
 
+def gather_and_write_tsv(path, out_hash, pos, contig, forward, first_record, names, k, fasta_path=None,
+                         with_pos=True, with_strand=False, with_seq=True, group=None):
+    """Seam S2 with several GPUs: every rank passes the minimizers of ITS record range (contig = local record ids,
+    first_record = global id of its first record; ranks hold contiguous ranges in rank order) and rank 0 writes the
+    assembly's one `<fasta>.k<k>.w<w>.tsv` exactly as a single process would (`names` = all record names; the
+    k-mer text of --seq comes from `fasta_path`, read on rank 0 with the engine's host reader)."""
+    import ctypes as C
+    import torch.distributed as dist
+    from ._lib import check, load_library
+    from .engine import HostSketch
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    mine = (np.asarray(out_hash, dtype=np.uint64), np.asarray(pos, dtype=np.uint32),
+            np.asarray(contig, dtype=np.uint32) + np.uint32(first_record), np.asarray(forward, dtype=np.uint8))
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object(mine, parts, dst=0, group=group)
+    if rank != 0:
+        return None
+    oh, ps, cg, fw = (np.concatenate([p[i] for p in parts]) for i in range(4))
+    offsets = seq = handle = None
+    lib = load_library()
+    try:
+        if with_seq:
+            handle = C.c_void_p()
+            check(lib, lib.mxe_fasta_read(str(fasta_path).encode(), C.byref(handle)))
+            n, offs, text = C.c_uint32(), C.c_void_p(), C.c_void_p()
+            check(lib, lib.mxe_fasta_view(handle, C.byref(n), C.byref(offs), C.byref(text)))
+            if n.value != len(names):
+                raise ValueError(f"{fasta_path} has {n.value} records, {len(names)} names were given")
+            offsets = np.ctypeslib.as_array(C.cast(offs, C.POINTER(C.c_uint64)), shape=(n.value + 1,))
+            total = int(offsets[-1])
+            seq = np.ctypeslib.as_array(C.cast(text, C.POINTER(C.c_uint8)), shape=(max(1, total),))
+        hs = HostSketch(oh, ps, cg, names, k, forward=fw, offsets=offsets, seq=seq)
+        try:
+            hs.write_tsv(path, pos=with_pos, strand=with_strand, seq=with_seq)
+        finally:
+            hs.close()
+    finally:
+        if handle is not None:
+            lib.mxe_fasta_free(handle)
+    return len(oh)
+
+
 class DeviceArray:
     """Zero-copy view of an engine-owned device array for torch.as_tensor (__cuda_array_interface__)."""
 

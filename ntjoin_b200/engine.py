@@ -442,3 +442,40 @@ class EngineA2AStages:
 
     def abort(self, handle):
         self._lib.mxe_a2a_free(handle)
+
+
+class HostSketch:
+    """Minimizers of one assembly held in host arrays (no engine, no GPU): mxe_sketch_from_arrays.  Used to write the
+    assembly's one `.tsv` (seam S2) from the record ranges that several GPUs sketched; see dist.gather_and_write_tsv."""
+
+    def __init__(self, out_hash, pos, contig, names, k, forward=None, min_hash=None, offsets=None, seq=None):
+        self._lib = load_library()
+        oh = np.ascontiguousarray(out_hash, dtype=np.uint64)
+        ps = np.ascontiguousarray(pos, dtype=np.uint32)
+        cg = np.ascontiguousarray(contig, dtype=np.uint32)
+        fw = None if forward is None else np.ascontiguousarray(forward, dtype=np.uint8)
+        mh = None if min_hash is None else np.ascontiguousarray(min_hash, dtype=np.uint64)
+        of = None if offsets is None else np.ascontiguousarray(offsets, dtype=np.uint64)
+        self._seq = None if seq is None else (np.frombuffer(seq, dtype=np.uint8) if isinstance(seq, (bytes, bytearray, memoryview))
+                                              else np.ascontiguousarray(seq, dtype=np.uint8))     # borrowed by the C side: keep alive
+        nm = (C.c_char_p * max(1, len(names)))(*[str(x).encode() for x in names])
+        h = C.c_void_p()
+        ptr = lambda a: None if a is None else C.c_void_p(a.ctypes.data)      # noqa: E731
+        check(self._lib, self._lib.mxe_sketch_from_arrays(ptr(oh), ptr(mh), ptr(ps), ptr(cg), ptr(fw), len(oh), nm,
+                                                          None if of is None else of.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                                          len(names), int(k), ptr(self._seq), C.byref(h)))
+        self._h, self.n, self.names = h, len(oh), [str(x) for x in names]
+
+    def write_tsv(self, path, pos=True, strand=False, seq=True):
+        check(self._lib, self._lib.mxe_write_tsv(self._h, str(path).encode(), int(pos), int(strand), int(seq)))
+
+    def close(self):
+        if self._h:
+            self._lib.mxe_sketch_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

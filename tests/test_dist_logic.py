@@ -147,3 +147,47 @@ def test_two_rank_gloo_distributed_filter(mode):
     for p in procs:
         p.join(timeout=60)
     assert sorted(r for r, _ in out) == [0, 1] and all(ok for _, ok in out)
+
+
+def _tsv_worker(rank, world, port, q, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import subprocess
+    import torch.distributed as dist
+    import oracle_lib
+    from ntjoin_b200.dist import gather_and_write_tsv
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    orc = oracle_lib.Oracle()
+    fa = os.path.join(tmp, "asm.fa")
+    names, seq, offs = oracle_lib.read_fasta(fa)
+    c0, c1 = shard_ranges([offs], world)[rank][0]
+    lo, hi = int(offs[c0]), int(offs[c1])
+    m = orc.sketch(seq[lo:hi], (offs[c0:c1 + 1] - offs[c0]).astype(np.uint64), 32, 50)     # this rank's record range
+    out = os.path.join(tmp, "asm.fa.k32.w50.tsv")
+    gather_and_write_tsv(out, m["out_hash"], m["pos"], m["contig"], m["forward"], c0, names, 32, fasta_path=fa)
+    ok = True
+    if rank == 0:
+        want = subprocess.check_output([oracle_lib.CLI, "--seq", "--long", "--pos", "-k", "32", "-w", "50", fa])
+        ok = open(out, "rb").read() == want
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_tsv_of_sharded_sketch(tmp_path):
+    """seam S2 with two ranks: each sketches its record range, rank 0 writes the assembly's one TSV, byte-equal to a
+    single-process `indexlr --seq --long --pos`"""
+    import torch.multiprocessing as mp
+    rseq, roffs, rnames = synth.make_reference(400_000, n_chrom=3, n_frac=0.01, seed=31)
+    seq, offs, names = synth.derive_target(rseq, roffs, min_len=500, max_len=30_000, seed=32)
+    synth.write_fasta(str(tmp_path / "asm.fa"), seq, offs, names, width=70)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_tsv_worker, args=(r, 2, port, q, str(tmp_path))) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(r for r, _ in out) == [0, 1] and all(ok for _, ok in out)
