@@ -174,6 +174,7 @@ int mxe_set_option(mxe_t* e, const char* name, double value)
     if (!strcmp(name, "tau")) { if (value <= 0) { set_error("tau must be > 0"); return MXE_ERR_ARG; } e->tau = value; }
     else if (!strcmp(name, "chunk")) { if (value != 0 && value < 32) { set_error("chunk must be 0 (auto) or >= 32"); return MXE_ERR_ARG; } e->chunk = (int)value; }
     else if (!strcmp(name, "cand_variant")) e->cand_variant = (int)value;
+    else if (!strcmp(name, "scan_lw")) e->scan_lw = (int)value;
     else if (!strcmp(name, "prune")) e->prune = value != 0;
     else if (!strcmp(name, "sort_bits")) e->sort_bits = (int)value;
     else if (!strcmp(name, "fma_offload")) e->fma_offload = value != 0;

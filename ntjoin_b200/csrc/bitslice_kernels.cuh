@@ -107,8 +107,8 @@ __host__ __device__ constexpr BsTab bs_make_tab()
 }
 
 // plain expressions: the compiler folds constants / negations into a single LOP3 lookup table
-__device__ __forceinline__ uint32_t bs_maj(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (a & c) | (b & c); }
-__device__ __forceinline__ uint32_t bs_xor3(uint32_t a, uint32_t b, uint32_t c) { return a ^ b ^ c; }
+__host__ __device__ __forceinline__ uint32_t bs_maj(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (a & c) | (b & c); }
+__host__ __device__ __forceinline__ uint32_t bs_xor3(uint32_t a, uint32_t b, uint32_t c) { return a ^ b ^ c; }
 
 struct BsParams {
     uint64_t n;            // bases

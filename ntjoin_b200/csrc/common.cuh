@@ -66,7 +66,8 @@ struct Engine {
     // tunables
     double tau = 9.0;        // candidate threshold: hash0>>33 <= tau * 2^31 / w
     int chunk = 0;           // positions per thread in the candidate kernel (multiple of 32; 0 = auto)
-    int cand_variant = 1;    // 0 = generic 64-bit, 1 = 31-bit lane prefilter
+    int cand_variant = 4;    // 0 = generic 64-bit, 1 = 31-bit lane prefilter, 2/3 = bit-sliced via plane_kernel, 4 = pack2 + bit-sliced scan (scan_kernels.cuh)
+    int scan_lw = 0;         // variant 4: pk words per stream (odd; 0 = by size)
     bool prune = false;      // drop dominated candidates on 31-bit bounds before the exact stages
     bool fma_offload = true; // cand31: additions of the threshold test as IMADs on the FMA pipe
     bool select_narrow = true;   // window selection in 32-bit arithmetic when the ordinals allow it

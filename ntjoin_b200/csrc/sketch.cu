@@ -2,9 +2,11 @@
 #include "engine.cuh"
 #include "sketch_kernels.cuh"
 #include "bitslice_kernels.cuh"
+#include "scan_kernels.cuh"
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 
 namespace mxe {
 
@@ -35,6 +37,40 @@ static void build_tables(int k, SketchTables* T)
 }
 
 static inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
+
+constexpr int BS2_H = 12, BS2_HS = 12;      // adder width / compared bits of the bit-sliced threshold test
+
+// Tile geometry of the bit-sliced front end: L = 16 * Lw starts per stream, Lw odd.  Long streams amortise the k-1
+// halo, short ones give more threads; pick the Lw that minimises (waves of resident threads) x (steps per thread).
+static void scan_geometry(mxe_engine* e, uint64_t n, int k, ScanGeom* G)
+{
+    static int blocks_per_sm = 0;
+    if (!blocks_per_sm) {
+        const size_t rsm = bs2_smem_bytes(32);
+        cudaFuncSetAttribute(scan_bs2_kernel<1, BS2_H, BS2_HS, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, scan_bs2_kernel<1, BS2_H, BS2_HS, 48>, BS2_THREADS, rsm) != cudaSuccess || blocks_per_sm < 1) {
+            cudaGetLastError();
+            blocks_per_sm = 3;
+        }
+    }
+    const uint64_t slots = (uint64_t)e->sm_count * blocks_per_sm * BS2_THREADS;
+    uint32_t best_lw = 9;
+    uint64_t best_cost = ~0ULL;
+    int lw_lo = 9, lw_hi = 63;
+    if (e->scan_lw > 0) lw_lo = lw_hi = e->scan_lw | 1;
+    for (int lw = lw_lo; lw <= lw_hi; lw += 2) {
+        const uint64_t tiles = (n + 512ull * lw - 1) / (512ull * lw);
+        const uint64_t waves = (tiles + slots - 1) / slots;
+        const uint64_t R = (16ull * lw + k - 1 + 15) / 16;
+        const uint64_t cost = waves * R;
+        if (cost <= best_cost) { best_cost = cost; best_lw = (uint32_t)lw; }
+    }
+    G->n = n; G->n_words = (n + 31) / 32; G->k = k;
+    G->Lw = best_lw;
+    G->n_tiles = (n + 512ull * best_lw - 1) / (512ull * best_lw);
+    G->R = (uint32_t)((16ull * best_lw + k - 1 + 15) / 16);
+    G->ext = (uint32_t)std::max(2, (31 + k - 1) / 32);
+}
 
 // Start the chunked host->device copy of `h` into slot `s` (two copy streams = two copy engines).  Does not wait for
 // the compute stream, only for the previous reader of the slot.
@@ -108,14 +144,21 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
     const uint64_t pk_words = 2 * nW + (uint64_t)(k / 16) + 16;
     P.pk_words = pk_words;
 
-    DBuf<uint32_t> pk, V, C, M;
+    // second-generation front end (scan_kernels.cuh): bit-sliced candidate scan fed by a tile-transposed copy of pk
+    const int kmod = k % 31;
+    const bool bs2 = e->cand_variant >= 4 && !P.canon_min && (kmod == 1 || kmod == 9 || kmod == 24) && k >= 16 && k <= BS2_MAX_K;
+    ScanGeom G;
+    memset(&G, 0, sizeof(G));
+    if (bs2) scan_geometry(e, n, k, &G);
+
+    DBuf<uint32_t> pk, V, C, M, PL, dirty;
     DBuf<uint64_t> vprefix, cprefix, mprefix, d_offsets, ostart;
     DBuf<uint32_t> vcounts, ccounts;
     MXE_TRY(vcounts.alloc(n_vblocks + 1, st));
     MXE_TRY(ccounts.alloc(n_vblocks + 1, st));
     MXE_TRY(pk.alloc(pk_words, st));
     MXE_TRY(V.alloc(nW, st));
-    MXE_TRY(C.alloc(nW, st));
+    MXE_TRY(C.alloc(bs2 ? std::max<uint64_t>(nW, G.n_tiles * 16ull * G.Lw) : nW, st));
     MXE_TRY(M.alloc(nW, st));
     MXE_TRY(vprefix.alloc(n_vblocks + 1, st));
     MXE_TRY(cprefix.alloc(n_vblocks + 1, st));
@@ -125,9 +168,45 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
     MXE_CUDA(cudaMemcpyAsync(d_offsets.p, offsets, (n_contigs + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     MXE_CUDA(cudaMemsetAsync(pk.p + 2 * nW, 0, (pk_words - 2 * nW) * sizeof(uint32_t), st));
     MXE_CUDA(cudaMemsetAsync(M.p, 0, nW * sizeof(uint32_t), st));
+    DirtyList DL{nullptr, nullptr, 0};
+    if (bs2) {
+        const uint32_t cap = (uint32_t)std::min<uint64_t>(nW / 16 + 4096, 0x7FFFFFFFu);
+        MXE_TRY(PL.alloc(G.n_tiles * (uint64_t)G.R * 32, st));
+        MXE_TRY(dirty.alloc((size_t)cap + 1, st));
+        DL = DirtyList{dirty.p + 1, dirty.p, cap};
+        MXE_CUDA(cudaMemsetAsync(dirty.p, 0, sizeof(uint32_t), st));
+        MXE_CUDA(cudaMemsetAsync(vcounts.p, 0, (n_vblocks + 1) * sizeof(uint32_t), st));
+        MXE_CUDA(cudaMemsetAsync(C.p, 0, std::max<uint64_t>(nW, G.n_tiles * 16ull * G.Lw) * sizeof(uint32_t), st));
+    }
 
     // ---- pack + validity
-    {
+    if (bs2) {
+        Span sp(e, "pack");
+        const size_t psm = pack2_smem_bytes(G.Lw, G.ext);
+        const uint64_t tile = 512ull * G.Lw;
+        if (!staged) {
+            MXE_LAUNCH(e, pack2_kernel, (unsigned)G.n_tiles, PACK2_THREADS, psm, d_seq, G, pk.p, PL.p, V.p, vcounts.p, DL, (uint64_t)0);
+        } else {
+            // host input: a tile is packed once its bytes and its halo (ext units) have landed
+            const uint64_t CH = staged->chunk;
+            uint64_t T0 = 0;
+            int i = 0;
+            for (uint64_t off = 0; off < n; off += CH, i++) {
+                const uint64_t len = std::min<uint64_t>(CH, n - off);
+                MXE_CUDA(cudaStreamWaitEvent(st, staged->ev[i], 0));
+                const bool last = off + len >= n;
+                const uint64_t have = off + len;
+                uint64_t T1 = last ? G.n_tiles : (have > 32ull * G.ext ? (have - 32ull * G.ext) / tile : 0);
+                if (T1 > G.n_tiles) T1 = G.n_tiles;
+                if (T1 > T0) MXE_LAUNCH(e, pack2_kernel, (unsigned)(T1 - T0), PACK2_THREADS, psm, d_seq, G, pk.p, PL.p, V.p, vcounts.p, DL, T0);
+                T0 = std::max(T0, T1);
+            }
+            MXE_CUDA(cudaEventRecord(staged->consumed, st));
+            staged->consumed_valid = true;
+            staged->h = nullptr;
+        }
+        if (n_contigs > 1) MXE_LAUNCH(e, boundary2_kernel, grid_for(n_contigs - 1, 128), 128, 0, d_offsets.p, n_contigs, n, k, V.p, vcounts.p, DL);
+    } else {
         Span sp(e, "pack");
         if (!staged) {
             MXE_LAUNCH(e, pack_kernel, grid_for(nW, 256), 256, 0, d_seq, P, pk.p, V.p, vcounts.p, (uint64_t)0, nW);
@@ -164,10 +243,29 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
         Span sp(e, "cand");
         uint64_t n_threads = (n + P.chunk - 1) / P.chunk;
         bool fast = e->cand_variant >= 1 && (k % 4 == 0) && k >= 4;
-        const int kmod = k % 31;
-        bool sliced = e->cand_variant >= 2 && !P.canon_min && (kmod == 1 || kmod == 9 || kmod == 24) && k >= 16 && k <= 256 &&
+        bool sliced = !bs2 && e->cand_variant >= 2 && !P.canon_min && (kmod == 1 || kmod == 9 || kmod == 24) && k >= 16 && k <= 256 &&
                       (e->cand_variant >= 3 || n >= ((uint64_t)1 << 29));
-        if (sliced) {
+        if (bs2) {
+            Bs2Params BP;
+            BP.f0 = Tb.f0; BP.r0 = Tb.r0;
+            const uint32_t TH = P.T >> (31 - BS2_H);
+            uint32_t Q = (TH + 1) >> (BS2_H - BS2_HS);
+            if (Q > (1u << BS2_HS) - 1) Q = (1u << BS2_HS) - 1;
+            const uint32_t K = ((1u << BS2_HS) - 1) - Q;
+            for (int i = 0; i < 16; i++) BP.kmask[i] = (i < BS2_HS && ((K >> i) & 1u)) ? 0xFFFFFFFFu : 0u;
+            const size_t rsm = bs2_smem_bytes(k);
+            const unsigned grid = grid_for(G.n_tiles, BS2_THREADS);
+#define MXE_BS2(KM, RG)                                                                                                               \
+    do {                                                                                                                              \
+        MXE_CUDA(cudaFuncSetAttribute(scan_bs2_kernel<KM, BS2_H, BS2_HS, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm)); \
+        MXE_LAUNCH(e, (scan_bs2_kernel<KM, BS2_H, BS2_HS, RG>), grid, BS2_THREADS, rsm, PL.p, G, BP, C.p);                            \
+    } while (0)
+            if (kmod == 1) MXE_BS2(1, 48);           // k = 32
+            else if (kmod == 9) MXE_BS2(9, 64);      // k = 40
+            else MXE_BS2(24, 48);                    // k = 24
+#undef MXE_BS2
+            MXE_LAUNCH(e, dirty_fix_kernel, (unsigned)(e->sm_count * 8), 256, 0, DL, V.p, C.p, nW);
+        } else if (sliced) {
             // bit-sliced kernel: transpose pk into bit planes, run 32 streams per thread, then C &= V with counts
             MXE_CUDA(cudaMemsetAsync(C.p, 0, nW * sizeof(uint32_t), st));      // it sets candidate bits with atomics; the others write whole words
             BsParams BP;

@@ -11,6 +11,7 @@ pytestmark = pytest.mark.gpu
 
 FIXTURES = ["ref.fa", "ref.multiple.fa", "scaf.f-f.fa", "scaf.f-f.termN.unassigned.fa", "scaf.multiple.fa",
             "scaf.more_seqs.fa", "scaf.f-f.overlapping.fa", "scaf.r-r.fa"]
+DEFAULT_VARIANT = 4      # pack2 + bit-sliced scan (falls back to cand31 / generic where it does not apply)
 KW = [(32, 1000), (32, 500), (32, 250), (15, 10), (24, 100), (40, 50), (21, 33), (32, 5000), (4, 3)]
 
 
@@ -33,7 +34,7 @@ def test_golden_tsv_bytes(engine, golden_dir, tmp_path, fname):
     assert out.read_bytes() == want
 
 
-@pytest.mark.parametrize("variant", [0, 1, 3])
+@pytest.mark.parametrize("variant", [0, 1, 3, 4])
 @pytest.mark.parametrize("canonical", ["sum", "min"])
 @pytest.mark.parametrize("fname", FIXTURES)
 def test_fixture_vs_oracle(engine, oracle, golden_dir, fname, canonical, variant):
@@ -43,7 +44,7 @@ def test_fixture_vs_oracle(engine, oracle, golden_dir, fname, canonical, variant
         ref = oracle.sketch(seq, offs, k, w, canonical=canonical)
         sk = engine.sketch_buffers(seq, offs, k, w, names=names, canonical=canonical)
         assert_same(sk, ref)
-    engine.set_option("cand_variant", 1)
+    engine.set_option("cand_variant", DEFAULT_VARIANT)
 
 
 def _messy(n, seed):
@@ -68,7 +69,7 @@ def _messy(n, seed):
     return seq, offs
 
 
-@pytest.mark.parametrize("variant", [0, 1, 3])
+@pytest.mark.parametrize("variant", [0, 1, 3, 4])
 @pytest.mark.parametrize("canonical", ["sum", "min"])
 def test_messy_synthetic(engine, oracle, canonical, variant):
     seq, offs = _messy(1_500_000, 7)
@@ -78,7 +79,7 @@ def test_messy_synthetic(engine, oracle, canonical, variant):
         ref = oracle.sketch(seq, offs, k, w, canonical=canonical)
         sk = engine.sketch_buffers(seq, offs, k, w, canonical=canonical)
         assert_same(sk, ref)
-    engine.set_option("cand_variant", 1)
+    engine.set_option("cand_variant", DEFAULT_VARIANT)
     engine.set_option("prune", 0)
 
 
@@ -94,6 +95,33 @@ def test_kernel_variants_behind_options(engine, oracle, option):
             assert_same(engine.sketch_buffers(seq, offs, k, w, canonical=canonical), ref)
     finally:
         engine.set_option(option, 1)
+
+
+@pytest.mark.parametrize("lw", [9, 11, 25, 63])
+def test_tile_geometry_independence(engine, oracle, lw):
+    """variant 4: the stream length (tile geometry) is a performance knob only -- N runs, record boundaries and the
+    sequence end fall at different places inside the tiles for every Lw"""
+    seq, offs = _messy(2_100_000, 31)
+    engine.set_option("scan_lw", lw)
+    try:
+        for k, w in [(32, 1000), (40, 100), (24, 250)]:
+            ref = oracle.sketch(seq, offs, k, w)
+            assert_same(engine.sketch_buffers(seq, offs, k, w), ref)
+    finally:
+        engine.set_option("scan_lw", 0)
+
+
+def test_invalid_bytes_every_value(engine, oracle):
+    """every byte value once, in every position class of a 32-base unit: the word-parallel validity screen of
+    pack2_kernel against the oracle's table (ACGTacgt valid, everything else breaks the k-mers that contain it)"""
+    rng = np.random.Generator(np.random.PCG64(5))
+    seq = synth.random_bases(256 * 200 + 64, rng)
+    for v in range(256):
+        seq[200 * v + 37 + (v % 32)] = v
+    offs = np.array([0, len(seq)], dtype=np.uint64)
+    for k, w in [(32, 20), (24, 10)]:
+        ref = oracle.sketch(seq, offs, k, w)
+        assert_same(engine.sketch_buffers(seq, offs, k, w), ref)
 
 
 @pytest.mark.parametrize("tau", [0.5, 3.0, 10.0, 1e9])
@@ -146,7 +174,7 @@ def test_tsv_with_seq_matches_oracle_cli(engine, golden_dir, tmp_path):
     assert out.read_bytes() == want
 
 
-@pytest.mark.parametrize("variant", [1, 3])
+@pytest.mark.parametrize("variant", [1, 3, 4])
 def test_config5_kw_sweep(engine, oracle, variant):
     """BASELINE configs[4]: k in {24,32,40} x w in {250,500,1000,5000}, scaled down, both candidate kernels"""
     rseq, roffs, _ = synth.make_reference(6_000_000, n_chrom=5, dup_frac=0.02, n_frac=0.005)
@@ -157,4 +185,4 @@ def test_config5_kw_sweep(engine, oracle, variant):
                 ref = oracle.sketch(rseq, roffs, k, w, threads=8)
                 assert_same(engine.sketch_buffers(rseq, roffs, k, w), ref)
     finally:
-        engine.set_option("cand_variant", 1)
+        engine.set_option("cand_variant", DEFAULT_VARIANT)
