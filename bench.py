@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument("--with-n", action="store_true", help="put 0.5%% of the reference in N runs (default: N-free headline variant)")
     ap.add_argument("--cpu-sample", type=float, default=0, help="bases per assembly for the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the comparison of the merged shards with the single-GPU result")
     return ap.parse_args()
 
 
@@ -218,9 +219,10 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------ CPU arm
-def cpu_reference_run(spec, args, steps, warmup, sample_bases=None):
+def cpu_reference_run(spec, args, steps, warmup, sample_bases=None, with_t4=False):
     """The reference path on host cores: oracle sketch (one record per worker thread, like indexlr -t)
-    + oracle steps 2-3, on a bounded sample of the same workload (same generator, smaller G)."""
+    + oracle steps 2-3, on a bounded sample of the same workload (same generator, smaller G).
+    with_t4: also time the sketch with 4 threads, the reference's default (`t=4`, ntJoin:48)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
     from ntjoin_b200 import synth
@@ -243,9 +245,19 @@ def cpu_reference_run(spec, args, steps, warmup, sample_bases=None):
             times.append(dt)
     total = len(asms) * sample_bases
     sec = float(np.mean(times))
-    return {"value": total / sec / 1e9, "unit": "Gbases/s", "cores": cores, "kind": "port",
-            "sample": f"{sample_bases} bp reference + derived target (same generator as the workload), k={K} w={W}, "
-                      f"{steps} step(s) after {warmup} warm-up, oracle/mxo.c with {cores} threads"}, sec
+    out = {"value": total / sec / 1e9, "unit": "Gbases/s", "cores": cores, "kind": "port",
+           "sample": f"{sample_bases} bp reference + derived target (same generator as the workload), k={K} w={W}, "
+                     f"{steps} step(s) after {warmup} warm-up, oracle/mxo.c with {cores} threads"}
+    if with_t4:
+        # the reference's default thread count, on a quarter of the sample (bounded CPU time)
+        sub = [(s[:int(o[max(1, len(o) // 4)])], o[:max(1, len(o) // 4) + 1]) for s, o in asms]
+        t0 = time.perf_counter()
+        sk4 = [orc.sketch(s, o, K, W, threads=4) for s, o in sub]
+        orc.filter_and_edges([m["out_hash"] for m in sk4], [m["contig"] for m in sk4], WEIGHTS)
+        dt = time.perf_counter() - t0
+        out["t4"] = {"value": sum(int(o[-1]) for _, o in sub) / dt / 1e9, "unit": "Gbases/s", "cores": 4,
+                     "note": "oracle sketch with 4 threads (the reference's default t=4, ntJoin:48) + oracle steps 2-3, first quarter of the sample's records"}
+    return out, sec
 
 
 def run_reference_arm(args, spec):
@@ -265,11 +277,12 @@ def run_reference_arm(args, spec):
 
 
 # ------------------------------------------------------------------------------------ the bound that actually binds
-ALU_OPS_PER_BASE = 9.1       # ALU-pipe instructions per base of cand31_kernel<0,1>, counted in its SASS
+ALU_OPS_PER_BASE = {"cand31_kernel": 9.1,      # ALU-pipe instructions per base, counted in the SASS
+                    "scan_bs2_kernel": 4.1}    # (LOP3 + SHF + PRMT + IADD3 + ISETP per 16-step group) / 512 positions, incl. the k-1 halo
 
 
-def alu_roofline(bases_per_launch, launch_ms):
-    """cand31_kernel against the INT32 ALU pipe (LOP3/SHF/IADD3/ISETP/PRMT): the secondary roofline of SURVEY.md 8(d).
+def alu_roofline(bases_per_launch, launch_ms, kernel="scan_bs2_kernel"):
+    """the candidate kernel against the INT32 ALU pipe (LOP3/SHF/IADD3/ISETP/PRMT): the secondary roofline of SURVEY.md 8(d).
     Peak = LOP3 rate measured on this GPU type by tools/alu_peak.cu (profiles/r01_l_alu_peak_microbench.jsonl), else the
     nominal 148 SMs x 64 lanes x 1.965 GHz."""
     try:
@@ -282,8 +295,9 @@ def alu_roofline(bases_per_launch, launch_ms):
                         peak, source = float(r["tera_thread_ops_per_s"]), "tools/alu_peak.cu LOP3 rate (profiles/r01_l_alu_peak_microbench.jsonl)"
         except (OSError, ValueError, KeyError):
             pass
-        achieved = ALU_OPS_PER_BASE * bases_per_launch / (launch_ms * 1e-3) / 1e12 if launch_ms > 0 else 0.0
-        return {"bound": "int32 alu pipe", "ops_per_base": ALU_OPS_PER_BASE, "achieved": achieved, "peak": peak, "unit": "Tops/s",
+        opb = ALU_OPS_PER_BASE.get(kernel, 9.1)
+        achieved = opb * bases_per_launch / (launch_ms * 1e-3) / 1e12 if launch_ms > 0 else 0.0
+        return {"bound": "int32 alu pipe", "kernel": kernel, "ops_per_base": opb, "achieved": achieved, "peak": peak, "unit": "Tops/s",
                 "frac": achieved / peak if peak else None, "peak_source": source}
     except Exception as exc:           # reporting only: never lose the bench line over it
         return {"error": str(exc)}
@@ -319,7 +333,9 @@ def run_sweep(args, spec, eng, shards, total_bases):
                 n_mx, _n, n_v, n_e = step()
             torch.cuda.synchronize()
             sec = (time.perf_counter() - t0) / args.steps
-            t_cand, n_cand = eng.timing("cand")
+            t_cand, n_cand = eng.timing("k_scan")
+            if not n_cand:
+                t_cand, n_cand = eng.timing("cand")
             cand_ms = t_cand / max(1, n_cand)
             per_launch = (total_bases + 16.0 * sum(n_mx)) / len(shards)
             achieved = per_launch / (cand_ms * 1e-3) / 1e9
@@ -328,7 +344,54 @@ def run_sweep(args, spec, eng, shards, total_bases):
                            "sketch_ms": eng.timing("sketch")[0] / args.steps, "filter_ms": eng.timing("filter")[0] / args.steps})
     print(json.dumps({"metric": "Gbases/s sketched+filtered, k x w sweep", "unit": "Gbases/s", "n_gpus": 1, "steps": args.steps,
                       "config": {"workload": spec["name"], "bases_per_step": total_bases}, "roofline_peak_gbs": peak,
-                      "roofline_kernel": "cand31_kernel (k % 4 == 0: all three k)", "sweep": points}), flush=True)
+                      "roofline_kernel": "the candidate kernel of each point (scan_bs2_kernel for k in {24, 32, 40})", "sweep": points}), flush=True)
+
+
+# ------------------------------------------------------------------------------------ N > 1 vs N = 1
+def result_digest(d):
+    """order-sensitive digest of a whole result (minimizer tuples, flags, vertices, edge list)"""
+    import hashlib
+    h = hashlib.sha256()
+    for key in ("out_hash", "pos", "contig", "forward", "uniq", "keep"):
+        for a in d[key]:
+            h.update(np.ascontiguousarray(a).astype(np.uint64 if key == "out_hash" else np.uint32 if key in ("pos", "contig") else np.uint8).tobytes())
+    for key, dt in (("vertices", np.uint64), ("edge_u", np.uint64), ("edge_v", np.uint64), ("support", np.uint32), ("weight", np.float64)):
+        h.update(np.ascontiguousarray(d[key], dtype=dt).tobytes())
+    return h.hexdigest()[:16]
+
+
+def multi_gpu_parity(eng, shards, gather_and_filter, single, rank, world, dist, dist_mode):
+    """One more step outside the timed regions: every rank contributes its minimizers and its fetched result shard,
+    rank 0 merges them (ntjoin_b200.dist.merge_shards) and compares field by field with the single-GPU result of the
+    same job.  A mismatch fails the run."""
+    from ntjoin_b200.dist import merge_shards
+    sks = [eng.sketch_device(s.data_ptr(), o, K, W) for s, o, _ in shards]
+    res = gather_and_filter(sks)
+    mine = {"sk": [(sk.out_hash.copy(), sk.pos.copy(), sk.contig.copy() + np.uint32(c0), sk.forward.copy()) for sk, (_, _, c0) in zip(sks, shards)],
+            "shard": {k: ([x.copy() for x in v] if isinstance(v, list) else np.array(v, copy=True)) for k, v in res.fetch().items()}}
+    for sk in sks:
+        sk.close()
+    res.close()
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object(mine, parts, dst=0)
+    if rank != 0:
+        return None
+    n_asm = len(shards)
+    merged = merge_shards([p["shard"] for p in parts])
+    merged["out_hash"] = [np.concatenate([p["sk"][a][0] for p in parts]) for a in range(n_asm)]
+    merged["pos"] = [np.concatenate([p["sk"][a][1] for p in parts]) for a in range(n_asm)]
+    merged["contig"] = [np.concatenate([p["sk"][a][2] for p in parts]) for a in range(n_asm)]
+    merged["forward"] = [np.concatenate([p["sk"][a][3] for p in parts]) for a in range(n_asm)]
+    bad = []
+    for key in ("out_hash", "pos", "contig", "forward", "uniq", "keep"):
+        for a in range(n_asm):
+            if not np.array_equal(np.asarray(merged[key][a]).astype(np.uint64), np.asarray(single[key][a]).astype(np.uint64)):
+                bad.append(f"{key}[{a}]")
+    for key in ("vertices", "edge_u", "edge_v", "support", "weight"):
+        if not np.array_equal(merged[key], single[key]):
+            bad.append(key)
+    return {"vs_single_gpu": not bad, "mismatch": bad, "digest": result_digest(merged), "single_gpu_digest": result_digest(single),
+            "dist_mode": dist_mode, "compared": "all minimizer tuples, uniq/keep flags, vertices, edge list (order, support, weight)"}
 
 
 # ------------------------------------------------------------------------------------ GPU arm
@@ -371,6 +434,20 @@ def main():
         lo, hi = int(offs[c0]), int(offs[c1])
         local_seq = seq[lo:hi].clone() if world > 1 else seq
         shards.append((local_seq, (offs[c0:c1 + 1] - offs[c0]).astype(np.uint64), c0))
+    parity = None
+    single = None
+    if world > 1 and rank == 0 and not args.no_parity:
+        # the whole job once on ONE GPU (rank 0 holds all assemblies at this point): the result every N must reproduce
+        sks = [eng.sketch_device(seq.data_ptr(), offs, K, W) for seq, offs in assemblies]
+        res = eng.filter_and_edges(sks, WEIGHTS)
+        f = res.fetch()
+        single = {"out_hash": [sk.out_hash.copy() for sk in sks], "pos": [sk.pos.copy() for sk in sks],
+                  "contig": [sk.contig.copy() for sk in sks], "forward": [sk.forward.copy() for sk in sks],
+                  "uniq": [u.copy() for u in f["uniq"]], "keep": [k.copy() for k in f["keep"]], "vertices": f["vertices"].copy(),
+                  "edge_u": f["edge_u"].copy(), "edge_v": f["edge_v"].copy(), "support": f["support"].copy(), "weight": f["weight"].copy()}
+        for sk in sks:
+            sk.close()
+        res.close()
     del assemblies
     if world > 1:
         torch.cuda.empty_cache()
@@ -406,7 +483,9 @@ def main():
         n_tot, n_v, n_e = res.counts()        # result stays resident in HBM; sizes only
         stats["n_mx"] = [sk.n for sk in sks]
         stats["edges"], stats["vertices"] = n_e, n_v
-        stats["d2h"] = n_tot * 2 + n_v * 8 + n_e * (28 if world == 1 else 36)
+        # e2e reads back: the minimizer tuples (out_hash u64, min_hash u64, pos u32, record u32, strand u8), the two flag
+        # bytes per minimizer, the vertices and the weighted edge list (u, v, support mask, weight [+ order key on shards])
+        stats["d2h"] = n_tot * 25 + n_tot * 2 + n_v * 8 + n_e * (28 if world == 1 else 36)
         for sk in sks:
             sk.close()
         res.close()
@@ -414,6 +493,8 @@ def main():
     def step_e2e():
         sks = eng.sketch_many([(h, o) for h, (_, o, _) in zip(host, shards)], K, W)   # H2D of assembly i+1 overlaps sketch i
         res = gather_and_filter(sks)
+        for sk in sks:
+            sk.fetch(copy=False)              # (out_hash, min_hash, pos, record, strand) of every minimizer into pinned host memory
         res.fetch(copy=False)                 # flags + vertices + weighted edge list into (pinned) host memory
         for sk in sks:
             sk.close()
@@ -456,6 +537,7 @@ def main():
     t_sketch, _ = eng.timing("sketch")
     t_filter, _ = eng.timing("filter")
     phases = {nm: eng.timing(nm)[0] / args.steps for nm in ("pack", "rank", "cand", "eval", "select", "gap", "emit", "sketch", "filter")}
+    kernel_times = {kname: eng.timing(span) for kname, span in (("pack2_kernel", "k_pack2"), ("scan_bs2_kernel", "k_scan"))}
     if comm:
         names = ("a2a_partition", "a2a_mark", "a2a_sightings", "a2a_finish") if dist_mode == "alltoall" else \
             ("dist_mark", "dist_adjacency", "dist_edges", "dist_finish")
@@ -466,6 +548,8 @@ def main():
         step_e2e()
     sec_e2e = timed(step_e2e, args.steps)
 
+    if world > 1 and not args.no_parity:
+        parity = multi_gpu_parity(eng, shards, gather_and_filter, single, rank, world, dist, dist_mode)
     if world > 1:   # whole-job totals for the report (outside the timed regions)
         tot = torch.tensor(stats["n_mx"] + [stats["vertices"], stats["edges"], stats["d2h"], my_bases], dtype=torch.int64, device=dev)
         dist.all_reduce(tot)
@@ -473,6 +557,7 @@ def main():
         stats["n_mx_total"], stats["vertices"], stats["edges"] = tot[:n_asm], tot[n_asm], tot[n_asm + 1]
         stats["d2h_total"], stats["h2d_total"] = tot[n_asm + 2], tot[n_asm + 3]
 
+    parity_failed = False
     if rank == 0:
         peaks = {}
         try:
@@ -480,17 +565,37 @@ def main():
         except OSError:
             pass
         peak = peaks.get("hbm_gbs", 6650.0)
-        traffic = None
-        try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["cand31_kernel"]
-            traffic = (tj["dram_read_bytes_per_base"] + tj["dram_write_bytes_per_base"]) * my_bases / n_asm   # ncu-measured DRAM bytes per launch
-        except (OSError, KeyError):
-            pass
-        # algorithmic bytes of the sketch: 1 B per base read + 16 B per emitted minimizer
+        # algorithmic bytes of the sketch: 1 B per base read + 16 B per emitted minimizer, whatever the
+        # internal representation.  Three scopes, all on CUDA events of the engine stream over the timed region:
+        #   per kernel   : one launch of the two front-end kernels (pack2_kernel reads the bases, scan_bs2_kernel decides
+        #                  which positions can be minimizers); `frac` is the DOMINANT (longest) one of the two
+        #   pack_cand    : both together (the packing pass inside the timed region)
+        #   sketch       : whole step 1 per assembly (T1 of SURVEY 8(d))
         n_mx_local = sum(stats["n_mx"])
         algo_bytes_per_launch = (my_bases + 16.0 * n_mx_local) / n_asm
-        cand_ms = t_cand / max(1, n_cand)
-        achieved = algo_bytes_per_launch / (cand_ms * 1e-3) / 1e9 if cand_ms > 0 else 0.0
+        traffic_tab = {}
+        try:
+            traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        except (OSError, ValueError):
+            pass
+        kernels = {}
+        for kname, (t_k, n_k) in kernel_times.items():
+            if n_k:
+                ms = t_k / n_k
+                tj = traffic_tab.get(kname)
+                kernels[kname] = {"launch_ms": ms, "launches": int(n_k), "achieved": algo_bytes_per_launch / (ms * 1e-3) / 1e9,
+                                  "frac": algo_bytes_per_launch / (ms * 1e-3) / 1e9 / peak,
+                                  "traffic": (tj["dram_read_bytes_per_base"] + tj["dram_write_bytes_per_base"]) * my_bases / n_asm if tj else None}
+        if kernels:
+            dom = max(kernels, key=lambda kn: kernels[kn]["launch_ms"])
+            cand_ms, achieved, traffic = kernels[dom]["launch_ms"], kernels[dom]["achieved"], kernels[dom]["traffic"]
+        else:       # a candidate kernel of the first generation was selected (MXE_CAND_VARIANT < 4, or k / canonical outside variant 4)
+            dom = "cand31_kernel"
+            cand_ms = t_cand / max(1, n_cand)
+            achieved = algo_bytes_per_launch / (cand_ms * 1e-3) / 1e9 if cand_ms > 0 else 0.0
+            traffic = None
+        sketch_ms_per_asm = t_sketch / args.steps / n_asm
+        pack_cand_ms_per_asm = (t_pack + t_cand) / args.steps / n_asm
         value = total_bases * args.steps / sec / 1e9
         line = {
             "metric": f"Gbases/s sketched+filtered at k={K} w={W}", "value": value, "unit": "Gbases/s",
@@ -504,22 +609,34 @@ def main():
             "e2e": {"value": total_bases * args.steps / sec_e2e / 1e9, "unit": "Gbases/s", "ms_per_step": sec_e2e / args.steps * 1e3,
                     "h2d_bytes_per_step": stats.get("h2d_total", my_bases), "d2h_bytes_per_step": stats.get("d2h_total", stats["d2h"])},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "cand31_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                          "launch_ms": cand_ms, "algorithmic_bytes_per_launch": algo_bytes_per_launch,
+                         "kernels": kernels,
+                         "pack_cand_frac": algo_bytes_per_launch / (pack_cand_ms_per_asm * 1e-3) / 1e9 / peak if pack_cand_ms_per_asm > 0 else None,
+                         "sketch_frac": algo_bytes_per_launch / (sketch_ms_per_asm * 1e-3) / 1e9 / peak if sketch_ms_per_asm > 0 else None,
+                         "sketch_ms_per_assembly": sketch_ms_per_asm, "pack_cand_ms_per_assembly": pack_cand_ms_per_asm,
                          "phase_ms_per_step": phases},
             "clocks": clocks,
         }
-        line["roofline"]["alu"] = alu_roofline(my_bases / n_asm, cand_ms)
+        alu_kernel = "scan_bs2_kernel" if "scan_bs2_kernel" in kernels else "cand31_kernel"
+        line["roofline"]["alu"] = alu_roofline(my_bases / n_asm, kernels[alu_kernel]["launch_ms"] if alu_kernel in kernels else cand_ms, alu_kernel)
+        if parity is not None:
+            line["parity"] = parity
         if not args.no_cpu_baseline:
-            cb, _ = cpu_reference_run(spec, args, 1, 1)
+            cb, _ = cpu_reference_run(spec, args, 1, 1, with_t4=True)
             line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)
+        if parity is not None and not parity["vs_single_gpu"]:
+            print("bench.py: the merged multi-GPU result differs from the single-GPU result: " + ", ".join(parity["mismatch"]), file=sys.stderr, flush=True)
+            parity_failed = True
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     eng.close()
+    if parity_failed:
+        sys.exit(3)
 
 
 if __name__ == "__main__":

@@ -13,6 +13,28 @@ import sys
 if os.environ.get("NTJOIN_B200", "0") not in ("", "0"):
     class _Patch(importlib.abc.MetaPathFinder):
         def find_spec(self, name, path, target=None):
+            if name == "btllib":
+                # bin/ntjoin_assemble.py:16 imports btllib for SeqReader (:313-316) and Indexlr (:478-481).  When the real
+                # package is installed it is used as is; when it is not, the engine's btllib-shaped module serves both.
+                sys.meta_path.remove(self)
+                try:
+                    real = importlib.util.find_spec(name)
+                except (ImportError, ValueError):
+                    real = None
+                finally:
+                    sys.meta_path.insert(0, self)
+                if real is not None:
+                    return None
+
+                class _Alias(importlib.abc.Loader):
+                    def create_module(self, spec):
+                        import ntjoin_b200.btllib_compat as compat
+                        return compat
+
+                    def exec_module(self, module):
+                        pass
+
+                return importlib.util.spec_from_loader(name, _Alias())
             if name not in ("ntjoin_utils", "ntjoin", "ntjoin_assemble"):
                 return None
             sys.meta_path.remove(self)

@@ -185,6 +185,7 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
         const size_t psm = pack2_smem_bytes(G.Lw, G.ext);
         const uint64_t tile = 512ull * G.Lw;
         if (!staged) {
+            Span k1(e, "k_pack2");
             MXE_LAUNCH(e, pack2_kernel, (unsigned)G.n_tiles, PACK2_THREADS, psm, d_seq, G, pk.p, PL.p, V.p, vcounts.p, DL, (uint64_t)0);
         } else {
             // host input: a tile is packed once its bytes and its halo (ext units) have landed
@@ -260,9 +261,12 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
         MXE_CUDA(cudaFuncSetAttribute(scan_bs2_kernel<KM, BS2_H, BS2_HS, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm)); \
         MXE_LAUNCH(e, (scan_bs2_kernel<KM, BS2_H, BS2_HS, RG>), grid, BS2_THREADS, rsm, PL.p, G, BP, C.p);                            \
     } while (0)
-            if (kmod == 1) MXE_BS2(1, 48);           // k = 32
-            else if (kmod == 9) MXE_BS2(9, 64);      // k = 40
-            else MXE_BS2(24, 48);                    // k = 24
+            {
+                Span k2(e, "k_scan");
+                if (kmod == 1) MXE_BS2(1, 48);           // k = 32
+                else if (kmod == 9) MXE_BS2(9, 64);      // k = 40
+                else MXE_BS2(24, 48);                    // k = 24
+            }
 #undef MXE_BS2
             MXE_LAUNCH(e, dirty_fix_kernel, (unsigned)(e->sm_count * 8), 256, 0, DL, V.p, C.p, nW);
         } else if (sliced) {

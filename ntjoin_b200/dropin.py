@@ -44,6 +44,39 @@ class MxLists(list):
     _result = None      # FilterResult shared by all assemblies after filter_minimizers
     _asm_index = None
 
+    def __reduce__(self):
+        # The reference keeps these lists in Ntjoin.list_mxs and pickles `self` into multiprocessing.Pool workers when
+        # -t / assemble_t > 1 (bin/ntjoin.py:173-174).  The engine handles (ctypes pointers) cannot and need not travel:
+        # the lists pickle as the plain list[list[str]] the reference expects.
+        return (list, (list(self),))
+
+
+MAX_ASSEMBLIES = 32              # support masks are 32 bits wide (include/mxe.h: n_asm <= 32)
+MAX_MINIMIZERS = (1 << 32) - 1   # steps 2-3 index minimizers with 32 bits
+
+
+def _engine_can_serve(vals):
+    return len(vals) <= MAX_ASSEMBLIES and sum(v._sketch.n for v in vals) < MAX_MINIMIZERS
+
+
+_LAST_FILTER = None              # (tuple of sketch ids, FilterResult): filter_minimizers and build_graph share one pass
+
+
+def _filter_once(eng, vals):
+    """steps 2-3 of these sketches, computed once per set of assemblies: uniqueness, intersection and the edge list do
+    not depend on the weights (a weight is the sum over the support mask, re-derived in build_graph)"""
+    global _LAST_FILTER
+    key = tuple(id(v._sketch) for v in vals)
+    if _LAST_FILTER is not None and _LAST_FILTER[0] == key:
+        _trace("filter_and_edges cached")
+        return _LAST_FILTER[1]
+    if _LAST_FILTER is not None:
+        _LAST_FILTER[1].close()
+    _trace("filter_and_edges engine")
+    res = eng.filter_and_edges([v._sketch for v in vals], [1.0] * len(vals))
+    _LAST_FILTER = (key, res, [v._sketch for v in vals])      # the sketches stay referenced: ids cannot be recycled
+    return res
+
 
 def _lists_from(sk, mask):
     """per-record lists (records with at least one minimizer in the TSV) of decimal strings"""
@@ -82,13 +115,12 @@ def make_read_minimizers(original):
 def make_filter_minimizers(original):
     def filter_minimizers(list_mxs):
         vals = list(list_mxs.values())
-        if not vals or not all(isinstance(v, MxLists) and v._sketch is not None for v in vals):
+        if not vals or not all(isinstance(v, MxLists) and v._sketch is not None for v in vals) or not _engine_can_serve(vals):
             _trace("filter_minimizers original")
             return original(list_mxs)
         _trace("filter_minimizers engine")
         eng = _engine()
-        sks = [v._sketch for v in vals]
-        res = eng.filter_and_edges(sks, [1.0] * len(sks))
+        res = _filter_once(eng, vals)
         out = {}
         for a, (asm, v) in enumerate(list_mxs.items()):
             keep = res.keep[a]
@@ -104,13 +136,14 @@ def make_build_graph(original, ig):
     def build_graph(list_mxs, weights, graph=None, black_list=None):
         vals = list(list_mxs.values())
         if graph is not None or black_list is not None or not vals or \
-                not all(isinstance(v, MxLists) and v._sketch is not None and v._asm_index is not None for v in vals):
+                not all(isinstance(v, MxLists) and v._sketch is not None and v._asm_index is not None for v in vals) or \
+                not _engine_can_serve(vals):
             _trace("build_graph original")
             return original(list_mxs, weights, graph, black_list)
         _trace("build_graph engine")
         eng = _engine()
         keys = list(list_mxs.keys())
-        res = eng.filter_and_edges([v._sketch for v in vals], [weights[k] for k in keys])
+        res = _filter_once(eng, vals)
         g = ig.Graph()
         vs = res.vertices
         g.add_vertices([str(v) for v in vs.tolist()])
@@ -118,10 +151,13 @@ def make_build_graph(original, ig):
         ev = np.searchsorted(vs, res.edge_v)
         g.add_edges(list(zip(eu.tolist(), ev.tolist())))
         n_asm = len(keys)
-        g.es["support"] = [[keys[a] for a in range(n_asm) if m >> a & 1] for m in res.support.tolist()]
-        g.es["weight"] = res.weight.tolist()
+        masks = res.support.tolist()
+        support_of = {m: [keys[a] for a in range(n_asm) if m >> a & 1] for m in set(masks)}
+        # calc_total_weight (bin/ntjoin_utils.py:54-56): Python's sum() over the support list, in assembly order
+        weight_of = {m: sum(weights[f] for f in sup) for m, sup in support_of.items()}
+        g.es["support"] = [list(support_of[m]) for m in masks]
+        g.es["weight"] = [weight_of[m] for m in masks]
         _attach_dot_payload(g, keys, vals, weights, vs, eu, ev, res)
-        res.close()
         return g
     build_graph.__doc__ = original.__doc__
     return build_graph

@@ -44,6 +44,18 @@ class Sketch:
             self._views = tuple(_np_view(x.value, n, d).copy() for x, d in zip(p, dt))
         return self._views
 
+    def fetch(self, copy=True):
+        """(out_hash, min_hash, pos, contig, forward) in host memory: one pinned device->host copy on first use.
+        copy=False returns views into the engine's pinned block (valid until close()) instead of numpy copies."""
+        if copy:
+            return self._view()
+        lib = self._e._lib
+        n = C.c_uint64()
+        p = [C.c_void_p() for _ in range(5)]
+        check(lib, lib.mxe_sketch_view(self._h, C.byref(n), *[C.byref(x) for x in p]))
+        dt = [np.uint64, np.uint64, np.uint32, np.uint32, np.uint8]
+        return tuple(_np_view(x.value, n.value, d) for x, d in zip(p, dt))
+
     out_hash = property(lambda s: s._view()[0])
     min_hash = property(lambda s: s._view()[1])
     pos = property(lambda s: s._view()[2])

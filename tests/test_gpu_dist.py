@@ -146,17 +146,28 @@ def _nccl_worker(rank, world, port, q, mode):
     eng.close()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-@pytest.mark.parametrize("mode", ["alltoall", "allreduce"])
-def test_two_process_nccl(mode):
+def _run_nccl(world, mode):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 32500 + os.getpid() % 2000
-    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port + (11 if mode == "alltoall" else 0), q, mode)) for r in range(2)]
+    port = 32500 + os.getpid() % 2000 + 17 * world
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port + (11 if mode == "alltoall" else 0), q, mode)) for r in range(world)]
     for p in procs:
         p.start()
     out = [q.get(timeout=600) for _ in procs]
     for p in procs:
         p.join(timeout=120)
-    assert sorted(r for r, _ in out) == [0, 1] and all(ok for _, ok in out)
+    assert sorted(r for r, _ in out) == list(range(world)) and all(ok for _, ok in out)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("mode", ["alltoall", "allreduce"])
+def test_two_process_nccl(mode):
+    _run_nccl(2, mode)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 3, reason="needs more than two GPUs")
+@pytest.mark.parametrize("mode", ["alltoall", "allreduce"])
+def test_all_devices_nccl(mode):
+    """one rank per visible GPU (4 or 8 on a multi-GPU box), real NCCL collectives, merged shards against the oracle"""
+    _run_nccl(torch.cuda.device_count(), mode)

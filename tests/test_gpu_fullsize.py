@@ -98,3 +98,51 @@ def test_config3_properties(engine, oracle):
             np.testing.assert_array_equal(mine, theirs)
             sel = (gpos >= lo) & (gpos < hi)
             np.testing.assert_array_equal(oh[sel], ref["out_hash"][(ref["pos"] + a >= lo) & (ref["pos"] + a < hi)])
+
+
+def test_config3_full_bit_exact(engine, oracle):
+    """BASELINE configs[2] at FULL size, the north_star's acceptance sentence: both 3 Gbp assemblies of bench.py's
+    workload in the with-N variant (reference with 0.5 % of its bases in N runs and 2 % in duplicated 5 kb segments;
+    target = its contigs cut, half reverse-complemented, mutated, shuffled) are sketched on the GPU and by the oracle
+    with every host thread, and ALL minimizer tuples must be equal; then steps 2-3 (6 M x 2 minimizers) against the
+    oracle's: flags, vertices, and the weighted edge list in the reference's order."""
+    import sys
+    import types
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    dev = torch.device("cuda", 0)
+    spec = bench.workload_spec(types.SimpleNamespace(workload="c3", bases=0))
+    assemblies = bench.gen_assemblies_gpu(spec, True, dev)            # with_n=True
+    cores = os.cpu_count() or 1
+    sks, refs = [], []
+    for seq, offs in assemblies:
+        sk = engine.sketch_device(seq.data_ptr(), offs, K, W)
+        host = seq.cpu().numpy()
+        ref = oracle.sketch(host, offs, K, W, threads=cores)
+        del host
+        assert sk.n == len(ref) and sk.n > 5_000_000
+        np.testing.assert_array_equal(sk.out_hash, ref["out_hash"])
+        np.testing.assert_array_equal(sk.min_hash, ref["min_hash"])
+        np.testing.assert_array_equal(sk.pos, ref["pos"].astype(np.uint32))
+        np.testing.assert_array_equal(sk.contig, ref["contig"])
+        np.testing.assert_array_equal(sk.forward.astype(np.uint32), ref["forward"])
+        assert sk.counts()["gap_windows"] > 0                          # the N runs put the dense gap path to work
+        sks.append(sk)
+        refs.append(ref)
+    del assemblies
+    res = engine.filter_and_edges(sks, [2.0, 1.0])
+    want = oracle.filter_and_edges([r["out_hash"] for r in refs], [r["contig"] for r in refs], [2.0, 1.0])
+    for a in range(2):
+        np.testing.assert_array_equal(res.uniq[a].astype(bool), want["uniq"][a])
+        np.testing.assert_array_equal(res.keep[a].astype(bool), want["keep"][a])
+    np.testing.assert_array_equal(res.vertices, want["vertices"])
+    np.testing.assert_array_equal(res.edge_u, want["edges"]["u"])
+    np.testing.assert_array_equal(res.edge_v, want["edges"]["v"])
+    np.testing.assert_array_equal(res.support, want["edges"]["support_mask"])
+    np.testing.assert_array_equal(res.weight, want["edges"]["weight"])
+    assert len(res.vertices) > 5_000_000 and len(res.edge_u) > 5_000_000
+    for sk in sks:
+        sk.close()
+    res.close()

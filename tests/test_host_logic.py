@@ -74,3 +74,22 @@ def test_indexlr_cli_argv_forms():
         with pytest.raises(SystemExit) as ei:
             cli.parse(bad)
         assert ei.value.code not in (0, None)
+
+
+def test_mxlists_pickle_as_plain_lists():
+    """bin/ntjoin.py:173-174 pickles the Ntjoin object (list_mxs included) into multiprocessing.Pool workers when
+    assemble_t > 1; the engine handles hidden in the drop-in's lists (ctypes pointers) must not break that"""
+    import ctypes
+    import pickle
+    from ntjoin_b200.dropin import MxLists
+
+    class FakeSketch:
+        def __init__(self):
+            self.handle = ctypes.c_void_p(1234)      # what makes a plain pickle fail
+
+    lists = MxLists([["1", "2"], [], ["3"]])
+    lists._sketch, lists._mask, lists._asm_index = FakeSketch(), np.array([True, False]), 0
+    with pytest.raises((ValueError, TypeError)):
+        pickle.dumps(lists._sketch.handle)
+    back = pickle.loads(pickle.dumps({"asm.tsv": lists}))
+    assert type(back["asm.tsv"]) is list and back["asm.tsv"] == [["1", "2"], [], ["3"]]

@@ -76,6 +76,8 @@ def test_reference_suite_with_dropin_layer(tmp_path):
     for fn in ("read_minimizers", "filter_minimizers", "build_graph", "print_graph", "find_mx_min_max"):
         assert trace.count(fn + " engine") >= 20, (fn, trace.count(fn + " engine"))
     assert trace.count("build_graph original") > 0 and trace.count("filter_minimizers original") > 0
+    # steps 2-3 run once per set of assemblies: build_graph reuses the pass filter_minimizers made
+    assert trace.count("filter_and_edges cached") >= 20 and trace.count("filter_and_edges engine") >= 20
     assert trace.count("print_graph original") == 0 and trace.count("find_mx_min_max original") == 0
     dots = sorted((tmp_path / "ntJoin" / "tests").glob("*.mx.dot"))
     assert dots
