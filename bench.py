@@ -424,8 +424,17 @@ def main():
     torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
     comm = TorchComm(dev, timing=True) if world > 1 else None
-    dist_mode = os.environ.get("MXE_DIST_MODE", "allreduce")     # or "alltoall" (measured slower at this size)
-    stages = (eng.a2a_stages() if dist_mode == "alltoall" else eng.dist_stages()) if world > 1 else None
+    # steps 2-3 across ranks: "p2p" = direct peer stores over NVLink + device-side barriers (csrc/p2p.cu, default);
+    # "allreduce" / "alltoall" = the NCCL formulations of round 1 (kept for comparison)
+    dist_mode = os.environ.get("MXE_DIST_MODE", "p2p")
+    stages = (eng.a2a_stages() if dist_mode == "alltoall" else eng.dist_stages()) if world > 1 and dist_mode != "p2p" else None
+    p2p = None
+    if world > 1 and dist_mode == "p2p":
+        cap_total = int((len(WEIGHTS)) * spec["G"] * 2.0 / (W + 1) * 1.15) + 100_000
+        p2p = eng.p2p(rank, world, cap_total, n_asm_max=max(4, len(WEIGHTS)))
+        handles = [None] * world
+        dist.all_gather_object(handles, p2p.handle())          # 64 bytes per rank, once
+        p2p.connect(handles)
 
     assemblies = gen_assemblies_gpu(spec, args.with_n, dev)
     my = shard_ranges([o for _, o in assemblies], world)[rank]
@@ -470,6 +479,9 @@ def main():
         if world == 1:
             res = eng.filter_and_edges(sks, WEIGHTS)
             return res
+        if p2p is not None:
+            from ntjoin_b200.dist import DistShard
+            return DistShard(p2p.run(sks, WEIGHTS), None, rank, None, None)      # this rank's shard of the result
         hashes, contigs = [], []
         for sk in sks:
             n, ph, _pp, pc = sk.device_pointers()
@@ -538,7 +550,9 @@ def main():
     t_filter, _ = eng.timing("filter")
     phases = {nm: eng.timing(nm)[0] / args.steps for nm in ("pack", "rank", "cand", "eval", "select", "gap", "emit", "sketch", "filter")}
     kernel_times = {kname: eng.timing(span) for kname, span in (("pack2_kernel", "k_pack2"), ("scan_bs2_kernel", "k_scan"))}
-    if comm:
+    if world == 1 or p2p is not None:
+        phases.update({nm: eng.timing(nm)[0] / args.steps for nm in ("p2p_scatter", "p2p_buckets", "p2p_adjacency", "p2p_edges", "p2p_finish")})
+    elif comm:
         names = ("a2a_partition", "a2a_mark", "a2a_sightings", "a2a_finish") if dist_mode == "alltoall" else \
             ("dist_mark", "dist_adjacency", "dist_edges", "dist_finish")
         phases.update({nm: eng.timing(nm)[0] / args.steps for nm in names})
@@ -604,7 +618,9 @@ def main():
             "config": {"workload": spec["name"], "k": K, "w": W, "bases_per_step": total_bases, "n_free": not args.with_n,
                        "l2": "inputs larger than L2 (>= 200 MB per assembly)", "sharding": f"contiguous record ranges over {world} rank(s)" +
                        (("; steps 2-3 by hash owner, 3 all-to-alls (NCCL): keys, marks, sightings" if dist_mode == "alltoall" else
-                         "; steps 2-3 by hash range / own records, 1 all-gather + 3 all-reduces (NCCL)") if world > 1 else ""),
+                         "; steps 2-3 by hash range / own records, 1 all-gather + 3 all-reduces (NCCL)" if dist_mode == "allreduce" else
+                         "; steps 2-3 by hash-bucket owner, exchanges as direct peer stores over NVLink (CUDA IPC) with device-side barriers, no collective library")
+                        if world > 1 else ""),
                        "minimizers": stats.get("n_mx_total", stats["n_mx"]), "vertices": stats["vertices"], "edges": stats["edges"]},
             "e2e": {"value": total_bases * args.steps / sec_e2e / 1e9, "unit": "Gbases/s", "ms_per_step": sec_e2e / args.steps * 1e3,
                     "h2d_bytes_per_step": stats.get("h2d_total", my_bases), "d2h_bytes_per_step": stats.get("d2h_total", stats["d2h"])},
@@ -631,6 +647,9 @@ def main():
         if parity is not None and not parity["vs_single_gpu"]:
             print("bench.py: the merged multi-GPU result differs from the single-GPU result: " + ", ".join(parity["mismatch"]), file=sys.stderr, flush=True)
             parity_failed = True
+    if p2p is not None:
+        dist.barrier()
+        p2p.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -32,6 +32,7 @@ typedef struct mxe_sketch mxe_sketch_t;
 typedef struct mxe_result mxe_result_t;
 typedef struct mxe_dist mxe_dist_t;
 typedef struct mxe_a2a mxe_a2a_t;
+typedef struct mxe_p2p mxe_p2p_t;
 typedef struct mxe_fasta mxe_fasta_t;
 
 enum {
@@ -256,7 +257,46 @@ int mxe_a2a_finish(mxe_a2a_t* x, const void* d_recv_records, uint64_t n_records,
                    const double* weights, mxe_result_t** out);
 void mxe_a2a_free(mxe_a2a_t* x);
 
-/* Global order key of every edge of a multi-GPU shard (ascending inside the shard). */
+/* ---- steps 2-3 across GPUs, exchanges as direct peer stores over NVLink (the default formulation) ----------------
+ *
+ * Same replaced reference code and same result shards as mxe_dist_* / mxe_a2a_* (bin/ntjoin_utils.py:182-192, :155-162,
+ * :94-115, :54-56), no collective library: every rank owns a SYMMETRIC device workspace that its peers map through
+ * CUDA IPC; minimizers are partitioned into hash buckets owned by ranks (bucket b -> rank (b * world) >> B, monotone
+ * in the hash), the producing kernels store into the consumer's workspace and a device-side barrier separates the
+ * five stages (csrc/p2p.cu).  One host round trip per call (sizes, in mxe_p2p_finish).  world = 1 is the single-GPU
+ * path of mxe_filter_and_edges.  world <= 16; capacity < 2^32 minimizers.
+ *
+ *   h = mxe_p2p_create(e, rank, world, cap_total, n_asm_max)     cap_total: upper bound of all minimizers of all
+ *                                                                assemblies and ranks (sizes the workspace)
+ *   mxe_p2p_handle(h, handle64)  -> exchange the 64-byte handles (e.g. torch.distributed.all_gather_object)
+ *   mxe_p2p_connect(h, handles)                                  one process per GPU
+ *   mxe_p2p_connect_pointers(h, bases)                           several ranks in one process (tests), from mxe_p2p_workspace
+ *   per job, on every rank, in this order (each call only enqueues work on the engine stream):
+ *   mxe_p2p_scatter(h, d_hash, d_contig, n, n_asm, weights)      own minimizers -> bucket owners
+ *   mxe_p2p_buckets(h)                                           owned buckets: uniqueness, found-in-all, vertex ranks
+ *   mxe_p2p_adjacency(h)                                         own records: survivors, adjacent pairs -> successor tables
+ *   mxe_p2p_edges(h)                                             support masks, edge ownership, first-source tables
+ *   mxe_p2p_finish(h, &result)                                   world 1: full result in the reference's order;
+ *                                                                world > 1: shard (own flags, owned vertices, own edges
+ *                                                                in creation order + mxe_result_edge_keys)
+ * A bucket that overflows its capacity (one hash repeated thousands of times) makes mxe_p2p_finish fail with
+ * MXE_ERR_INTERNAL; mxe_filter_and_edges then falls back to the sort-based formulation by itself.
+ */
+int mxe_p2p_create(mxe_t* e, int rank, int world, uint64_t cap_total, int n_asm_max, mxe_p2p_t** out);
+int mxe_p2p_handle(mxe_p2p_t* h, void* handle64, uint64_t* workspace_bytes);
+int mxe_p2p_connect(mxe_p2p_t* h, const void* handles);
+int mxe_p2p_workspace(mxe_p2p_t* h, void** ptr);
+int mxe_p2p_connect_pointers(mxe_p2p_t* h, void* const* bases);
+int mxe_p2p_scatter(mxe_p2p_t* h, const void* const* d_hash, const void* const* d_contig, const uint64_t* n, int n_asm,
+                    const double* weights);
+int mxe_p2p_buckets(mxe_p2p_t* h);
+int mxe_p2p_adjacency(mxe_p2p_t* h);
+int mxe_p2p_edges(mxe_p2p_t* h);
+int mxe_p2p_finish(mxe_p2p_t* h, mxe_result_t** out);
+void mxe_p2p_free(mxe_p2p_t* h);
+
+/* Global order key of every edge of a multi-GPU shard (mxe_dist / mxe_a2a: ascending inside the shard; mxe_p2p: the
+ * shard is in creation order -- merge by key either way). */
 int mxe_result_edge_keys(mxe_result_t* r, uint64_t* n_edges, const uint64_t** keys);
 
 /* ---- measurement hooks (bench.py) -------------------------------------------------------- */

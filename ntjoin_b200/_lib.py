@@ -15,6 +15,8 @@ SYMBOLS = [
     "mxe_result_free", "mxe_write_dot", "mxe_timing", "mxe_timing_reset", "mxe_kernel_launches",
     "mxe_dist_mark", "mxe_dist_adjacency", "mxe_dist_edges", "mxe_dist_finish", "mxe_dist_free", "mxe_result_edge_keys",
     "mxe_a2a_partition", "mxe_a2a_mark", "mxe_a2a_sightings", "mxe_a2a_finish", "mxe_a2a_free",
+    "mxe_p2p_create", "mxe_p2p_handle", "mxe_p2p_connect", "mxe_p2p_workspace", "mxe_p2p_connect_pointers", "mxe_p2p_scatter",
+    "mxe_p2p_buckets", "mxe_p2p_adjacency", "mxe_p2p_edges", "mxe_p2p_finish", "mxe_p2p_free",
 ]
 
 
@@ -87,6 +89,18 @@ def load_library():
     lib.mxe_a2a_finish.argtypes = [vp, vp, C.c_uint64, C.c_uint64, C.POINTER(C.c_double), pp]
     lib.mxe_a2a_free.argtypes = [vp]
     lib.mxe_a2a_free.restype = None
+    lib.mxe_p2p_create.argtypes = [vp, C.c_int, C.c_int, C.c_uint64, C.c_int, pp]
+    lib.mxe_p2p_handle.argtypes = [vp, vp, u64p]
+    lib.mxe_p2p_connect.argtypes = [vp, vp]
+    lib.mxe_p2p_workspace.argtypes = [vp, pp]
+    lib.mxe_p2p_connect_pointers.argtypes = [vp, pp]
+    lib.mxe_p2p_scatter.argtypes = [vp, pp, pp, u64p, C.c_int, C.POINTER(C.c_double)]
+    lib.mxe_p2p_buckets.argtypes = [vp]
+    lib.mxe_p2p_adjacency.argtypes = [vp]
+    lib.mxe_p2p_edges.argtypes = [vp]
+    lib.mxe_p2p_finish.argtypes = [vp, pp]
+    lib.mxe_p2p_free.argtypes = [vp]
+    lib.mxe_p2p_free.restype = None
     lib.mxe_write_dot.argtypes = [C.c_char_p, C.c_uint64, vp, C.c_int, C.POINTER(C.c_char_p), pp, pp, pp,
                                   C.c_uint64, vp, vp, vp, C.POINTER(C.c_char_p)]
     lib.mxe_timing.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), u64p]

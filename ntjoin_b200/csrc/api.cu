@@ -78,6 +78,21 @@ void Engine::span_end(const char* name, cudaEvent_t a, uint64_t n_launch)
 
 using namespace mxe;
 
+// Engines that are still alive.  Objects handed out by an engine (sketches, results, stage handles) may be released
+// after it -- a garbage-collected host language frees in any order at interpreter exit -- and must then not touch it:
+// their device memory went with the engine's context, only the host struct is left to delete.
+#include <mutex>
+#include <set>
+static std::mutex g_live_mu;
+static std::set<const void*> g_live_engines;
+namespace mxe {
+bool engine_alive(const void* e)
+{
+    std::lock_guard<std::mutex> lk(g_live_mu);
+    return g_live_engines.count(e) != 0;
+}
+}
+
 void* mxe_engine::pinned_alloc(size_t bytes)
 {
     if (bytes == 0) bytes = 1;
@@ -134,20 +149,24 @@ int mxe_create(int device, mxe_t** out)
     if (const char* s = getenv("MXE_CAND_VARIANT")) e->cand_variant = atoi(s);
     if (const char* s = getenv("MXE_PRUNE")) e->prune = atoi(s) != 0;
     if (const char* s = getenv("MXE_SORT_BITS")) e->sort_bits = atoi(s);
+    if (const char* s = getenv("MXE_FILTER_VARIANT")) e->filter_variant = atoi(s);
     if (const char* s = getenv("MXE_FMA_OFFLOAD")) e->fma_offload = atoi(s) != 0;
     if (const char* s = getenv("MXE_SELECT_NARROW")) e->select_narrow = atoi(s) != 0;
+    { std::lock_guard<std::mutex> lk(g_live_mu); g_live_engines.insert(e); }
     *out = e;
     return MXE_OK;
 }
 
 void mxe_destroy(mxe_t* e)
 {
-    if (!e) return;
+    if (!e || !engine_alive(e)) return;
+    { std::lock_guard<std::mutex> lk(g_live_mu); g_live_engines.erase(e); }
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     for (auto& kv : e->timers)
         for (auto& sp : kv.second.spans) { cudaEventDestroy(sp.first); cudaEventDestroy(sp.second); }
     for (auto ev : e->event_pool) cudaEventDestroy(ev);
+    if (e->local_p2p) { p2p_release(e->local_p2p, true); e->local_p2p = nullptr; }
     for (auto& p : e->pinned_free) cudaFreeHost(p.p);
     e->arena.destroy();
     for (int c = 0; c < 2; c++) if (e->copy_stream[c]) { cudaStreamSynchronize(e->copy_stream[c]); cudaStreamDestroy(e->copy_stream[c]); }
@@ -177,6 +196,7 @@ int mxe_set_option(mxe_t* e, const char* name, double value)
     else if (!strcmp(name, "scan_lw")) e->scan_lw = (int)value;
     else if (!strcmp(name, "prune")) e->prune = value != 0;
     else if (!strcmp(name, "sort_bits")) e->sort_bits = (int)value;
+    else if (!strcmp(name, "filter_variant")) e->filter_variant = (int)value;
     else if (!strcmp(name, "fma_offload")) e->fma_offload = value != 0;
     else if (!strcmp(name, "select_narrow")) e->select_narrow = value != 0;
     else if (!strcmp(name, "timing")) e->timing = value != 0;
@@ -486,6 +506,7 @@ int mxe_sketch_from_arrays(const uint64_t* out_hash, const uint64_t* min_hash, c
 void mxe_sketch_free(mxe_sketch_t* S)
 {
     if (!S) return;
+    if (S->eng && !engine_alive(S->eng)) { delete S; return; }
     if (S->eng) {
         cudaSetDevice(S->eng->device);
         cudaStream_t st = S->eng->stream;
@@ -560,6 +581,28 @@ int mxe_filter_and_edges_device(mxe_t* e, const void* const* d_hash, const void*
 {
     if (!e || !d_hash || !d_contig || !n || !weights || !out) { set_error("null argument"); return MXE_ERR_ARG; }
     MXE_CUDA(cudaSetDevice(e->device));
+    if (e->filter_variant >= 1 && n_asm >= 1 && n_asm <= 32) {
+        // hash buckets in shared memory (csrc/p2p.cu with world = 1); a bucket overflow falls back to the global sort
+        uint64_t N = 0;
+        for (int a = 0; a < n_asm; a++) N += n[a];
+        if (N > 0 && N < (1ULL << 32) - 8192) {
+            if (!e->local_p2p || e->local_p2p_cap < N || e->local_p2p_asm < n_asm) {
+                if (e->local_p2p) { mxe_p2p_free(e->local_p2p); e->local_p2p = nullptr; }
+                const uint64_t cap = std::min<uint64_t>(N + N / 8 + 65536, (1ULL << 32) - 1);
+                int rc0 = mxe_p2p_create(e, 0, 1, cap, std::max(n_asm, 4), &e->local_p2p);
+                if (rc0 != MXE_OK) return rc0;
+                e->local_p2p_cap = cap; e->local_p2p_asm = std::max(n_asm, 4);
+            }
+            mxe_p2p* X = e->local_p2p;
+            int rc1 = mxe_p2p_scatter(X, d_hash, d_contig, n, n_asm, weights);
+            if (rc1 == MXE_OK) rc1 = mxe_p2p_buckets(X);
+            if (rc1 == MXE_OK) rc1 = mxe_p2p_adjacency(X);
+            if (rc1 == MXE_OK) rc1 = mxe_p2p_edges(X);
+            if (rc1 == MXE_OK) rc1 = mxe_p2p_finish(X, out);
+            if (rc1 == MXE_OK) return MXE_OK;
+            if (rc1 != MXE_ERR_INTERNAL) return rc1;
+        }
+    }
     mxe_result* R = new mxe_result();
     int rc;
     {
@@ -656,6 +699,7 @@ int mxe_result_graph(mxe_result_t* r, uint64_t* n_vertices, const uint64_t** ver
 void mxe_result_free(mxe_result_t* r)
 {
     if (!r) return;
+    if (r->eng && !engine_alive(r->eng)) { delete r; return; }
     if (r->eng) {
         cudaSetDevice(r->eng->device);
         cudaStream_t st = r->eng->stream;
@@ -729,7 +773,7 @@ int mxe_dist_finish(mxe_dist_t* X, const void* d_srcmin, const double* weights, 
 void mxe_dist_free(mxe_dist_t* X)
 {
     if (!X) return;
-    if (X->eng) {
+    if (X->eng && engine_alive(X->eng)) {
         cudaSetDevice(X->eng->device);
         for (void* p : X->owned) if (p) cudaFreeAsync(p, X->eng->stream);
     }
@@ -789,7 +833,7 @@ int mxe_a2a_finish(mxe_a2a_t* X, const void* d_recv_records, uint64_t n_records,
 void mxe_a2a_free(mxe_a2a_t* X)
 {
     if (!X) return;
-    if (X->eng) {
+    if (X->eng && engine_alive(X->eng)) {
         cudaSetDevice(X->eng->device);
         for (void* p : X->owned) if (p) cudaFreeAsync(p, X->eng->stream);
     }

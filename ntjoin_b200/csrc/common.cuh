@@ -71,6 +71,7 @@ struct Engine {
     bool prune = false;      // drop dominated candidates on 31-bit bounds before the exact stages
     bool fma_offload = true; // cand31: additions of the threshold test as IMADs on the FMA pipe
     bool select_narrow = true;   // window selection in 32-bit arithmetic when the ordinals allow it
+    int filter_variant = 1;  // steps 2-3: 0 = global radix sort (filter.cu), 1 = hash buckets in shared memory (p2p.cu)
     int sort_bits = 0;       // steps 2-3: top hash bits covered by the radix sort (24/32/40; 0 = by size), rest by the fix-up
     bool timing = false;
     // accounting

@@ -42,6 +42,8 @@ struct mxe_engine : public mxe::Engine {
     // pinned host block pool (grow-only, reused across steps)
     struct Pinned { void* p; size_t bytes; };
     std::vector<Pinned> pinned_free;
+    struct mxe_p2p* local_p2p = nullptr;    // world-1 instance behind mxe_filter_and_edges (grow-only capacity)
+    uint64_t local_p2p_cap = 0; int local_p2p_asm = 0;
     void* pinned_alloc(size_t bytes);
     void pinned_release(void* p, size_t bytes);
 };
@@ -139,6 +141,8 @@ struct mxe_a2a {
 };
 
 namespace mxe {
+bool engine_alive(const void* e);
+void p2p_release(struct ::mxe_p2p* X, bool engine_is_alive);
 int a2a_partition_impl(mxe_engine* e, const uint64_t* const* d_hash, const uint64_t* n, int n_asm, int rank, int world,
                        mxe_a2a* X, uint64_t* counts, const void** d_send_keys);
 int a2a_mark_impl(mxe_a2a* X, const uint64_t* d_recv, const uint64_t* recv_counts, uint32_t* d_ret, uint64_t* nv_local);

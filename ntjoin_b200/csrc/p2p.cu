@@ -1,0 +1,881 @@
+// p2p.cu -- steps 2-3, second generation: bucket partition by hash owner, exchanges as direct peer stores.
+//
+// Replaces (reference, Python): per-assembly uniqueness (bin/ntjoin_utils.py:182-192), the found-in-all intersection
+// and ordered filtering (:155-162), the adjacent-pair edge dictionary with its support lists (:94-115) and the edge
+// weights (:54-56) -- same results as filter.cu, different machine mapping:
+//
+//   * no global sort.  The 64-bit out_hash is uniformly mixed, so its top B bits cut the minimizers of all assemblies
+//     into 2^B BUCKETS of ~700 records; a bucket is sorted and analysed by one CTA in shared memory (uniqueness per
+//     assembly, found-in-all runs, vertex ranks), the kernels before and after it are single passes.
+//   * one code path for 1..16 GPUs.  Bucket b belongs to rank (b * world) >> B (monotone in the hash, so the ranks'
+//     vertex lists concatenate to the ascending single-GPU order).  Every rank holds the same SYMMETRIC workspace; the
+//     producing kernels write straight into the consumer's copy over NVLink (plain stores into peer memory mapped
+//     through CUDA IPC, a few atomics for the first-source tables), and a device-side barrier (one flag store per peer,
+//     one spinning warp) separates the stages.  No collective library, no host round trip between the stages:
+//
+//       scatter    (source)  record {hash, asm | rank | local index} -> bucket sub-slot [bucket][source] at the OWNER
+//       --- barrier 1 (per-(bucket, source) counts and the per-rank minimizer counts ride along)
+//       buckets    (owner)   sort + run analysis in shared memory; the mark of every record goes back to its SOURCE,
+//                            the bucket's survivor count to EVERY rank
+//       --- barrier 2
+//       adjacency  (source)  vertex ids from the bucket prefix, ordered survivors of own records, adjacent pairs;
+//                            successor entries -> table of the vertex OWNER
+//       --- barrier 3
+//       edges      (source)  support mask of every sighting from the successor tables (peer loads), edge ownership,
+//                            first-source index / source mask -> tables of the vertex owner (peer atomics)
+//       --- barrier 4
+//       finish     (source)  world == 1: edges placed directly in the reference's formatted_edges order (a prefix sum
+//                            over first edges; no sort).  world > 1: this rank's shard with 64-bit global order keys.
+//
+// Uniqueness is per ASSEMBLY, not per GPU (bin/ntjoin_utils.py:182-187): the owner of a bucket sees the full multiset.
+// A bucket or sub-slot that overflows (adversarial input: one hash repeated thousands of times) raises an error flag
+// and the caller falls back to the sort-based formulation of filter.cu.
+#include "engine.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace mxe {
+
+constexpr int P2P_MAX_WORLD = 16;
+constexpr int P2P_BK_MAX = 1024;          // records of one bucket (shared memory of the bucket kernel)
+constexpr int P2P_BK_THREADS = 128;       // = digits of the in-bucket counting sort (7 bits)
+constexpr int P2P_N_BARRIERS = 8;
+
+struct PeerPtrs { char* base[P2P_MAX_WORLD]; };
+struct PtrTab { const void* p[32]; };
+
+struct P2PLayout {
+    int world, rank, n_asm_max, B;
+    uint32_t n_buckets;                    // 2^B
+    uint32_t fb[P2P_MAX_WORLD + 1];        // first bucket of every rank
+    uint32_t nb_own_max;                   // most buckets one rank owns
+    uint32_t cap_sub;                      // records per (bucket, source) sub-slot
+    uint64_t L_cap;                        // minimizers of one rank, all assemblies
+    uint64_t nv_cap;                       // vertices of one owner
+    // byte offsets inside every rank's workspace
+    uint64_t off_flags, off_err, off_counts, off_rec_cnt, off_nkeep, off_rec, off_mk, off_succ, off_vgid, bytes;
+};
+
+struct P2PRecord { uint64_t key, tag; };   // tag = asm << 40 | source rank << 32 | local index
+
+__host__ __device__ __forceinline__ uint32_t p2p_owner(uint32_t b, int world, int B) { return (uint32_t)(((uint64_t)b * (uint64_t)world) >> B); }
+
+__device__ __forceinline__ int p2p_slice_of(const LocalSlices& S, uint64_t l)
+{
+    int a = 0;
+    while (a + 1 < S.n && l >= S.lofs[a + 1]) a++;
+    return a;
+}
+
+// ---------------------------------------------------------------- device-side barrier
+// signal: after everything this rank issued before it (stream order; the stage kernels have completed, their peer
+// stores are performed), store the epoch into slot [bar][rank] of every peer.  wait: spin until all peers' epochs have
+// arrived here.  The spin is bounded (~2 s): a lost peer sets the error flag instead of hanging the GPU.
+__global__ void p2p_signal_kernel(PeerPtrs P, P2PLayout Y, int bar, uint32_t epoch)
+{
+    __threadfence_system();
+    if ((int)threadIdx.x < Y.world) {
+        volatile uint32_t* f = reinterpret_cast<volatile uint32_t*>(P.base[threadIdx.x] + Y.off_flags) + bar * P2P_MAX_WORLD + Y.rank;
+        *f = epoch;
+    }
+    __threadfence_system();
+}
+
+__global__ void p2p_wait_kernel(PeerPtrs P, P2PLayout Y, int bar, uint32_t epoch)
+{
+    if ((int)threadIdx.x < Y.world) {
+        volatile uint32_t* f = reinterpret_cast<volatile uint32_t*>(P.base[Y.rank] + Y.off_flags) + bar * P2P_MAX_WORLD + threadIdx.x;
+        const long long t0 = clock64();
+        while ((int32_t)(*f - epoch) < 0) {
+            if (clock64() - t0 > 4000000000LL) { *reinterpret_cast<volatile uint32_t*>(P.base[Y.rank] + Y.off_err) = 0x100u + bar; break; }
+            __nanosleep(200);
+        }
+    }
+    __threadfence_system();
+}
+
+// ---------------------------------------------------------------- stage 1: scatter to the bucket owners
+__global__ void __launch_bounds__(256) p2p_scatter_kernel(PtrTab H, LocalSlices S, uint64_t L, PeerPtrs P, P2PLayout Y, uint32_t* __restrict__ cursor)
+{
+    const uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= L) return;
+    const int a = p2p_slice_of(S, l);
+    const uint64_t key = reinterpret_cast<const uint64_t*>(H.p[a])[l - S.lofs[a]];
+    const uint32_t b = (uint32_t)(key >> (64 - Y.B));
+    const uint32_t o = p2p_owner(b, Y.world, Y.B);
+    const uint32_t slot = atomicAdd(&cursor[b], 1u);
+    if (slot >= Y.cap_sub) { *reinterpret_cast<uint32_t*>(P.base[Y.rank] + Y.off_err) = 1u; return; }
+    P2PRecord* dst = reinterpret_cast<P2PRecord*>(P.base[o] + Y.off_rec) + ((uint64_t)(b - Y.fb[o]) * Y.world + Y.rank) * Y.cap_sub + slot;
+    *reinterpret_cast<ulonglong2*>(dst) = make_ulonglong2(key, ((uint64_t)a << 40) | ((uint64_t)Y.rank << 32) | l);
+}
+
+// per-(bucket, source) counts to the owners; this rank's minimizer counts to everybody
+struct AsmCounts { uint64_t n[32]; int n_asm; };
+__global__ void __launch_bounds__(256) p2p_push_counts_kernel(const uint32_t* __restrict__ cursor, AsmCounts C, PeerPtrs P, P2PLayout Y)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < Y.n_buckets) {
+        const uint32_t o = p2p_owner(b, Y.world, Y.B);
+        const uint32_t c = cursor[b] < Y.cap_sub ? cursor[b] : Y.cap_sub;
+        reinterpret_cast<uint32_t*>(P.base[o] + Y.off_rec_cnt)[(uint64_t)(b - Y.fb[o]) * Y.world + Y.rank] = c;
+    }
+    if (b < (uint32_t)(Y.world * C.n_asm)) {
+        const int p = b / C.n_asm, a = b % C.n_asm;
+        reinterpret_cast<uint64_t*>(P.base[p] + Y.off_counts)[Y.rank * Y.n_asm_max + a] = C.n[a];
+    }
+}
+
+// ---------------------------------------------------------------- stage 2: one CTA per owned bucket
+__device__ __forceinline__ bool rec_greater(uint64_t ka, uint64_t ta, uint64_t kb, uint64_t tb) { return ka > kb || (ka == kb && ta > tb); }
+
+__global__ void __launch_bounds__(P2P_BK_THREADS) p2p_bucket_kernel(PeerPtrs P, P2PLayout Y, int n_asm)
+{
+    extern __shared__ uint64_t bk_smem[];
+    uint64_t* skey = bk_smem;                          // sorted records
+    uint64_t* stag = bk_smem + P2P_BK_MAX;
+    uint64_t* ukey = bk_smem + 2 * P2P_BK_MAX;         // as loaded
+    uint64_t* utag = bk_smem + 3 * P2P_BK_MAX;
+    uint32_t* srank = reinterpret_cast<uint32_t*>(ukey);   // (after the sort) head flag -> exclusive rank of the kept runs
+    __shared__ uint32_t dstart[P2P_BK_THREADS + 1];
+    __shared__ uint32_t dfill[P2P_BK_THREADS];
+    __shared__ uint32_t soff[P2P_MAX_WORLD + 1];
+    __shared__ uint32_t swarp[P2P_BK_THREADS / 32];
+    const uint32_t bl = blockIdx.x;                                  // local bucket
+    const uint32_t b = Y.fb[Y.rank] + bl;
+    char* me = P.base[Y.rank];
+    const uint32_t* cnt = reinterpret_cast<const uint32_t*>(me + Y.off_rec_cnt) + (uint64_t)bl * Y.world;
+    P2PRecord* region = reinterpret_cast<P2PRecord*>(me + Y.off_rec) + (uint64_t)bl * Y.world * Y.cap_sub;
+    if (threadIdx.x == 0) {
+        uint32_t at = 0;
+        for (int s = 0; s < Y.world; s++) { soff[s] = at; at += cnt[s]; }
+        soff[Y.world] = at;
+    }
+    dfill[threadIdx.x] = 0u;
+    __syncthreads();
+    const uint32_t n = soff[Y.world];
+    if (n > P2P_BK_MAX) {
+        if (threadIdx.x == 0) {
+            *reinterpret_cast<uint32_t*>(me + Y.off_err) = 2u;
+            for (int p = 0; p < Y.world; p++) reinterpret_cast<uint32_t*>(P.base[p] + Y.off_nkeep)[b] = 0u;
+        }
+        return;
+    }
+    // Sort by (hash, tag): equal hashes end up grouped by assembly, then source rank, then position.  The hash is
+    // uniformly mixed, so a counting sort on its next 7 bits leaves ~3 records per digit, finished by one thread per
+    // digit with an insertion sort (a bitonic network moves every record log^2(n) / 2 times through shared memory:
+    // measured 1.3 ms for 12 M records; this is four passes).
+    const int dshift = 64 - Y.B - 7;
+    for (int s = 0; s < Y.world; s++) {
+        const uint32_t c = soff[s + 1] - soff[s];
+        const P2PRecord* src = region + (uint64_t)s * Y.cap_sub;
+        for (uint32_t i = threadIdx.x; i < c; i += P2P_BK_THREADS) {
+            const ulonglong2 r = *reinterpret_cast<const ulonglong2*>(src + i);
+            ukey[soff[s] + i] = r.x;
+            utag[soff[s] + i] = r.y;
+            atomicAdd(&dfill[(uint32_t)(r.x >> dshift) & (P2P_BK_THREADS - 1)], 1u);
+        }
+    }
+    __syncthreads();
+    {   // exclusive scan of the digit counts (one per thread)
+        const uint32_t v = dfill[threadIdx.x];
+        uint32_t x = v;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+        if (lane == 31) swarp[warp] = x;
+        __syncthreads();
+        uint32_t base = 0;
+        for (int wv = 0; wv < warp; wv++) base += swarp[wv];
+        dstart[threadIdx.x] = base + x - v;
+        if (threadIdx.x == P2P_BK_THREADS - 1) dstart[P2P_BK_THREADS] = base + x;
+        dfill[threadIdx.x] = 0u;
+        __syncthreads();
+    }
+    for (uint32_t i = threadIdx.x; i < n; i += P2P_BK_THREADS) {
+        const uint64_t k = ukey[i];
+        const uint32_t d = (uint32_t)(k >> dshift) & (P2P_BK_THREADS - 1);
+        const uint32_t pos = dstart[d] + atomicAdd(&dfill[d], 1u);
+        skey[pos] = k;
+        stag[pos] = utag[i];
+    }
+    __syncthreads();
+    {
+        const uint32_t s0 = dstart[threadIdx.x], s1 = dstart[threadIdx.x + 1];
+        for (uint32_t i = s0 + 1; i < s1; i++) {
+            const uint64_t kk = skey[i], tt = stag[i];
+            uint32_t j = i;
+            while (j > s0 && rec_greater(skey[j - 1], stag[j - 1], kk, tt)) { skey[j] = skey[j - 1]; stag[j] = stag[j - 1]; j--; }
+            skey[j] = kk; stag[j] = tt;
+        }
+    }
+    __syncthreads();
+    uint32_t Pn = n;
+    // run analysis (as mark_kernel): unique inside its assembly; run = exactly one element of every assembly
+    uint32_t marks[P2P_BK_MAX / P2P_BK_THREADS];
+#pragma unroll
+    for (int q = 0; q < P2P_BK_MAX / P2P_BK_THREADS; q++) {
+        const uint32_t i = threadIdx.x + q * P2P_BK_THREADS;
+        uint32_t m = 0, head = 0;
+        if (i < n) {
+            const uint64_t K = skey[i];
+            const int a = (int)((stag[i] >> 40) & 0xFF);
+            const bool prev_same = i > 0 && skey[i - 1] == K && (int)((stag[i - 1] >> 40) & 0xFF) == a;
+            const bool next_same = i + 1 < n && skey[i + 1] == K && (int)((stag[i + 1] >> 40) & 0xFF) == a;
+            const uint32_t uniq = !(prev_same || next_same);
+            bool in_all = false;
+            if ((uint32_t)a <= i && i - a + n_asm <= n) {
+                const uint32_t s0 = i - a;
+                in_all = (s0 == 0 || skey[s0 - 1] != K) && (s0 + n_asm == n || skey[s0 + n_asm] != K);
+                for (int j = 0; in_all && j < n_asm; j++) in_all = skey[s0 + j] == K && (int)((stag[s0 + j] >> 40) & 0xFF) == j;
+            }
+            m = (uniq << 31) | (in_all ? 1u : 0u);
+            head = in_all && a == 0;
+        }
+        marks[q] = m;
+        if (i < P2P_BK_MAX) srank[i] = head;
+    }
+    __syncthreads();
+    // exclusive scan of the head flags over [0, Pn): thread t owns the contiguous chunk [t * per, (t + 1) * per)
+    {
+        const uint32_t per = (Pn + P2P_BK_THREADS - 1) / P2P_BK_THREADS;
+        const uint32_t i0 = threadIdx.x * per;
+        uint32_t sum = 0;
+        for (uint32_t i = i0; i < i0 + per && i < n; i++) sum += srank[i];
+        uint32_t x = sum;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+        if (lane == 31) swarp[warp] = x;
+        __syncthreads();
+        uint32_t base = 0;
+        for (int wv = 0; wv < warp; wv++) base += swarp[wv];
+        uint32_t run = base + x - sum;
+        for (uint32_t i = i0; i < i0 + per && i < n; i++) { const uint32_t h = srank[i]; srank[i] = run; run += h; }
+        __syncthreads();
+    }
+    uint32_t nk = 0;
+    for (int wv = 0; wv < P2P_BK_THREADS / 32; wv++) nk += swarp[wv];
+    // marks back to the sources; the kept hashes (ascending) stay at the start of the bucket's own region
+    uint64_t* kept = reinterpret_cast<uint64_t*>(region);
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < P2P_BK_MAX / P2P_BK_THREADS; q++) {
+        const uint32_t i = threadIdx.x + q * P2P_BK_THREADS;
+        if (i >= n) continue;
+        const uint64_t t = stag[i];
+        const int a = (int)((t >> 40) & 0xFF);
+        const uint32_t src = (uint32_t)((t >> 32) & 0xFF);
+        const uint32_t keep = marks[q] & 1u;
+        const uint32_t rk = keep ? srank[i - a] : 0u;
+        reinterpret_cast<uint32_t*>(P.base[src] + Y.off_mk)[(uint32_t)t] = (marks[q] & 0x80000000u) | (keep ? rk + 1u : 0u);
+        if (keep && a == 0) kept[rk] = skey[i];
+    }
+    if (threadIdx.x == 0)
+        for (int p = 0; p < Y.world; p++) reinterpret_cast<uint32_t*>(P.base[p] + Y.off_nkeep)[b] = nk;
+}
+
+// ---------------------------------------------------------------- stage 3: home rank
+// exclusive prefix of the per-bucket survivor counts (all ranks' buckets) -> global vertex id base of every bucket;
+// global index of this rank's first minimizer of every assembly
+struct HomeTabs {
+    uint32_t* vbase;        // n_buckets + 1
+    uint32_t* vown;         // world + 1: first vertex id of every owner
+    uint64_t* goff;         // n_asm: global index of this rank's first minimizer of assembly a  (+ [n_asm] = N)
+};
+
+__global__ void __launch_bounds__(1024) p2p_vbase_kernel(PeerPtrs P, P2PLayout Y, int n_asm, HomeTabs T)
+{
+    __shared__ uint32_t sw[32];
+    __shared__ uint32_t carry_s;
+    const uint32_t* nkeep = reinterpret_cast<const uint32_t*>(P.base[Y.rank] + Y.off_nkeep);
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < Y.n_buckets; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < Y.n_buckets ? nkeep[i] : 0u;
+        uint32_t x = v;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+        if (lane == 31) sw[warp] = x;
+        __syncthreads();
+        uint32_t wb = 0;
+        for (int wv = 0; wv < warp; wv++) wb += sw[wv];
+        const uint32_t carry = carry_s;
+        if (i < Y.n_buckets) T.vbase[i] = carry + wb + x - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + wb + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) T.vbase[Y.n_buckets] = carry_s;
+    __syncthreads();
+    if ((int)threadIdx.x <= Y.world) T.vown[threadIdx.x] = T.vbase[Y.fb[threadIdx.x]];
+    if ((int)threadIdx.x <= n_asm) {
+        // global index space: assemblies in order, inside an assembly the ranks in order
+        const uint64_t* cnt = reinterpret_cast<const uint64_t*>(P.base[Y.rank] + Y.off_counts);
+        const int t = (int)threadIdx.x;
+        uint64_t g = 0;
+        for (int a = 0; a < t && a < n_asm; a++)
+            for (int r = 0; r < Y.world; r++) g += cnt[r * Y.n_asm_max + a];
+        if (t < n_asm)
+            for (int r = 0; r < Y.rank; r++) g += cnt[r * Y.n_asm_max + t];
+        T.goff[t] = g;
+    }
+}
+
+// the owner's vertices (ascending hash): bucket by bucket from the kept lists
+__global__ void __launch_bounds__(128) p2p_vertices_kernel(PeerPtrs P, P2PLayout Y, HomeTabs T, uint64_t* __restrict__ vertices)
+{
+    const uint32_t bl = blockIdx.x, b = Y.fb[Y.rank] + bl;
+    const uint32_t v0 = T.vbase[b] - T.vown[Y.rank], nk = T.vbase[b + 1] - T.vbase[b];
+    const uint64_t* kept = reinterpret_cast<const uint64_t*>(reinterpret_cast<const P2PRecord*>(P.base[Y.rank] + Y.off_rec) + (uint64_t)bl * Y.world * Y.cap_sub);
+    for (uint32_t i = threadIdx.x; i < nk; i += 128) vertices[v0 + i] = kept[i];
+}
+
+__global__ void __launch_bounds__(256) p2p_flags_kernel(const uint32_t* __restrict__ mk, uint64_t L, uint32_t* __restrict__ kflag,
+                                                         uint8_t* __restrict__ luniq, uint8_t* __restrict__ lkeep)
+{
+    const uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= L) return;
+    const uint32_t m = mk[l];
+    const uint32_t k = (m & 0x7FFFFFFFu) != 0;
+    kflag[l] = k;
+    luniq[l] = (uint8_t)(m >> 31);
+    lkeep[l] = (uint8_t)k;
+}
+
+// ordered survivors: global vertex id, global (creation) index, local index
+__global__ void __launch_bounds__(256) p2p_compact_kernel(const uint32_t* __restrict__ mk, PtrTab H, LocalSlices S, uint64_t L,
+                                                           const uint64_t* __restrict__ kprefix, P2PLayout Y, HomeTabs T,
+                                                           uint32_t* __restrict__ cvid, uint32_t* __restrict__ cg, uint32_t* __restrict__ cloc)
+{
+    const uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= L) return;
+    const uint32_t k = mk[l] & 0x7FFFFFFFu;
+    if (!k) return;
+    const int a = p2p_slice_of(S, l);
+    const uint64_t key = reinterpret_cast<const uint64_t*>(H.p[a])[l - S.lofs[a]];
+    const uint64_t j = kprefix[l];
+    cvid[j] = T.vbase[(uint32_t)(key >> (64 - Y.B))] + k - 1u;
+    cg[j] = (uint32_t)(T.goff[a] + (l - S.lofs[a]));
+    cloc[j] = (uint32_t)l;
+}
+
+__device__ __forceinline__ int p2p_vowner(const uint32_t* vown, int world, uint32_t v)
+{
+    int o = 0;
+    while (o + 1 < world && v >= vown[o + 1]) o++;
+    return o;
+}
+
+// adjacent survivors of the same record and assembly: sighting flag + successor entry at the owner of the source
+__global__ void __launch_bounds__(256) p2p_succ_kernel(const uint32_t* __restrict__ cvid, const uint32_t* __restrict__ cg,
+                                                        const uint32_t* __restrict__ cloc,
+                                                        const uint64_t* __restrict__ kprefix, uint64_t L, LocalSlices S, PtrTab Ctg,
+                                                        PeerPtrs P, P2PLayout Y, HomeTabs T, uint32_t* __restrict__ eflag)
+{
+    const uint64_t n_keep = kprefix[L];
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_keep) return;
+    uint32_t f = 0;
+    {
+        // creation index of this survivor, by (assembly, vertex): the first-source index of a vertex is read from here
+        const uint32_t l1 = cloc[j];
+        const int a = p2p_slice_of(S, l1);
+        const uint32_t v = cvid[j];
+        const int o = p2p_vowner(T.vown, Y.world, v);
+        reinterpret_cast<uint32_t*>(P.base[o] + Y.off_vgid)[(uint64_t)a * Y.nv_cap + (v - T.vown[o])] = cg[j];
+    }
+    if (j + 1 < n_keep) {
+        const uint32_t l1 = cloc[j], l2 = cloc[j + 1];
+        const int a = p2p_slice_of(S, l1);
+        if (a == p2p_slice_of(S, l2)) {
+            const uint32_t* ctg = reinterpret_cast<const uint32_t*>(Ctg.p[a]);
+            f = ctg[l1 - S.lofs[a]] == ctg[l2 - S.lofs[a]];
+            if (f) {
+                const uint32_t v = cvid[j], x = cvid[j + 1];
+                const int o = p2p_vowner(T.vown, Y.world, v);
+                reinterpret_cast<uint32_t*>(P.base[o] + Y.off_succ)[(uint64_t)a * Y.nv_cap + (v - T.vown[o])] = x + 1u;
+            }
+        }
+    }
+    eflag[j] = f;
+}
+
+// Edge de-duplication without sorting (as filter.cu): a surviving hash occurs once per assembly, so a vertex has at
+// most one successor per assembly; assembly b supports {v, x} iff succ_b[v] == x or succ_b[x] == v; the sighting in
+// the first supporting assembly owns the edge (first-seen orientation, bin/ntjoin_utils.py:101-108).
+__global__ void __launch_bounds__(256) p2p_edge_owner_kernel(const uint32_t* __restrict__ cvid, const uint32_t* __restrict__ cg,
+                                                              const uint32_t* __restrict__ cloc, const uint32_t* __restrict__ eflag,
+                                                              const uint64_t* __restrict__ kprefix, uint64_t L, LocalSlices S, int n_asm,
+                                                              PeerPtrs P, P2PLayout Y, HomeTabs T, uint32_t* __restrict__ own, uint32_t* __restrict__ mask_out)
+{
+    const uint64_t n_keep = kprefix[L];
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_keep) return;
+    uint32_t is_owner = 0;
+    if (eflag[j]) {
+        const int a = p2p_slice_of(S, cloc[j]);
+        const uint32_t v = cvid[j], x = cvid[j + 1];
+        const int ov = p2p_vowner(T.vown, Y.world, v), ox = p2p_vowner(T.vown, Y.world, x);
+        uint32_t* sv = reinterpret_cast<uint32_t*>(P.base[ov] + Y.off_succ) + (v - T.vown[ov]);
+        const uint32_t* sx = reinterpret_cast<const uint32_t*>(P.base[ox] + Y.off_succ) + (x - T.vown[ox]);
+        uint32_t mask = 0;
+        for (int b = 0; b < n_asm; b++)       // bit 31 of an entry is its ownership mark (below): compare the low 31 bits
+            if ((sv[(uint64_t)b * Y.nv_cap] & 0x7FFFFFFFu) == x + 1u || (sx[(uint64_t)b * Y.nv_cap] & 0x7FFFFFFFu) == v + 1u) mask |= 1u << b;
+        is_owner = (__ffs(mask) - 1) == a;
+        mask_out[j] = mask;
+        // "vertex v is the source of an edge created in assembly a": entry (a, v) has this sighting as its only writer,
+        // so a plain store marks it (no atomics; readers of the successor ignore the bit)
+        if (is_owner) sv[(uint64_t)a * Y.nv_cap] = (x + 1u) | 0x80000000u;
+    }
+    own[j] = is_owner;
+}
+
+// in which assemblies vertex v (local index at its owner o) is the source of a created edge, and the creation index of
+// its first one (a vertex occurs once per assembly; edges of one source are created in assembly order)
+__device__ __forceinline__ uint32_t p2p_source_info(const PeerPtrs& P, const P2PLayout& Y, int o, uint32_t vloc, int n_asm, uint32_t* first_gid)
+{
+    const uint32_t* sv = reinterpret_cast<const uint32_t*>(P.base[o] + Y.off_succ) + vloc;
+    uint32_t smask = 0;
+    for (int b = 0; b < n_asm; b++) smask |= (sv[(uint64_t)b * Y.nv_cap] >> 31) << b;
+    *first_gid = smask ? reinterpret_cast<const uint32_t*>(P.base[o] + Y.off_vgid)[(uint64_t)(__ffs(smask) - 1) * Y.nv_cap + vloc] : 0xFFFFFFFFu;
+    return smask;
+}
+
+// formatted_edges order (bin/ntjoin_utils.py:115): sources in order of their first edge, the edges of a source in creation
+// order (= assembly order: a source owns at most one edge per assembly).  Owned edges are compacted in creation order
+// (uprefix); the first edge of a source carries the number of edges of that source, a prefix sum over them gives every
+// source's block -> each edge is PLACED, not sorted.  (world == 1)
+__global__ void __launch_bounds__(256) p2p_first_count_kernel(const uint32_t* __restrict__ cvid, const uint32_t* __restrict__ cg,
+                                                               const uint32_t* __restrict__ own, const uint64_t* __restrict__ uprefix,
+                                                               const uint64_t* __restrict__ kprefix, uint64_t L, PeerPtrs P, P2PLayout Y, int n_asm,
+                                                               uint32_t* __restrict__ fcount)
+{
+    const uint64_t n_keep = kprefix[L];
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_keep || !own[j]) return;
+    uint32_t smin;
+    const uint32_t smask = p2p_source_info(P, Y, 0, cvid[j], n_asm, &smin);
+    fcount[uprefix[j]] = smin == cg[j] ? (uint32_t)__popc(smask) : 0u;
+}
+
+__global__ void __launch_bounds__(256) p2p_first_start_kernel(const uint32_t* __restrict__ cvid, const uint32_t* __restrict__ cg,
+                                                               const uint32_t* __restrict__ own, const uint64_t* __restrict__ uprefix,
+                                                               const uint64_t* __restrict__ fprefix, const uint64_t* __restrict__ kprefix, uint64_t L,
+                                                               PeerPtrs P, P2PLayout Y, int n_asm, uint32_t* __restrict__ vstart)
+{
+    const uint64_t n_keep = kprefix[L];
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_keep || !own[j]) return;
+    const uint32_t v = cvid[j];
+    uint32_t smin;
+    p2p_source_info(P, Y, 0, v, n_asm, &smin);
+    if (smin == cg[j]) vstart[v] = (uint32_t)fprefix[uprefix[j]];
+}
+
+// own[] is only written for j < n_keep; the scan over it runs over L entries
+__global__ void __launch_bounds__(256) p2p_clear_tail_kernel(uint32_t* __restrict__ own, const uint64_t* __restrict__ kprefix, uint64_t L)
+{
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < L && j >= kprefix[L]) own[j] = 0u;
+}
+
+struct EdgeOut { uint64_t *eu, *ev, *ekey; uint32_t* emask; double* ew; };
+
+__global__ void __launch_bounds__(256) p2p_edge_emit_kernel(const uint32_t* __restrict__ cvid, const uint32_t* __restrict__ cg,
+                                                             const uint32_t* __restrict__ cloc, const uint32_t* __restrict__ own,
+                                                             const uint32_t* __restrict__ mask_in, const uint64_t* __restrict__ uprefix,
+                                                             const uint64_t* __restrict__ kprefix, uint64_t L, LocalSlices S, PtrTab H, AsmOffsets A,
+                                                             PeerPtrs P, P2PLayout Y, HomeTabs T, const uint32_t* __restrict__ vstart, EdgeOut E)
+{
+    const uint64_t n_keep = kprefix[L];
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_keep || !own[j]) return;
+    const uint32_t l1 = cloc[j], l2 = cloc[j + 1];
+    const int a = p2p_slice_of(S, l1);
+    const uint64_t* hs = reinterpret_cast<const uint64_t*>(H.p[a]);
+    const uint32_t v = cvid[j];
+    const int ov = p2p_vowner(T.vown, Y.world, v);
+    const uint32_t vloc = v - T.vown[ov];
+    uint64_t o;
+    uint32_t smin;
+    const uint32_t smask = p2p_source_info(P, Y, ov, vloc, A.n, &smin);
+    if (vstart) {       // single GPU: final position
+        o = (uint64_t)vstart[v] + (uint32_t)__popc(smask & ((1u << a) - 1u));
+    } else {            // shard: creation order + global order key (first creation index of the source, creation index)
+        o = uprefix[j];
+        E.ekey[o] = ((uint64_t)smin << 32) | (uint64_t)cg[j];
+    }
+    const uint32_t mask = mask_in[j];
+    E.eu[o] = hs[l1 - S.lofs[a]];
+    E.ev[o] = hs[l2 - S.lofs[a]];
+    E.emask[o] = mask;
+    double wsum = 0.0;   // Python: sum() starts at int 0 and adds in support-list (= assembly) order
+    for (int b = 0; b < A.n; b++)
+        if (mask & (1u << b)) wsum += A.weight[b];
+    E.ew[o] = wsum;
+}
+
+}  // namespace mxe
+
+using namespace mxe;
+
+// ====================================================================================================
+// host side
+// ====================================================================================================
+struct mxe_p2p {
+    mxe_engine* eng = nullptr;
+    P2PLayout Y;
+    PeerPtrs P;
+    char* ws = nullptr;                    // this rank's symmetric workspace (cudaMalloc: exportable through CUDA IPC)
+    std::vector<void*> opened;             // peer mappings opened through IPC
+    uint32_t epoch = 0;
+    // per-call local workspace (grow-only)
+    char* lws = nullptr; size_t lws_bytes = 0, lws_used = 0;
+    // state of the call in flight
+    int n_asm = 0;
+    uint64_t L = 0;
+    LocalSlices S;
+    PtrTab H, Ctg;
+    AsmOffsets A;
+    uint32_t *cursor = nullptr, *kflag = nullptr, *cvid = nullptr, *cg = nullptr, *cloc = nullptr, *eflag = nullptr, *own = nullptr, *emask_j = nullptr;
+    uint64_t *kprefix = nullptr, *uprefix = nullptr;
+    uint8_t *luniq = nullptr, *lkeep = nullptr;
+    uint64_t* vertices = nullptr;
+    HomeTabs T;
+    void* lalloc(size_t bytes)
+    {
+        bytes = (bytes + 255) & ~(size_t)255;
+        if (lws_used + bytes > lws_bytes) return nullptr;
+        void* p = lws + lws_used;
+        lws_used += bytes;
+        return p;
+    }
+};
+
+namespace mxe {
+void p2p_release(mxe_p2p* X, bool engine_is_alive)
+{
+    if (engine_is_alive) {
+        cudaSetDevice(X->eng->device);
+        cudaStreamSynchronize(X->eng->stream);
+        for (void* p : X->opened) cudaIpcCloseMemHandle(p);
+        if (X->ws) cudaFree(X->ws);
+        if (X->lws) cudaFree(X->lws);
+        if (X->luniq) cudaFree(X->luniq);
+        if (X->lkeep) cudaFree(X->lkeep);
+    }
+    delete X;
+}
+}
+
+static inline unsigned p2p_grid(uint64_t n) { return (unsigned)((n + 255) / 256); }
+
+static int p2p_barrier_signal(mxe_p2p* X, int bar)
+{
+    if (X->Y.world == 1) return MXE_OK;
+    MXE_LAUNCH(X->eng, p2p_signal_kernel, 1, 32, 0, X->P, X->Y, bar, X->epoch);
+    return MXE_OK;
+}
+static int p2p_barrier_wait(mxe_p2p* X, int bar)
+{
+    if (X->Y.world == 1) return MXE_OK;
+    MXE_LAUNCH(X->eng, p2p_wait_kernel, 1, 32, 0, X->P, X->Y, bar, X->epoch);
+    return MXE_OK;
+}
+
+extern "C" {
+
+int mxe_p2p_create(mxe_t* e, int rank, int world, uint64_t cap_total, int n_asm_max, mxe_p2p_t** out)
+{
+    if (!e || !out || world < 1 || world > P2P_MAX_WORLD || rank < 0 || rank >= world || n_asm_max < 1 || n_asm_max > 32) {
+        set_error("bad rank/world/n_asm_max (world <= %d)", P2P_MAX_WORLD);
+        return MXE_ERR_ARG;
+    }
+    if (cap_total < 1024) cap_total = 1024;
+    if (cap_total >= (1ULL << 32)) { set_error("capacity beyond 2^32 minimizers"); return MXE_ERR_ARG; }
+    MXE_CUDA(cudaSetDevice(e->device));
+    mxe_p2p* X = new mxe_p2p();
+    X->eng = e;
+    P2PLayout& Y = X->Y;
+    memset(&Y, 0, sizeof(Y));
+    Y.world = world; Y.rank = rank; Y.n_asm_max = n_asm_max;
+    int B = 6;
+    while (B < 20 && (cap_total >> B) > 400) B++;                 // <= 400 records per bucket on average at full capacity
+    Y.B = B;
+    Y.n_buckets = 1u << B;
+    for (int r = 0; r <= world; r++) Y.fb[r] = (uint32_t)((((uint64_t)r << B) + world - 1) / world);
+    Y.nb_own_max = 0;
+    for (int r = 0; r < world; r++) Y.nb_own_max = std::max(Y.nb_own_max, Y.fb[r + 1] - Y.fb[r]);
+    const double per_sub = (double)cap_total / ((double)Y.n_buckets * world);
+    Y.cap_sub = (uint32_t)(per_sub * 1.5 + 6.0 * std::sqrt(per_sub + 1.0) + 32.0);
+    Y.L_cap = (uint64_t)((double)cap_total / world * 1.25) + 4096;
+    if (Y.L_cap > cap_total + 4096) Y.L_cap = cap_total + 4096;
+    Y.nv_cap = (uint64_t)((double)cap_total / world * 1.1) + 4096;
+    uint64_t at = 0;
+    auto take = [&](uint64_t bytes) { uint64_t o = at; at += (bytes + 255) & ~255ULL; return o; };
+    Y.off_flags = take(P2P_N_BARRIERS * P2P_MAX_WORLD * 4);
+    Y.off_err = take(256);
+    Y.off_counts = take((uint64_t)world * n_asm_max * 8);
+    Y.off_rec_cnt = take((uint64_t)Y.nb_own_max * world * 4);
+    Y.off_nkeep = take((uint64_t)Y.n_buckets * 4);
+    Y.off_rec = take((uint64_t)Y.nb_own_max * world * Y.cap_sub * sizeof(P2PRecord));
+    Y.off_mk = take(Y.L_cap * 4);
+    Y.off_succ = take((uint64_t)n_asm_max * Y.nv_cap * 4);
+    Y.off_vgid = take((uint64_t)n_asm_max * Y.nv_cap * 4);
+    Y.bytes = at;
+    cudaError_t err = cudaMalloc((void**)&X->ws, Y.bytes);
+    if (err != cudaSuccess) { set_error("symmetric workspace of %llu bytes: %s", (unsigned long long)Y.bytes, cudaGetErrorString(err)); delete X; return MXE_ERR_NOMEM; }
+    cudaMemset(X->ws, 0, Y.off_rec);      // flags, error word, count tables
+    for (int r = 0; r < P2P_MAX_WORLD; r++) X->P.base[r] = nullptr;
+    X->P.base[rank] = X->ws;
+    *out = X;
+    return MXE_OK;
+}
+
+/* CUDA IPC handle of this rank's symmetric workspace (64 bytes) */
+int mxe_p2p_handle(mxe_p2p_t* X, void* handle64, uint64_t* bytes)
+{
+    if (!X || !handle64) { set_error("null argument"); return MXE_ERR_ARG; }
+    cudaIpcMemHandle_t h;
+    MXE_CUDA(cudaIpcGetMemHandle(&h, X->ws));
+    memcpy(handle64, &h, sizeof(h));
+    if (bytes) *bytes = X->Y.bytes;
+    return MXE_OK;
+}
+
+/* handles: world x 64 bytes, in rank order (one process per GPU) */
+int mxe_p2p_connect(mxe_p2p_t* X, const void* handles)
+{
+    if (!X || !handles) { set_error("null argument"); return MXE_ERR_ARG; }
+    MXE_CUDA(cudaSetDevice(X->eng->device));
+    for (int r = 0; r < X->Y.world; r++) {
+        if (r == X->Y.rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)handles + (size_t)r * sizeof(h), sizeof(h));
+        void* p = nullptr;
+        cudaError_t err = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (err != cudaSuccess) { set_error("cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(err)); return MXE_ERR_CUDA; }
+        X->opened.push_back(p);
+        X->P.base[r] = (char*)p;
+    }
+    return MXE_OK;
+}
+
+/* same-process ranks (tests: several engines on one device): raw workspace pointers instead of IPC */
+int mxe_p2p_workspace(mxe_p2p_t* X, void** ptr)
+{
+    if (!X || !ptr) { set_error("null argument"); return MXE_ERR_ARG; }
+    *ptr = X->ws;
+    return MXE_OK;
+}
+int mxe_p2p_connect_pointers(mxe_p2p_t* X, void* const* bases)
+{
+    if (!X || !bases) { set_error("null argument"); return MXE_ERR_ARG; }
+    for (int r = 0; r < X->Y.world; r++) X->P.base[r] = (char*)bases[r];
+    return MXE_OK;
+}
+
+void mxe_p2p_free(mxe_p2p_t* X)
+{
+    if (!X) return;
+    mxe::p2p_release(X, mxe::engine_alive(X->eng));
+}
+
+/* stage 1: scatter this rank's minimizers to the bucket owners.  d_hash[a] / d_contig[a]: n[a] uint64 out_hash in
+ * (record, pos) order and their uint32 record ids (device arrays that stay alive until mxe_p2p_finish). */
+int mxe_p2p_scatter(mxe_p2p_t* X, const void* const* d_hash, const void* const* d_contig, const uint64_t* n, int n_asm, const double* weights)
+{
+    if (!X || !d_hash || !d_contig || !n || n_asm < 1 || n_asm > X->Y.n_asm_max) { set_error("bad arguments"); return MXE_ERR_ARG; }
+    mxe_engine* e = X->eng;
+    MXE_CUDA(cudaSetDevice(e->device));
+    cudaStream_t st = e->stream;
+    const P2PLayout& Y = X->Y;
+    Span whole(e, "filter");
+    Span part(e, "p2p_scatter");
+    X->n_asm = n_asm;
+    X->S.n = n_asm; X->S.lofs[0] = 0;
+    X->A.n = n_asm;
+    for (int a = 0; a < n_asm; a++) {
+        X->S.lofs[a + 1] = X->S.lofs[a] + n[a]; X->S.goff[a] = 0;
+        X->H.p[a] = d_hash[a]; X->Ctg.p[a] = d_contig[a];
+        X->A.weight[a] = weights[a];
+    }
+    const uint64_t L = X->S.lofs[n_asm];
+    X->L = L;
+    if (L > Y.L_cap) { set_error("%llu minimizers on this rank exceed the workspace capacity %llu", (unsigned long long)L, (unsigned long long)Y.L_cap); return MXE_ERR_ARG; }
+    // local workspace for this call
+    const size_t need = (size_t)Y.n_buckets * 8 + (L + 1) * (7 * 4 + 2 * 8 + 2) + (Y.n_buckets + 64) * 4 + 4096 * 4 + 64 * 1024;
+    if (X->lws_bytes < need) {
+        if (X->lws) { MXE_CUDA(cudaStreamSynchronize(st)); MXE_CUDA(cudaFree(X->lws)); X->lws = nullptr; }
+        MXE_CUDA(cudaMalloc((void**)&X->lws, need + need / 8));
+        X->lws_bytes = need + need / 8;
+    }
+    X->lws_used = 0;
+    X->cursor = (uint32_t*)X->lalloc((size_t)Y.n_buckets * 4);
+    X->kflag = (uint32_t*)X->lalloc((L + 1) * 4); X->cvid = (uint32_t*)X->lalloc((L + 1) * 4); X->cg = (uint32_t*)X->lalloc((L + 1) * 4);
+    X->cloc = (uint32_t*)X->lalloc((L + 1) * 4); X->eflag = (uint32_t*)X->lalloc((L + 1) * 4); X->own = (uint32_t*)X->lalloc((L + 1) * 4);
+    X->emask_j = (uint32_t*)X->lalloc((L + 1) * 4);
+    X->kprefix = (uint64_t*)X->lalloc((L + 2) * 8); X->uprefix = (uint64_t*)X->lalloc((L + 2) * 8);
+    X->T.vbase = (uint32_t*)X->lalloc((size_t)(Y.n_buckets + 1) * 4); X->T.vown = (uint32_t*)X->lalloc(64 * 4); X->T.goff = (uint64_t*)X->lalloc(64 * 8);
+    if (!X->T.goff) { set_error("local workspace too small"); return MXE_ERR_INTERNAL; }
+    X->epoch++;
+    MXE_CUDA(cudaMemsetAsync(X->cursor, 0, (size_t)Y.n_buckets * 4, st));
+    // barrier 0: every rank has finished the previous call (its reads of peer tables included) before anybody clears
+    // its own tables or writes into a peer's workspace again
+    MXE_TRY(p2p_barrier_signal(X, 0));
+    MXE_TRY(p2p_barrier_wait(X, 0));
+    MXE_CUDA(cudaMemsetAsync(X->ws + Y.off_succ, 0, (size_t)n_asm * Y.nv_cap * 4, st));
+    if (L) MXE_LAUNCH(e, p2p_scatter_kernel, p2p_grid(L), 256, 0, X->H, X->S, L, X->P, Y, X->cursor);
+    AsmCounts C;
+    C.n_asm = n_asm;
+    for (int a = 0; a < n_asm; a++) C.n[a] = n[a];
+    MXE_LAUNCH(e, p2p_push_counts_kernel, p2p_grid(std::max<uint64_t>(Y.n_buckets, (uint64_t)Y.world * n_asm)), 256, 0, X->cursor, C, X->P, Y);
+    MXE_TRY(p2p_barrier_signal(X, 1));
+    MXE_CUDA(cudaGetLastError());
+    return MXE_OK;
+}
+
+/* stage 2: the owned buckets */
+int mxe_p2p_buckets(mxe_p2p_t* X)
+{
+    mxe_engine* e = X->eng;
+    MXE_CUDA(cudaSetDevice(e->device));
+    const P2PLayout& Y = X->Y;
+    Span whole(e, "filter");
+    Span part(e, "p2p_buckets");
+    MXE_TRY(p2p_barrier_wait(X, 1));
+    const uint32_t nb = Y.fb[Y.rank + 1] - Y.fb[Y.rank];
+    const size_t bk_smem = (size_t)4 * P2P_BK_MAX * sizeof(uint64_t);
+    MXE_CUDA(cudaFuncSetAttribute(p2p_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bk_smem));
+    if (nb) MXE_LAUNCH(e, p2p_bucket_kernel, nb, P2P_BK_THREADS, bk_smem, X->P, Y, X->n_asm);
+    MXE_TRY(p2p_barrier_signal(X, 2));
+    MXE_CUDA(cudaGetLastError());
+    return MXE_OK;
+}
+
+/* stage 3: vertex ids, ordered survivors of own records, successor entries to the vertex owners */
+int mxe_p2p_adjacency(mxe_p2p_t* X)
+{
+    mxe_engine* e = X->eng;
+    MXE_CUDA(cudaSetDevice(e->device));
+    cudaStream_t st = e->stream;
+    const P2PLayout& Y = X->Y;
+    Span whole(e, "filter");
+    Span part(e, "p2p_adjacency");
+    const uint64_t L = X->L;
+    MXE_TRY(p2p_barrier_wait(X, 2));
+    MXE_LAUNCH(e, p2p_vbase_kernel, 1, 1024, 0, X->P, Y, X->n_asm, X->T);
+    // shard outputs that do not depend on sizes read back: flags of own minimizers
+    X->luniq = nullptr; X->lkeep = nullptr;
+    MXE_CUDA(cudaMallocAsync((void**)&X->luniq, L ? L : 1, st));
+    MXE_CUDA(cudaMallocAsync((void**)&X->lkeep, L ? L : 1, st));
+    const uint32_t* mk = reinterpret_cast<const uint32_t*>(X->ws + Y.off_mk);
+    if (L) MXE_LAUNCH(e, p2p_flags_kernel, p2p_grid(L), 256, 0, mk, L, X->kflag, X->luniq, X->lkeep);
+    {
+        ArenaScope scope(e);
+        MXE_TRY(exclusive_scan_u32_u64(e, X->kflag, X->kprefix, L));
+    }
+    if (L) {
+        MXE_LAUNCH(e, p2p_compact_kernel, p2p_grid(L), 256, 0, mk, X->H, X->S, L, X->kprefix, Y, X->T, X->cvid, X->cg, X->cloc);
+        MXE_LAUNCH(e, p2p_succ_kernel, p2p_grid(L), 256, 0, X->cvid, X->cg, X->cloc, X->kprefix, L, X->S, X->Ctg, X->P, Y, X->T, X->eflag);
+    }
+    MXE_TRY(p2p_barrier_signal(X, 3));
+    MXE_CUDA(cudaGetLastError());
+    return MXE_OK;
+}
+
+/* stage 4: support masks, edge ownership, first-source tables at the vertex owners */
+int mxe_p2p_edges(mxe_p2p_t* X)
+{
+    mxe_engine* e = X->eng;
+    MXE_CUDA(cudaSetDevice(e->device));
+    const P2PLayout& Y = X->Y;
+    Span whole(e, "filter");
+    Span part(e, "p2p_edges");
+    const uint64_t L = X->L;
+    MXE_TRY(p2p_barrier_wait(X, 3));
+    if (L) MXE_LAUNCH(e, p2p_edge_owner_kernel, p2p_grid(L), 256, 0, X->cvid, X->cg, X->cloc, X->eflag, X->kprefix, L, X->S, X->n_asm, X->P, Y, X->T, X->own, X->emask_j);
+    MXE_TRY(p2p_barrier_signal(X, 4));
+    MXE_CUDA(cudaGetLastError());
+    return MXE_OK;
+}
+
+/* stage 5: sizes (the one host round trip), outputs.  world == 1: the complete result in final order;
+ * world > 1: this rank's shard (flags of own minimizers, vertices of the owned hash range, own edges + order keys). */
+int mxe_p2p_finish(mxe_p2p_t* X, mxe_result_t** out)
+{
+    if (!X || !out) { set_error("null argument"); return MXE_ERR_ARG; }
+    mxe_engine* e = X->eng;
+    MXE_CUDA(cudaSetDevice(e->device));
+    cudaStream_t st = e->stream;
+    const P2PLayout& Y = X->Y;
+    Span whole(e, "filter");
+    Span part(e, "p2p_finish");
+    const uint64_t L = X->L;
+    const int n_asm = X->n_asm;
+    MXE_TRY(p2p_barrier_wait(X, 4));
+    // owned edges in creation order: kprefix[L] = survivors; own[] beyond them is never read
+    // (scan length = L: entries past n_keep must be zero)
+    {
+        ArenaScope scope(e);
+        if (L) MXE_LAUNCH(e, p2p_clear_tail_kernel, p2p_grid(L), 256, 0, X->own, X->kprefix, L);
+        MXE_TRY(exclusive_scan_u32_u64(e, X->own, X->uprefix, L));
+    }
+    uint64_t sizes[2] = {0, 0};
+    uint32_t verts[2] = {0, 0}, errw = 0;
+    MXE_CUDA(cudaMemcpyAsync(&sizes[0], X->kprefix + L, 8, cudaMemcpyDeviceToHost, st));
+    MXE_CUDA(cudaMemcpyAsync(&sizes[1], X->uprefix + L, 8, cudaMemcpyDeviceToHost, st));
+    MXE_CUDA(cudaMemcpyAsync(&verts[0], X->T.vown + Y.rank, 8, cudaMemcpyDeviceToHost, st));
+    MXE_CUDA(cudaMemcpyAsync(&errw, X->ws + Y.off_err, 4, cudaMemcpyDeviceToHost, st));
+    MXE_CUDA(cudaStreamSynchronize(st));
+    if (errw) {
+        cudaMemsetAsync(X->ws + Y.off_err, 0, 4, st);
+        cudaFreeAsync(X->luniq, st); cudaFreeAsync(X->lkeep, st);
+        X->luniq = X->lkeep = nullptr;
+        set_error(errw >= 0x100 ? "device barrier %u timed out (a peer rank is gone)" : errw == 1 ? "bucket sub-slot overflow (code %u)" : "bucket overflow (code %u)",
+                  errw >= 0x100 ? errw - 0x100 : errw);
+        return errw >= 0x100 ? MXE_ERR_CUDA : MXE_ERR_INTERNAL;
+    }
+    const uint64_t nE = sizes[1], nV = verts[1] - verts[0];
+    mxe_result* R = new mxe_result();
+    R->eng = e; R->n_asm = n_asm; R->N = L; R->nV = nV; R->nE = nE;
+    for (int a = 0; a <= n_asm; a++) R->asm_off[a] = X->S.lofs[a];
+    R->d_uniq = X->luniq; R->d_keep = X->lkeep;
+    X->luniq = X->lkeep = nullptr;
+    if (nV) {
+        MXE_CUDA(cudaMallocAsync((void**)&R->d_vertices, nV * 8, st));
+        MXE_LAUNCH(e, p2p_vertices_kernel, Y.fb[Y.rank + 1] - Y.fb[Y.rank], 128, 0, X->P, Y, X->T, R->d_vertices);
+    }
+    if (nE) {
+        EdgeOut E;
+        memset(&E, 0, sizeof(E));
+        MXE_CUDA(cudaMallocAsync((void**)&R->d_eu, nE * 8, st)); MXE_CUDA(cudaMallocAsync((void**)&R->d_ev, nE * 8, st));
+        MXE_CUDA(cudaMallocAsync((void**)&R->d_emask, nE * 4, st)); MXE_CUDA(cudaMallocAsync((void**)&R->d_ew, nE * 8, st));
+        E.eu = R->d_eu; E.ev = R->d_ev; E.emask = R->d_emask; E.ew = R->d_ew;
+        uint32_t* vstart = nullptr;
+        ArenaScope scope(e);
+        DBuf<uint32_t> fcount, vst;
+        DBuf<uint64_t> fprefix;
+        if (Y.world == 1) {
+            MXE_TRY(fcount.alloc(nE, st)); MXE_TRY(fprefix.alloc(nE + 1, st)); MXE_TRY(vst.alloc(nV ? nV : 1, st));
+            MXE_LAUNCH(e, p2p_first_count_kernel, p2p_grid(L), 256, 0, X->cvid, X->cg, X->own, X->uprefix, X->kprefix, L, X->P, Y, n_asm, fcount.p);
+            MXE_TRY(exclusive_scan_u32_u64(e, fcount.p, fprefix.p, nE));
+            MXE_LAUNCH(e, p2p_first_start_kernel, p2p_grid(L), 256, 0, X->cvid, X->cg, X->own, X->uprefix, fprefix.p, X->kprefix, L, X->P, Y, n_asm, vst.p);
+            vstart = vst.p;
+        } else {
+            MXE_CUDA(cudaMallocAsync((void**)&R->d_ekey, nE * 8, st));
+            E.ekey = R->d_ekey;
+        }
+        MXE_LAUNCH(e, p2p_edge_emit_kernel, p2p_grid(L), 256, 0, X->cvid, X->cg, X->cloc, X->own, X->emask_j, X->uprefix, X->kprefix, L, X->S, X->H, X->A,
+                   X->P, Y, X->T, vstart, E);
+    }
+    MXE_CUDA(cudaGetLastError());
+    *out = R;
+    return MXE_OK;
+}
+
+}  // extern "C"

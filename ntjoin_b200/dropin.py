@@ -28,12 +28,31 @@ def _trace(what):
             fh.write(what + "\n")
 
 
+def _shutdown():
+    """release the cached result and the engine in order (the interpreter frees module globals in any order)"""
+    global _ENGINE, _LAST_FILTER
+    if _LAST_FILTER is not None:
+        try:
+            _LAST_FILTER[1].close()
+        except Exception:
+            pass
+        _LAST_FILTER = None
+    if _ENGINE is not None:
+        try:
+            _ENGINE.close()
+        except Exception:
+            pass
+        _ENGINE = None
+
+
 def _engine():
     global _ENGINE
     if _ENGINE is None:
+        import atexit
         import os
         from .engine import Engine
         _ENGINE = Engine(int(os.environ.get("MXE_DEVICE", "0")))
+        atexit.register(_shutdown)
     return _ENGINE
 
 

@@ -325,6 +325,10 @@ class Engine:
         """Engine-backed stages of the multi-GPU steps 2-3, all-to-all formulation (ntjoin_b200.dist; work ~ 1/world)."""
         return EngineA2AStages(self)
 
+    def p2p(self, rank, world, cap_total, n_asm_max=4):
+        """Steps 2-3 across `world` GPUs with direct peer stores over NVLink (include/mxe.h: mxe_p2p_*); see P2PFilter."""
+        return P2PFilter(self, rank, world, cap_total, n_asm_max)
+
     def timing(self, name):
         ms, nl = C.c_double(), C.c_uint64()
         check(self._lib, self._lib.mxe_timing(self._h, name.encode(), C.byref(ms), C.byref(nl)))
@@ -349,6 +353,89 @@ class Engine:
         except Exception:
             pass
 
+
+
+class P2PFilter:
+    """One rank of the peer-store formulation of steps 2-3 (csrc/p2p.cu).  Life cycle: create on every rank, exchange
+    the 64-byte IPC handles (`handle()` -> `connect(handles)`; ranks that share a process use `workspace()` ->
+    `connect_pointers`), then per job the five stages in order on every rank (`run` issues them back to back)."""
+
+    STAGES = ("scatter", "buckets", "adjacency", "edges", "finish")
+
+    def __init__(self, engine, rank, world, cap_total, n_asm_max=4):
+        self._e, self._lib, self.rank, self.world = engine, engine._lib, int(rank), int(world)
+        h = C.c_void_p()
+        check(self._lib, self._lib.mxe_p2p_create(engine._h, int(rank), int(world), int(cap_total), int(n_asm_max), C.byref(h)))
+        self._h = h
+        self._keep = None
+
+    def handle(self):
+        buf = C.create_string_buffer(64)
+        check(self._lib, self._lib.mxe_p2p_handle(self._h, buf, None))
+        return buf.raw
+
+    def connect(self, handles):
+        """handles: the 64-byte handles of all ranks, in rank order"""
+        blob = b"".join(handles)
+        check(self._lib, self._lib.mxe_p2p_connect(self._h, C.c_char_p(blob)))
+
+    def workspace(self):
+        p = C.c_void_p()
+        check(self._lib, self._lib.mxe_p2p_workspace(self._h, C.byref(p)))
+        return p.value
+
+    def connect_pointers(self, bases):
+        arr = (C.c_void_p * len(bases))(*[C.c_void_p(int(b)) for b in bases])
+        check(self._lib, self._lib.mxe_p2p_connect_pointers(self._h, arr))
+
+    def scatter(self, hash_ptrs, contig_ptrs, counts, weights):
+        """raw device addresses of this rank's out_hash (uint64) / record id (uint32) arrays per assembly"""
+        n = len(counts)
+        dh = (C.c_void_p * n)(*[C.c_void_p(int(p) or None) for p in hash_ptrs])
+        dc = (C.c_void_p * n)(*[C.c_void_p(int(p) or None) for p in contig_ptrs])
+        cn = (C.c_uint64 * n)(*[int(x) for x in counts])
+        ws = (C.c_double * n)(*[float(x) for x in weights])
+        self._n_asm = n
+        check(self._lib, self._lib.mxe_p2p_scatter(self._h, dh, dc, cn, n, ws))
+
+    def scatter_sketches(self, sketches, weights):
+        ptrs = [sk.device_pointers() for sk in sketches]
+        self._keep = list(sketches)
+        self.scatter([p[1] for p in ptrs], [p[3] for p in ptrs], [p[0] for p in ptrs], weights)
+
+    def buckets(self):
+        check(self._lib, self._lib.mxe_p2p_buckets(self._h))
+
+    def adjacency(self):
+        check(self._lib, self._lib.mxe_p2p_adjacency(self._h))
+
+    def edges(self):
+        check(self._lib, self._lib.mxe_p2p_edges(self._h))
+
+    def finish(self):
+        out = C.c_void_p()
+        check(self._lib, self._lib.mxe_p2p_finish(self._h, C.byref(out)))
+        self._keep = None
+        return FilterResult(self._e, out, self._n_asm)
+
+    def run(self, sketches, weights):
+        """all five stages for this rank (the other ranks run theirs in their own processes)"""
+        self.scatter_sketches(sketches, weights)
+        self.buckets()
+        self.adjacency()
+        self.edges()
+        return self.finish()
+
+    def close(self):
+        if self._h:
+            self._lib.mxe_p2p_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def _u64arr(values):

@@ -17,6 +17,7 @@ class FakeSketch:
         self.out_hash = np.asarray(out_hash, dtype=np.uint64)
         self.pos = np.asarray(pos, dtype=np.uint32)
         self.contig = np.asarray(contig, dtype=np.uint32)
+        self.n = len(self.out_hash)
 
     def close(self):
         pass
