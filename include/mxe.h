@@ -121,6 +121,11 @@ int mxe_sketch_view(mxe_sketch_t* s, uint64_t* n,
 int mxe_sketch_device_view(mxe_sketch_t* s, uint64_t* n, const void** d_out_hash,
                            const void** d_pos, const void** d_contig);
 
+/* Index (in the SoA above) of the first minimizer whose record id is >= `record`: where the minimizers of a record
+ * range start.  Several assemblies can be sketched in ONE call as one list of records (windows never cross records, so
+ * the result is the same as sketching them separately) and split afterwards at the record where each assembly starts. */
+int mxe_sketch_record_start(mxe_sketch_t* s, uint32_t record, uint64_t* index);
+
 /* Record name (header up to the first whitespace) of record `idx`; valid until mxe_sketch_free. */
 int mxe_sketch_contig_name(mxe_sketch_t* s, uint32_t idx, const char** name);
 

@@ -435,6 +435,33 @@ int mxe_sketch_device_view(mxe_sketch_t* S, uint64_t* n, const void** d_out_hash
     return MXE_OK;
 }
 
+// index of the first minimizer whose record id is >= `record` (one thread, log2(n) dependent loads)
+__global__ void record_start_kernel(const uint32_t* __restrict__ contig, uint64_t n, uint32_t record, uint64_t* __restrict__ out)
+{
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (contig[mid] < record) lo = mid + 1; else hi = mid;
+    }
+    *out = lo;
+}
+
+int mxe_sketch_record_start(mxe_sketch_t* s, uint32_t record, uint64_t* index)
+{
+    if (!s || !index) { set_error("null argument"); return MXE_ERR_ARG; }
+    if (!s->eng || !s->n) { *index = 0; return MXE_OK; }
+    mxe_engine* e = s->eng;
+    MXE_CUDA(cudaSetDevice(e->device));
+    uint64_t* d = nullptr;
+    MXE_CUDA(cudaMallocAsync((void**)&d, 8, e->stream));
+    record_start_kernel<<<1, 1, 0, e->stream>>>(s->d_contig, s->n, record, d);
+    e->launches++;
+    MXE_CUDA(cudaMemcpyAsync(index, d, 8, cudaMemcpyDeviceToHost, e->stream));
+    MXE_CUDA(cudaFreeAsync(d, e->stream));
+    MXE_CUDA(cudaStreamSynchronize(e->stream));
+    return MXE_OK;
+}
+
 int mxe_sketch_contig_name(mxe_sketch_t* S, uint32_t idx, const char** name)
 {
     if (!S || !name || idx >= S->names.size()) { set_error("bad record index"); return MXE_ERR_ARG; }

@@ -19,13 +19,13 @@
 //                            the bucket's survivor count to EVERY rank
 //       --- barrier 2
 //       adjacency  (source)  vertex ids from the bucket prefix, ordered survivors of own records, adjacent pairs;
-//                            successor entries -> table of the vertex OWNER
+//                            every sighting -> the OWNERS of its two vertices (successor / predecessor record)
 //       --- barrier 3
-//       edges      (source)  support mask of every sighting from the successor tables (peer loads), edge ownership,
-//                            first-source index / source mask -> tables of the vertex owner (peer atomics)
-//       --- barrier 4
-//       finish     (source)  world == 1: edges placed directly in the reference's formatted_edges order (a prefix sum
-//                            over first edges; no sort).  world > 1: this rank's shard with 64-bit global order keys.
+//       edges      (owner)   successor / predecessor tables of the own vertices, support masks, edge ownership,
+//                            first-source index: local loads only
+//       finish     (owner)   world == 1: edges placed directly in the reference's formatted_edges order (a prefix sum
+//                            over first edges; no sort).  world > 1: this rank's shard (flags of its own minimizers,
+//                            vertices of its hash range, the edges whose source vertex it owns) with 64-bit order keys.
 //
 // Uniqueness is per ASSEMBLY, not per GPU (bin/ntjoin_utils.py:182-187): the owner of a bucket sees the full multiset.
 // A bucket or sub-slot that overflows (adversarial input: one hash repeated thousands of times) raises an error flag
@@ -55,7 +55,8 @@ struct P2PLayout {
     uint64_t L_cap;                        // minimizers of one rank, all assemblies
     uint64_t nv_cap;                       // vertices of one owner
     // byte offsets inside every rank's workspace
-    uint64_t off_flags, off_err, off_counts, off_rec_cnt, off_nkeep, off_rec, off_mk, off_succ, off_vgid, bytes;
+    uint64_t off_flags, off_err, off_counts, off_rec_cnt, off_nkeep, off_rec, off_mk, off_succ, off_vgid, off_pred, off_cnt2, off_rec2, bytes;
+    uint64_t cap2;                         // sighting records per (owner, source) segment (world > 1)
 };
 
 struct P2PRecord { uint64_t key, tag; };   // tag = asm << 40 | source rank << 32 | local index
@@ -519,6 +520,141 @@ __global__ void __launch_bounds__(256) p2p_edge_emit_kernel(const uint32_t* __re
     E.ew[o] = wsum;
 }
 
+// ---------------------------------------------------------------- world > 1: sightings travel to the vertex owners
+// Two 24-byte records per sighting (a: v -> x, creation index g), written into segment [source rank] of the owner:
+//   SUCC -> owner(v): { hash(x), local(v) << 32 | x, g << 8 | a << 1 | 0 }
+//   PRED -> owner(x): { hash(v), local(x) << 32 | v,          a << 1 | 1 }
+// so that the owner of a vertex holds its successor AND predecessor in every assembly and decides support masks, edge
+// ownership, first-source index and order keys with local loads only (a remote 4-byte load costs a NVLink round trip;
+// the stores are fire-and-forget).  Slots are reserved per CTA: one shared-memory count per destination, one global
+// atomic per (CTA, destination).
+__global__ void __launch_bounds__(256) p2p_sight_kernel(const uint32_t* __restrict__ cvid, const uint32_t* __restrict__ cg,
+                                                         const uint32_t* __restrict__ cloc, const uint64_t* __restrict__ kprefix, uint64_t L,
+                                                         LocalSlices S, PtrTab H, PtrTab Ctg, PeerPtrs P, P2PLayout Y, HomeTabs T,
+                                                         uint32_t* __restrict__ cur2)
+{
+    __shared__ uint32_t scount[P2P_MAX_WORLD];
+    __shared__ uint32_t sbase[P2P_MAX_WORLD];
+    const uint64_t n_keep = kprefix[L];
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (threadIdx.x < P2P_MAX_WORLD) scount[threadIdx.x] = 0u;
+    __syncthreads();
+    bool f = false;
+    uint32_t v = 0, x = 0;
+    uint64_t hv = 0, hx = 0;
+    int a = 0, ov = 0, ox = 0;
+    uint32_t s0 = 0, s1 = 0;
+    if (j + 1 < n_keep) {
+        const uint32_t l1 = cloc[j], l2 = cloc[j + 1];
+        a = p2p_slice_of(S, l1);
+        if (a == p2p_slice_of(S, l2)) {
+            const uint32_t* ctg = reinterpret_cast<const uint32_t*>(Ctg.p[a]);
+            f = ctg[l1 - S.lofs[a]] == ctg[l2 - S.lofs[a]];
+            if (f) {
+                const uint64_t* hs = reinterpret_cast<const uint64_t*>(H.p[a]);
+                v = cvid[j]; x = cvid[j + 1];
+                hv = hs[l1 - S.lofs[a]]; hx = hs[l2 - S.lofs[a]];
+                ov = p2p_vowner(T.vown, Y.world, v); ox = p2p_vowner(T.vown, Y.world, x);
+                s0 = atomicAdd(&scount[ov], 1u);
+                s1 = atomicAdd(&scount[ox], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < Y.world) sbase[threadIdx.x] = scount[threadIdx.x] ? atomicAdd(&cur2[threadIdx.x], scount[threadIdx.x]) : 0u;
+    __syncthreads();
+    if (!f) return;
+    const uint64_t p0 = (uint64_t)sbase[ov] + s0, p1 = (uint64_t)sbase[ox] + s1;
+    if (p0 >= Y.cap2 || p1 >= Y.cap2) { *reinterpret_cast<uint32_t*>(P.base[Y.rank] + Y.off_err) = 3u; return; }
+    uint64_t* r0 = reinterpret_cast<uint64_t*>(P.base[ov] + Y.off_rec2) + ((uint64_t)Y.rank * Y.cap2 + p0) * 3;
+    uint64_t* r1 = reinterpret_cast<uint64_t*>(P.base[ox] + Y.off_rec2) + ((uint64_t)Y.rank * Y.cap2 + p1) * 3;
+    r0[0] = hx; r0[1] = ((uint64_t)(v - T.vown[ov]) << 32) | x; r0[2] = ((uint64_t)cg[j] << 8) | ((uint64_t)a << 1);
+    r1[0] = hv; r1[1] = ((uint64_t)(x - T.vown[ox]) << 32) | v; r1[2] = ((uint64_t)a << 1) | 1ULL;
+}
+
+__global__ void p2p_push_cnt2_kernel(const uint32_t* __restrict__ cur2, PeerPtrs P, P2PLayout Y)
+{
+    if ((int)threadIdx.x < Y.world) {
+        const uint32_t c = cur2[threadIdx.x] < Y.cap2 ? cur2[threadIdx.x] : (uint32_t)Y.cap2;
+        reinterpret_cast<uint32_t*>(P.base[threadIdx.x] + Y.off_cnt2)[Y.rank] = c;
+    }
+}
+
+// owner side.  Record index space: segment s (source rank) x cap2; entries at or beyond the segment's count are skipped.
+__device__ __forceinline__ const uint64_t* p2p_rec2(const PeerPtrs& P, const P2PLayout& Y, uint64_t idx, bool* valid)
+{
+    const uint32_t seg = (uint32_t)(idx / Y.cap2);
+    const uint64_t i = idx - (uint64_t)seg * Y.cap2;
+    *valid = seg < (uint32_t)Y.world && i < reinterpret_cast<const uint32_t*>(P.base[Y.rank] + Y.off_cnt2)[seg];
+    return reinterpret_cast<const uint64_t*>(P.base[Y.rank] + Y.off_rec2) + idx * 3;
+}
+
+// successor (+ creation index) / predecessor of every own vertex in every assembly (entries 1 + vertex id, 0 = none)
+__global__ void __launch_bounds__(256) p2p_table_kernel(PeerPtrs P, P2PLayout Y)
+{
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool ok;
+    const uint64_t* r = p2p_rec2(P, Y, idx, &ok);
+    if (!ok) return;
+    const uint64_t w1 = r[1], w2 = r[2];
+    const uint64_t a = (w2 >> 1) & 0x7F, vloc = w1 >> 32;
+    const uint32_t other = (uint32_t)w1 + 1u;
+    char* me = P.base[Y.rank];
+    if (w2 & 1ULL) {
+        reinterpret_cast<uint32_t*>(me + Y.off_pred)[a * Y.nv_cap + vloc] = other;
+    } else {
+        reinterpret_cast<uint32_t*>(me + Y.off_succ)[a * Y.nv_cap + vloc] = other;
+        reinterpret_cast<uint32_t*>(me + Y.off_vgid)[a * Y.nv_cap + vloc] = (uint32_t)(w2 >> 8);
+    }
+}
+
+__global__ void __launch_bounds__(256) p2p_rec_owner_kernel(PeerPtrs P, P2PLayout Y, int n_asm, uint32_t* __restrict__ own, uint32_t* __restrict__ mask_out)
+{
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (uint64_t)Y.world * Y.cap2) return;
+    bool ok;
+    const uint64_t* r = p2p_rec2(P, Y, idx, &ok);
+    uint32_t is_owner = 0;
+    if (ok && !(r[2] & 1ULL)) {
+        const uint64_t w1 = r[1], w2 = r[2];
+        const int a = (int)((w2 >> 1) & 0x7F);
+        const uint64_t vloc = w1 >> 32;
+        const uint32_t x1 = (uint32_t)w1 + 1u;
+        char* me = P.base[Y.rank];
+        uint32_t* sv = reinterpret_cast<uint32_t*>(me + Y.off_succ) + vloc;
+        const uint32_t* pv = reinterpret_cast<const uint32_t*>(me + Y.off_pred) + vloc;
+        uint32_t mask = 0;
+        for (int b = 0; b < n_asm; b++)
+            if ((sv[(uint64_t)b * Y.nv_cap] & 0x7FFFFFFFu) == x1 || pv[(uint64_t)b * Y.nv_cap] == x1) mask |= 1u << b;
+        is_owner = (__ffs(mask) - 1) == a;
+        mask_out[idx] = mask;
+        if (is_owner) sv[(uint64_t)a * Y.nv_cap] = x1 | 0x80000000u;      // ownership mark (see p2p_edge_owner_kernel)
+    }
+    own[idx] = is_owner;
+}
+
+__global__ void __launch_bounds__(256) p2p_rec_emit_kernel(PeerPtrs P, P2PLayout Y, AsmOffsets A, const uint32_t* __restrict__ own,
+                                                            const uint32_t* __restrict__ mask_in, const uint64_t* __restrict__ uprefix,
+                                                            const uint64_t* __restrict__ vertices, EdgeOut E)
+{
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (uint64_t)Y.world * Y.cap2 || !own[idx]) return;
+    const uint64_t* r = reinterpret_cast<const uint64_t*>(P.base[Y.rank] + Y.off_rec2) + idx * 3;
+    const uint32_t vloc = (uint32_t)(r[1] >> 32);
+    uint32_t smin;
+    p2p_source_info(P, Y, Y.rank, vloc, A.n, &smin);
+    const uint64_t o = uprefix[idx];
+    const uint32_t mask = mask_in[idx];
+    E.eu[o] = vertices[vloc];
+    E.ev[o] = r[0];
+    E.emask[o] = mask;
+    E.ekey[o] = ((uint64_t)smin << 32) | (r[2] >> 8);
+    double wsum = 0.0;
+    for (int b = 0; b < A.n; b++)
+        if (mask & (1u << b)) wsum += A.weight[b];
+    E.ew[o] = wsum;
+}
+
 }  // namespace mxe
 
 using namespace mxe;
@@ -543,6 +679,9 @@ struct mxe_p2p {
     AsmOffsets A;
     uint32_t *cursor = nullptr, *kflag = nullptr, *cvid = nullptr, *cg = nullptr, *cloc = nullptr, *eflag = nullptr, *own = nullptr, *emask_j = nullptr;
     uint64_t *kprefix = nullptr, *uprefix = nullptr;
+    uint32_t* cur2 = nullptr;
+    bool records = false;                  // world > 1: false = successor tables at the vertex owners read with peer loads (measured: 2.96 vs 3.46 ms
+                                           // per step at 2 GPUs, 1.59 vs 1.56 at 8); true (MXE_P2P_RECORDS=1) = sightings travel to the owners as records
     uint8_t *luniq = nullptr, *lkeep = nullptr;
     uint64_t* vertices = nullptr;
     HomeTabs T;
@@ -600,6 +739,7 @@ int mxe_p2p_create(mxe_t* e, int rank, int world, uint64_t cap_total, int n_asm_
     MXE_CUDA(cudaSetDevice(e->device));
     mxe_p2p* X = new mxe_p2p();
     X->eng = e;
+    if (const char* sv = getenv("MXE_P2P_RECORDS")) X->records = atoi(sv) != 0;
     P2PLayout& Y = X->Y;
     memset(&Y, 0, sizeof(Y));
     Y.world = world; Y.rank = rank; Y.n_asm_max = n_asm_max;
@@ -626,6 +766,11 @@ int mxe_p2p_create(mxe_t* e, int rank, int world, uint64_t cap_total, int n_asm_
     Y.off_mk = take(Y.L_cap * 4);
     Y.off_succ = take((uint64_t)n_asm_max * Y.nv_cap * 4);
     Y.off_vgid = take((uint64_t)n_asm_max * Y.nv_cap * 4);
+    // world > 1: every sighting travels to the owners of its two vertices as a 24-byte record (no remote loads)
+    Y.cap2 = world > 1 ? (uint64_t)((double)cap_total / world / world * 2.0 * 1.3) + 8192 : 0;
+    Y.off_pred = take(world > 1 ? (uint64_t)n_asm_max * Y.nv_cap * 4 : 0);
+    Y.off_cnt2 = take(256);
+    Y.off_rec2 = take((uint64_t)world * Y.cap2 * 24);
     Y.bytes = at;
     cudaError_t err = cudaMalloc((void**)&X->ws, Y.bytes);
     if (err != cudaSuccess) { set_error("symmetric workspace of %llu bytes: %s", (unsigned long long)Y.bytes, cudaGetErrorString(err)); delete X; return MXE_ERR_NOMEM; }
@@ -708,7 +853,8 @@ int mxe_p2p_scatter(mxe_p2p_t* X, const void* const* d_hash, const void* const* 
     X->L = L;
     if (L > Y.L_cap) { set_error("%llu minimizers on this rank exceed the workspace capacity %llu", (unsigned long long)L, (unsigned long long)Y.L_cap); return MXE_ERR_ARG; }
     // local workspace for this call
-    const size_t need = (size_t)Y.n_buckets * 8 + (L + 1) * (7 * 4 + 2 * 8 + 2) + (Y.n_buckets + 64) * 4 + 4096 * 4 + 64 * 1024;
+    const uint64_t n_own = Y.world > 1 ? std::max<uint64_t>(L + 1, (uint64_t)Y.world * Y.cap2 + 1) : L + 1;      // entries of own[] / emask_j[] / uprefix[]
+    const size_t need = (size_t)Y.n_buckets * 8 + (L + 1) * (5 * 4 + 8 + 2) + n_own * (2 * 4 + 8) + (Y.n_buckets + 64) * 4 + 4096 * 4 + 64 * 1024;
     if (X->lws_bytes < need) {
         if (X->lws) { MXE_CUDA(cudaStreamSynchronize(st)); MXE_CUDA(cudaFree(X->lws)); X->lws = nullptr; }
         MXE_CUDA(cudaMalloc((void**)&X->lws, need + need / 8));
@@ -717,18 +863,21 @@ int mxe_p2p_scatter(mxe_p2p_t* X, const void* const* d_hash, const void* const* 
     X->lws_used = 0;
     X->cursor = (uint32_t*)X->lalloc((size_t)Y.n_buckets * 4);
     X->kflag = (uint32_t*)X->lalloc((L + 1) * 4); X->cvid = (uint32_t*)X->lalloc((L + 1) * 4); X->cg = (uint32_t*)X->lalloc((L + 1) * 4);
-    X->cloc = (uint32_t*)X->lalloc((L + 1) * 4); X->eflag = (uint32_t*)X->lalloc((L + 1) * 4); X->own = (uint32_t*)X->lalloc((L + 1) * 4);
-    X->emask_j = (uint32_t*)X->lalloc((L + 1) * 4);
-    X->kprefix = (uint64_t*)X->lalloc((L + 2) * 8); X->uprefix = (uint64_t*)X->lalloc((L + 2) * 8);
+    X->cloc = (uint32_t*)X->lalloc((L + 1) * 4); X->eflag = (uint32_t*)X->lalloc((L + 1) * 4); X->own = (uint32_t*)X->lalloc(n_own * 4);
+    X->emask_j = (uint32_t*)X->lalloc(n_own * 4);
+    X->kprefix = (uint64_t*)X->lalloc((L + 2) * 8); X->uprefix = (uint64_t*)X->lalloc((n_own + 1) * 8);
+    X->cur2 = (uint32_t*)X->lalloc(64 * 4);
     X->T.vbase = (uint32_t*)X->lalloc((size_t)(Y.n_buckets + 1) * 4); X->T.vown = (uint32_t*)X->lalloc(64 * 4); X->T.goff = (uint64_t*)X->lalloc(64 * 8);
     if (!X->T.goff) { set_error("local workspace too small"); return MXE_ERR_INTERNAL; }
     X->epoch++;
     MXE_CUDA(cudaMemsetAsync(X->cursor, 0, (size_t)Y.n_buckets * 4, st));
+    MXE_CUDA(cudaMemsetAsync(X->cur2, 0, 64 * 4, st));
     // barrier 0: every rank has finished the previous call (its reads of peer tables included) before anybody clears
     // its own tables or writes into a peer's workspace again
     MXE_TRY(p2p_barrier_signal(X, 0));
     MXE_TRY(p2p_barrier_wait(X, 0));
     MXE_CUDA(cudaMemsetAsync(X->ws + Y.off_succ, 0, (size_t)n_asm * Y.nv_cap * 4, st));
+    if (Y.world > 1) MXE_CUDA(cudaMemsetAsync(X->ws + Y.off_pred, 0, (size_t)n_asm * Y.nv_cap * 4, st));
     if (L) MXE_LAUNCH(e, p2p_scatter_kernel, p2p_grid(L), 256, 0, X->H, X->S, L, X->P, Y, X->cursor);
     AsmCounts C;
     C.n_asm = n_asm;
@@ -781,8 +930,12 @@ int mxe_p2p_adjacency(mxe_p2p_t* X)
     }
     if (L) {
         MXE_LAUNCH(e, p2p_compact_kernel, p2p_grid(L), 256, 0, mk, X->H, X->S, L, X->kprefix, Y, X->T, X->cvid, X->cg, X->cloc);
-        MXE_LAUNCH(e, p2p_succ_kernel, p2p_grid(L), 256, 0, X->cvid, X->cg, X->cloc, X->kprefix, L, X->S, X->Ctg, X->P, Y, X->T, X->eflag);
+        if (Y.world == 1 || !X->records)
+            MXE_LAUNCH(e, p2p_succ_kernel, p2p_grid(L), 256, 0, X->cvid, X->cg, X->cloc, X->kprefix, L, X->S, X->Ctg, X->P, Y, X->T, X->eflag);
+        else
+            MXE_LAUNCH(e, p2p_sight_kernel, p2p_grid(L), 256, 0, X->cvid, X->cg, X->cloc, X->kprefix, L, X->S, X->H, X->Ctg, X->P, Y, X->T, X->cur2);
     }
+    if (Y.world > 1 && X->records) MXE_LAUNCH(e, p2p_push_cnt2_kernel, 1, 32, 0, X->cur2, X->P, Y);
     MXE_TRY(p2p_barrier_signal(X, 3));
     MXE_CUDA(cudaGetLastError());
     return MXE_OK;
@@ -798,8 +951,14 @@ int mxe_p2p_edges(mxe_p2p_t* X)
     Span part(e, "p2p_edges");
     const uint64_t L = X->L;
     MXE_TRY(p2p_barrier_wait(X, 3));
-    if (L) MXE_LAUNCH(e, p2p_edge_owner_kernel, p2p_grid(L), 256, 0, X->cvid, X->cg, X->cloc, X->eflag, X->kprefix, L, X->S, X->n_asm, X->P, Y, X->T, X->own, X->emask_j);
-    MXE_TRY(p2p_barrier_signal(X, 4));
+    if (Y.world == 1 || !X->records) {
+        if (L) MXE_LAUNCH(e, p2p_edge_owner_kernel, p2p_grid(L), 256, 0, X->cvid, X->cg, X->cloc, X->eflag, X->kprefix, L, X->S, X->n_asm, X->P, Y, X->T, X->own, X->emask_j);
+        MXE_TRY(p2p_barrier_signal(X, 4));
+    } else {
+        const uint64_t n_idx = (uint64_t)Y.world * Y.cap2;
+        MXE_LAUNCH(e, p2p_table_kernel, p2p_grid(n_idx), 256, 0, X->P, Y);
+        MXE_LAUNCH(e, p2p_rec_owner_kernel, p2p_grid(n_idx), 256, 0, X->P, Y, X->n_asm, X->own, X->emask_j);
+    }
     MXE_CUDA(cudaGetLastError());
     return MXE_OK;
 }
@@ -817,18 +976,20 @@ int mxe_p2p_finish(mxe_p2p_t* X, mxe_result_t** out)
     Span part(e, "p2p_finish");
     const uint64_t L = X->L;
     const int n_asm = X->n_asm;
-    MXE_TRY(p2p_barrier_wait(X, 4));
-    // owned edges in creation order: kprefix[L] = survivors; own[] beyond them is never read
-    // (scan length = L: entries past n_keep must be zero)
+    const bool home = Y.world == 1 || !X->records;       // edges emitted by the rank that sketched the sighting
+    if (home) MXE_TRY(p2p_barrier_wait(X, 4));
+    // owned edges: world == 1 in creation order over the survivors (own[] past n_keep is cleared first: the scan runs
+    // over L entries); world > 1 over the record index space of this owner
+    const uint64_t n_scan = home ? L : (uint64_t)Y.world * Y.cap2;
     {
         ArenaScope scope(e);
-        if (L) MXE_LAUNCH(e, p2p_clear_tail_kernel, p2p_grid(L), 256, 0, X->own, X->kprefix, L);
-        MXE_TRY(exclusive_scan_u32_u64(e, X->own, X->uprefix, L));
+        if (home && L) MXE_LAUNCH(e, p2p_clear_tail_kernel, p2p_grid(L), 256, 0, X->own, X->kprefix, L);
+        MXE_TRY(exclusive_scan_u32_u64(e, X->own, X->uprefix, n_scan));
     }
     uint64_t sizes[2] = {0, 0};
     uint32_t verts[2] = {0, 0}, errw = 0;
     MXE_CUDA(cudaMemcpyAsync(&sizes[0], X->kprefix + L, 8, cudaMemcpyDeviceToHost, st));
-    MXE_CUDA(cudaMemcpyAsync(&sizes[1], X->uprefix + L, 8, cudaMemcpyDeviceToHost, st));
+    MXE_CUDA(cudaMemcpyAsync(&sizes[1], X->uprefix + n_scan, 8, cudaMemcpyDeviceToHost, st));
     MXE_CUDA(cudaMemcpyAsync(&verts[0], X->T.vown + Y.rank, 8, cudaMemcpyDeviceToHost, st));
     MXE_CUDA(cudaMemcpyAsync(&errw, X->ws + Y.off_err, 4, cudaMemcpyDeviceToHost, st));
     MXE_CUDA(cudaStreamSynchronize(st));
@@ -836,7 +997,7 @@ int mxe_p2p_finish(mxe_p2p_t* X, mxe_result_t** out)
         cudaMemsetAsync(X->ws + Y.off_err, 0, 4, st);
         cudaFreeAsync(X->luniq, st); cudaFreeAsync(X->lkeep, st);
         X->luniq = X->lkeep = nullptr;
-        set_error(errw >= 0x100 ? "device barrier %u timed out (a peer rank is gone)" : errw == 1 ? "bucket sub-slot overflow (code %u)" : "bucket overflow (code %u)",
+        set_error(errw >= 0x100 ? "device barrier %u timed out (a peer rank is gone)" : errw == 1 ? "bucket sub-slot overflow (code %u)" : errw == 3 ? "sighting segment overflow (code %u)" : "bucket overflow (code %u)",
                   errw >= 0x100 ? errw - 0x100 : errw);
         return errw >= 0x100 ? MXE_ERR_CUDA : MXE_ERR_INTERNAL;
     }
@@ -866,12 +1027,18 @@ int mxe_p2p_finish(mxe_p2p_t* X, mxe_result_t** out)
             MXE_TRY(exclusive_scan_u32_u64(e, fcount.p, fprefix.p, nE));
             MXE_LAUNCH(e, p2p_first_start_kernel, p2p_grid(L), 256, 0, X->cvid, X->cg, X->own, X->uprefix, fprefix.p, X->kprefix, L, X->P, Y, n_asm, vst.p);
             vstart = vst.p;
+            MXE_LAUNCH(e, p2p_edge_emit_kernel, p2p_grid(L), 256, 0, X->cvid, X->cg, X->cloc, X->own, X->emask_j, X->uprefix, X->kprefix, L, X->S, X->H, X->A,
+                       X->P, Y, X->T, vstart, E);
+        } else if (home) {
+            MXE_CUDA(cudaMallocAsync((void**)&R->d_ekey, nE * 8, st));
+            E.ekey = R->d_ekey;
+            MXE_LAUNCH(e, p2p_edge_emit_kernel, p2p_grid(L), 256, 0, X->cvid, X->cg, X->cloc, X->own, X->emask_j, X->uprefix, X->kprefix, L, X->S, X->H, X->A,
+                       X->P, Y, X->T, vstart, E);
         } else {
             MXE_CUDA(cudaMallocAsync((void**)&R->d_ekey, nE * 8, st));
             E.ekey = R->d_ekey;
+            MXE_LAUNCH(e, p2p_rec_emit_kernel, p2p_grid(n_scan), 256, 0, X->P, Y, X->A, X->own, X->emask_j, X->uprefix, R->d_vertices, E);
         }
-        MXE_LAUNCH(e, p2p_edge_emit_kernel, p2p_grid(L), 256, 0, X->cvid, X->cg, X->cloc, X->own, X->emask_j, X->uprefix, X->kprefix, L, X->S, X->H, X->A,
-                   X->P, Y, X->T, vstart, E);
     }
     MXE_CUDA(cudaGetLastError());
     *out = R;

@@ -159,7 +159,7 @@ __device__ __noinline__ uint32_t pack_unit_tail(const uint8_t* __restrict__ seq,
     return bad;
 }
 
-constexpr int PACK2_THREADS = 256;
+constexpr int PACK2_THREADS = 256;      // most; short tiles are packed by 128-thread CTAs (blockDim.x is what the kernel uses)
 constexpr int PACK2_INFLIGHT = 4;      // 32-base units per thread whose loads are issued before any is consumed
 __host__ __device__ inline size_t pack2_smem_bytes(uint32_t Lw, uint32_t ext) { return (size_t)3 * (16u * Lw + ext) * sizeof(uint32_t); }
 
@@ -177,11 +177,11 @@ __global__ void __launch_bounds__(PACK2_THREADS) pack2_kernel(const uint8_t* __r
     const uint64_t T = T0 + blockIdx.x;
     const uint64_t u_base = T * (uint64_t)L;       // first global unit of the tile
     int seen_bad = 0;
-    for (uint32_t ub = 0; ub < U; ub += PACK2_THREADS * PACK2_INFLIGHT) {
+    for (uint32_t ub = 0; ub < U; ub += blockDim.x * PACK2_INFLIGHT) {
         uint4 a[PACK2_INFLIGHT], b[PACK2_INFLIGHT];
 #pragma unroll
         for (int i = 0; i < PACK2_INFLIGHT; i++) {           // all loads of this thread first: the kernel lives on bytes in flight
-            const uint32_t u = ub + i * PACK2_THREADS + threadIdx.x;
+            const uint32_t u = ub + i * blockDim.x + threadIdx.x;
             const uint64_t gu = u_base + u;
             if (u < U && (gu << 5) + 32 <= G.n) {
                 const uint4* src = reinterpret_cast<const uint4*>(seq + (gu << 5));
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(PACK2_THREADS) pack2_kernel(const uint8_t* __r
         }
 #pragma unroll
         for (int i = 0; i < PACK2_INFLIGHT; i++) {
-            const uint32_t u = ub + i * PACK2_THREADS + threadIdx.x;
+            const uint32_t u = ub + i * blockDim.x + threadIdx.x;
             const uint64_t gu = u_base + u;
             if (u >= U) continue;
             uint32_t pkw[2] = {0u, 0u};
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(PACK2_THREADS) pack2_kernel(const uint8_t* __r
     const int lane = threadIdx.x & 31;
     if (!__syncthreads_or(seen_bad)) {
         // the usual tile: every base valid and the sequence continues past the halo -> V is all ones
-        for (uint32_t u0 = 0; u0 < L; u0 += PACK2_THREADS) {
+        for (uint32_t u0 = 0; u0 < L; u0 += blockDim.x) {
             const uint32_t u = u0 + threadIdx.x;
             if (u < L) V[u_base + u] = 0xFFFFFFFFu;
             const uint32_t w0 = u0 + (threadIdx.x & ~31u);                     // first unit of this warp
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(PACK2_THREADS) pack2_kernel(const uint8_t* __r
     } else {
         // V + rank counts (a warp's 32 consecutive units touch at most two 1024-bit rank blocks)
         const int reach = (31 + G.k - 1) / 32;
-        for (uint32_t u0 = 0; u0 < L; u0 += PACK2_THREADS) {
+        for (uint32_t u0 = 0; u0 < L; u0 += blockDim.x) {
             const uint32_t u = u0 + threadIdx.x;
             const uint64_t gu = u_base + u;
             const bool act = u < L && gu < G.n_words;
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(PACK2_THREADS) pack2_kernel(const uint8_t* __r
     // Bit planes for scan_bs2_kernel: thread g takes word g of every stream (stream j starts at pk word j * Lw; Lw odd
     // and consecutive g -> conflict-free), transposes 32 x 32 bits in registers and writes one 128-byte row.  pack2 is
     // bound by memory latency with the ALU pipe half idle, scan_bs2 by the ALU pipe: the transposition costs less here.
-    for (uint32_t g = threadIdx.x; g < G.R; g += PACK2_THREADS) {
+    for (uint32_t g = threadIdx.x; g < G.R; g += blockDim.x) {
         uint32_t x[32];
 #pragma unroll
         for (int j = 0; j < 32; j++) x[j] = pkS[(uint32_t)j * G.Lw + g];

@@ -183,10 +183,11 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
     if (bs2) {
         Span sp(e, "pack");
         const size_t psm = pack2_smem_bytes(G.Lw, G.ext);
+        const unsigned pthreads = 16u * G.Lw + G.ext <= 320 ? 128 : PACK2_THREADS;      // short tiles: fewer idle lanes per CTA
         const uint64_t tile = 512ull * G.Lw;
         if (!staged) {
             Span k1(e, "k_pack2");
-            MXE_LAUNCH(e, pack2_kernel, (unsigned)G.n_tiles, PACK2_THREADS, psm, d_seq, G, pk.p, PL.p, V.p, vcounts.p, DL, (uint64_t)0);
+            MXE_LAUNCH(e, pack2_kernel, (unsigned)G.n_tiles, pthreads, psm, d_seq, G, pk.p, PL.p, V.p, vcounts.p, DL, (uint64_t)0);
         } else {
             // host input: a tile is packed once its bytes and its halo (ext units) have landed
             const uint64_t CH = staged->chunk;
@@ -199,7 +200,7 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
                 const uint64_t have = off + len;
                 uint64_t T1 = last ? G.n_tiles : (have > 32ull * G.ext ? (have - 32ull * G.ext) / tile : 0);
                 if (T1 > G.n_tiles) T1 = G.n_tiles;
-                if (T1 > T0) MXE_LAUNCH(e, pack2_kernel, (unsigned)(T1 - T0), PACK2_THREADS, psm, d_seq, G, pk.p, PL.p, V.p, vcounts.p, DL, T0);
+                if (T1 > T0) MXE_LAUNCH(e, pack2_kernel, (unsigned)(T1 - T0), pthreads, psm, d_seq, G, pk.p, PL.p, V.p, vcounts.p, DL, T0);
                 T0 = std::max(T0, T1);
             }
             MXE_CUDA(cudaEventRecord(staged->consumed, st));

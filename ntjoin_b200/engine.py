@@ -111,6 +111,33 @@ class Sketch:
             pass
 
 
+class SketchSlice:
+    """The minimizers of one assembly inside a sketch of several assemblies made in one call
+    (Engine.sketch_device_multi): a contiguous record range [rec0, rec1) = a contiguous index range [i0, i1)."""
+
+    def __init__(self, parent, rec0, rec1, i0, i1):
+        self._p, self.rec0, self.rec1, self.i0, self.i1 = parent, int(rec0), int(rec1), int(i0), int(i1)
+        self.names = parent.names[self.rec0:self.rec1]
+        self._e = parent._e
+
+    n = property(lambda s: s.i1 - s.i0)
+    out_hash = property(lambda s: s._p.out_hash[s.i0:s.i1])
+    min_hash = property(lambda s: s._p.min_hash[s.i0:s.i1])
+    pos = property(lambda s: s._p.pos[s.i0:s.i1])
+    contig = property(lambda s: s._p.contig[s.i0:s.i1] - np.uint32(s.rec0))
+    forward = property(lambda s: s._p.forward[s.i0:s.i1])
+
+    def device_pointers(self):
+        n, ph, pp, pc = self._p.device_pointers()
+        return (self.n, ph + 8 * self.i0, pp + 4 * self.i0, pc + 4 * self.i0)
+
+    def fetch(self, copy=True):
+        return tuple(x[self.i0:self.i1] for x in self._p.fetch(copy=copy))
+
+    def close(self):
+        pass          # the parent owns the arrays
+
+
 class FilterResult:
     """Outcome of steps 2-3: per-assembly flags + the weighted edge list.  Arrays stay on the device
     until first touched (then one pinned device->host copy)."""
@@ -297,8 +324,48 @@ class Engine:
                                                     n, carr, int(k), int(w), self._flags(canonical), C.byref(out)))
         return Sketch(self, out, pynames)
 
+    def sketch_device_multi(self, dptr, offsets_list, k, w, canonical="sum", starts=None):
+        """Several assemblies resident in ONE device buffer, sketched in one call: offsets_list[a] are the record starts
+        of assembly a relative to the assembly's own first base (n_records + 1 entries); starts[a] = byte offset of
+        assembly a in the buffer (default: back to back; a gap between two assemblies -- e.g. alignment padding --
+        becomes a record of its own that belongs to no assembly).  Returns (parent sketch, [SketchSlice per assembly]).
+        Windows never cross records, so every slice equals the sketch of its assembly alone; what is saved is one set
+        of launches and host round trips per extra assembly, which is what a small per-GPU share of a multi-GPU job is
+        made of."""
+        offs, ranges, at, nrec = [np.zeros(1, dtype=np.uint64)], [], 0, 0
+        for a, o in enumerate(offsets_list):
+            o = np.ascontiguousarray(o, dtype=np.uint64)
+            begin = at if starts is None else int(starts[a])
+            if begin < at:
+                raise ValueError("assemblies overlap in the buffer")
+            if begin > at:                                   # gap record
+                offs.append(np.array([begin], dtype=np.uint64))
+                nrec += 1
+            offs.append(o[1:] + np.uint64(begin))
+            ranges.append((nrec, nrec + len(o) - 1))
+            nrec += len(o) - 1
+            at = begin + int(o[-1])
+        parent = self.sketch_device(dptr, np.concatenate(offs), k, w, canonical=canonical)
+        out = []
+        for r0, r1 in ranges:
+            idx = []
+            for b in (r0, r1):
+                if b == 0:
+                    idx.append(0)
+                elif b == nrec:
+                    idx.append(parent.n)
+                else:
+                    v = C.c_uint64()
+                    check(self._lib, self._lib.mxe_sketch_record_start(parent._h, int(b), C.byref(v)))
+                    idx.append(v.value)
+            out.append(SketchSlice(parent, r0, r1, idx[0], idx[1]))
+        return parent, out
+
     def filter_and_edges(self, sketches, weights):
         """sketches in assembly order: references (CLI order) then target (bin/ntjoin.py:181-185)."""
+        if any(isinstance(s, SketchSlice) for s in sketches):
+            ptrs = [s.device_pointers() for s in sketches]
+            return self.filter_and_edges_device([p[1] for p in ptrs], [p[3] for p in ptrs], [p[0] for p in ptrs], weights)
         n = len(sketches)
         hs = (C.c_void_p * n)(*[s._h for s in sketches])
         ws = (C.c_double * n)(*[float(x) for x in weights])

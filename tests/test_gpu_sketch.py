@@ -186,3 +186,36 @@ def test_config5_kw_sweep(engine, oracle, variant):
                 assert_same(engine.sketch_buffers(rseq, roffs, k, w), ref)
     finally:
         engine.set_option("cand_variant", DEFAULT_VARIANT)
+
+
+def test_multi_assembly_single_call(engine, oracle):
+    """several assemblies in one device buffer sketched in ONE call (Engine.sketch_device_multi): every slice must
+    equal the sketch of its assembly alone, with and without alignment gaps between the assemblies, and steps 2-3 on
+    the slices must equal steps 2-3 on separate sketches"""
+    import torch
+    a = synth.make_reference(700_000, n_chrom=4, seed=11, dup_frac=0.02, n_frac=0.004)
+    b = synth.derive_target(a[0], a[1], min_len=3_000, max_len=90_000)
+    c = synth.make_reference(123_457, n_chrom=1, seed=12)
+    asms = [(a[0], a[1]), (b[0], b[1]), (c[0], c[1])]
+    for k, w in [(32, 100), (12, 7)]:
+        refs = [oracle.sketch(s, o, k, w) for s, o in asms]
+        for aligned in (False, True):
+            starts, at = [], 0
+            for s, _ in asms:
+                starts.append(at)
+                at += (len(s) + 15) // 16 * 16 if aligned else len(s)
+            buf = np.full(at + 16, ord("A"), dtype=np.uint8)          # gap bytes are valid bases: the gap record must not leak
+            for (s, _), st in zip(asms, starts):
+                buf[st:st + len(s)] = s
+            dbuf = torch.from_numpy(buf).cuda()
+            parent, slices = engine.sketch_device_multi(dbuf.data_ptr(), [o for _, o in asms], k, w, starts=starts)
+            for sl, ref in zip(slices, refs):
+                assert_same(sl, ref)
+            res = engine.filter_and_edges(slices, [2.0, 2.0, 1.0])
+            want = oracle.filter_and_edges([r["out_hash"] for r in refs], [r["contig"] for r in refs], [2.0, 2.0, 1.0])
+            np.testing.assert_array_equal(res.vertices, want["vertices"])
+            np.testing.assert_array_equal(res.edge_u, want["edges"]["u"])
+            np.testing.assert_array_equal(res.edge_v, want["edges"]["v"])
+            np.testing.assert_array_equal(res.support, want["edges"]["support_mask"])
+            res.close()
+            parent.close()
