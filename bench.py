@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--with-n", action="store_true", help="put 0.5%% of the reference in N runs (default: N-free headline variant)")
     ap.add_argument("--cpu-sample", type=float, default=0, help="bases per assembly for the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-t3", action="store_true", help="skip the file-seam measurement (FASTA file -> TSV file -> Python objects)")
+    ap.add_argument("--t3-bases", type=float, default=200e6, help="bases per assembly of the file-seam measurement")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the comparison of the merged shards with the single-GPU result")
     return ap.parse_args()
 
@@ -218,6 +220,24 @@ class ClockSampler:
                 "reasons": sorted({x for r in self.rows for x in r[3]})}
 
 
+def find_real_indexlr():
+    """a btllib `indexlr` that is neither this repo's drop-in nor the oracle's CLI (prefer it as the CPU
+    baseline and byte-compare against it when one exists; tests/test_real_indexlr.py does the comparison)"""
+    import glob
+    import shutil
+    ours = {os.path.realpath(os.path.join(ROOT, "bin", "indexlr")), os.path.realpath(os.path.join(ROOT, "oracle", "_build", "mxo_indexlr"))}
+    for c in [shutil.which("indexlr")] + glob.glob(os.path.join(ROOT, "baseline", "_ref", "**", "indexlr"), recursive=True):
+        if c and os.path.isfile(c) and os.access(c, os.X_OK) and os.path.realpath(c) not in ours:
+            try:
+                head = open(c, "rb").read(4096)
+            except OSError:
+                continue
+            if b"ntjoin_b200" in head or b"mxo_indexlr" in head:
+                continue
+            return c
+    return None
+
+
 # ------------------------------------------------------------------------------------ CPU arm
 def cpu_reference_run(spec, args, steps, warmup, sample_bases=None, with_t4=False):
     """The reference path on host cores: oracle sketch (one record per worker thread, like indexlr -t)
@@ -245,7 +265,9 @@ def cpu_reference_run(spec, args, steps, warmup, sample_bases=None, with_t4=Fals
             times.append(dt)
     total = len(asms) * sample_bases
     sec = float(np.mean(times))
+    real = find_real_indexlr()
     out = {"value": total / sec / 1e9, "unit": "Gbases/s", "cores": cores, "kind": "port",
+           "real_indexlr": real or "none found (probed: PATH, baseline/_ref/); the oracle restatement stands in",
            "sample": f"{sample_bases} bp reference + derived target (same generator as the workload), k={K} w={W}, "
                      f"{steps} step(s) after {warmup} warm-up, oracle/mxo.c with {cores} threads"}
     if with_t4:
@@ -278,7 +300,8 @@ def run_reference_arm(args, spec):
 
 # ------------------------------------------------------------------------------------ the bound that actually binds
 ALU_OPS_PER_BASE = {"cand31_kernel": 9.1,      # ALU-pipe instructions per base, counted in the SASS
-                    "scan_bs2_kernel": 4.1}    # (LOP3 + SHF + PRMT + IADD3 + ISETP per 16-step group) / 512 positions, incl. the k-1 halo
+                    "scan_bs2_kernel": 3.9}    # ALU-pipe instructions of the 16-step loop body / 512 positions (tests/test_sass_counts.py);
+                                               # the k-1 halo of every stream adds (k - 1) / L on top
 
 
 def alu_roofline(bases_per_launch, launch_ms, kernel="scan_bs2_kernel"):
@@ -345,6 +368,104 @@ def run_sweep(args, spec, eng, shards, total_bases):
     print(json.dumps({"metric": "Gbases/s sketched+filtered, k x w sweep", "unit": "Gbases/s", "n_gpus": 1, "steps": args.steps,
                       "config": {"workload": spec["name"], "bases_per_step": total_bases}, "roofline_peak_gbs": peak,
                       "roofline_kernel": "the candidate kernel of each point (scan_bs2_kernel for k in {24, 32, 40})", "sweep": points}), flush=True)
+
+
+# ------------------------------------------------------------------------------------ T3: the file seam
+def run_t3(args, eng, spec, dev):
+    """what a user of `bin/with-b200` gets.  Page-cache-warm FASTA files -> `<fasta>.k.w.tsv` on disk
+    (Engine.sketch_file + write_tsv = bin/indexlr, seams S1/S2) -> the drop-in read_minimizers / filter_minimizers /
+    build_graph (seam S3: Python dict / list / graph objects exactly as bin/ntjoin_utils.py returns them).  Beside it,
+    on the same files and host: the CPU sketch (oracle/mxo_indexlr.c; the reference's own is an un-vendored binary) with
+    the reference's default 4 threads (ntJoin:48) and with all cores, then steps 2-3 in plain Python as the reference
+    does them (tests/ref_py.py follows bin/ntjoin_utils.py:167-193, :152-165, :83-141 statement by statement; the
+    reference itself is not on the GPU box).  A bounded workload (--t3-bases per assembly): the Python side costs
+    ~3 us per minimizer."""
+    import shutil
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    import ref_py
+    from ntjoin_b200 import dropin
+    oracle_lib.build()
+    small = dict(spec)
+    small["G"] = int(args.t3_bases)
+    small["hi"] = min(spec["hi"], max(spec["lo"] * 2, small["G"] // 16))
+    asms = gen_assemblies_gpu(small, False, dev)
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    tmp = tempfile.mkdtemp(prefix="mxe_t3_", dir=base)
+    out = {"workload": f"{len(asms)} assemblies x {small['G']} bp (same generator as the headline workload), k={K} w={W}, FASTA in {base or 'tmp'} (page-cache warm)"}
+    try:
+        paths = []
+        for i, (seq, offs) in enumerate(asms):
+            host = seq.cpu().numpy()
+            path = os.path.join(tmp, ("ref%d.fa" % i) if i + 1 < len(asms) else "target.fa")
+            with open(path, "wb") as fh:
+                for c in range(len(offs) - 1):
+                    fh.write(b">ctg%06d\n" % c)
+                    fh.write(host[int(offs[c]):int(offs[c + 1])].tobytes())
+                    fh.write(b"\n")
+            paths.append(path)
+            del host
+        del asms
+        total = small["G"] * len(paths)
+        weights = {p + f".k{K}.w{W}.tsv": w for p, w in zip(paths, WEIGHTS)}
+        mod = dropin.install(ref_py.as_module())
+        dropin._ENGINE = eng                                   # the bench's engine serves the drop-in layer
+
+        def engine_run():
+            t = {}
+            t0 = time.perf_counter()
+            for p in paths:
+                sk = eng.sketch_file(p, K, W)
+                sk.write_tsv(p + f".k{K}.w{W}.tsv", pos=True, strand=False, seq=True)
+                sk.close()
+            t["fasta_to_tsv_s"] = time.perf_counter() - t0
+            t1 = time.perf_counter()
+            list_mx_info, list_mxs = {}, {}
+            for p in paths:
+                tsv = p + f".k{K}.w{W}.tsv"
+                list_mx_info[tsv], list_mxs[tsv] = mod.read_minimizers(tsv)
+            list_mxs = mod.filter_minimizers(list_mxs)
+            g = mod.build_graph(list_mxs, weights)
+            t["tsv_to_graph_objects_s"] = time.perf_counter() - t1
+            t["total_s"] = time.perf_counter() - t0
+            t["edges"] = len(g.es)
+            return t
+
+        engine_run()                                            # warm-up (page cache, allocations)
+        t = engine_run()
+        out["engine"] = dict(t, gbases_per_s=total / t["total_s"] / 1e9)
+        cores = os.cpu_count() or 1
+        baseline = {}
+        for label, threads in (("t4", 4), ("all", cores)):
+            t0 = time.perf_counter()
+            for p in paths:
+                subprocess.check_call([oracle_lib.CLI, "--seq", "--long", "--pos", "-k", str(K), "-w", str(W), "-t", str(threads),
+                                       "-o", p + ".cpu.tsv", p])
+            baseline[f"sketch_{label}_s"] = time.perf_counter() - t0
+            baseline[f"sketch_{label}_threads"] = threads
+        orig = ref_py.as_module()
+        t0 = time.perf_counter()
+        lm = {}
+        for p in paths:
+            _info, lm[p + ".cpu.tsv"] = orig.read_minimizers(p + ".cpu.tsv")
+        lm = orig.filter_minimizers(lm)
+        gb = orig.build_graph(lm, {p + ".cpu.tsv": w for p, w in zip(paths, WEIGHTS)})
+        baseline["python_steps23_s"] = time.perf_counter() - t0
+        baseline["edges"] = len(gb.es)
+        baseline["total_t4_s"] = baseline["sketch_t4_s"] + baseline["python_steps23_s"]
+        baseline["total_all_s"] = baseline["sketch_all_s"] + baseline["python_steps23_s"]
+        baseline["gbases_per_s_t4"] = total / baseline["total_t4_s"] / 1e9
+        baseline["kind"] = "port (oracle/mxo_indexlr.c + tests/ref_py.py): the reference's own step 1 is an un-vendored binary, its bin/ is not on this box"
+        out["cpu"] = baseline
+        out["same_edge_count"] = baseline["edges"] == t["edges"]
+        out["speedup_vs_t4"] = baseline["total_t4_s"] / t["total_s"]
+        out["speedup_vs_all_cores"] = baseline["total_all_s"] / t["total_s"]
+    finally:
+        dropin._ENGINE = None
+        dropin._LAST_FILTER = None
+        shutil.rmtree(tmp, ignore_errors=True)
+    return out
 
 
 # ------------------------------------------------------------------------------------ N > 1 vs N = 1
@@ -572,6 +693,8 @@ def main():
     kernel_times = {kname: eng.timing(span) for kname, span in (("pack2_kernel", "k_pack2"), ("scan_bs2_kernel", "k_scan"))}
     if world == 1 or p2p is not None:
         phases.update({nm: eng.timing(nm)[0] / args.steps for nm in ("p2p_scatter", "p2p_buckets", "p2p_adjacency", "p2p_edges", "p2p_finish")})
+        if p2p is not None:      # of which: waiting at the device-side barriers (sketch-time skew between ranks lands in wait0)
+            phases.update({nm: eng.timing(nm)[0] / args.steps for nm in ("p2p_wait0", "p2p_wait1", "p2p_wait2", "p2p_wait3", "p2p_wait4")})
     elif comm:
         names = ("a2a_partition", "a2a_mark", "a2a_sightings", "a2a_finish") if dist_mode == "alltoall" else \
             ("dist_mark", "dist_adjacency", "dist_edges", "dist_finish")
@@ -663,6 +786,13 @@ def main():
         if not args.no_cpu_baseline:
             cb, _ = cpu_reference_run(spec, args, 1, 1, with_t4=True)
             line["cpu_baseline"] = cb
+        if world == 1 and not args.no_t3 and not args.no_cpu_baseline:
+            try:
+                del shards, combo, host
+                torch.cuda.empty_cache()
+                line["t3"] = run_t3(args, eng, spec, dev)
+            except Exception as exc:           # reporting only: never lose the bench line over it
+                line["t3"] = {"error": repr(exc)}
         print(json.dumps(line), flush=True)
         if parity is not None and not parity["vs_single_gpu"]:
             print("bench.py: the merged multi-GPU result differs from the single-GPU result: " + ", ".join(parity["mismatch"]), file=sys.stderr, flush=True)

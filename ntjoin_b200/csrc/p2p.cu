@@ -722,6 +722,8 @@ static int p2p_barrier_signal(mxe_p2p* X, int bar)
 static int p2p_barrier_wait(mxe_p2p* X, int bar)
 {
     if (X->Y.world == 1) return MXE_OK;
+    static const char* const names[P2P_N_BARRIERS] = {"p2p_wait0", "p2p_wait1", "p2p_wait2", "p2p_wait3", "p2p_wait4", "p2p_wait5", "p2p_wait6", "p2p_wait7"};
+    Span sp(X->eng, names[bar]);        // time spent waiting for the slowest peer (timing option only)
     MXE_LAUNCH(X->eng, p2p_wait_kernel, 1, 32, 0, X->P, X->Y, bar, X->epoch);
     return MXE_OK;
 }

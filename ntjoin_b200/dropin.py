@@ -62,6 +62,7 @@ class MxLists(list):
     _mask = None        # bool mask over the sketch selecting the entries present in these lists
     _result = None      # FilterResult shared by all assemblies after filter_minimizers
     _asm_index = None
+    _strs = None        # decimal strings of every minimizer of the sketch (made once, in read_minimizers)
 
     def __reduce__(self):
         # The reference keeps these lists in Ntjoin.list_mxs and pickles `self` into multiprocessing.Pool workers when
@@ -97,10 +98,11 @@ def _filter_once(eng, vals):
     return res
 
 
-def _lists_from(sk, mask):
+def _lists_from(sk, mask, strs=None):
     """per-record lists (records with at least one minimizer in the TSV) of decimal strings"""
     oh, cg = sk.out_hash, sk.contig
-    strs = np.array([str(h) for h in oh.tolist()], dtype=object)
+    if strs is None:
+        strs = np.array([str(h) for h in oh.tolist()], dtype=object)
     present = np.unique(cg)
     bounds = np.searchsorted(cg, np.arange(len(sk.names) + 1))
     out = MxLists()
@@ -124,7 +126,7 @@ def make_read_minimizers(original):
         names = sk.names
         cg, ps = sk.contig[uniq].tolist(), sk.pos[uniq].tolist()
         mx_info = {h: (names[c], p) for h, c, p in zip(strs[uniq].tolist(), cg, ps)}
-        mxs._sketch, mxs._mask = sk, uniq
+        mxs._sketch, mxs._mask, mxs._strs = sk, uniq, strs
         res.close()
         return mx_info, mxs
     read_minimizers.__doc__ = original.__doc__
@@ -143,8 +145,8 @@ def make_filter_minimizers(original):
         out = {}
         for a, (asm, v) in enumerate(list_mxs.items()):
             keep = res.keep[a]
-            lists, _ = _lists_from(v._sketch, keep)
-            lists._sketch, lists._mask, lists._asm_index = v._sketch, keep, a
+            lists, _ = _lists_from(v._sketch, keep, v._strs)
+            lists._sketch, lists._mask, lists._asm_index, lists._strs = v._sketch, keep, a, v._strs
             out[asm] = lists
         return out
     filter_minimizers.__doc__ = original.__doc__

@@ -16,8 +16,8 @@ FMA = ("IMAD", "FFMA", "FMUL")
 LSU = ("LDS", "STS", "LDG", "STG", "LD", "ST", "ATOMS", "RED")
 
 
-def main_loop(sass):
-    """instructions of the innermost loop that holds the sixteen LDS.64 table lookups (one group of 16 bases)"""
+def main_loop(sass, outermost=False):
+    """instructions of the innermost (or outermost) loop that holds sixteen LDS.64 (one group of 16 bases / steps)"""
     ins = []
     for line in sass.splitlines():
         m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", line)
@@ -28,7 +28,7 @@ def main_loop(sass):
         m = re.search(r"BRA\s+(?:`\(\S+\)|0x([0-9a-f]+))", text)
         if m and m.group(1) and int(m.group(1), 16) < addr:
             body = [t for a, t in ins if int(m.group(1), 16) <= a <= addr]
-            if sum("LDS.64" in t for t in body) == 16 and (best is None or len(body) < len(best)):
+            if sum("LDS.64" in t for t in body) == 16 and (best is None or (len(body) > len(best) if outermost else len(body) < len(best))):
                 best = body
     return best
 
@@ -52,6 +52,30 @@ def test_cand31_instruction_mix_per_base():
     lsu = sum(o in LSU for o in ops) / 16.0
     # 16 bases per trip: the roll is 5 ALU ops per base (2 rotations x 2 + ... ), test + accumulate on the FMA pipe
     assert sum(t.startswith("LDS.64") or " LDS.64" in t for t in body) == 16
-    assert abs(alu - bench.ALU_OPS_PER_BASE) <= 0.25, (alu, fma, lsu)
+    assert abs(alu - bench.ALU_OPS_PER_BASE["cand31_kernel"]) <= 0.25, (alu, fma, lsu)
     assert 4.0 <= fma <= 6.0 and 1.0 <= lsu <= 2.0, (alu, fma, lsu)
     assert len(ops) / 16.0 < 17.5            # whole trip, including loop overhead
+
+
+@pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump not on PATH")
+def test_scan_bs2_instruction_mix_per_base():
+    """scan_bs2_kernel (k = 32): the loop over groups of 16 steps serves 16 x 32 = 512 positions per trip.  One LOP3 per
+    state bit (62) + the base combos (10) + the 12-bit threshold adder (35) per step, i.e. ~113 LOP3 per 32 positions;
+    a compiler that re-derives the combos inside the state updates costs 96 instead of 72 (scan_kernels.cuh)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    out = subprocess.run(["cuobjdump", "-sass", ntjoin_b200.library_path()], capture_output=True, text=True, check=True).stdout
+    fn = [c for c in out.split("Function : ") if c.startswith("_ZN3mxe15scan_bs2_kernelILi1E")]
+    assert len(fn) == 1, "scan_bs2_kernel<1, ...> (k = 32) not found in libmxe.so"
+    assert "LDG.E.EFL2.256" in fn[0] or ".256" in fn[0], "the plane rows are read with 256-bit loads (sm_100)"
+    body = main_loop(fn[0], outermost=True)
+    assert body is not None, "group loop with 16 LDS.64 (the planes that leave the k-mer) not found"
+    op = lambda t: re.sub(r"^@!?U?P\d+\s+", "", t).split()[0].split(".")[0]      # noqa: E731
+    ops = [op(t) for t in body]
+    alu = sum(o in ALU for o in ops) / 512.0
+    lop3 = sum(o == "LOP3" for o in ops) / 16.0
+    assert abs(alu - bench.ALU_OPS_PER_BASE["scan_bs2_kernel"]) <= 0.2, alu
+    assert 105 <= lop3 <= 120, lop3            # per step of 32 positions
+    assert len(ops) / 512.0 < 4.4              # whole trip
