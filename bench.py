@@ -327,9 +327,10 @@ def alu_roofline(bases_per_launch, launch_ms, kernel="scan_bs2_kernel"):
 
 
 # ------------------------------------------------------------------------------------ k x w sweep (configs[4])
-def run_sweep(args, spec, eng, shards, total_bases):
-    """Device-resident step time and roofline fraction of the dominant sketch kernel per (k, w) point."""
-    import torch
+def run_sweep(args, spec, eng, world, rank, step_device, timed, stats, my_bases, total_bases, n_asm, dist_mode):
+    """configs[4]: k in {24, 32, 40} x w in {250, 500, 1000, 5000}.  Per point the device-resident step (whole job, all
+    ranks; max over ranks like the headline number) and the roofline fractions of the sketch at its three scopes."""
+    global K, W
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -339,35 +340,35 @@ def run_sweep(args, spec, eng, shards, total_bases):
     points = []
     for k in (24, 32, 40):
         for w in (250, 500, 1000, 5000):
-            def step():
-                sks = [eng.sketch_device(s.data_ptr(), o, k, w) for s, o, _ in shards]
-                res = eng.filter_and_edges(sks, WEIGHTS)
-                out = ([sk.n for sk in sks],) + tuple(res.counts())
-                for sk in sks:
-                    sk.close()
-                res.close()
-                return out
+            K, W = k, w
             for _ in range(max(1, min(args.warmup, 2))):
-                step()
+                step_device()
             eng.timing_reset()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for _ in range(args.steps):
-                n_mx, _n, n_v, n_e = step()
-            torch.cuda.synchronize()
-            sec = (time.perf_counter() - t0) / args.steps
-            t_cand, n_cand = eng.timing("k_scan")
-            if not n_cand:
-                t_cand, n_cand = eng.timing("cand")
-            cand_ms = t_cand / max(1, n_cand)
-            per_launch = (total_bases + 16.0 * sum(n_mx)) / len(shards)
-            achieved = per_launch / (cand_ms * 1e-3) / 1e9
-            points.append({"k": k, "w": w, "value": total_bases / sec / 1e9, "ms_per_step": sec * 1e3, "cand_ms": cand_ms,
-                           "roofline_frac": achieved / peak, "minimizers": n_mx, "vertices": n_v, "edges": n_e,
-                           "sketch_ms": eng.timing("sketch")[0] / args.steps, "filter_ms": eng.timing("filter")[0] / args.steps})
-    print(json.dumps({"metric": "Gbases/s sketched+filtered, k x w sweep", "unit": "Gbases/s", "n_gpus": 1, "steps": args.steps,
-                      "config": {"workload": spec["name"], "bases_per_step": total_bases}, "roofline_peak_gbs": peak,
-                      "roofline_kernel": "the candidate kernel of each point (scan_bs2_kernel for k in {24, 32, 40})", "sweep": points}), flush=True)
+            sec = timed(step_device, args.steps) / args.steps
+            if rank != 0:
+                continue
+            algo = (my_bases + 16.0 * sum(stats["n_mx"])) / n_asm          # algorithmic bytes per assembly of this rank
+            kt = {}
+            for name, span in (("pack2_kernel", "k_pack2"), ("scan_bs2_kernel", "k_scan")):
+                t_k, n_k = eng.timing(span)
+                if n_k:
+                    kt[name] = t_k / n_k
+            t_sketch, n_sk = eng.timing("sketch")
+            t_pack, t_cand = eng.timing("pack")[0], eng.timing("cand")[0]
+            asm_per_call = n_asm if n_sk and n_sk <= args.steps * 1.5 else 1       # one sketch call may cover all assemblies
+            per_asm = lambda t: t / args.steps / n_asm                              # noqa: E731
+            dom = max(kt, key=kt.get) if kt else None
+            points.append({"k": k, "w": w, "value": total_bases / sec / 1e9, "ms_per_step": sec * 1e3,
+                           "kernel_ms": {n: v / asm_per_call for n, v in kt.items()},
+                           "roofline_kernel": dom, "roofline_frac": algo * asm_per_call / (kt[dom] * 1e-3) / 1e9 / peak if dom else None,
+                           "pack_cand_frac": algo / (per_asm(t_pack + t_cand) * 1e-3) / 1e9 / peak if t_pack + t_cand > 0 else None,
+                           "sketch_frac": algo / (per_asm(t_sketch) * 1e-3) / 1e9 / peak if t_sketch > 0 else None,
+                           "minimizers_rank0": stats["n_mx"], "vertices_rank0": stats["vertices"], "edges_rank0": stats["edges"],
+                           "sketch_ms": t_sketch / args.steps, "filter_ms": eng.timing("filter")[0] / args.steps})
+    if rank == 0:
+        print(json.dumps({"metric": "Gbases/s sketched+filtered, k x w sweep", "unit": "Gbases/s", "n_gpus": world, "steps": args.steps,
+                          "config": {"workload": spec["name"], "bases_per_step": total_bases, "dist_mode": dist_mode if world > 1 else None},
+                          "roofline_peak_gbs": peak, "sweep": points}), flush=True)
 
 
 # ------------------------------------------------------------------------------------ T3: the file seam
@@ -541,6 +542,9 @@ def main():
     dev = torch.device("cuda", local)
 
     eng = ntjoin_b200.Engine(local, timing=True)
+    fine = os.environ.get("MXE_TIMING_FINE", "0") not in ("", "0")       # per-kernel times of steps 2-3 (costs two event records per launch)
+    if fine:
+        eng.set_option("timing", 2)
     stream = torch.cuda.Stream()          # one real stream for the engine, the torch ops and the timing events
     torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
@@ -551,7 +555,7 @@ def main():
     stages = (eng.a2a_stages() if dist_mode == "alltoall" else eng.dist_stages()) if world > 1 and dist_mode != "p2p" else None
     p2p = None
     if world > 1 and dist_mode == "p2p":
-        cap_total = int((len(WEIGHTS)) * spec["G"] * 2.0 / (W + 1) * 1.15) + 100_000
+        cap_total = int((len(WEIGHTS)) * spec["G"] * 2.0 / ((250 if args.sweep else W) + 1) * 1.15) + 100_000
         p2p = eng.p2p(rank, world, cap_total, n_asm_max=max(4, len(WEIGHTS)))
         handles = [None] * world
         dist.all_gather_object(handles, p2p.handle())          # 64 bytes per rank, once
@@ -604,11 +608,6 @@ def main():
     n_asm = len(shards)
     stats = {}
 
-    if args.sweep:
-        run_sweep(args, spec, eng, shards, total_bases)
-        eng.close()
-        return
-
     def gather_and_filter(sks):
         if world == 1:
             res = eng.filter_and_edges(sks, WEIGHTS)
@@ -625,9 +624,10 @@ def main():
 
     # one sketch call for all assemblies of the rank while their valid k-mer ordinals fit 32 bits (the window selection
     # has a 32-bit variant: measured 1.13 vs 1.57 ms per step on 6 Gbp), else one call per assembly
-    use_multi = my_bases + (sum(len(o) for _, o, _ in shards) + 8) * W < 0xF0000000
+    n_records = sum(len(o) for _, o, _ in shards)
 
     def step_device():
+        use_multi = my_bases + (n_records + 8) * W < 0xF0000000
         if use_multi:
             parent, sks = eng.sketch_device_multi(combo.data_ptr(), [o for _, o, _ in shards], K, W, starts=starts)
         else:
@@ -674,6 +674,17 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    if args.sweep:
+        run_sweep(args, spec, eng, world, rank, step_device, timed, stats, my_bases, total_bases, n_asm, dist_mode)
+        if p2p is not None:
+            dist.barrier()
+            p2p.close()
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        eng.close()
+        return
+
     for _ in range(args.warmup):
         step_device()
     eng.timing_reset()
@@ -693,8 +704,14 @@ def main():
     kernel_times = {kname: eng.timing(span) for kname, span in (("pack2_kernel", "k_pack2"), ("scan_bs2_kernel", "k_scan"))}
     if world == 1 or p2p is not None:
         phases.update({nm: eng.timing(nm)[0] / args.steps for nm in ("p2p_scatter", "p2p_buckets", "p2p_adjacency", "p2p_edges", "p2p_finish")})
-        if p2p is not None:      # of which: waiting at the device-side barriers (sketch-time skew between ranks lands in wait0)
-            phases.update({nm: eng.timing(nm)[0] / args.steps for nm in ("p2p_wait0", "p2p_wait1", "p2p_wait2", "p2p_wait3", "p2p_wait4")})
+        if fine:                 # every kernel of steps 2-3, and the waits at the device-side barriers (sketch-time skew lands in wait0)
+            for nm in ("p2p_wait0", "p2p_wait1", "p2p_wait2", "p2p_wait3", "p2p_wait4", "k_p2p_scatter_kernel", "k_p2p_push_counts_kernel",
+                       "k_p2p_bucket_kernel", "k_p2p_vbase_kernel", "k_p2p_flags_kernel", "k_p2p_compact_kernel", "k_p2p_succ_kernel",
+                       "k_p2p_sight_kernel", "k_p2p_edge_owner_kernel", "k_p2p_table_kernel", "k_p2p_rec_owner_kernel", "k_p2p_clear_tail_kernel",
+                       "k_p2p_vertices_kernel", "k_p2p_first_count_kernel", "k_p2p_first_start_kernel", "k_p2p_edge_emit_kernel", "k_p2p_rec_emit_kernel"):
+                t_k = eng.timing(nm)[0]
+                if t_k:
+                    phases[nm] = t_k / args.steps
     elif comm:
         names = ("a2a_partition", "a2a_mark", "a2a_sightings", "a2a_finish") if dist_mode == "alltoall" else \
             ("dist_mark", "dist_adjacency", "dist_edges", "dist_finish")

@@ -199,7 +199,7 @@ int mxe_set_option(mxe_t* e, const char* name, double value)
     else if (!strcmp(name, "filter_variant")) e->filter_variant = (int)value;
     else if (!strcmp(name, "fma_offload")) e->fma_offload = value != 0;
     else if (!strcmp(name, "select_narrow")) e->select_narrow = value != 0;
-    else if (!strcmp(name, "timing")) e->timing = value != 0;
+    else if (!strcmp(name, "timing")) { e->timing = value != 0; e->timing_fine = value >= 2; }
     else { set_error("unknown option %s", name); return MXE_ERR_ARG; }
     return MXE_OK;
 }

@@ -74,6 +74,7 @@ struct Engine {
     int filter_variant = 1;  // steps 2-3: 0 = global radix sort (filter.cu), 1 = hash buckets in shared memory (p2p.cu)
     int sort_bits = 0;       // steps 2-3: top hash bits covered by the radix sort (24/32/40; 0 = by size), rest by the fix-up
     bool timing = false;
+    bool timing_fine = false;   // also time every kernel of steps 2-3 and the barrier waits (option timing = 2)
     // accounting
     uint64_t launches = 0;
     std::map<std::string, PhaseTimer> timers;
@@ -87,7 +88,8 @@ struct Engine {
 // RAII span: records CUDA events on the engine stream around a group of launches when timing is on.
 struct Span {
     Engine* e; const char* name; cudaEvent_t a = nullptr; uint64_t l0;
-    Span(Engine* e_, const char* n) : e(e_), name(n), l0(e_->launches) { if (e->timing) e->span_begin(name, &a); }
+    static bool fine(const char* n) { return (n[0] == 'k' && n[1] == '_' && n[2] == 'p' && n[3] == '2') || (n[0] == 'p' && n[1] == '2' && n[2] == 'p' && n[3] == '_' && n[4] == 'w'); }
+    Span(Engine* e_, const char* n) : e(e_), name(n), l0(e_->launches) { if (e->timing && (e->timing_fine || !fine(n))) e->span_begin(name, &a); }
     ~Span() { if (a) e->span_end(name, a, e->launches - l0); }
 };
 

@@ -55,7 +55,8 @@ struct P2PLayout {
     uint64_t L_cap;                        // minimizers of one rank, all assemblies
     uint64_t nv_cap;                       // vertices of one owner
     // byte offsets inside every rank's workspace
-    uint64_t off_flags, off_err, off_counts, off_rec_cnt, off_nkeep, off_rec, off_mk, off_succ, off_vgid, off_pred, off_cnt2, off_rec2, bytes;
+    uint64_t off_flags, off_err, off_counts, off_rec_cnt, off_nkeep, off_rec, off_mk, off_succ, off_vgid, off_pred, off_cnt2, off_rec2, off_cnt1, off_seg1, bytes;
+    uint64_t cap1;                         // minimizer records per (owner, source) segment (world > 1)
     uint64_t cap2;                         // sighting records per (owner, source) segment (world > 1)
 };
 
@@ -128,6 +129,97 @@ __global__ void __launch_bounds__(256) p2p_push_counts_kernel(const uint32_t* __
     }
 }
 
+// ---------------------------------------------------------------- CTA-staged appends to peer segments (world > 1)
+// A remote store is a NVLink packet: 4- or 16-byte stores to random addresses of a peer cost ~0.1 us each and, over a
+// window of hundreds of MB, thrash the TLB of the peer mapping (measured: 45 ms per step at 55 M records capacity).
+// So nothing is scattered remotely: every CTA groups the records of its threads by destination rank in shared memory,
+// reserves one contiguous range per destination in that rank's segment [source] (cursor of the SOURCE: no remote
+// atomics) and copies each range with consecutive threads on consecutive 8-byte words.
+struct CtaAppendState { uint32_t cnt[P2P_MAX_WORLD], off[P2P_MAX_WORLD + 1], base[P2P_MAX_WORLD]; };
+
+template <int WORDS, int SLOTS>
+__device__ __forceinline__ void cta_append(CtaAppendState& sh, uint64_t* stage, const int (&dest)[SLOTS], const uint64_t (&rec)[SLOTS][WORDS],
+                                           uint32_t* __restrict__ cur, const PeerPtrs& P, uint64_t off_seg, uint64_t cap, const P2PLayout& Y, uint32_t err_code)
+{
+    if (threadIdx.x < P2P_MAX_WORLD) sh.cnt[threadIdx.x] = 0u;
+    __syncthreads();
+    uint32_t local[SLOTS];
+#pragma unroll
+    for (int q = 0; q < SLOTS; q++) local[q] = dest[q] >= 0 ? atomicAdd(&sh.cnt[dest[q]], 1u) : 0u;
+    __syncthreads();
+    if ((int)threadIdx.x < Y.world) sh.base[threadIdx.x] = sh.cnt[threadIdx.x] ? atomicAdd(&cur[threadIdx.x], sh.cnt[threadIdx.x]) : 0u;
+    if (threadIdx.x == 0) {
+        uint32_t at = 0;
+        for (int d = 0; d < Y.world; d++) { sh.off[d] = at; at += sh.cnt[d]; }
+        sh.off[Y.world] = at;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < SLOTS; q++)
+        if (dest[q] >= 0) {
+            uint64_t* dstw = stage + (size_t)(sh.off[dest[q]] + local[q]) * WORDS;
+#pragma unroll
+            for (int w = 0; w < WORDS; w++) dstw[w] = rec[q][w];
+        }
+    __syncthreads();
+    const uint32_t total = sh.off[Y.world] * WORDS;
+    for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+        const uint32_t r = i / WORDS, w = i - r * WORDS;
+        int d = 0;
+        while (d + 1 < Y.world && r >= sh.off[d + 1]) d++;
+        const uint64_t pos = (uint64_t)sh.base[d] + (r - sh.off[d]);
+        if (pos < cap) reinterpret_cast<uint64_t*>(P.base[d] + off_seg)[((uint64_t)Y.rank * cap + pos) * WORDS + w] = stage[i];
+        else *reinterpret_cast<uint32_t*>(P.base[Y.rank] + Y.off_err) = err_code;
+    }
+}
+
+// stage 1 (world > 1): own minimizers -> segment [this rank] of the owner of their bucket
+__global__ void __launch_bounds__(256) p2p_scatter_seg_kernel(PtrTab H, LocalSlices S, uint64_t L, PeerPtrs P, P2PLayout Y, uint32_t* __restrict__ cur1)
+{
+    __shared__ CtaAppendState sh;
+    __shared__ uint64_t stage[256 * 2];
+    const uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int dest[1] = {-1};
+    uint64_t rec[1][2] = {{0, 0}};
+    if (l < L) {
+        const int a = p2p_slice_of(S, l);
+        const uint64_t key = reinterpret_cast<const uint64_t*>(H.p[a])[l - S.lofs[a]];
+        dest[0] = (int)p2p_owner((uint32_t)(key >> (64 - Y.B)), Y.world, Y.B);
+        rec[0][0] = key;
+        rec[0][1] = ((uint64_t)a << 40) | ((uint64_t)Y.rank << 32) | l;
+    }
+    cta_append<2, 1>(sh, stage, dest, rec, cur1, P, Y.off_seg1, Y.cap1, Y, 4u);
+}
+
+// segment counts to the owners; this rank's minimizer counts to everybody
+__global__ void p2p_push_cnt1_kernel(const uint32_t* __restrict__ cur1, AsmCounts C, PeerPtrs P, P2PLayout Y)
+{
+    if ((int)threadIdx.x < Y.world) {
+        const uint32_t c = cur1[threadIdx.x] < Y.cap1 ? cur1[threadIdx.x] : (uint32_t)Y.cap1;
+        reinterpret_cast<uint32_t*>(P.base[threadIdx.x] + Y.off_cnt1)[Y.rank] = c;
+    }
+    if ((int)threadIdx.x < Y.world * C.n_asm) {
+        const int p = threadIdx.x / C.n_asm, a = threadIdx.x % C.n_asm;
+        reinterpret_cast<uint64_t*>(P.base[p] + Y.off_counts)[Y.rank * Y.n_asm_max + a] = C.n[a];
+    }
+}
+
+// owner: the received records of every source -> bucket sub-slots (local stores, local atomics)
+__global__ void __launch_bounds__(256) p2p_partition_kernel(PeerPtrs P, P2PLayout Y)
+{
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t seg = (uint32_t)(idx / Y.cap1);
+    if (seg >= (uint32_t)Y.world) return;
+    const uint64_t i = idx - (uint64_t)seg * Y.cap1;
+    char* me = P.base[Y.rank];
+    if (i >= reinterpret_cast<const uint32_t*>(me + Y.off_cnt1)[seg]) return;
+    const ulonglong2 r = reinterpret_cast<const ulonglong2*>(me + Y.off_seg1)[idx];
+    const uint32_t bl = (uint32_t)(r.x >> (64 - Y.B)) - Y.fb[Y.rank];
+    const uint32_t slot = atomicAdd(reinterpret_cast<uint32_t*>(me + Y.off_rec_cnt) + (uint64_t)bl * Y.world + seg, 1u);
+    if (slot >= Y.cap_sub) { *reinterpret_cast<uint32_t*>(me + Y.off_err) = 1u; return; }
+    reinterpret_cast<ulonglong2*>(me + Y.off_rec)[((uint64_t)bl * Y.world + seg) * Y.cap_sub + slot] = r;
+}
+
 // ---------------------------------------------------------------- stage 2: one CTA per owned bucket
 __device__ __forceinline__ bool rec_greater(uint64_t ka, uint64_t ta, uint64_t kb, uint64_t tb) { return ka > kb || (ka == kb && ta > tb); }
 
@@ -150,7 +242,7 @@ __global__ void __launch_bounds__(P2P_BK_THREADS) p2p_bucket_kernel(PeerPtrs P, 
     P2PRecord* region = reinterpret_cast<P2PRecord*>(me + Y.off_rec) + (uint64_t)bl * Y.world * Y.cap_sub;
     if (threadIdx.x == 0) {
         uint32_t at = 0;
-        for (int s = 0; s < Y.world; s++) { soff[s] = at; at += cnt[s]; }
+        for (int s = 0; s < Y.world; s++) { soff[s] = at; at += cnt[s] < Y.cap_sub ? cnt[s] : Y.cap_sub; }
         soff[Y.world] = at;
     }
     dfill[threadIdx.x] = 0u;
@@ -533,43 +625,28 @@ __global__ void __launch_bounds__(256) p2p_sight_kernel(const uint32_t* __restri
                                                          LocalSlices S, PtrTab H, PtrTab Ctg, PeerPtrs P, P2PLayout Y, HomeTabs T,
                                                          uint32_t* __restrict__ cur2)
 {
-    __shared__ uint32_t scount[P2P_MAX_WORLD];
-    __shared__ uint32_t sbase[P2P_MAX_WORLD];
+    __shared__ CtaAppendState sh;
+    __shared__ uint64_t stage[256 * 2 * 3];
     const uint64_t n_keep = kprefix[L];
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (threadIdx.x < P2P_MAX_WORLD) scount[threadIdx.x] = 0u;
-    __syncthreads();
-    bool f = false;
-    uint32_t v = 0, x = 0;
-    uint64_t hv = 0, hx = 0;
-    int a = 0, ov = 0, ox = 0;
-    uint32_t s0 = 0, s1 = 0;
+    int dest[2] = {-1, -1};
+    uint64_t rec[2][3] = {{0, 0, 0}, {0, 0, 0}};
     if (j + 1 < n_keep) {
         const uint32_t l1 = cloc[j], l2 = cloc[j + 1];
-        a = p2p_slice_of(S, l1);
+        const int a = p2p_slice_of(S, l1);
         if (a == p2p_slice_of(S, l2)) {
             const uint32_t* ctg = reinterpret_cast<const uint32_t*>(Ctg.p[a]);
-            f = ctg[l1 - S.lofs[a]] == ctg[l2 - S.lofs[a]];
-            if (f) {
+            if (ctg[l1 - S.lofs[a]] == ctg[l2 - S.lofs[a]]) {
                 const uint64_t* hs = reinterpret_cast<const uint64_t*>(H.p[a]);
-                v = cvid[j]; x = cvid[j + 1];
-                hv = hs[l1 - S.lofs[a]]; hx = hs[l2 - S.lofs[a]];
-                ov = p2p_vowner(T.vown, Y.world, v); ox = p2p_vowner(T.vown, Y.world, x);
-                s0 = atomicAdd(&scount[ov], 1u);
-                s1 = atomicAdd(&scount[ox], 1u);
+                const uint32_t v = cvid[j], x = cvid[j + 1];
+                const int ov = p2p_vowner(T.vown, Y.world, v), ox = p2p_vowner(T.vown, Y.world, x);
+                dest[0] = ov; dest[1] = ox;
+                rec[0][0] = hs[l2 - S.lofs[a]]; rec[0][1] = ((uint64_t)(v - T.vown[ov]) << 32) | x; rec[0][2] = ((uint64_t)cg[j] << 8) | ((uint64_t)a << 1);
+                rec[1][0] = hs[l1 - S.lofs[a]]; rec[1][1] = ((uint64_t)(x - T.vown[ox]) << 32) | v; rec[1][2] = ((uint64_t)a << 1) | 1ULL;
             }
         }
     }
-    __syncthreads();
-    if ((int)threadIdx.x < Y.world) sbase[threadIdx.x] = scount[threadIdx.x] ? atomicAdd(&cur2[threadIdx.x], scount[threadIdx.x]) : 0u;
-    __syncthreads();
-    if (!f) return;
-    const uint64_t p0 = (uint64_t)sbase[ov] + s0, p1 = (uint64_t)sbase[ox] + s1;
-    if (p0 >= Y.cap2 || p1 >= Y.cap2) { *reinterpret_cast<uint32_t*>(P.base[Y.rank] + Y.off_err) = 3u; return; }
-    uint64_t* r0 = reinterpret_cast<uint64_t*>(P.base[ov] + Y.off_rec2) + ((uint64_t)Y.rank * Y.cap2 + p0) * 3;
-    uint64_t* r1 = reinterpret_cast<uint64_t*>(P.base[ox] + Y.off_rec2) + ((uint64_t)Y.rank * Y.cap2 + p1) * 3;
-    r0[0] = hx; r0[1] = ((uint64_t)(v - T.vown[ov]) << 32) | x; r0[2] = ((uint64_t)cg[j] << 8) | ((uint64_t)a << 1);
-    r1[0] = hv; r1[1] = ((uint64_t)(x - T.vown[ox]) << 32) | v; r1[2] = ((uint64_t)a << 1) | 1ULL;
+    cta_append<3, 2>(sh, stage, dest, rec, cur2, P, Y.off_rec2, Y.cap2, Y, 3u);
 }
 
 __global__ void p2p_push_cnt2_kernel(const uint32_t* __restrict__ cur2, PeerPtrs P, P2PLayout Y)
@@ -680,8 +757,9 @@ struct mxe_p2p {
     uint32_t *cursor = nullptr, *kflag = nullptr, *cvid = nullptr, *cg = nullptr, *cloc = nullptr, *eflag = nullptr, *own = nullptr, *emask_j = nullptr;
     uint64_t *kprefix = nullptr, *uprefix = nullptr;
     uint32_t* cur2 = nullptr;
-    bool records = false;                  // world > 1: false = successor tables at the vertex owners read with peer loads (measured: 2.96 vs 3.46 ms
-                                           // per step at 2 GPUs, 1.59 vs 1.56 at 8); true (MXE_P2P_RECORDS=1) = sightings travel to the owners as records
+    uint32_t* cur1 = nullptr;
+    bool records = true;                   // world > 1: sightings travel to the owners of their vertices as records (CTA-staged, coalesced);
+                                           // false (MXE_P2P_RECORDS=0) = successor tables at the owners written / read with fine-grained peer accesses
     uint8_t *luniq = nullptr, *lkeep = nullptr;
     uint64_t* vertices = nullptr;
     HomeTabs T;
@@ -773,7 +851,28 @@ int mxe_p2p_create(mxe_t* e, int rank, int world, uint64_t cap_total, int n_asm_
     Y.off_pred = take(world > 1 ? (uint64_t)n_asm_max * Y.nv_cap * 4 : 0);
     Y.off_cnt2 = take(256);
     Y.off_rec2 = take((uint64_t)world * Y.cap2 * 24);
+    // world > 1: minimizer records arrive per source in one sequential segment (coalesced remote stores, one TLB-friendly
+    // stream per peer) and the OWNER cuts them into buckets with local stores
+    Y.cap1 = world > 1 ? (uint64_t)((double)cap_total / world / world * 1.3) + 8192 : 0;
+    Y.off_cnt1 = take(256);
+    Y.off_seg1 = take((uint64_t)world * Y.cap1 * 16);
     Y.bytes = at;
+    {
+        // Load every kernel of this file now.  With lazy module loading the FIRST launch of a kernel can wait for the
+        // device to go idle; a rank whose stream holds a spinning barrier kernel would then stall its own host thread
+        // (and, when several ranks share a process, everybody) until the barrier times out.
+        cudaFuncAttributes fa;
+        const void* kernels[] = {(const void*)p2p_signal_kernel, (const void*)p2p_wait_kernel, (const void*)p2p_scatter_kernel,
+                                 (const void*)p2p_push_counts_kernel, (const void*)p2p_scatter_seg_kernel, (const void*)p2p_push_cnt1_kernel,
+                                 (const void*)p2p_partition_kernel, (const void*)p2p_bucket_kernel, (const void*)p2p_vbase_kernel,
+                                 (const void*)p2p_vertices_kernel, (const void*)p2p_flags_kernel, (const void*)p2p_compact_kernel,
+                                 (const void*)p2p_succ_kernel, (const void*)p2p_edge_owner_kernel, (const void*)p2p_first_count_kernel,
+                                 (const void*)p2p_first_start_kernel, (const void*)p2p_clear_tail_kernel, (const void*)p2p_edge_emit_kernel,
+                                 (const void*)p2p_sight_kernel, (const void*)p2p_push_cnt2_kernel, (const void*)p2p_table_kernel,
+                                 (const void*)p2p_rec_owner_kernel, (const void*)p2p_rec_emit_kernel};
+        for (const void* k : kernels) cudaFuncGetAttributes(&fa, k);
+        cudaGetLastError();
+    }
     cudaError_t err = cudaMalloc((void**)&X->ws, Y.bytes);
     if (err != cudaSuccess) { set_error("symmetric workspace of %llu bytes: %s", (unsigned long long)Y.bytes, cudaGetErrorString(err)); delete X; return MXE_ERR_NOMEM; }
     cudaMemset(X->ws, 0, Y.off_rec);      // flags, error word, count tables
@@ -869,22 +968,31 @@ int mxe_p2p_scatter(mxe_p2p_t* X, const void* const* d_hash, const void* const* 
     X->emask_j = (uint32_t*)X->lalloc(n_own * 4);
     X->kprefix = (uint64_t*)X->lalloc((L + 2) * 8); X->uprefix = (uint64_t*)X->lalloc((n_own + 1) * 8);
     X->cur2 = (uint32_t*)X->lalloc(64 * 4);
+    X->cur1 = (uint32_t*)X->lalloc(64 * 4);
     X->T.vbase = (uint32_t*)X->lalloc((size_t)(Y.n_buckets + 1) * 4); X->T.vown = (uint32_t*)X->lalloc(64 * 4); X->T.goff = (uint64_t*)X->lalloc(64 * 8);
     if (!X->T.goff) { set_error("local workspace too small"); return MXE_ERR_INTERNAL; }
     X->epoch++;
     MXE_CUDA(cudaMemsetAsync(X->cursor, 0, (size_t)Y.n_buckets * 4, st));
     MXE_CUDA(cudaMemsetAsync(X->cur2, 0, 64 * 4, st));
+    MXE_CUDA(cudaMemsetAsync(X->cur1, 0, 64 * 4, st));
     // barrier 0: every rank has finished the previous call (its reads of peer tables included) before anybody clears
     // its own tables or writes into a peer's workspace again
     MXE_TRY(p2p_barrier_signal(X, 0));
     MXE_TRY(p2p_barrier_wait(X, 0));
     MXE_CUDA(cudaMemsetAsync(X->ws + Y.off_succ, 0, (size_t)n_asm * Y.nv_cap * 4, st));
     if (Y.world > 1) MXE_CUDA(cudaMemsetAsync(X->ws + Y.off_pred, 0, (size_t)n_asm * Y.nv_cap * 4, st));
-    if (L) MXE_LAUNCH(e, p2p_scatter_kernel, p2p_grid(L), 256, 0, X->H, X->S, L, X->P, Y, X->cursor);
     AsmCounts C;
     C.n_asm = n_asm;
     for (int a = 0; a < n_asm; a++) C.n[a] = n[a];
-    MXE_LAUNCH(e, p2p_push_counts_kernel, p2p_grid(std::max<uint64_t>(Y.n_buckets, (uint64_t)Y.world * n_asm)), 256, 0, X->cursor, C, X->P, Y);
+    if (Y.world == 1) {
+        if (L) { Span k_(e, "k_p2p_scatter_kernel"); MXE_LAUNCH(e, p2p_scatter_kernel, p2p_grid(L), 256, 0, X->H, X->S, L, X->P, Y, X->cursor); }
+        { Span k_(e, "k_p2p_push_counts_kernel"); MXE_LAUNCH(e, p2p_push_counts_kernel, p2p_grid(std::max<uint64_t>(Y.n_buckets, (uint64_t)Y.world * n_asm)), 256, 0, X->cursor, C, X->P, Y); }
+    } else {
+        // own bucket-count table is filled by the partition pass of stage 2 (local atomics): clear it now
+        MXE_CUDA(cudaMemsetAsync(X->ws + Y.off_rec_cnt, 0, (size_t)Y.nb_own_max * Y.world * 4, st));
+        if (L) { Span k_(e, "k_p2p_scatter_seg_kernel"); MXE_LAUNCH(e, p2p_scatter_seg_kernel, p2p_grid(L), 256, 0, X->H, X->S, L, X->P, Y, X->cur1); }
+        { Span k_(e, "k_p2p_push_cnt1_kernel"); MXE_LAUNCH(e, p2p_push_cnt1_kernel, 1, 512, 0, X->cur1, C, X->P, Y); }
+    }
     MXE_TRY(p2p_barrier_signal(X, 1));
     MXE_CUDA(cudaGetLastError());
     return MXE_OK;
@@ -902,7 +1010,8 @@ int mxe_p2p_buckets(mxe_p2p_t* X)
     const uint32_t nb = Y.fb[Y.rank + 1] - Y.fb[Y.rank];
     const size_t bk_smem = (size_t)4 * P2P_BK_MAX * sizeof(uint64_t);
     MXE_CUDA(cudaFuncSetAttribute(p2p_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bk_smem));
-    if (nb) MXE_LAUNCH(e, p2p_bucket_kernel, nb, P2P_BK_THREADS, bk_smem, X->P, Y, X->n_asm);
+    if (Y.world > 1) { Span k_(e, "k_p2p_partition_kernel"); MXE_LAUNCH(e, p2p_partition_kernel, p2p_grid((uint64_t)Y.world * Y.cap1), 256, 0, X->P, Y); }
+    if (nb) { Span k_(e, "k_p2p_bucket_kernel"); MXE_LAUNCH(e, p2p_bucket_kernel, nb, P2P_BK_THREADS, bk_smem, X->P, Y, X->n_asm); }
     MXE_TRY(p2p_barrier_signal(X, 2));
     MXE_CUDA(cudaGetLastError());
     return MXE_OK;
@@ -919,25 +1028,25 @@ int mxe_p2p_adjacency(mxe_p2p_t* X)
     Span part(e, "p2p_adjacency");
     const uint64_t L = X->L;
     MXE_TRY(p2p_barrier_wait(X, 2));
-    MXE_LAUNCH(e, p2p_vbase_kernel, 1, 1024, 0, X->P, Y, X->n_asm, X->T);
+    { Span k_(e, "k_p2p_vbase_kernel"); MXE_LAUNCH(e, p2p_vbase_kernel, 1, 1024, 0, X->P, Y, X->n_asm, X->T); }
     // shard outputs that do not depend on sizes read back: flags of own minimizers
     X->luniq = nullptr; X->lkeep = nullptr;
     MXE_CUDA(cudaMallocAsync((void**)&X->luniq, L ? L : 1, st));
     MXE_CUDA(cudaMallocAsync((void**)&X->lkeep, L ? L : 1, st));
     const uint32_t* mk = reinterpret_cast<const uint32_t*>(X->ws + Y.off_mk);
-    if (L) MXE_LAUNCH(e, p2p_flags_kernel, p2p_grid(L), 256, 0, mk, L, X->kflag, X->luniq, X->lkeep);
+    if (L) { Span k_(e, "k_p2p_flags_kernel"); MXE_LAUNCH(e, p2p_flags_kernel, p2p_grid(L), 256, 0, mk, L, X->kflag, X->luniq, X->lkeep); }
     {
         ArenaScope scope(e);
         MXE_TRY(exclusive_scan_u32_u64(e, X->kflag, X->kprefix, L));
     }
     if (L) {
-        MXE_LAUNCH(e, p2p_compact_kernel, p2p_grid(L), 256, 0, mk, X->H, X->S, L, X->kprefix, Y, X->T, X->cvid, X->cg, X->cloc);
+        { Span k_(e, "k_p2p_compact_kernel"); MXE_LAUNCH(e, p2p_compact_kernel, p2p_grid(L), 256, 0, mk, X->H, X->S, L, X->kprefix, Y, X->T, X->cvid, X->cg, X->cloc); }
         if (Y.world == 1 || !X->records)
-            MXE_LAUNCH(e, p2p_succ_kernel, p2p_grid(L), 256, 0, X->cvid, X->cg, X->cloc, X->kprefix, L, X->S, X->Ctg, X->P, Y, X->T, X->eflag);
+            { Span k_(e, "k_p2p_succ_kernel"); MXE_LAUNCH(e, p2p_succ_kernel, p2p_grid(L), 256, 0, X->cvid, X->cg, X->cloc, X->kprefix, L, X->S, X->Ctg, X->P, Y, X->T, X->eflag); }
         else
-            MXE_LAUNCH(e, p2p_sight_kernel, p2p_grid(L), 256, 0, X->cvid, X->cg, X->cloc, X->kprefix, L, X->S, X->H, X->Ctg, X->P, Y, X->T, X->cur2);
+            { Span k_(e, "k_p2p_sight_kernel"); MXE_LAUNCH(e, p2p_sight_kernel, p2p_grid(L), 256, 0, X->cvid, X->cg, X->cloc, X->kprefix, L, X->S, X->H, X->Ctg, X->P, Y, X->T, X->cur2); }
     }
-    if (Y.world > 1 && X->records) MXE_LAUNCH(e, p2p_push_cnt2_kernel, 1, 32, 0, X->cur2, X->P, Y);
+    if (Y.world > 1 && X->records) { Span k_(e, "k_p2p_push_cnt2_kernel"); MXE_LAUNCH(e, p2p_push_cnt2_kernel, 1, 32, 0, X->cur2, X->P, Y); }
     MXE_TRY(p2p_barrier_signal(X, 3));
     MXE_CUDA(cudaGetLastError());
     return MXE_OK;
@@ -954,12 +1063,12 @@ int mxe_p2p_edges(mxe_p2p_t* X)
     const uint64_t L = X->L;
     MXE_TRY(p2p_barrier_wait(X, 3));
     if (Y.world == 1 || !X->records) {
-        if (L) MXE_LAUNCH(e, p2p_edge_owner_kernel, p2p_grid(L), 256, 0, X->cvid, X->cg, X->cloc, X->eflag, X->kprefix, L, X->S, X->n_asm, X->P, Y, X->T, X->own, X->emask_j);
+        if (L) { Span k_(e, "k_p2p_edge_owner_kernel"); MXE_LAUNCH(e, p2p_edge_owner_kernel, p2p_grid(L), 256, 0, X->cvid, X->cg, X->cloc, X->eflag, X->kprefix, L, X->S, X->n_asm, X->P, Y, X->T, X->own, X->emask_j); }
         MXE_TRY(p2p_barrier_signal(X, 4));
     } else {
         const uint64_t n_idx = (uint64_t)Y.world * Y.cap2;
-        MXE_LAUNCH(e, p2p_table_kernel, p2p_grid(n_idx), 256, 0, X->P, Y);
-        MXE_LAUNCH(e, p2p_rec_owner_kernel, p2p_grid(n_idx), 256, 0, X->P, Y, X->n_asm, X->own, X->emask_j);
+        { Span k_(e, "k_p2p_table_kernel"); MXE_LAUNCH(e, p2p_table_kernel, p2p_grid(n_idx), 256, 0, X->P, Y); }
+        { Span k_(e, "k_p2p_rec_owner_kernel"); MXE_LAUNCH(e, p2p_rec_owner_kernel, p2p_grid(n_idx), 256, 0, X->P, Y, X->n_asm, X->own, X->emask_j); }
     }
     MXE_CUDA(cudaGetLastError());
     return MXE_OK;
@@ -985,7 +1094,7 @@ int mxe_p2p_finish(mxe_p2p_t* X, mxe_result_t** out)
     const uint64_t n_scan = home ? L : (uint64_t)Y.world * Y.cap2;
     {
         ArenaScope scope(e);
-        if (home && L) MXE_LAUNCH(e, p2p_clear_tail_kernel, p2p_grid(L), 256, 0, X->own, X->kprefix, L);
+        if (home && L) { Span k_(e, "k_p2p_clear_tail_kernel"); MXE_LAUNCH(e, p2p_clear_tail_kernel, p2p_grid(L), 256, 0, X->own, X->kprefix, L); }
         MXE_TRY(exclusive_scan_u32_u64(e, X->own, X->uprefix, n_scan));
     }
     uint64_t sizes[2] = {0, 0};
@@ -1011,7 +1120,7 @@ int mxe_p2p_finish(mxe_p2p_t* X, mxe_result_t** out)
     X->luniq = X->lkeep = nullptr;
     if (nV) {
         MXE_CUDA(cudaMallocAsync((void**)&R->d_vertices, nV * 8, st));
-        MXE_LAUNCH(e, p2p_vertices_kernel, Y.fb[Y.rank + 1] - Y.fb[Y.rank], 128, 0, X->P, Y, X->T, R->d_vertices);
+        { Span k_(e, "k_p2p_vertices_kernel"); MXE_LAUNCH(e, p2p_vertices_kernel, Y.fb[Y.rank + 1] - Y.fb[Y.rank], 128, 0, X->P, Y, X->T, R->d_vertices); }
     }
     if (nE) {
         EdgeOut E;
@@ -1025,21 +1134,21 @@ int mxe_p2p_finish(mxe_p2p_t* X, mxe_result_t** out)
         DBuf<uint64_t> fprefix;
         if (Y.world == 1) {
             MXE_TRY(fcount.alloc(nE, st)); MXE_TRY(fprefix.alloc(nE + 1, st)); MXE_TRY(vst.alloc(nV ? nV : 1, st));
-            MXE_LAUNCH(e, p2p_first_count_kernel, p2p_grid(L), 256, 0, X->cvid, X->cg, X->own, X->uprefix, X->kprefix, L, X->P, Y, n_asm, fcount.p);
+            { Span k_(e, "k_p2p_first_count_kernel"); MXE_LAUNCH(e, p2p_first_count_kernel, p2p_grid(L), 256, 0, X->cvid, X->cg, X->own, X->uprefix, X->kprefix, L, X->P, Y, n_asm, fcount.p); }
             MXE_TRY(exclusive_scan_u32_u64(e, fcount.p, fprefix.p, nE));
-            MXE_LAUNCH(e, p2p_first_start_kernel, p2p_grid(L), 256, 0, X->cvid, X->cg, X->own, X->uprefix, fprefix.p, X->kprefix, L, X->P, Y, n_asm, vst.p);
+            { Span k_(e, "k_p2p_first_start_kernel"); MXE_LAUNCH(e, p2p_first_start_kernel, p2p_grid(L), 256, 0, X->cvid, X->cg, X->own, X->uprefix, fprefix.p, X->kprefix, L, X->P, Y, n_asm, vst.p); }
             vstart = vst.p;
-            MXE_LAUNCH(e, p2p_edge_emit_kernel, p2p_grid(L), 256, 0, X->cvid, X->cg, X->cloc, X->own, X->emask_j, X->uprefix, X->kprefix, L, X->S, X->H, X->A,
-                       X->P, Y, X->T, vstart, E);
+            { Span k_(e, "k_p2p_edge_emit_kernel"); MXE_LAUNCH(e, p2p_edge_emit_kernel, p2p_grid(L), 256, 0, X->cvid, X->cg, X->cloc, X->own, X->emask_j, X->uprefix, X->kprefix, L, X->S, X->H, X->A,
+                       X->P, Y, X->T, vstart, E); }
         } else if (home) {
             MXE_CUDA(cudaMallocAsync((void**)&R->d_ekey, nE * 8, st));
             E.ekey = R->d_ekey;
-            MXE_LAUNCH(e, p2p_edge_emit_kernel, p2p_grid(L), 256, 0, X->cvid, X->cg, X->cloc, X->own, X->emask_j, X->uprefix, X->kprefix, L, X->S, X->H, X->A,
-                       X->P, Y, X->T, vstart, E);
+            { Span k_(e, "k_p2p_edge_emit_kernel"); MXE_LAUNCH(e, p2p_edge_emit_kernel, p2p_grid(L), 256, 0, X->cvid, X->cg, X->cloc, X->own, X->emask_j, X->uprefix, X->kprefix, L, X->S, X->H, X->A,
+                       X->P, Y, X->T, vstart, E); }
         } else {
             MXE_CUDA(cudaMallocAsync((void**)&R->d_ekey, nE * 8, st));
             E.ekey = R->d_ekey;
-            MXE_LAUNCH(e, p2p_rec_emit_kernel, p2p_grid(n_scan), 256, 0, X->P, Y, X->A, X->own, X->emask_j, X->uprefix, R->d_vertices, E);
+            { Span k_(e, "k_p2p_rec_emit_kernel"); MXE_LAUNCH(e, p2p_rec_emit_kernel, p2p_grid(n_scan), 256, 0, X->P, Y, X->A, X->own, X->emask_j, X->uprefix, R->d_vertices, E); }
         }
     }
     MXE_CUDA(cudaGetLastError());
