@@ -133,17 +133,27 @@ int mxe_create(int device, mxe_t** out)
     MXE_CUDA(cudaSetDevice(device));
     mxe_engine* e = new mxe_engine();
     e->device = device;
-    MXE_CUDA(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+    // on any failure below the half-built engine is released again (streams included)
+    auto fail = [&](const char* what, cudaError_t err) {
+        set_error("%s: %s", what, cudaGetErrorString(err));
+        for (int c = 0; c < 2; c++) if (e->copy_stream[c]) cudaStreamDestroy(e->copy_stream[c]);
+        if (e->own_stream) cudaStreamDestroy(e->own_stream);
+        delete e;
+        return MXE_ERR_CUDA;
+    };
+    cudaError_t err0;
+    if ((err0 = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", err0);
     e->stream = e->own_stream;
-    for (int c = 0; c < 2; c++) MXE_CUDA(cudaStreamCreateWithFlags(&e->copy_stream[c], cudaStreamNonBlocking));
+    for (int c = 0; c < 2; c++)
+        if ((err0 = cudaStreamCreateWithFlags(&e->copy_stream[c], cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", err0);
     if (const char* s = getenv("MXE_H2D_CHUNK_MB")) e->h2d_chunk_mb = std::max(1, atoi(s));
     cudaDeviceProp prop;
-    MXE_CUDA(cudaGetDeviceProperties(&prop, device));
+    if ((err0 = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail("cudaGetDeviceProperties", err0);
     e->sm_count = prop.multiProcessorCount;
     cudaMemPool_t pool;
-    MXE_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    if ((err0 = cudaDeviceGetDefaultMemPool(&pool, device)) != cudaSuccess) return fail("cudaDeviceGetDefaultMemPool", err0);
     uint64_t thresh = ~0ULL;   // keep freed blocks cached in the pool across steps
-    MXE_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    if ((err0 = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh)) != cudaSuccess) return fail("cudaMemPoolSetAttribute", err0);
     if (const char* s = getenv("MXE_TAU")) e->tau = atof(s);
     if (const char* s = getenv("MXE_CHUNK")) e->chunk = atoi(s);
     if (const char* s = getenv("MXE_CAND_VARIANT")) e->cand_variant = atoi(s);

@@ -69,6 +69,7 @@ static int parse_fastq(const char* base, size_t size, HostText& seq, std::vector
     auto eol = [&](const char* q) { const char* nl = q < end ? (const char*)memchr(q, '\n', end - q) : nullptr; return nl ? nl : end; };
     while (p < end) {
         const char* nl = eol(p);
+        if (nl == p || (nl == p + 1 && *p == '\r')) { p = nl < end ? nl + 1 : end; continue; }     // blank line (e.g. at the end of the file): no record
         names.push_back(header_id(p + 1, nl));
         offsets.push_back(at);
         p = nl < end ? nl + 1 : end;
@@ -127,6 +128,19 @@ int read_fasta(const char* path, HostText& seq, std::vector<uint64_t>& offsets, 
     if (base == (const char*)MAP_FAILED) { set_error("cannot map %s: %s", path, strerror(errno)); return MXE_ERR_IO; }
     madvise((void*)base, size, MADV_SEQUENTIAL);
     struct Unmap { const char* p; size_t n; ~Unmap() { munmap((void*)p, n); } } unmap{base, size};
+    // btllib reads gzip / bzip2 / xz / zstd input through external decompressors; this reader takes plain text only and
+    // says so instead of sketching compressed bytes as if they were bases (the make driver stops: non-zero exit)
+    if (size >= 2 && (((unsigned char)base[0] == 0x1f && (unsigned char)base[1] == 0x8b) ||                 // gzip
+                      (base[0] == 'B' && base[1] == 'Z') ||                                                  // bzip2
+                      ((unsigned char)base[0] == 0xfd && base[1] == '7') ||                                  // xz
+                      ((unsigned char)base[0] == 0x28 && (unsigned char)base[1] == 0xb5))) {                 // zstd
+        set_error("%s is compressed: decompress it first (e.g. `gzip -dc`); this reader takes plain FASTA / FASTQ text", path);
+        return MXE_ERR_IO;
+    }
+    if (base[0] != '>' && base[0] != '@' && base[0] != '\n' && base[0] != '\r' && (base[0] < 0x20 || (unsigned char)base[0] > 0x7e)) {
+        set_error("%s does not look like FASTA / FASTQ text (first byte 0x%02x)", path, (unsigned char)base[0]);
+        return MXE_ERR_IO;
+    }
     if (base[0] == '@') return parse_fastq(base, size, seq, offsets, names);
 
     const int threads = host_threads();

@@ -290,6 +290,9 @@ class Engine:
         overlap the sketch of the previous one.  Returns the object to pass to sketch_buffers."""
         ptr, keep, n = self._host_ptr(seq)
         check(self._lib, self._lib.mxe_prefetch_buffers(self._h, C.c_void_p(ptr), n))
+        # the copy is asynchronous: the engine keeps the buffer alive until it has been sketched (or the engine closes),
+        # so that a caller who drops its own reference cannot have the memory recycled under the copy
+        self._prefetched = getattr(self, "_prefetched", [])[-3:] + [keep]
         return keep
 
     def sketch_many(self, assemblies, k, w, canonical="sum"):

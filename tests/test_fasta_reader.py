@@ -93,3 +93,33 @@ def test_reader_edge_files(tmp_path):
         p = tmp_path / name
         p.write_bytes(data)
         assert _records(p) == want, name
+
+
+def test_compressed_input_is_refused(tmp_path):
+    """btllib reads .gz transparently; this reader takes plain text and must say so (MXE_ERR_IO) rather than sketch
+    compressed bytes as bases and exit 0"""
+    import ctypes as C
+    import gzip
+    from ntjoin_b200._lib import load_library
+    lib = load_library()
+    p = tmp_path / "x.fa.gz"
+    with gzip.open(p, "wb") as fh:
+        fh.write(b">a\nACGTACGTACGT\n")
+    h = C.c_void_p()
+    rc = lib.mxe_fasta_read(str(p).encode(), C.byref(h))
+    assert rc == -2 and b"compressed" in lib.mxe_last_error()
+
+
+def test_fastq_trailing_blank_line(tmp_path):
+    import ctypes as C
+    from ntjoin_b200._lib import load_library
+    lib = load_library()
+    p = tmp_path / "x.fq"
+    p.write_bytes(b"@r1 d\nACGT\n+\nIIII\n@r2\nGGCC\n+\nIIII\n\n")
+    h = C.c_void_p()
+    assert lib.mxe_fasta_read(str(p).encode(), C.byref(h)) == 0
+    n = C.c_uint32()
+    offs, text = C.c_void_p(), C.c_void_p()
+    assert lib.mxe_fasta_view(h, C.byref(n), C.byref(offs), C.byref(text)) == 0
+    assert n.value == 2
+    lib.mxe_fasta_free(h)
