@@ -95,6 +95,13 @@ int mxe_prefetch_buffers(mxe_t* e, const uint8_t* seq, uint64_t n);
 int mxe_sketch_device(mxe_t* e, const void* d_seq, const uint64_t* offsets, uint32_t n_contigs,
                       const char* const* names, int k, int w, int flags, mxe_sketch_t** out);
 
+/* Several device-resident assemblies (d_seq[a], offsets[a] with n_contigs[a] + 1 entries) in one call: their kernels are
+ * enqueued on two streams and run concurrently -- the bandwidth- and latency-bound kernels of one assembly share the SMs
+ * with the ALU-bound candidate scan of the other -- and the sizes are read in one host round trip per assembly at the end.
+ * Same results as n_asm calls of mxe_sketch_device; out[a] are ordinary sketch objects (names = record indices). */
+int mxe_sketch_device_many(mxe_t* e, int n_asm, const void* const* d_seq, const uint64_t* const* offsets, const uint32_t* n_contigs,
+                           int k, int w, int flags, mxe_sketch_t** out);
+
 /* Host only (no engine): a sketch object over caller-provided arrays (copied) -- e.g. the minimizers of one assembly
  * gathered from several GPUs -- so that mxe_write_tsv / mxe_sketch_view serve them like a sketch computed here.
  * contig[] ascending; min_hash / forward may be NULL; offsets (n_contigs + 1 record starts in `seq`) and `seq`

@@ -185,6 +185,8 @@ void mxe_destroy(mxe_t* e)
         if (sl.consumed) cudaEventDestroy(sl.consumed);
         if (sl.d) cudaFree(sl.d);
     }
+    if (e->aux_stream) { cudaStreamSynchronize(e->aux_stream); cudaStreamDestroy(e->aux_stream); }
+    if (e->aux_event) cudaEventDestroy(e->aux_event);
     cudaStreamDestroy(e->own_stream);
     delete e;
 }
@@ -207,6 +209,8 @@ int mxe_set_option(mxe_t* e, const char* name, double value)
     else if (!strcmp(name, "prune")) e->prune = value != 0;
     else if (!strcmp(name, "sort_bits")) e->sort_bits = (int)value;
     else if (!strcmp(name, "filter_variant")) e->filter_variant = (int)value;
+    else if (!strcmp(name, "async_sizes")) e->async_sizes = value != 0;
+    else if (!strcmp(name, "bound_scale")) { if (value <= 0) { set_error("bound_scale must be > 0"); return MXE_ERR_ARG; } e->bound_scale = value; }
     else if (!strcmp(name, "fma_offload")) e->fma_offload = value != 0;
     else if (!strcmp(name, "select_narrow")) e->select_narrow = value != 0;
     else if (!strcmp(name, "timing")) { e->timing = value != 0; e->timing_fine = value >= 2; }
@@ -278,6 +282,23 @@ int mxe_sketch_device(mxe_t* e, const void* d_seq, const uint64_t* offsets, uint
     }
     if (rc != MXE_OK) { mxe_sketch_free(S); return rc; }
     *out = S;
+    return MXE_OK;
+}
+
+int mxe_sketch_device_many(mxe_t* e, int n_asm, const void* const* d_seq, const uint64_t* const* offsets, const uint32_t* n_contigs,
+                           int k, int w, int flags, mxe_sketch_t** out)
+{
+    if (!e || !d_seq || !offsets || !n_contigs || !out || n_asm < 1 || n_asm > 32) { set_error("bad arguments"); return MXE_ERR_ARG; }
+    MXE_CUDA(cudaSetDevice(e->device));
+    std::vector<mxe_sketch*> S((size_t)n_asm);
+    for (int a = 0; a < n_asm; a++) { S[a] = new mxe_sketch(); set_names(S[a], nullptr, n_contigs[a]); }
+    int rc;
+    {
+        ArenaScope scope(e);
+        rc = sketch_device_many_impl(e, n_asm, (const uint8_t* const*)d_seq, offsets, n_contigs, k, w, flags, S.data());
+    }
+    if (rc != MXE_OK) { for (auto* s : S) mxe_sketch_free(s); return rc; }
+    for (int a = 0; a < n_asm; a++) out[a] = S[a];
     return MXE_OK;
 }
 

@@ -73,6 +73,8 @@ struct Engine {
     bool select_narrow = true;   // window selection in 32-bit arithmetic when the ordinals allow it
     int filter_variant = 1;  // steps 2-3: 0 = global radix sort (filter.cu), 1 = hash buckets in shared memory (p2p.cu)
     int sort_bits = 0;       // steps 2-3: top hash bits covered by the radix sort (24/32/40; 0 = by size), rest by the fix-up
+    double bound_scale = 1.0;   // scales the size bounds of the asynchronous path (tests: < 1 forces the overflow / repeat path)
+    bool async_sizes = true; // sketch: arrays sized from bounds, counts stay on the device, one host round trip per sketch
     bool timing = false;
     bool timing_fine = false;   // also time every kernel of steps 2-3 and the barrier waits (option timing = 2)
     // accounting
@@ -156,7 +158,8 @@ int radix_sort_pairs(Engine* e, uint64_t* d_keys, uint32_t* d_vals, uint64_t* d_
 constexpr int RANK_BLOCK_BITS = 1024;
 constexpr int RANK_BLOCK_WORDS = RANK_BLOCK_BITS / 32;
 int bitmap_rank_build(Engine* e, const uint32_t* d_bits, size_t n_words, uint64_t* d_prefix /* n_blocks+1 */);
-// Sorted positions of the set bits (d_out sized from prefix total).
-int bitmap_extract(Engine* e, const uint32_t* d_bits, size_t n_words, const uint64_t* d_prefix, uint64_t* d_out);
+// Sorted positions of the set bits; d_out holds `cap` entries (bits beyond it are dropped: the caller detects the overflow
+// from the prefix total).
+int bitmap_extract(Engine* e, const uint32_t* d_bits, size_t n_words, const uint64_t* d_prefix, uint64_t* d_out, uint64_t cap);
 
 }  // namespace mxe

@@ -37,6 +37,8 @@ struct H2DSlot {
 
 struct mxe_engine : public mxe::Engine {
     cudaStream_t copy_stream[2] = {nullptr, nullptr};
+    cudaStream_t aux_stream = nullptr;      // second compute stream: sketches of several assemblies run concurrently
+    cudaEvent_t aux_event = nullptr;
     H2DSlot slot[2];
     int h2d_chunk_mb = 256;
     // pinned host block pool (grow-only, reused across steps)
@@ -152,6 +154,8 @@ int a2a_finish_impl(mxe_a2a* X, const uint64_t* d_rec, uint64_t n_rec, uint64_t 
 int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const uint64_t* offsets, uint32_t n_contigs,
                        int k, int w, int flags, mxe_sketch* out, H2DSlot* staged = nullptr);
 int h2d_issue(mxe_engine* e, H2DSlot& s, const uint8_t* h, uint64_t n);
+int sketch_device_many_impl(mxe_engine* e, int n_asm, const uint8_t* const* d_seq, const uint64_t* const* offsets, const uint32_t* n_contigs,
+                            int k, int w, int flags, mxe_sketch* const* S);
 // host side of the file seam (hostio.cu): multi-threaded FASTA/FASTQ ingest and TSV text
 int host_threads();
 int read_fasta(const char* path, HostText& seq, std::vector<uint64_t>& offsets, std::vector<std::string>& names);

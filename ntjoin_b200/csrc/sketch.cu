@@ -102,8 +102,93 @@ int h2d_issue(mxe_engine* e, H2DSlot& s, const uint8_t* h, uint64_t n)
     return MXE_OK;
 }
 
+// A sketch whose kernels are all enqueued but whose counts have not been read yet: lets the sketches of several
+// assemblies run concurrently on two streams (sketch_device_many_impl) -- the bandwidth- and latency-bound kernels of
+// one assembly fill the SMs that the ALU-bound candidate scan of the other leaves idle, and the other way round.
+struct SketchPending {
+    bool active = false;
+    cudaStream_t stream = nullptr;
+    uint64_t* host = nullptr;              // pinned: n_valid, n_cand, n_mx, gap count, gap windows
+    uint64_t cand_cap = 0, gap_cap = 0, mx_cap = 0;
+};
+
+static int sketch_device_pass(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const uint64_t* offsets, uint32_t n_contigs,
+                              int k, int w, int flags, mxe_sketch* S, H2DSlot* staged, bool force_exact, bool* redo_exact,
+                              SketchPending* defer = nullptr);
+
+// second half of a deferred sketch: the one host round trip; *redo = a size bound was exceeded
+static int sketch_complete(mxe_engine* e, mxe_sketch* S, SketchPending* D, bool* redo)
+{
+    *redo = false;
+    if (!D->active) return MXE_OK;                     // empty input: nothing was enqueued
+    MXE_CUDA(cudaStreamSynchronize(D->stream));
+    const uint64_t n_valid = D->host[0], n_cand = D->host[1], n_mx = D->host[2], g0 = D->host[3], g1 = D->host[4];
+    e->pinned_release(D->host, 64);
+    D->host = nullptr;
+    if (n_cand > D->cand_cap || g0 > D->gap_cap || n_mx > D->mx_cap) {
+        void* outs[] = {S->d_out_hash, S->d_min_hash, S->d_pos, S->d_contig, S->d_forward};
+        for (void* q : outs) if (q) cudaFreeAsync(q, D->stream);
+        S->d_out_hash = S->d_min_hash = nullptr; S->d_pos = S->d_contig = nullptr; S->d_forward = nullptr;
+        *redo = true;
+        return MXE_OK;
+    }
+    S->n_valid = n_valid; S->n_cand = n_cand; S->n_gaps = g0; S->n_gap_windows = g1; S->n = n_mx;
+    return MXE_OK;
+}
+
+// Several device-resident assemblies: assembly a is enqueued on stream (a & 1) -- the engine stream and its auxiliary
+// stream -- and the counts are read after everything has been issued.
+int sketch_device_many_impl(mxe_engine* e, int n_asm, const uint8_t* const* d_seq, const uint64_t* const* offsets, const uint32_t* n_contigs,
+                            int k, int w, int flags, mxe_sketch* const* S)
+{
+    if (!e->aux_stream) MXE_CUDA(cudaStreamCreateWithFlags(&e->aux_stream, cudaStreamNonBlocking));
+    if (!e->aux_event) MXE_CUDA(cudaEventCreateWithFlags(&e->aux_event, cudaEventDisableTiming));
+    cudaStream_t main_stream = e->stream;
+    MXE_CUDA(cudaEventRecord(e->aux_event, main_stream));              // inputs are ready in engine-stream order
+    MXE_CUDA(cudaStreamWaitEvent(e->aux_stream, e->aux_event, 0));
+    std::vector<SketchPending> pend((size_t)n_asm);
+    int rc = MXE_OK;
+    for (int a = 0; a < n_asm && rc == MXE_OK; a++) {
+        const uint64_t n = n_contigs[a] ? offsets[a][n_contigs[a]] : 0;
+        bool redo = false;
+        e->stream = (a & 1) ? e->aux_stream : main_stream;
+        rc = sketch_device_pass(e, d_seq[a], n, offsets[a], n_contigs[a], k, w, flags, S[a], nullptr, false, &redo, &pend[a]);
+        e->stream = main_stream;
+    }
+    for (int a = 0; a < n_asm; a++) {
+        bool redo = false;
+        int rc2 = sketch_complete(e, S[a], &pend[a], &redo);
+        if (rc == MXE_OK) rc = rc2;
+        if (rc == MXE_OK && redo) {                                    // rare: bounds exceeded -> exact sizes, on the engine stream
+            const uint64_t n = n_contigs[a] ? offsets[a][n_contigs[a]] : 0;
+            MXE_CUDA(cudaStreamSynchronize(e->aux_stream));
+            rc = sketch_device_pass(e, d_seq[a], n, offsets[a], n_contigs[a], k, w, flags, S[a], nullptr, true, &redo);
+        }
+    }
+    // later work on the engine stream (steps 2-3, copies) sees the results of the auxiliary stream
+    MXE_CUDA(cudaEventRecord(e->aux_event, e->aux_stream));
+    MXE_CUDA(cudaStreamWaitEvent(main_stream, e->aux_event, 0));
+    return rc;
+}
+
 int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const uint64_t* offsets, uint32_t n_contigs,
                        int k, int w, int flags, mxe_sketch* S, H2DSlot* staged)
+{
+    bool redo = false;
+    int rc = sketch_device_pass(e, d_seq, n, offsets, n_contigs, k, w, flags, S, staged, false, &redo);
+    if (rc == MXE_OK && redo) {
+        // a size bound of the asynchronous path was exceeded (rare: dense candidates).  The input is still resident --
+        // a staged host buffer stays in its slot until the next copy is issued -- so the whole sketch is simply repeated
+        // with exact sizes read back at every stage.
+        e->arena.begin(e->stream);
+        rc = sketch_device_pass(e, d_seq, n, offsets, n_contigs, k, w, flags, S, nullptr, true, &redo);
+    }
+    return rc;
+}
+
+static int sketch_device_pass(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const uint64_t* offsets, uint32_t n_contigs,
+                              int k, int w, int flags, mxe_sketch* S, H2DSlot* staged, bool force_exact, bool* redo_exact,
+                              SketchPending* defer)
 {
     if (k < 1 || k > 1024 || w < 1) { set_error("bad k/w (k=%d w=%d)", k, w); return MXE_ERR_ARG; }
     if (n_contigs && offsets[0] != 0) { set_error("offsets[0] must be 0"); return MXE_ERR_ARG; }
@@ -320,26 +405,44 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
         else MXE_TRY(bitmap_rank_build(e, C.p, nW, cprefix.p));
     }
 
-    uint64_t totals[2] = {0, 0};
-    MXE_CUDA(cudaMemcpyAsync(&totals[0], vprefix.p + n_vblocks, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    MXE_CUDA(cudaMemcpyAsync(&totals[1], cprefix.p + n_vblocks, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    MXE_CUDA(cudaStreamSynchronize(st));
-    const uint64_t n_valid = totals[0], n_cand = totals[1];
-    S->n_valid = n_valid; S->n_cand = n_cand;
+    // ---- sizes.  Default: arrays and grids from upper bounds, the exact counts stay on the device (kernels read them through
+    // pointers) and come back in ONE host round trip at the end of the sketch; if a bound turns out too small (dense
+    // candidates: low-complexity sequence) the tail is repeated with exact sizes.  `exact` = the round-1 path: a round trip
+    // after the candidate count, after the gap count and after the minimizer count.
+    const bool exact = force_exact || !e->async_sizes || e->prune;
+    uint64_t n_valid = 0, n_cand = 0;
+    const uint64_t* d_ncand = cprefix.p + n_vblocks;
+    const uint64_t* d_nmx = mprefix.p + n_vblocks;
+    uint64_t cand_cap, mx_cap;
+    if (exact) {
+        uint64_t totals[2] = {0, 0};
+        MXE_CUDA(cudaMemcpyAsync(&totals[0], vprefix.p + n_vblocks, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        MXE_CUDA(cudaMemcpyAsync(&totals[1], cprefix.p + n_vblocks, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        MXE_CUDA(cudaStreamSynchronize(st));
+        n_valid = totals[0]; n_cand = totals[1];
+        cand_cap = n_cand;
+        d_ncand = nullptr;
+        mx_cap = 0;
+    } else {
+        const double dens = std::min(1.0, (e->tau * 1.08 + 0.5) / (double)w);                // candidate density incl. the superset margin
+        cand_cap = std::min<uint64_t>(n, (uint64_t)(((double)n * dens * 1.25 + (double)n_contigs + (double)(1u << 18)) * e->bound_scale) + 1);
+        mx_cap = std::min<uint64_t>(n, (uint64_t)(((double)n * 2.0 / ((double)w + 1.0) * 1.25 + 2.0 * n_contigs + (double)(1u << 16)) * e->bound_scale) + 1);
+    }
 
     // ---- candidate evaluation + sparse window selection
     DBuf<uint64_t> cpos, ch0, cord;
     DBuf<uint32_t> cctg;
     DBuf<Gap> gaps;
     DBuf<unsigned long long> gcount;
-    MXE_TRY(cpos.alloc(n_cand, st));
-    MXE_TRY(ch0.alloc(n_cand, st));
-    MXE_TRY(cord.alloc(n_cand, st));
-    MXE_TRY(cctg.alloc(n_cand, st));
+    MXE_TRY(cpos.alloc(cand_cap, st));
+    MXE_TRY(ch0.alloc(cand_cap, st));
+    MXE_TRY(cord.alloc(cand_cap, st));
+    MXE_TRY(cctg.alloc(cand_cap, st));
     MXE_TRY(gcount.alloc(2, st));
-    uint64_t gap_cap = std::max<uint64_t>(65536, n_cand / 8 + n_contigs);   // grown on demand below
+    uint64_t gap_cap = std::max<uint64_t>(65536, cand_cap / 8 + n_contigs);   // grown on demand below (exact path)
     unsigned long long gc[2] = {0, 0};
-    uint64_t n_sel = n_cand;        // candidates that reach the exact stages
+    uint64_t n_sel = cand_cap;      // candidates that reach the exact stages (upper bound on the async path)
+    const uint64_t* d_nsel = d_ncand;
     uint64_t *s_pos = cpos.p, *s_ord = cord.p;
     uint32_t* s_ctg = cctg.p;
     DBuf<uint64_t> cpos2, cord2, pprefix;
@@ -350,10 +453,10 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
     const size_t hsm = (size_t)2 * G4 * 256 * sizeof(uint64_t);
     {
         Span sp(e, "eval");
-        if (n_cand) {
+        if (cand_cap) {
             MXE_LAUNCH(e, cand_extract_kernel, grid_for((n_vblocks + XBLOCKS - 1) / XBLOCKS * 32, 256), 256, 0, C.p, V.p, nW, cprefix.p, vprefix.p, n_vblocks,
-                       d_offsets.p, n_contigs, (uint64_t)w, cpos.p, cord.p, cctg.p);
-            if (e->prune) {
+                       d_offsets.p, n_contigs, (uint64_t)w, cpos.p, cord.p, cctg.p, cand_cap);
+            if (e->prune && exact) {
                 MXE_TRY(klo.alloc(n_cand, st)); MXE_TRY(khi.alloc(n_cand, st)); MXE_TRY(pflag.alloc(n_cand, st));
                 MXE_TRY(pprefix.alloc(n_cand + 1, st));
                 MXE_LAUNCH(e, cand_key31_kernel, grid_for(n_cand, 256), 256, 0, cpos.p, n_cand, pk.p, P, Tb, klo.p, khi.p);
@@ -373,9 +476,9 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
                     MXE_LAUNCH(e, hash_pos_tables_kernel, G4, 256, 0, Tb, k, PF.p, PR.p);
                     MXE_CUDA(cudaFuncSetAttribute(cand_hash_pos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
                     const unsigned grid = (unsigned)std::min<uint64_t>(grid_for(n_sel, 256), (uint64_t)e->sm_count * 5);
-                    MXE_LAUNCH(e, cand_hash_pos_kernel, grid, 256, hsm, s_pos, n_sel, pk.p, P, Tb, PF.p, PR.p, ch0.p);
+                    MXE_LAUNCH(e, cand_hash_pos_kernel, grid, 256, hsm, s_pos, d_nsel, n_sel, pk.p, P, Tb, PF.p, PR.p, ch0.p);
                 } else {
-                    MXE_LAUNCH(e, cand_hash_kernel, grid_for(n_sel, 256), 256, 0, s_pos, n_sel, pk.p, P, Tb, ch0.p);
+                    MXE_LAUNCH(e, cand_hash_kernel, grid_for(n_sel, 256), 256, 0, s_pos, d_nsel, n_sel, pk.p, P, Tb, ch0.p);
                 }
             }
         }
@@ -386,33 +489,36 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
             MXE_TRY(gaps.alloc(gap_cap, st));
             MXE_CUDA(cudaMemsetAsync(gcount.p, 0, 2 * sizeof(unsigned long long), st));
             GapList G{gaps.p, gcount.p, gcount.p + 1, gap_cap};
-            // 32-bit window arithmetic whenever every padded ordinal (+ 2w) fits (see select_kernel)
+            // 32-bit window arithmetic whenever every padded ordinal (+ 2w) fits (see select_kernel); the number of valid
+            // k-mers is bounded by the number of bases where it is not known on the host
+            const uint64_t nv_bound = exact ? n_valid : n;
             const bool narrow = e->select_narrow && n_sel < 0xFFFFFFFFULL &&
-                                n_valid + ((uint64_t)n_contigs + 2) * (uint64_t)w < 0xFFFFFFFFULL;
+                                nv_bound + ((uint64_t)n_contigs + 2) * (uint64_t)w < 0xFFFFFFFFULL;
             if (n_sel && narrow)
-                MXE_LAUNCH(e, select_kernel<true>, grid_for(n_sel, 256), 256, 0, s_pos, ch0.p, s_ord, s_ctg, n_sel, ostart.p, P, M.p, G);
+                MXE_LAUNCH(e, select_kernel<true>, grid_for(n_sel, 256), 256, 0, s_pos, ch0.p, s_ord, s_ctg, d_nsel, n_sel, ostart.p, P, M.p, G);
             else if (n_sel)
-                MXE_LAUNCH(e, select_kernel<false>, grid_for(n_sel, 256), 256, 0, s_pos, ch0.p, s_ord, s_ctg, n_sel, ostart.p, P, M.p, G);
-            MXE_LAUNCH(e, empty_contig_gap_kernel, grid_for(n_contigs, 128), 128, 0, s_pos, n_sel, d_offsets.p, n_contigs, ostart.p, P, G);
+                MXE_LAUNCH(e, select_kernel<false>, grid_for(n_sel, 256), 256, 0, s_pos, ch0.p, s_ord, s_ctg, d_nsel, n_sel, ostart.p, P, M.p, G);
+            MXE_LAUNCH(e, empty_contig_gap_kernel, grid_for(n_contigs, 128), 128, 0, s_pos, d_nsel, n_sel, d_offsets.p, n_contigs, ostart.p, P, G);
+            if (!exact) break;
             MXE_CUDA(cudaMemcpyAsync(gc, gcount.p, sizeof(gc), cudaMemcpyDeviceToHost, st));
             MXE_CUDA(cudaStreamSynchronize(st));
             if (gc[0] <= gap_cap) break;
             gap_cap = gc[0];   // rerun with exact capacity (M updates are idempotent)
         }
     }
-    S->n_gaps = gc[0]; S->n_gap_windows = gc[1];
 
     // ---- dense gap windows
-    if (gc[0]) {
+    if (gc[0] || !exact) {
         Span sp(e, "gap");
-        unsigned grid = (unsigned)std::min<uint64_t>(gc[0], (uint64_t)e->sm_count * 4);
+        unsigned grid = exact ? (unsigned)std::min<uint64_t>(gc[0], (uint64_t)e->sm_count * 4) : (unsigned)(e->sm_count * 4);
         DBuf<uint64_t> sh, sq, sbm, sbi;
         uint64_t stride = (uint64_t)GAP_CHUNK + (uint64_t)w;
         MXE_TRY(sh.alloc(stride * grid, st));
         MXE_TRY(sq.alloc(stride * grid, st));
         MXE_TRY(sbm.alloc((stride / 32 + 2) * grid, st));
         MXE_TRY(sbi.alloc((stride / 32 + 2) * grid, st));
-        MXE_LAUNCH(e, gap_kernel, grid, 256, 0, gaps.p, (uint64_t)gc[0], pk.p, V.p, vprefix.p, n_vblocks, P, Tb, sh.p, sq.p, sbm.p, sbi.p, M.p);
+        MXE_LAUNCH(e, gap_kernel, grid, 256, 0, gaps.p, exact ? (const unsigned long long*)nullptr : gcount.p, exact ? (uint64_t)gc[0] : gap_cap,
+                   pk.p, V.p, vprefix.p, n_vblocks, P, Tb, sh.p, sq.p, sbm.p, sbi.p, M.p);
     }
 
     // ---- ordered emission
@@ -421,23 +527,60 @@ int sketch_device_impl(mxe_engine* e, const uint8_t* d_seq, uint64_t n, const ui
         MXE_TRY(bitmap_rank_build(e, M.p, nW, mprefix.p));
     }
     uint64_t n_mx = 0;
-    MXE_CUDA(cudaMemcpyAsync(&n_mx, mprefix.p + n_vblocks, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    MXE_CUDA(cudaStreamSynchronize(st));
-    S->n = n_mx;
-    if (n_mx) {
+    if (exact) {
+        MXE_CUDA(cudaMemcpyAsync(&n_mx, mprefix.p + n_vblocks, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        MXE_CUDA(cudaStreamSynchronize(st));
+        mx_cap = n_mx;
+        d_nmx = nullptr;
+    }
+    if (mx_cap) {
         Span sp(e, "emit");
-        MXE_CUDA(cudaMallocAsync((void**)&S->d_out_hash, n_mx * sizeof(uint64_t), st));
-        MXE_CUDA(cudaMallocAsync((void**)&S->d_min_hash, n_mx * sizeof(uint64_t), st));
-        MXE_CUDA(cudaMallocAsync((void**)&S->d_pos, n_mx * sizeof(uint32_t), st));
-        MXE_CUDA(cudaMallocAsync((void**)&S->d_contig, n_mx * sizeof(uint32_t), st));
-        MXE_CUDA(cudaMallocAsync((void**)&S->d_forward, n_mx * sizeof(uint8_t), st));
+        MXE_CUDA(cudaMallocAsync((void**)&S->d_out_hash, mx_cap * sizeof(uint64_t), st));
+        MXE_CUDA(cudaMallocAsync((void**)&S->d_min_hash, mx_cap * sizeof(uint64_t), st));
+        MXE_CUDA(cudaMallocAsync((void**)&S->d_pos, mx_cap * sizeof(uint32_t), st));
+        MXE_CUDA(cudaMallocAsync((void**)&S->d_contig, mx_cap * sizeof(uint32_t), st));
+        MXE_CUDA(cudaMallocAsync((void**)&S->d_forward, mx_cap * sizeof(uint8_t), st));
         DBuf<uint64_t> mpos;
-        MXE_TRY(mpos.alloc(n_mx, st));
-        MXE_TRY(bitmap_extract(e, M.p, nW, mprefix.p, mpos.p));
+        MXE_TRY(mpos.alloc(mx_cap, st));
+        MXE_TRY(bitmap_extract(e, M.p, nW, mprefix.p, mpos.p, mx_cap));
         // (the position-specific tables of the candidate stage do not pay here: 6 M items cannot amortise staging 32 KB per CTA)
-        MXE_LAUNCH(e, final_eval_kernel, grid_for(n_mx, 256), 256, 0, mpos.p, n_mx, pk.p, d_offsets.p, n_contigs, P, Tb,
+        MXE_LAUNCH(e, final_eval_kernel, grid_for(mx_cap, 256), 256, 0, mpos.p, d_nmx, mx_cap, pk.p, d_offsets.p, n_contigs, P, Tb,
                    S->d_out_hash, S->d_min_hash, S->d_pos, S->d_contig, S->d_forward);
     }
+    if (!exact && defer) {
+        // counts into pinned memory; the caller reads them after it has enqueued the other assemblies (sketch_complete)
+        defer->host = (uint64_t*)e->pinned_alloc(64);
+        if (!defer->host) { set_error("pinned allocation failed"); return MXE_ERR_NOMEM; }
+        MXE_CUDA(cudaMemcpyAsync(&defer->host[0], vprefix.p + n_vblocks, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        MXE_CUDA(cudaMemcpyAsync(&defer->host[1], cprefix.p + n_vblocks, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        MXE_CUDA(cudaMemcpyAsync(&defer->host[2], mprefix.p + n_vblocks, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        MXE_CUDA(cudaMemcpyAsync(&defer->host[3], gcount.p, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        defer->active = true; defer->stream = st;
+        defer->cand_cap = cand_cap; defer->gap_cap = gap_cap; defer->mx_cap = mx_cap;
+        MXE_CUDA(cudaGetLastError());
+        return MXE_OK;
+    }
+    if (!exact) {
+        // the one host round trip of the sketch: every count at once
+        uint64_t back[3] = {0, 0, 0};
+        MXE_CUDA(cudaMemcpyAsync(&back[0], vprefix.p + n_vblocks, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        MXE_CUDA(cudaMemcpyAsync(&back[1], cprefix.p + n_vblocks, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        MXE_CUDA(cudaMemcpyAsync(&back[2], mprefix.p + n_vblocks, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        MXE_CUDA(cudaMemcpyAsync(gc, gcount.p, sizeof(gc), cudaMemcpyDeviceToHost, st));
+        MXE_CUDA(cudaStreamSynchronize(st));
+        n_valid = back[0]; n_cand = back[1]; n_mx = back[2];
+        if (n_cand > cand_cap || gc[0] > gap_cap || n_mx > mx_cap) {
+            // a bound was too small: drop what was produced and do the tail again with exact sizes
+            void* outs[] = {S->d_out_hash, S->d_min_hash, S->d_pos, S->d_contig, S->d_forward};
+            for (void* q : outs) if (q) cudaFreeAsync(q, st);
+            S->d_out_hash = S->d_min_hash = nullptr; S->d_pos = S->d_contig = nullptr; S->d_forward = nullptr;
+            *redo_exact = true;
+            return MXE_OK;
+        }
+    }
+    S->n_valid = n_valid; S->n_cand = n_cand;
+    S->n_gaps = gc[0]; S->n_gap_windows = gc[1];
+    S->n = n_mx;
     MXE_CUDA(cudaGetLastError());
     return MXE_OK;
 }

@@ -582,6 +582,16 @@ __global__ void __launch_bounds__(CAND_THREADS) cand31_kernel(const uint32_t* __
 }
 #undef MXE_CAND_STEP
 
+// Sizes that are only known on the device.  The host sizes arrays and grids from upper bounds and passes the pointer to the
+// exact count; kernels clamp it to the bound (an overflow is detected at the single host round trip at the end of the sketch,
+// which then repeats the call with exact sizes).  d_n == nullptr: n_max is the exact count.
+__device__ __forceinline__ uint64_t dev_count(const uint64_t* __restrict__ d_n, uint64_t n_max)
+{
+    if (!d_n) return n_max;
+    const uint64_t v = *d_n;
+    return v < n_max ? v : n_max;
+}
+
 // ---------------------------------------------------------------- candidate extraction + evaluation
 // One warp per 8192 bits of C (8 rank blocks), one lane per 8 consecutive words: two 16-byte loads of C and of V per
 // lane are in flight together and one warp scan serves eight rank blocks (the one-warp-per-block version was latency
@@ -606,7 +616,7 @@ __device__ __forceinline__ void load_words8(const uint32_t* __restrict__ bits, u
 __global__ void __launch_bounds__(256) cand_extract_kernel(const uint32_t* __restrict__ C, const uint32_t* __restrict__ V, uint64_t n_words,
                                                             const uint64_t* __restrict__ cprefix, const uint64_t* __restrict__ vprefix, uint64_t n_blocks,
                                                             const uint64_t* __restrict__ offsets, uint32_t n_contigs, uint64_t w,
-                                                            uint64_t* __restrict__ cpos, uint64_t* __restrict__ cord, uint32_t* __restrict__ cctg)
+                                                            uint64_t* __restrict__ cpos, uint64_t* __restrict__ cord, uint32_t* __restrict__ cctg, uint64_t cap)
 {
     const uint64_t sb = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -642,20 +652,23 @@ __global__ void __launch_bounds__(256) cand_extract_kernel(const uint32_t* __res
             wv &= wv - 1;
             const uint64_t p = base + b;
             while (p >= nextb) { c++; vb += w; nextb = c + 1 < n_contigs ? offsets[c + 1] : ~0ULL; }
-            cpos[o] = p;
-            cord[o] = vb + __popc(vw[j] & ((1u << b) - 1u));
-            cctg[o] = c;
+            if (o < cap) {
+                cpos[o] = p;
+                cord[o] = vb + __popc(vw[j] & ((1u << b) - 1u));
+                cctg[o] = c;
+            }
             o++;
         }
         vb += __popc(vw[j]);
     }
 }
 
-__global__ void __launch_bounds__(256) cand_hash_kernel(const uint64_t* __restrict__ cpos, uint64_t n_cand, const uint32_t* __restrict__ pk,
-                                                         SketchParams P, SketchTables Tb, uint64_t* __restrict__ h0)
+__global__ void __launch_bounds__(256) cand_hash_kernel(const uint64_t* __restrict__ cpos, const uint64_t* __restrict__ d_n, uint64_t n_max,
+                                                         const uint32_t* __restrict__ pk, SketchParams P, SketchTables Tb, uint64_t* __restrict__ h0)
 {
     __shared__ HashTabs H;
     build_hash_tabs(&H, Tb, P.k);
+    const uint64_t n_cand = dev_count(d_n, n_max);
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_cand) return;
     uint64_t f, r;
@@ -737,8 +750,8 @@ __device__ __forceinline__ void stage_pos_tables(const SketchTables& Tb, int k, 
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) cand_hash_pos_kernel(const uint64_t* __restrict__ cpos, uint64_t n_cand, const uint32_t* __restrict__ pk,
-                                                             SketchParams P, SketchTables Tb, const uint64_t* __restrict__ PF,
+__global__ void __launch_bounds__(256) cand_hash_pos_kernel(const uint64_t* __restrict__ cpos, const uint64_t* __restrict__ d_n, uint64_t n_max,
+                                                             const uint32_t* __restrict__ pk, SketchParams P, SketchTables Tb, const uint64_t* __restrict__ PF,
                                                              const uint64_t* __restrict__ PR, uint64_t* __restrict__ h0)
 {
     extern __shared__ uint64_t hp[];
@@ -747,6 +760,7 @@ __global__ void __launch_bounds__(256) cand_hash_pos_kernel(const uint64_t* __re
     uint64_t* pr = hp + G * 256;
     __shared__ uint64_t s1[8];
     stage_pos_tables(Tb, P.k, PF, PR, pf, pr, s1);
+    const uint64_t n_cand = dev_count(d_n, n_max);
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cand; i += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t f, r;
         kmer_hash64_pos(pk, cpos[i], P.k, pf, pr, s1, f, r);
@@ -900,9 +914,10 @@ __device__ __forceinline__ void push_gap(const GapList& G, uint64_t ja, uint64_t
 template <bool NARROW>
 __global__ void __launch_bounds__(256) select_kernel(const uint64_t* __restrict__ cpos, const uint64_t* __restrict__ h0,
                                                       const uint64_t* __restrict__ gord, const uint32_t* __restrict__ ctg,
-                                                      uint64_t n_cand, const uint64_t* __restrict__ ostart,
+                                                      const uint64_t* __restrict__ d_n, uint64_t n_max, const uint64_t* __restrict__ ostart,
                                                       SketchParams P, uint32_t* __restrict__ M, GapList G)
 {
+    const uint64_t n_cand = dev_count(d_n, n_max);
     typedef typename std::conditional<NARROW, uint32_t, uint64_t>::type ord_t;   // ordinals
     typedef typename std::conditional<NARROW, uint32_t, uint64_t>::type idx_t;   // candidate indices
     const idx_t i = (idx_t)((uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
@@ -957,10 +972,11 @@ __global__ void __launch_bounds__(256) select_kernel(const uint64_t* __restrict_
 }
 
 // records that have windows but no candidate at all
-__global__ void empty_contig_gap_kernel(const uint64_t* __restrict__ cpos, uint64_t n_cand,
+__global__ void empty_contig_gap_kernel(const uint64_t* __restrict__ cpos, const uint64_t* __restrict__ d_n, uint64_t n_max,
                                         const uint64_t* __restrict__ offsets, uint32_t n_contigs,
                                         const uint64_t* __restrict__ ostart, SketchParams P, GapList G)
 {
+    const uint64_t n_cand = dev_count(d_n, n_max);
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_contigs) return;
     uint64_t os = ostart[c], oe = ostart[c + 1];
@@ -978,7 +994,7 @@ __global__ void empty_contig_gap_kernel(const uint64_t* __restrict__ cpos, uint6
 constexpr int GAP_CHUNK = 1024;   // window ends per chunk
 constexpr int GAP_RUN = 16;       // consecutive ordinals hashed by one thread (rolling)
 
-__global__ void __launch_bounds__(256) gap_kernel(const Gap* __restrict__ gaps, uint64_t n_gaps,
+__global__ void __launch_bounds__(256) gap_kernel(const Gap* __restrict__ gaps, const unsigned long long* __restrict__ d_n_gaps, uint64_t n_gaps_max,
                                                    const uint32_t* __restrict__ pk, const uint32_t* __restrict__ V,
                                                    const uint64_t* __restrict__ vprefix, uint64_t n_vblocks,
                                                    SketchParams P, SketchTables Tb,
@@ -994,6 +1010,7 @@ __global__ void __launch_bounds__(256) gap_kernel(const Gap* __restrict__ gaps, 
     uint64_t* Q = scratch_p + (uint64_t)blockIdx.x * stride;
     uint64_t* BM = scratch_bm + (uint64_t)blockIdx.x * (stride / 32 + 2);
     uint64_t* BI = scratch_bi + (uint64_t)blockIdx.x * (stride / 32 + 2);
+    const uint64_t n_gaps = dev_count(reinterpret_cast<const uint64_t*>(d_n_gaps), n_gaps_max);
     for (uint64_t g = blockIdx.x; g < n_gaps; g += gridDim.x) {
         const uint64_t ja = gaps[g].ja, jb = gaps[g].jb;
         for (uint64_t ca = ja; ca <= jb; ca += GAP_CHUNK) {
@@ -1070,7 +1087,7 @@ __device__ __forceinline__ void emit_minimizer(uint64_t i, uint64_t p, uint64_t 
     forward[i] = f <= r;
 }
 
-__global__ void __launch_bounds__(256) final_eval_kernel(const uint64_t* __restrict__ mpos, uint64_t n_mx,
+__global__ void __launch_bounds__(256) final_eval_kernel(const uint64_t* __restrict__ mpos, const uint64_t* __restrict__ d_n, uint64_t n_max,
                                                           const uint32_t* __restrict__ pk,
                                                           const uint64_t* __restrict__ offsets, uint32_t n_contigs,
                                                           SketchParams P, SketchTables Tb,
@@ -1080,6 +1097,7 @@ __global__ void __launch_bounds__(256) final_eval_kernel(const uint64_t* __restr
 {
     __shared__ HashTabs H;
     build_hash_tabs(&H, Tb, P.k);
+    const uint64_t n_mx = dev_count(d_n, n_max);
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_mx) return;
     const uint64_t p = mpos[i];

@@ -155,7 +155,7 @@ int bitmap_rank_build(Engine* e, const uint32_t* d_bits, size_t n_words, uint64_
 
 __global__ void __launch_bounds__(256) bitmap_extract_kernel(const uint32_t* __restrict__ bits, size_t n_words,
                                                               const uint64_t* __restrict__ prefix, size_t n_blocks,
-                                                              uint64_t* __restrict__ out)
+                                                              uint64_t* __restrict__ out, uint64_t cap)
 {
     const size_t sb = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -184,17 +184,18 @@ __global__ void __launch_bounds__(256) bitmap_extract_kernel(const uint32_t* __r
         while (v) {
             int b = __ffs(v) - 1;
             v &= v - 1;
-            out[o++] = base + b;
+            if (o < cap) out[o] = base + b;
+            o++;
         }
     }
 }
 
-int bitmap_extract(Engine* e, const uint32_t* d_bits, size_t n_words, const uint64_t* d_prefix, uint64_t* d_out)
+int bitmap_extract(Engine* e, const uint32_t* d_bits, size_t n_words, const uint64_t* d_prefix, uint64_t* d_out, uint64_t cap)
 {
     size_t n_blocks = (n_words + RANK_BLOCK_WORDS - 1) / RANK_BLOCK_WORDS;
     if (!n_blocks) return MXE_OK;
     unsigned grid = (unsigned)(((n_blocks + BBLOCKS - 1) / BBLOCKS * 32 + 255) / 256);
-    MXE_LAUNCH(e, bitmap_extract_kernel, grid, 256, 0, d_bits, n_words, d_prefix, n_blocks, d_out);
+    MXE_LAUNCH(e, bitmap_extract_kernel, grid, 256, 0, d_bits, n_words, d_prefix, n_blocks, d_out, cap);
     MXE_CUDA(cudaGetLastError());
     return MXE_OK;
 }

@@ -327,6 +327,18 @@ class Engine:
                                                     n, carr, int(k), int(w), self._flags(canonical), C.byref(out)))
         return Sketch(self, out, pynames)
 
+    def sketch_device_many(self, dptrs, offsets_list, k, w, canonical="sum"):
+        """Several device-resident assemblies, each in its own buffer: enqueued on two streams so that they run
+        concurrently (mxe_sketch_device_many).  Returns one Sketch per assembly."""
+        n = len(dptrs)
+        offs = [np.ascontiguousarray(o, dtype=np.uint64) for o in offsets_list]
+        dp = (C.c_void_p * n)(*[C.c_void_p(int(p) or None) for p in dptrs])
+        op = (C.POINTER(C.c_uint64) * n)(*[o.ctypes.data_as(C.POINTER(C.c_uint64)) for o in offs])
+        nc = (C.c_uint32 * n)(*[len(o) - 1 for o in offs])
+        out = (C.c_void_p * n)()
+        check(self._lib, self._lib.mxe_sketch_device_many(self._h, n, dp, op, nc, int(k), int(w), self._flags(canonical), out))
+        return [Sketch(self, C.c_void_p(out[a]), [str(i) for i in range(len(offs[a]) - 1)]) for a in range(n)]
+
     def sketch_device_multi(self, dptr, offsets_list, k, w, canonical="sum", starts=None):
         """Several assemblies resident in ONE device buffer, sketched in one call: offsets_list[a] are the record starts
         of assembly a relative to the assembly's own first base (n_records + 1 entries); starts[a] = byte offset of

@@ -219,3 +219,56 @@ def test_multi_assembly_single_call(engine, oracle):
             np.testing.assert_array_equal(res.support, want["edges"]["support_mask"])
             res.close()
             parent.close()
+
+
+@pytest.mark.parametrize("scale", [0.002, 0.05])
+def test_size_bounds_overflow_repeats_exactly(engine, oracle, scale):
+    """the sketch sizes its candidate / gap / minimizer arrays from bounds and reads the exact counts once, at the end;
+    when a bound is too small (forced here by shrinking them) the call repeats itself with exact sizes -- same result,
+    from device and from host buffers, and the same as with the round trips of the exact path"""
+    import torch
+    seq, offs = _messy(900_000, 41)
+    ref = oracle.sketch(seq, offs, 32, 100)
+    engine.set_option("bound_scale", scale)
+    try:
+        assert_same(engine.sketch_buffers(seq, offs, 32, 100), ref)
+        dseq = torch.from_numpy(np.ascontiguousarray(seq)).cuda()
+        assert_same(engine.sketch_device(dseq.data_ptr(), offs, 32, 100), ref)
+    finally:
+        engine.set_option("bound_scale", 1.0)
+    engine.set_option("async_sizes", 0)
+    try:
+        assert_same(engine.sketch_buffers(seq, offs, 32, 100), ref)
+    finally:
+        engine.set_option("async_sizes", 1)
+
+
+def test_concurrent_sketches_two_streams(engine, oracle):
+    """Engine.sketch_device_many: several assemblies enqueued on two streams; same tuples as one call each, and the
+    filter that follows on the engine stream sees both results"""
+    import torch
+    a = synth.make_reference(2_000_000, n_chrom=4, seed=21, dup_frac=0.02, n_frac=0.004)
+    b = synth.derive_target(a[0], a[1], min_len=3_000, max_len=200_000)
+    c = synth.make_reference(300_001, n_chrom=2, seed=22)
+    asms = [(a[0], a[1]), (b[0], b[1]), (c[0], c[1])]
+    refs = [oracle.sketch(s, o, 32, 250) for s, o in asms]
+    dev = [torch.from_numpy(np.ascontiguousarray(s)).cuda() for s, _ in asms]
+    for rep in range(3):
+        sks = engine.sketch_device_many([d.data_ptr() for d in dev], [o for _, o in asms], 32, 250)
+        res = engine.filter_and_edges(sks, [2.0, 1.0, 1.0])
+        for sk, ref in zip(sks, refs):
+            assert_same(sk, ref)
+        want = oracle.filter_and_edges([r["out_hash"] for r in refs], [r["contig"] for r in refs], [2.0, 1.0, 1.0])
+        np.testing.assert_array_equal(res.vertices, want["vertices"])
+        np.testing.assert_array_equal(res.edge_u, want["edges"]["u"])
+        res.close()
+        for sk in sks:
+            sk.close()
+    # a too-small size bound on one of them: that assembly repeats itself with exact sizes
+    engine.set_option("bound_scale", 0.01)
+    try:
+        sks = engine.sketch_device_many([d.data_ptr() for d in dev], [o for _, o in asms], 32, 250)
+        for sk, ref in zip(sks, refs):
+            assert_same(sk, ref)
+    finally:
+        engine.set_option("bound_scale", 1.0)
