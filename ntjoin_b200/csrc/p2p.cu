@@ -980,6 +980,9 @@ int mxe_p2p_scatter(mxe_p2p_t* X, const void* const* d_hash, const void* const* 
     MXE_TRY(p2p_barrier_signal(X, 0));
     MXE_TRY(p2p_barrier_wait(X, 0));
     MXE_CUDA(cudaMemsetAsync(X->ws + Y.off_succ, 0, (size_t)n_asm * Y.nv_cap * 4, st));
+    // marks of own minimizers: every record that reaches its bucket gets one; a record dropped by an overflowing bucket
+    // (the call then fails and falls back) must not leave an unwritten word behind
+    if (L) MXE_CUDA(cudaMemsetAsync(X->ws + Y.off_mk, 0, L * 4, st));
     if (Y.world > 1) MXE_CUDA(cudaMemsetAsync(X->ws + Y.off_pred, 0, (size_t)n_asm * Y.nv_cap * 4, st));
     AsmCounts C;
     C.n_asm = n_asm;

@@ -543,9 +543,16 @@ static int sketch_device_pass(mxe_engine* e, const uint8_t* d_seq, uint64_t n, c
         DBuf<uint64_t> mpos;
         MXE_TRY(mpos.alloc(mx_cap, st));
         MXE_TRY(bitmap_extract(e, M.p, nW, mprefix.p, mpos.p, mx_cap));
-        // (the position-specific tables of the candidate stage do not pay here: 6 M items cannot amortise staging 32 KB per CTA)
-        MXE_LAUNCH(e, final_eval_kernel, grid_for(mx_cap, 256), 256, 0, mpos.p, d_nmx, mx_cap, pk.p, d_offsets.p, n_contigs, P, Tb,
-                   S->d_out_hash, S->d_min_hash, S->d_pos, S->d_contig, S->d_forward);
+        if (pos_tables && PF.p) {
+            // the position-specific tables of the candidate stage, staged once per CTA of a persistent grid
+            MXE_CUDA(cudaFuncSetAttribute(final_eval_pos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
+            const unsigned grid = (unsigned)std::min<uint64_t>(grid_for(mx_cap, 256), (uint64_t)e->sm_count * 4);
+            MXE_LAUNCH(e, final_eval_pos_kernel, grid, 256, hsm, mpos.p, d_nmx, mx_cap, pk.p, d_offsets.p, n_contigs, P, Tb, PF.p, PR.p,
+                       S->d_out_hash, S->d_min_hash, S->d_pos, S->d_contig, S->d_forward);
+        } else {
+            MXE_LAUNCH(e, final_eval_kernel, grid_for(mx_cap, 256), 256, 0, mpos.p, d_nmx, mx_cap, pk.p, d_offsets.p, n_contigs, P, Tb,
+                       S->d_out_hash, S->d_min_hash, S->d_pos, S->d_contig, S->d_forward);
+        }
     }
     if (!exact && defer) {
         // counts into pinned memory; the caller reads them after it has enqueued the other assemblies (sketch_complete)

@@ -1106,4 +1106,32 @@ __global__ void __launch_bounds__(256) final_eval_kernel(const uint64_t* __restr
     emit_minimizer(i, p, f, r, offsets, n_contigs, P, out_hash, min_hash, pos, contig, forward);
 }
 
+// The same with the position-specific tables of the candidate stage (k / 4 <= HASHPOS_MAX_GROUPS), persistent grid: the
+// tables are staged once per CTA and every thread loops over minimizers.  final_eval_kernel rebuilds its 4-base tables
+// in every CTA (~300 instructions per thread for ONE minimizer per thread: measured 200 M warp instructions, ALU pipe
+// 92 %, 0.25 ms per 6 M minimizers).
+__global__ void __launch_bounds__(256) final_eval_pos_kernel(const uint64_t* __restrict__ mpos, const uint64_t* __restrict__ d_n, uint64_t n_max,
+                                                              const uint32_t* __restrict__ pk,
+                                                              const uint64_t* __restrict__ offsets, uint32_t n_contigs,
+                                                              SketchParams P, SketchTables Tb, const uint64_t* __restrict__ PF,
+                                                              const uint64_t* __restrict__ PR,
+                                                              uint64_t* __restrict__ out_hash, uint64_t* __restrict__ min_hash,
+                                                              uint32_t* __restrict__ pos, uint32_t* __restrict__ contig,
+                                                              uint8_t* __restrict__ forward)
+{
+    extern __shared__ uint64_t hp[];
+    const int G = P.k / 4;
+    uint64_t* pf = hp;
+    uint64_t* pr = hp + G * 256;
+    __shared__ uint64_t s1[8];
+    stage_pos_tables(Tb, P.k, PF, PR, pf, pr, s1);
+    const uint64_t n_mx = dev_count(d_n, n_max);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_mx; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t p = mpos[i];
+        uint64_t f, r;
+        kmer_hash64_pos(pk, p, P.k, pf, pr, s1, f, r);
+        emit_minimizer(i, p, f, r, offsets, n_contigs, P, out_hash, min_hash, pos, contig, forward);
+    }
+}
+
 }  // namespace mxe
