@@ -654,7 +654,9 @@ def main():
         res.close()
 
     def step_e2e():
-        sks = eng.sketch_many([(h, o) for h, (_, o, _) in zip(host, shards)], K, W)   # H2D of assembly i+1 overlaps sketch i
+        # H2D of assembly i+1 overlaps sketch i; the tuples of assembly i start their way back as soon as sketch i is done
+        # (the other PCIe direction), beside the H2D / sketch of assembly i+1 and steps 2-3
+        sks = eng.sketch_many([(h, o) for h, (_, o, _) in zip(host, shards)], K, W, prefetch_host=True)
         res = gather_and_filter(sks)
         for sk in sks:
             sk.fetch(copy=False)              # (out_hash, min_hash, pos, record, strand) of every minimizer into pinned host memory
@@ -723,7 +725,7 @@ def main():
         if fine:                 # every kernel of steps 2-3, and the waits at the device-side barriers (sketch-time skew lands in wait0)
             for nm in ("p2p_wait0", "p2p_wait1", "p2p_wait2", "p2p_wait3", "p2p_wait4", "k_p2p_scatter_kernel", "k_p2p_push_counts_kernel",
                        "k_p2p_bucket_kernel", "k_p2p_vbase_kernel", "k_p2p_flags_kernel", "k_p2p_compact_kernel", "k_p2p_succ_kernel",
-                       "k_p2p_sight_kernel", "k_p2p_edge_owner_kernel", "k_p2p_table_kernel", "k_p2p_rec_owner_kernel", "k_p2p_clear_tail_kernel",
+                       "k_p2p_sight_kernel", "k_p2p_edge_owner_kernel", "k_p2p_table_kernel", "k_p2p_rec_owner_kernel",
                        "k_p2p_vertices_kernel", "k_p2p_first_count_kernel", "k_p2p_first_start_kernel", "k_p2p_edge_emit_kernel", "k_p2p_rec_emit_kernel"):
                 t_k = eng.timing(nm)[0]
                 if t_k:

@@ -124,6 +124,11 @@ int mxe_sketch_view(mxe_sketch_t* s, uint64_t* n,
                     const uint32_t** contig,     /* record index                                */
                     const uint8_t**  forward);   /* fwd <= rev                                  */
 
+/* Start the device->host copy behind mxe_sketch_view now, on a copy stream of the engine, and return at once: the copy
+ * runs beside the next assembly's host->device copy and sketch (PCIe is full duplex) instead of after them.  A later
+ * mxe_sketch_view only waits for it.  No-op for host-only sketches and when the host copy already exists. */
+int mxe_sketch_prefetch_host(mxe_sketch_t* s);
+
 /* Device view (valid only with MXE_KEEP_DEVICE): raw device pointers of the same SoA. */
 int mxe_sketch_device_view(mxe_sketch_t* s, uint64_t* n, const void** d_out_hash,
                            const void** d_pos, const void** d_contig);

@@ -9,7 +9,7 @@ _LIB = None
 SYMBOLS = [
     "mxe_version", "mxe_last_error", "mxe_create", "mxe_destroy", "mxe_set_stream", "mxe_set_option",
     "mxe_fasta_read", "mxe_fasta_view", "mxe_fasta_name", "mxe_fasta_free",
-    "mxe_sketch_file", "mxe_sketch_buffers", "mxe_prefetch_buffers", "mxe_sketch_device", "mxe_sketch_device_many", "mxe_sketch_from_arrays", "mxe_sketch_load_tsv", "mxe_sketch_view",
+    "mxe_sketch_file", "mxe_sketch_buffers", "mxe_prefetch_buffers", "mxe_sketch_device", "mxe_sketch_device_many", "mxe_sketch_from_arrays", "mxe_sketch_load_tsv", "mxe_sketch_view", "mxe_sketch_prefetch_host",
     "mxe_sketch_device_view", "mxe_sketch_record_start", "mxe_sketch_contig_name", "mxe_sketch_counts", "mxe_write_tsv", "mxe_sketch_free",
     "mxe_filter_and_edges", "mxe_filter_and_edges_device", "mxe_result_counts", "mxe_result_flags", "mxe_result_graph",
     "mxe_result_free", "mxe_write_dot", "mxe_timing", "mxe_timing_reset", "mxe_kernel_launches",
@@ -64,6 +64,7 @@ def load_library():
     lib.mxe_sketch_from_arrays.argtypes = [vp, vp, vp, vp, vp, C.c_uint64, C.POINTER(C.c_char_p), u64p, C.c_uint32, C.c_int, vp, pp]
     lib.mxe_sketch_load_tsv.argtypes = [vp, C.c_char_p, pp]
     lib.mxe_sketch_view.argtypes = [vp, u64p, pp, pp, pp, pp, pp]
+    lib.mxe_sketch_prefetch_host.argtypes = [vp]
     lib.mxe_sketch_device_view.argtypes = [vp, u64p, pp, pp, pp]
     lib.mxe_sketch_record_start.argtypes = [vp, C.c_uint32, u64p]
     lib.mxe_sketch_contig_name.argtypes = [vp, C.c_uint32, C.POINTER(C.c_char_p)]

@@ -187,6 +187,8 @@ void mxe_destroy(mxe_t* e)
     }
     if (e->aux_stream) { cudaStreamSynchronize(e->aux_stream); cudaStreamDestroy(e->aux_stream); }
     if (e->aux_event) cudaEventDestroy(e->aux_event);
+    if (e->d2h_stream) { cudaStreamSynchronize(e->d2h_stream); cudaStreamDestroy(e->d2h_stream); }
+    if (e->d2h_event) cudaEventDestroy(e->d2h_event);
     cudaStreamDestroy(e->own_stream);
     delete e;
 }
@@ -417,11 +419,10 @@ int mxe_sketch_load_tsv(mxe_t* e, const char* tsv_path, mxe_sketch_t** out)
     return MXE_OK;
 }
 
-static int ensure_host(mxe_sketch* S)
+// pinned block behind the host view of a sketch
+static int host_block(mxe_sketch* S)
 {
-    if (S->h_block || S->n == 0) return MXE_OK;
     mxe_engine* e = S->eng;
-    MXE_CUDA(cudaSetDevice(e->device));
     size_t n = S->n;
     size_t bytes = n * (8 + 8 + 4 + 4 + 1) + 64;
     char* blk = (char*)e->pinned_alloc(bytes);
@@ -432,13 +433,55 @@ static int ensure_host(mxe_sketch* S)
     S->h_pos = (uint32_t*)(blk + 16 * n);
     S->h_contig = (uint32_t*)(blk + 20 * n);
     S->h_forward = (uint8_t*)(blk + 24 * n);
-    cudaStream_t st = e->stream;
+    return MXE_OK;
+}
+
+static int host_copies(mxe_sketch* S, cudaStream_t st)
+{
+    const size_t n = S->n;
     MXE_CUDA(cudaMemcpyAsync(S->h_out_hash, S->d_out_hash, 8 * n, cudaMemcpyDeviceToHost, st));
     MXE_CUDA(cudaMemcpyAsync(S->h_min_hash, S->d_min_hash, 8 * n, cudaMemcpyDeviceToHost, st));
     MXE_CUDA(cudaMemcpyAsync(S->h_pos, S->d_pos, 4 * n, cudaMemcpyDeviceToHost, st));
     MXE_CUDA(cudaMemcpyAsync(S->h_contig, S->d_contig, 4 * n, cudaMemcpyDeviceToHost, st));
     MXE_CUDA(cudaMemcpyAsync(S->h_forward, S->d_forward, n, cudaMemcpyDeviceToHost, st));
-    MXE_CUDA(cudaStreamSynchronize(st));
+    return MXE_OK;
+}
+
+static int ensure_host(mxe_sketch* S)
+{
+    if (S->h_block) {
+        if (S->h_pending) {                        // started by mxe_sketch_prefetch_host: wait for it, nothing else
+            MXE_CUDA(cudaEventSynchronize(S->h_ready));
+            S->h_pending = false;
+        }
+        return MXE_OK;
+    }
+    if (S->n == 0) return MXE_OK;
+    mxe_engine* e = S->eng;
+    MXE_CUDA(cudaSetDevice(e->device));
+    MXE_TRY(host_block(S));
+    MXE_TRY(host_copies(S, e->stream));
+    MXE_CUDA(cudaStreamSynchronize(e->stream));
+    return MXE_OK;
+}
+
+int mxe_sketch_prefetch_host(mxe_sketch_t* S)
+{
+    if (!S) { set_error("null sketch"); return MXE_ERR_ARG; }
+    if (!S->eng || S->h_block || S->n == 0) return MXE_OK;      // host-only sketch, copy already there or in flight, nothing to copy
+    mxe_engine* e = S->eng;
+    MXE_CUDA(cudaSetDevice(e->device));
+    if (!e->d2h_stream) MXE_CUDA(cudaStreamCreateWithFlags(&e->d2h_stream, cudaStreamNonBlocking));
+    if (!e->d2h_event) MXE_CUDA(cudaEventCreateWithFlags(&e->d2h_event, cudaEventDisableTiming));
+    if (!S->h_ready) MXE_CUDA(cudaEventCreateWithFlags(&S->h_ready, cudaEventDisableTiming));
+    MXE_TRY(host_block(S));
+    // the arrays were produced in engine-stream order; the copies run on their own stream, beside whatever the engine
+    // stream and the host->device copy streams do next (PCIe is full duplex)
+    MXE_CUDA(cudaEventRecord(e->d2h_event, e->stream));
+    MXE_CUDA(cudaStreamWaitEvent(e->d2h_stream, e->d2h_event, 0));
+    MXE_TRY(host_copies(S, e->d2h_stream));
+    MXE_CUDA(cudaEventRecord(S->h_ready, e->d2h_stream));
+    S->h_pending = true;
     return MXE_OK;
 }
 
@@ -568,6 +611,8 @@ void mxe_sketch_free(mxe_sketch_t* S)
     if (S->eng) {
         cudaSetDevice(S->eng->device);
         cudaStream_t st = S->eng->stream;
+        if (S->h_pending) cudaEventSynchronize(S->h_ready);      // the pinned block and the arrays are still being read
+        if (S->h_ready) cudaEventDestroy(S->h_ready);
         if (S->d_out_hash) cudaFreeAsync(S->d_out_hash, st);
         if (S->d_min_hash) cudaFreeAsync(S->d_min_hash, st);
         if (S->d_pos) cudaFreeAsync(S->d_pos, st);

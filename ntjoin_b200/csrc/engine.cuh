@@ -39,6 +39,8 @@ struct mxe_engine : public mxe::Engine {
     cudaStream_t copy_stream[2] = {nullptr, nullptr};
     cudaStream_t aux_stream = nullptr;      // second compute stream: sketches of several assemblies run concurrently
     cudaEvent_t aux_event = nullptr;
+    cudaStream_t d2h_stream = nullptr;      // device->host copies that run beside the next assembly's host->device copy (mxe_sketch_prefetch_host)
+    cudaEvent_t d2h_event = nullptr;
     H2DSlot slot[2];
     int h2d_chunk_mb = 256;
     // pinned host block pool (grow-only, reused across steps)
@@ -68,6 +70,7 @@ struct mxe_sketch {
     void* h_block = nullptr; size_t h_bytes = 0;
     uint64_t* h_out_hash = nullptr; uint64_t* h_min_hash = nullptr;
     uint32_t* h_pos = nullptr; uint32_t* h_contig = nullptr; uint8_t* h_forward = nullptr;
+    cudaEvent_t h_ready = nullptr; bool h_pending = false;      // host copy in flight on the engine's d2h stream (mxe_sketch_prefetch_host)
     // sequence text for --seq output: either an owned copy of the whole input or nothing
     mxe::HostText seq_text;           // upper-cased concatenated sequence (mxe_sketch_file)
     const uint8_t* seq_borrowed = nullptr;   // caller buffer (mxe_sketch_buffers), valid while caller keeps it

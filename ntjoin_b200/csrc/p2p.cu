@@ -28,8 +28,12 @@
 //                            vertices of its hash range, the edges whose source vertex it owns) with 64-bit order keys.
 //
 // Uniqueness is per ASSEMBLY, not per GPU (bin/ntjoin_utils.py:182-187): the owner of a bucket sees the full multiset.
-// A bucket or sub-slot that overflows (adversarial input: one hash repeated thousands of times) raises an error flag
-// and the caller falls back to the sort-based formulation of filter.cu.
+// Repeated sequence puts thousands of copies of one hash into one bucket.  world > 1: the owner cuts the received
+// records into EXACTLY sized bucket ranges (count, prefix sum, place), and a bucket larger than the shared memory of
+// its CTA is reduced while it is loaded: at most two copies of every (hash, assembly) pair are kept -- two already
+// prove "not unique", the dropped copies keep the mark 0 = "not unique, not kept" their slots were cleared to.
+// world == 1 keeps fixed sub-slots (one pass); an overflow there raises an error flag and mxe_filter_and_edges falls
+// back to the sort-based formulation of filter.cu by itself.
 #include "engine.cuh"
 
 #include <algorithm>
@@ -39,7 +43,7 @@
 namespace mxe {
 
 constexpr int P2P_MAX_WORLD = 16;
-constexpr int P2P_BK_MAX = 1024;          // records of one bucket (shared memory of the bucket kernel)
+constexpr int P2P_BK_MAX = 1024;          // most records a bucket CTA can hold in shared memory (P2PLayout::bk_max: 512 or 1024)
 constexpr int P2P_BK_THREADS = 128;       // = digits of the in-bucket counting sort (7 bits)
 constexpr int P2P_N_BARRIERS = 8;
 
@@ -48,14 +52,16 @@ struct PtrTab { const void* p[32]; };
 
 struct P2PLayout {
     int world, rank, n_asm_max, B;
+    int n_asm;                             // assemblies of the call in flight (set by mxe_p2p_scatter): stride of the vertex tables
     uint32_t n_buckets;                    // 2^B
     uint32_t fb[P2P_MAX_WORLD + 1];        // first bucket of every rank
     uint32_t nb_own_max;                   // most buckets one rank owns
-    uint32_t cap_sub;                      // records per (bucket, source) sub-slot
+    uint32_t cap_sub;                      // records per bucket sub-slot (world == 1; world > 1 places buckets at exact offsets)
+    int bk_max;                            // records a bucket CTA holds in shared memory: 512 or 1024
     uint64_t L_cap;                        // minimizers of one rank, all assemblies
     uint64_t nv_cap;                       // vertices of one owner
     // byte offsets inside every rank's workspace
-    uint64_t off_flags, off_err, off_counts, off_rec_cnt, off_nkeep, off_rec, off_mk, off_succ, off_vgid, off_pred, off_cnt2, off_rec2, off_cnt1, off_seg1, bytes;
+    uint64_t off_flags, off_err, off_counts, off_rec_cnt, off_nkeep, off_rec, off_mk, off_tab, off_pred, off_cnt2, off_rec2, off_cnt1, off_seg1, bytes;
     uint64_t cap1;                         // minimizer records per (owner, source) segment (world > 1)
     uint64_t cap2;                         // sighting records per (owner, source) segment (world > 1)
 };
@@ -63,6 +69,23 @@ struct P2PLayout {
 struct P2PRecord { uint64_t key, tag; };   // tag = asm << 40 | source rank << 32 | local index
 
 __host__ __device__ __forceinline__ uint32_t p2p_owner(uint32_t b, int world, int B) { return (uint32_t)(((uint64_t)b * (uint64_t)world) >> B); }
+
+// Vertex tables of an owner, INTERLEAVED by assembly: the entries of one vertex in all assemblies share a sector, so the
+// support test of a sighting (the successors of v and of x in every assembly) costs two sector reads instead of
+// 2 * n_asm (the per-assembly planes [a][vertex] of the first version made these kernels the most expensive of steps 2-3:
+// ~146 M random 4-byte accesses per step of configs[2]).
+//   tab[(vloc * n_asm + a) * 2]     = 1 + successor vertex of vloc in assembly a (0 = none); bit 31 = "this sighting
+//                                      created an edge" (ownership mark, p2p_edge_owner_kernel)
+//   tab[(vloc * n_asm + a) * 2 + 1] = creation index of the survivor (a, vloc)
+//   pred[vloc * n_asm + a]          = 1 + predecessor vertex (world > 1, records mode)
+__device__ __forceinline__ uint32_t* p2p_tab(const PeerPtrs& P, const P2PLayout& Y, int o, uint64_t vloc)
+{
+    return reinterpret_cast<uint32_t*>(P.base[o] + Y.off_tab) + vloc * (uint64_t)(2 * Y.n_asm);
+}
+__device__ __forceinline__ uint32_t* p2p_pred(const PeerPtrs& P, const P2PLayout& Y, int o, uint64_t vloc)
+{
+    return reinterpret_cast<uint32_t*>(P.base[o] + Y.off_pred) + vloc * (uint64_t)Y.n_asm;
+}
 
 __device__ __forceinline__ int p2p_slice_of(const LocalSlices& S, uint64_t l)
 {
@@ -204,71 +227,162 @@ __global__ void p2p_push_cnt1_kernel(const uint32_t* __restrict__ cur1, AsmCount
     }
 }
 
-// owner: the received records of every source -> bucket sub-slots (local stores, local atomics)
-__global__ void __launch_bounds__(256) p2p_partition_kernel(PeerPtrs P, P2PLayout Y)
+// owner: the received records of every source -> bucket ranges of EXACT size (local stores, local atomics): count per
+// bucket, exclusive prefix, place.  No per-bucket capacity: a hash repeated 50,000 times makes one long bucket instead
+// of an error (p2p_bucket_kernel reduces it while loading).
+__device__ __forceinline__ bool p2p_seg_record(const PeerPtrs& P, const P2PLayout& Y, uint64_t idx, ulonglong2* r)
 {
-    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t seg = (uint32_t)(idx / Y.cap1);
-    if (seg >= (uint32_t)Y.world) return;
+    if (seg >= (uint32_t)Y.world) return false;
     const uint64_t i = idx - (uint64_t)seg * Y.cap1;
+    const char* me = P.base[Y.rank];
+    if (i >= reinterpret_cast<const uint32_t*>(me + Y.off_cnt1)[seg]) return false;
+    *r = reinterpret_cast<const ulonglong2*>(me + Y.off_seg1)[idx];
+    return true;
+}
+
+__global__ void __launch_bounds__(256) p2p_part_count_kernel(PeerPtrs P, P2PLayout Y, uint32_t* __restrict__ bcount)
+{
+    ulonglong2 r;
+    if (!p2p_seg_record(P, Y, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, &r)) return;
+    atomicAdd(&bcount[(uint32_t)(r.x >> (64 - Y.B)) - Y.fb[Y.rank]], 1u);
+}
+
+// one CTA: bstart[bl] = exclusive prefix of the bucket counts (nb + 1 entries, in the workspace: the bucket and vertex
+// kernels read it); the counts are replaced by the same values = placement cursors
+__global__ void __launch_bounds__(1024) p2p_part_start_kernel(PeerPtrs P, P2PLayout Y, uint32_t* __restrict__ bcount)
+{
+    __shared__ uint32_t sw[32];
+    __shared__ uint32_t carry_s;
+    uint32_t* bstart = reinterpret_cast<uint32_t*>(P.base[Y.rank] + Y.off_rec_cnt);
+    const uint32_t nb = Y.fb[Y.rank + 1] - Y.fb[Y.rank];
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nb; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < nb ? bcount[i] : 0u;
+        uint32_t x = v;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+        if (lane == 31) sw[warp] = x;
+        __syncthreads();
+        uint32_t wb = 0;
+        for (int wv = 0; wv < warp; wv++) wb += sw[wv];
+        const uint32_t carry = carry_s;
+        if (i < nb) { bstart[i] = carry + wb + x - v; bcount[i] = carry + wb + x - v; }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + wb + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) bstart[nb] = carry_s;
+}
+
+__global__ void __launch_bounds__(256) p2p_part_place_kernel(PeerPtrs P, P2PLayout Y, uint32_t* __restrict__ bcursor)
+{
+    ulonglong2 r;
+    if (!p2p_seg_record(P, Y, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, &r)) return;
+    const uint32_t pos = atomicAdd(&bcursor[(uint32_t)(r.x >> (64 - Y.B)) - Y.fb[Y.rank]], 1u);
+    reinterpret_cast<ulonglong2*>(P.base[Y.rank] + Y.off_rec)[pos] = r;      // pos < sum of the segment counts <= world * cap1
+}
+
+// the records of local bucket bl: one contiguous range.  world == 1: the bucket's fixed sub-slot (filled by
+// p2p_scatter_kernel, count pushed by p2p_push_counts_kernel); world > 1: [bstart[bl], bstart[bl + 1]).
+__device__ __forceinline__ P2PRecord* p2p_bucket_range(const PeerPtrs& P, const P2PLayout& Y, uint32_t bl, uint32_t* n)
+{
     char* me = P.base[Y.rank];
-    if (i >= reinterpret_cast<const uint32_t*>(me + Y.off_cnt1)[seg]) return;
-    const ulonglong2 r = reinterpret_cast<const ulonglong2*>(me + Y.off_seg1)[idx];
-    const uint32_t bl = (uint32_t)(r.x >> (64 - Y.B)) - Y.fb[Y.rank];
-    const uint32_t slot = atomicAdd(reinterpret_cast<uint32_t*>(me + Y.off_rec_cnt) + (uint64_t)bl * Y.world + seg, 1u);
-    if (slot >= Y.cap_sub) { *reinterpret_cast<uint32_t*>(me + Y.off_err) = 1u; return; }
-    reinterpret_cast<ulonglong2*>(me + Y.off_rec)[((uint64_t)bl * Y.world + seg) * Y.cap_sub + slot] = r;
+    const uint32_t* tab = reinterpret_cast<const uint32_t*>(me + Y.off_rec_cnt);
+    P2PRecord* rec = reinterpret_cast<P2PRecord*>(me + Y.off_rec);
+    if (Y.world == 1) {
+        *n = tab[bl] < Y.cap_sub ? tab[bl] : Y.cap_sub;
+        return rec + (uint64_t)bl * Y.cap_sub;
+    }
+    *n = tab[bl + 1] - tab[bl];
+    return rec + tab[bl];
 }
 
 // ---------------------------------------------------------------- stage 2: one CTA per owned bucket
 __device__ __forceinline__ bool rec_greater(uint64_t ka, uint64_t ta, uint64_t kb, uint64_t tb) { return ka > kb || (ka == kb && ta > tb); }
 
+constexpr uint64_t P2P_EMPTY = ~0ULL;      // free slot of the reduction table of an oversized bucket
+
+template <int BKMAX>
 __global__ void __launch_bounds__(P2P_BK_THREADS) p2p_bucket_kernel(PeerPtrs P, P2PLayout Y, int n_asm)
 {
     extern __shared__ uint64_t bk_smem[];
     uint64_t* skey = bk_smem;                          // sorted records
-    uint64_t* stag = bk_smem + P2P_BK_MAX;
-    uint64_t* ukey = bk_smem + 2 * P2P_BK_MAX;         // as loaded
-    uint64_t* utag = bk_smem + 3 * P2P_BK_MAX;
+    uint64_t* stag = bk_smem + BKMAX;
+    uint64_t* ukey = bk_smem + 2 * BKMAX;              // as loaded
+    uint64_t* utag = bk_smem + 3 * BKMAX;
     uint32_t* srank = reinterpret_cast<uint32_t*>(ukey);   // (after the sort) head flag -> exclusive rank of the kept runs
     __shared__ uint32_t dstart[P2P_BK_THREADS + 1];
     __shared__ uint32_t dfill[P2P_BK_THREADS];
-    __shared__ uint32_t soff[P2P_MAX_WORLD + 1];
     __shared__ uint32_t swarp[P2P_BK_THREADS / 32];
+    __shared__ uint32_t n_red_s, fail_s;
     const uint32_t bl = blockIdx.x;                                  // local bucket
     const uint32_t b = Y.fb[Y.rank] + bl;
     char* me = P.base[Y.rank];
-    const uint32_t* cnt = reinterpret_cast<const uint32_t*>(me + Y.off_rec_cnt) + (uint64_t)bl * Y.world;
-    P2PRecord* region = reinterpret_cast<P2PRecord*>(me + Y.off_rec) + (uint64_t)bl * Y.world * Y.cap_sub;
-    if (threadIdx.x == 0) {
-        uint32_t at = 0;
-        for (int s = 0; s < Y.world; s++) { soff[s] = at; at += cnt[s] < Y.cap_sub ? cnt[s] : Y.cap_sub; }
-        soff[Y.world] = at;
-    }
+    uint32_t n_in;
+    P2PRecord* region = p2p_bucket_range(P, Y, bl, &n_in);
     dfill[threadIdx.x] = 0u;
-    __syncthreads();
-    const uint32_t n = soff[Y.world];
-    if (n > P2P_BK_MAX) {
-        if (threadIdx.x == 0) {
-            *reinterpret_cast<uint32_t*>(me + Y.off_err) = 2u;
-            for (int p = 0; p < Y.world; p++) reinterpret_cast<uint32_t*>(P.base[p] + Y.off_nkeep)[b] = 0u;
-        }
-        return;
-    }
+    if (threadIdx.x == 0) { n_red_s = 0u; fail_s = 0u; }
     // Sort by (hash, tag): equal hashes end up grouped by assembly, then source rank, then position.  The hash is
     // uniformly mixed, so a counting sort on its next 7 bits leaves ~3 records per digit, finished by one thread per
     // digit with an insertion sort (a bitonic network moves every record log^2(n) / 2 times through shared memory:
     // measured 1.3 ms for 12 M records; this is four passes).
     const int dshift = 64 - Y.B - 7;
-    for (int s = 0; s < Y.world; s++) {
-        const uint32_t c = soff[s + 1] - soff[s];
-        const P2PRecord* src = region + (uint64_t)s * Y.cap_sub;
-        for (uint32_t i = threadIdx.x; i < c; i += P2P_BK_THREADS) {
-            const ulonglong2 r = *reinterpret_cast<const ulonglong2*>(src + i);
-            ukey[soff[s] + i] = r.x;
-            utag[soff[s] + i] = r.y;
+    uint32_t n = n_in;
+    if (n_in <= (uint32_t)BKMAX) {
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < n_in; i += P2P_BK_THREADS) {
+            const ulonglong2 r = *reinterpret_cast<const ulonglong2*>(region + i);
+            ukey[i] = r.x;
+            utag[i] = r.y;
             atomicAdd(&dfill[(uint32_t)(r.x >> dshift) & (P2P_BK_THREADS - 1)], 1u);
         }
+    } else {
+        // Oversized bucket = repeated sequence: thousands of copies of a few hashes beside the usual ~200 records.  Only
+        // "once" or "more than once" per (hash, assembly) matters (bin/ntjoin_utils.py:182-187), so at most TWO copies
+        // of every pair are loaded; the others are dropped here and keep mark 0 (not unique, not kept).  Table in the
+        // space of the sorted arrays: skey = hash (open addressing), stag = two bits per assembly (n_asm <= 32).
+        for (uint32_t i = threadIdx.x; i < (uint32_t)BKMAX; i += P2P_BK_THREADS) { skey[i] = P2P_EMPTY; stag[i] = 0ULL; }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < n_in; i += P2P_BK_THREADS) {
+            const ulonglong2 r = *reinterpret_cast<const ulonglong2*>(region + i);
+            if (r.x == P2P_EMPTY) { fail_s = 1u; continue; }        // cannot be told from a free slot (one hash value in 2^64)
+            uint32_t sl = ((uint32_t)r.x ^ (uint32_t)(r.x >> 29)) & (BKMAX - 1);
+            int probes = 0;
+            for (; probes < BKMAX; probes++, sl = (sl + 1) & (BKMAX - 1)) {
+                const unsigned long long cur = atomicCAS(reinterpret_cast<unsigned long long*>(&skey[sl]), (unsigned long long)P2P_EMPTY, (unsigned long long)r.x);
+                if (cur == P2P_EMPTY || cur == r.x) break;
+            }
+            if (probes == BKMAX) { fail_s = 1u; continue; }         // more distinct hashes than the table holds
+            const unsigned long long first = 1ULL << (2 * (int)((r.y >> 40) & 0x1F));
+            unsigned long long old = atomicOr(reinterpret_cast<unsigned long long*>(&stag[sl]), first);
+            bool keep = !(old & first);
+            if (!keep) {
+                old = atomicOr(reinterpret_cast<unsigned long long*>(&stag[sl]), first << 1);
+                keep = !(old & (first << 1));
+            }
+            if (keep) {
+                const uint32_t pos = atomicAdd(&n_red_s, 1u);
+                if (pos < (uint32_t)BKMAX) {
+                    ukey[pos] = r.x;
+                    utag[pos] = r.y;
+                    atomicAdd(&dfill[(uint32_t)(r.x >> dshift) & (P2P_BK_THREADS - 1)], 1u);
+                }
+            }
+        }
+        __syncthreads();
+        n = n_red_s;
+        if (fail_s) n = BKMAX + 1;
+    }
+    if (n > (uint32_t)BKMAX) {                                       // block-uniform
+        if (threadIdx.x == 0) {
+            *reinterpret_cast<uint32_t*>(me + Y.off_err) = 2u;
+            for (int p = 0; p < Y.world; p++) reinterpret_cast<uint32_t*>(P.base[p] + Y.off_nkeep)[b] = 0u;
+        }
+        return;
     }
     __syncthreads();
     {   // exclusive scan of the digit counts (one per thread)
@@ -306,9 +420,9 @@ __global__ void __launch_bounds__(P2P_BK_THREADS) p2p_bucket_kernel(PeerPtrs P, 
     __syncthreads();
     uint32_t Pn = n;
     // run analysis (as mark_kernel): unique inside its assembly; run = exactly one element of every assembly
-    uint32_t marks[P2P_BK_MAX / P2P_BK_THREADS];
+    uint32_t marks[BKMAX / P2P_BK_THREADS];
 #pragma unroll
-    for (int q = 0; q < P2P_BK_MAX / P2P_BK_THREADS; q++) {
+    for (int q = 0; q < BKMAX / P2P_BK_THREADS; q++) {
         const uint32_t i = threadIdx.x + q * P2P_BK_THREADS;
         uint32_t m = 0, head = 0;
         if (i < n) {
@@ -327,7 +441,7 @@ __global__ void __launch_bounds__(P2P_BK_THREADS) p2p_bucket_kernel(PeerPtrs P, 
             head = in_all && a == 0;
         }
         marks[q] = m;
-        if (i < P2P_BK_MAX) srank[i] = head;
+        if (i < BKMAX) srank[i] = head;
     }
     __syncthreads();
     // exclusive scan of the head flags over [0, Pn): thread t owns the contiguous chunk [t * per, (t + 1) * per)
@@ -354,7 +468,7 @@ __global__ void __launch_bounds__(P2P_BK_THREADS) p2p_bucket_kernel(PeerPtrs P, 
     uint64_t* kept = reinterpret_cast<uint64_t*>(region);
     __syncthreads();
 #pragma unroll
-    for (int q = 0; q < P2P_BK_MAX / P2P_BK_THREADS; q++) {
+    for (int q = 0; q < BKMAX / P2P_BK_THREADS; q++) {
         const uint32_t i = threadIdx.x + q * P2P_BK_THREADS;
         if (i >= n) continue;
         const uint64_t t = stag[i];
@@ -423,7 +537,8 @@ __global__ void __launch_bounds__(128) p2p_vertices_kernel(PeerPtrs P, P2PLayout
 {
     const uint32_t bl = blockIdx.x, b = Y.fb[Y.rank] + bl;
     const uint32_t v0 = T.vbase[b] - T.vown[Y.rank], nk = T.vbase[b + 1] - T.vbase[b];
-    const uint64_t* kept = reinterpret_cast<const uint64_t*>(reinterpret_cast<const P2PRecord*>(P.base[Y.rank] + Y.off_rec) + (uint64_t)bl * Y.world * Y.cap_sub);
+    uint32_t n_in;
+    const uint64_t* kept = reinterpret_cast<const uint64_t*>(p2p_bucket_range(P, Y, bl, &n_in));
     for (uint32_t i = threadIdx.x; i < nk; i += 128) vertices[v0 + i] = kept[i];
 }
 
@@ -463,7 +578,9 @@ __device__ __forceinline__ int p2p_vowner(const uint32_t* vown, int world, uint3
     return o;
 }
 
-// adjacent survivors of the same record and assembly: sighting flag + successor entry at the owner of the source
+// adjacent survivors of the same record and assembly: sighting flag; the table entry (a, v) -- successor and creation
+// index in ONE 8-byte store -- at the owner of v.  Every vertex has exactly one survivor in every assembly, so every
+// entry of every vertex is written here: the tables need no clearing in this mode.
 __global__ void __launch_bounds__(256) p2p_succ_kernel(const uint32_t* __restrict__ cvid, const uint32_t* __restrict__ cg,
                                                         const uint32_t* __restrict__ cloc,
                                                         const uint64_t* __restrict__ kprefix, uint64_t L, LocalSlices S, PtrTab Ctg,
@@ -472,28 +589,20 @@ __global__ void __launch_bounds__(256) p2p_succ_kernel(const uint32_t* __restric
     const uint64_t n_keep = kprefix[L];
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_keep) return;
-    uint32_t f = 0;
-    {
-        // creation index of this survivor, by (assembly, vertex): the first-source index of a vertex is read from here
-        const uint32_t l1 = cloc[j];
-        const int a = p2p_slice_of(S, l1);
-        const uint32_t v = cvid[j];
-        const int o = p2p_vowner(T.vown, Y.world, v);
-        reinterpret_cast<uint32_t*>(P.base[o] + Y.off_vgid)[(uint64_t)a * Y.nv_cap + (v - T.vown[o])] = cg[j];
-    }
+    const uint32_t l1 = cloc[j];
+    const int a = p2p_slice_of(S, l1);
+    const uint32_t v = cvid[j];
+    uint32_t f = 0, x = 0;
     if (j + 1 < n_keep) {
-        const uint32_t l1 = cloc[j], l2 = cloc[j + 1];
-        const int a = p2p_slice_of(S, l1);
+        const uint32_t l2 = cloc[j + 1];
         if (a == p2p_slice_of(S, l2)) {
             const uint32_t* ctg = reinterpret_cast<const uint32_t*>(Ctg.p[a]);
             f = ctg[l1 - S.lofs[a]] == ctg[l2 - S.lofs[a]];
-            if (f) {
-                const uint32_t v = cvid[j], x = cvid[j + 1];
-                const int o = p2p_vowner(T.vown, Y.world, v);
-                reinterpret_cast<uint32_t*>(P.base[o] + Y.off_succ)[(uint64_t)a * Y.nv_cap + (v - T.vown[o])] = x + 1u;
-            }
+            x = cvid[j + 1];
         }
     }
+    const int o = p2p_vowner(T.vown, Y.world, v);
+    *reinterpret_cast<uint2*>(p2p_tab(P, Y, o, v - T.vown[o]) + 2 * a) = make_uint2(f ? x + 1u : 0u, cg[j]);
     eflag[j] = f;
 }
 
@@ -507,34 +616,42 @@ __global__ void __launch_bounds__(256) p2p_edge_owner_kernel(const uint32_t* __r
 {
     const uint64_t n_keep = kprefix[L];
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_keep) return;
+    if (j >= L) return;
+    if (j >= n_keep) { own[j] = 0u; return; }        // the scan over own[] runs over L entries
     uint32_t is_owner = 0;
     if (eflag[j]) {
         const int a = p2p_slice_of(S, cloc[j]);
         const uint32_t v = cvid[j], x = cvid[j + 1];
         const int ov = p2p_vowner(T.vown, Y.world, v), ox = p2p_vowner(T.vown, Y.world, x);
-        uint32_t* sv = reinterpret_cast<uint32_t*>(P.base[ov] + Y.off_succ) + (v - T.vown[ov]);
-        const uint32_t* sx = reinterpret_cast<const uint32_t*>(P.base[ox] + Y.off_succ) + (x - T.vown[ox]);
+        uint32_t* tv = p2p_tab(P, Y, ov, v - T.vown[ov]);
+        const uint32_t* tx = p2p_tab(P, Y, ox, x - T.vown[ox]);
         uint32_t mask = 0;
         for (int b = 0; b < n_asm; b++)       // bit 31 of an entry is its ownership mark (below): compare the low 31 bits
-            if ((sv[(uint64_t)b * Y.nv_cap] & 0x7FFFFFFFu) == x + 1u || (sx[(uint64_t)b * Y.nv_cap] & 0x7FFFFFFFu) == v + 1u) mask |= 1u << b;
+            if ((tv[2 * b] & 0x7FFFFFFFu) == x + 1u || (tx[2 * b] & 0x7FFFFFFFu) == v + 1u) mask |= 1u << b;
         is_owner = (__ffs(mask) - 1) == a;
         mask_out[j] = mask;
         // "vertex v is the source of an edge created in assembly a": entry (a, v) has this sighting as its only writer,
         // so a plain store marks it (no atomics; readers of the successor ignore the bit)
-        if (is_owner) sv[(uint64_t)a * Y.nv_cap] = (x + 1u) | 0x80000000u;
+        if (is_owner) tv[2 * a] = (x + 1u) | 0x80000000u;
     }
     own[j] = is_owner;
 }
 
-// in which assemblies vertex v (local index at its owner o) is the source of a created edge, and the creation index of
-// its first one (a vertex occurs once per assembly; edges of one source are created in assembly order)
+// in which assemblies vertex v (local index at its owner o) is the source of a created edge (a vertex occurs once per
+// assembly; the edges of one source are created in assembly order, so the FIRST edge of a source is the one of the lowest
+// assembly in the mask)
+__device__ __forceinline__ uint32_t p2p_source_mask(const PeerPtrs& P, const P2PLayout& Y, int o, uint32_t vloc, int n_asm)
+{
+    const uint32_t* tv = p2p_tab(P, Y, o, vloc);
+    uint32_t smask = 0;
+    for (int b = 0; b < n_asm; b++) smask |= (tv[2 * b] >> 31) << b;
+    return smask;
+}
+// ... and the creation index of its first one (the order key of its block of edges)
 __device__ __forceinline__ uint32_t p2p_source_info(const PeerPtrs& P, const P2PLayout& Y, int o, uint32_t vloc, int n_asm, uint32_t* first_gid)
 {
-    const uint32_t* sv = reinterpret_cast<const uint32_t*>(P.base[o] + Y.off_succ) + vloc;
-    uint32_t smask = 0;
-    for (int b = 0; b < n_asm; b++) smask |= (sv[(uint64_t)b * Y.nv_cap] >> 31) << b;
-    *first_gid = smask ? reinterpret_cast<const uint32_t*>(P.base[o] + Y.off_vgid)[(uint64_t)(__ffs(smask) - 1) * Y.nv_cap + vloc] : 0xFFFFFFFFu;
+    const uint32_t smask = p2p_source_mask(P, Y, o, vloc, n_asm);
+    *first_gid = smask ? p2p_tab(P, Y, o, vloc)[2 * (__ffs(smask) - 1) + 1] : 0xFFFFFFFFu;
     return smask;
 }
 
@@ -542,45 +659,42 @@ __device__ __forceinline__ uint32_t p2p_source_info(const PeerPtrs& P, const P2P
 // order (= assembly order: a source owns at most one edge per assembly).  Owned edges are compacted in creation order
 // (uprefix); the first edge of a source carries the number of edges of that source, a prefix sum over them gives every
 // source's block -> each edge is PLACED, not sorted.  (world == 1)
-__global__ void __launch_bounds__(256) p2p_first_count_kernel(const uint32_t* __restrict__ cvid, const uint32_t* __restrict__ cg,
+// The source mask is read from the vertex table ONCE per edge (here) and kept by sighting (smask_j); the position of a
+// first edge is its own prefix entry, so only the later edges of a source that owns several go through vstart[] --
+// p2p_first_start_kernel and p2p_edge_emit_kernel are sequential passes for everything else.
+__global__ void __launch_bounds__(256) p2p_first_count_kernel(const uint32_t* __restrict__ cvid, const uint32_t* __restrict__ cloc,
                                                                const uint32_t* __restrict__ own, const uint64_t* __restrict__ uprefix,
-                                                               const uint64_t* __restrict__ kprefix, uint64_t L, PeerPtrs P, P2PLayout Y, int n_asm,
-                                                               uint32_t* __restrict__ fcount)
+                                                               const uint64_t* __restrict__ kprefix, uint64_t L, LocalSlices S, PeerPtrs P, P2PLayout Y, int n_asm,
+                                                               uint32_t* __restrict__ fcount, uint32_t* __restrict__ smask_j)
 {
     const uint64_t n_keep = kprefix[L];
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_keep || !own[j]) return;
-    uint32_t smin;
-    const uint32_t smask = p2p_source_info(P, Y, 0, cvid[j], n_asm, &smin);
-    fcount[uprefix[j]] = smin == cg[j] ? (uint32_t)__popc(smask) : 0u;
+    const int a = p2p_slice_of(S, cloc[j]);
+    const uint32_t smask = p2p_source_mask(P, Y, 0, cvid[j], n_asm);        // bit a is set: this sighting owns an edge
+    smask_j[j] = smask;
+    fcount[uprefix[j]] = (__ffs(smask) - 1) == a ? (uint32_t)__popc(smask) : 0u;
 }
 
-__global__ void __launch_bounds__(256) p2p_first_start_kernel(const uint32_t* __restrict__ cvid, const uint32_t* __restrict__ cg,
-                                                               const uint32_t* __restrict__ own, const uint64_t* __restrict__ uprefix,
-                                                               const uint64_t* __restrict__ fprefix, const uint64_t* __restrict__ kprefix, uint64_t L,
-                                                               PeerPtrs P, P2PLayout Y, int n_asm, uint32_t* __restrict__ vstart)
+__global__ void __launch_bounds__(256) p2p_first_start_kernel(const uint32_t* __restrict__ cvid, const uint32_t* __restrict__ cloc,
+                                                               const uint32_t* __restrict__ own, const uint32_t* __restrict__ smask_j,
+                                                               const uint64_t* __restrict__ uprefix, const uint64_t* __restrict__ fprefix,
+                                                               const uint64_t* __restrict__ kprefix, uint64_t L, LocalSlices S,
+                                                               uint32_t* __restrict__ vstart)
 {
     const uint64_t n_keep = kprefix[L];
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_keep || !own[j]) return;
-    const uint32_t v = cvid[j];
-    uint32_t smin;
-    p2p_source_info(P, Y, 0, v, n_asm, &smin);
-    if (smin == cg[j]) vstart[v] = (uint32_t)fprefix[uprefix[j]];
-}
-
-// own[] is only written for j < n_keep; the scan over it runs over L entries
-__global__ void __launch_bounds__(256) p2p_clear_tail_kernel(uint32_t* __restrict__ own, const uint64_t* __restrict__ kprefix, uint64_t L)
-{
-    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < L && j >= kprefix[L]) own[j] = 0u;
+    const uint32_t smask = smask_j[j];
+    if (__popc(smask) > 1 && (__ffs(smask) - 1) == p2p_slice_of(S, cloc[j])) vstart[cvid[j]] = (uint32_t)fprefix[uprefix[j]];
 }
 
 struct EdgeOut { uint64_t *eu, *ev, *ekey; uint32_t* emask; double* ew; };
 
 __global__ void __launch_bounds__(256) p2p_edge_emit_kernel(const uint32_t* __restrict__ cvid, const uint32_t* __restrict__ cg,
                                                              const uint32_t* __restrict__ cloc, const uint32_t* __restrict__ own,
-                                                             const uint32_t* __restrict__ mask_in, const uint64_t* __restrict__ uprefix,
+                                                             const uint32_t* __restrict__ mask_in, const uint32_t* __restrict__ smask_j,
+                                                             const uint64_t* __restrict__ uprefix, const uint64_t* __restrict__ fprefix,
                                                              const uint64_t* __restrict__ kprefix, uint64_t L, LocalSlices S, PtrTab H, AsmOffsets A,
                                                              PeerPtrs P, P2PLayout Y, HomeTabs T, const uint32_t* __restrict__ vstart, EdgeOut E)
 {
@@ -591,14 +705,14 @@ __global__ void __launch_bounds__(256) p2p_edge_emit_kernel(const uint32_t* __re
     const int a = p2p_slice_of(S, l1);
     const uint64_t* hs = reinterpret_cast<const uint64_t*>(H.p[a]);
     const uint32_t v = cvid[j];
-    const int ov = p2p_vowner(T.vown, Y.world, v);
-    const uint32_t vloc = v - T.vown[ov];
     uint64_t o;
-    uint32_t smin;
-    const uint32_t smask = p2p_source_info(P, Y, ov, vloc, A.n, &smin);
-    if (vstart) {       // single GPU: final position
-        o = (uint64_t)vstart[v] + (uint32_t)__popc(smask & ((1u << a) - 1u));
+    if (vstart) {       // single GPU: final position (first edge of its source: the start of the source's block)
+        const uint32_t smask = smask_j[j];
+        o = (__ffs(smask) - 1) == a ? fprefix[uprefix[j]] : (uint64_t)vstart[v] + (uint32_t)__popc(smask & ((1u << a) - 1u));
     } else {            // shard: creation order + global order key (first creation index of the source, creation index)
+        const int ov = p2p_vowner(T.vown, Y.world, v);
+        uint32_t smin;
+        p2p_source_info(P, Y, ov, v - T.vown[ov], A.n, &smin);
         o = uprefix[j];
         E.ekey[o] = ((uint64_t)smin << 32) | (uint64_t)cg[j];
     }
@@ -676,13 +790,8 @@ __global__ void __launch_bounds__(256) p2p_table_kernel(PeerPtrs P, P2PLayout Y)
     const uint64_t w1 = r[1], w2 = r[2];
     const uint64_t a = (w2 >> 1) & 0x7F, vloc = w1 >> 32;
     const uint32_t other = (uint32_t)w1 + 1u;
-    char* me = P.base[Y.rank];
-    if (w2 & 1ULL) {
-        reinterpret_cast<uint32_t*>(me + Y.off_pred)[a * Y.nv_cap + vloc] = other;
-    } else {
-        reinterpret_cast<uint32_t*>(me + Y.off_succ)[a * Y.nv_cap + vloc] = other;
-        reinterpret_cast<uint32_t*>(me + Y.off_vgid)[a * Y.nv_cap + vloc] = (uint32_t)(w2 >> 8);
-    }
+    if (w2 & 1ULL) p2p_pred(P, Y, Y.rank, vloc)[a] = other;
+    else *reinterpret_cast<uint2*>(p2p_tab(P, Y, Y.rank, vloc) + 2 * a) = make_uint2(other, (uint32_t)(w2 >> 8));
 }
 
 __global__ void __launch_bounds__(256) p2p_rec_owner_kernel(PeerPtrs P, P2PLayout Y, int n_asm, uint32_t* __restrict__ own, uint32_t* __restrict__ mask_out)
@@ -697,15 +806,14 @@ __global__ void __launch_bounds__(256) p2p_rec_owner_kernel(PeerPtrs P, P2PLayou
         const int a = (int)((w2 >> 1) & 0x7F);
         const uint64_t vloc = w1 >> 32;
         const uint32_t x1 = (uint32_t)w1 + 1u;
-        char* me = P.base[Y.rank];
-        uint32_t* sv = reinterpret_cast<uint32_t*>(me + Y.off_succ) + vloc;
-        const uint32_t* pv = reinterpret_cast<const uint32_t*>(me + Y.off_pred) + vloc;
+        uint32_t* tv = p2p_tab(P, Y, Y.rank, vloc);
+        const uint32_t* pv = p2p_pred(P, Y, Y.rank, vloc);
         uint32_t mask = 0;
         for (int b = 0; b < n_asm; b++)
-            if ((sv[(uint64_t)b * Y.nv_cap] & 0x7FFFFFFFu) == x1 || pv[(uint64_t)b * Y.nv_cap] == x1) mask |= 1u << b;
+            if ((tv[2 * b] & 0x7FFFFFFFu) == x1 || pv[b] == x1) mask |= 1u << b;
         is_owner = (__ffs(mask) - 1) == a;
         mask_out[idx] = mask;
-        if (is_owner) sv[(uint64_t)a * Y.nv_cap] = x1 | 0x80000000u;      // ownership mark (see p2p_edge_owner_kernel)
+        if (is_owner) tv[2 * a] = x1 | 0x80000000u;      // ownership mark (see p2p_edge_owner_kernel)
     }
     own[idx] = is_owner;
 }
@@ -824,7 +932,9 @@ int mxe_p2p_create(mxe_t* e, int rank, int world, uint64_t cap_total, int n_asm_
     memset(&Y, 0, sizeof(Y));
     Y.world = world; Y.rank = rank; Y.n_asm_max = n_asm_max;
     int B = 6;
-    while (B < 20 && (cap_total >> B) > 400) B++;                 // <= 400 records per bucket on average at full capacity
+    uint64_t per_bucket = 400;                                    // <= 400 records per bucket on average at full capacity
+    if (const char* sv = getenv("MXE_P2P_BUCKET_AVG")) { const long v = atol(sv); if (v >= 32 && v <= P2P_BK_MAX / 2) per_bucket = (uint64_t)v; }
+    while (B < 20 && (cap_total >> B) > per_bucket) B++;
     Y.B = B;
     Y.n_buckets = 1u << B;
     for (int r = 0; r <= world; r++) Y.fb[r] = (uint32_t)((((uint64_t)r << B) + world - 1) / world);
@@ -840,20 +950,24 @@ int mxe_p2p_create(mxe_t* e, int rank, int world, uint64_t cap_total, int n_asm_
     Y.off_flags = take(P2P_N_BARRIERS * P2P_MAX_WORLD * 4);
     Y.off_err = take(256);
     Y.off_counts = take((uint64_t)world * n_asm_max * 8);
-    Y.off_rec_cnt = take((uint64_t)Y.nb_own_max * world * 4);
+    Y.off_rec_cnt = take(((uint64_t)Y.nb_own_max + 1) * 4);        // world == 1: records per bucket; world > 1: first record of every bucket (+ end)
     Y.off_nkeep = take((uint64_t)Y.n_buckets * 4);
-    Y.off_rec = take((uint64_t)Y.nb_own_max * world * Y.cap_sub * sizeof(P2PRecord));
+    // world > 1: minimizer records arrive per source in one sequential segment (coalesced remote stores, one TLB-friendly
+    // stream per peer) and the OWNER cuts them into buckets with local stores
+    Y.cap1 = world > 1 ? (uint64_t)((double)cap_total / world / world * 1.3) + 8192 : 0;
+    Y.off_rec = take(std::max<uint64_t>((uint64_t)Y.nb_own_max * world * Y.cap_sub, (uint64_t)world * Y.cap1) * sizeof(P2PRecord));
+    // shared memory of a bucket CTA: 4 x bk_max x 8 bytes.  512 records (16 KB, 14 CTAs per SM) where the average bucket
+    // at full capacity leaves room for its fluctuations, else 1024
+    Y.bk_max = (double)(cap_total >> B) * 1.5 + 64.0 <= 512.0 ? 512 : 1024;
+    if (const char* sv = getenv("MXE_P2P_BKMAX")) { const int v = atoi(sv); if (v == 512 || v == 1024) Y.bk_max = v; }
+    if (world == 1 && Y.cap_sub > (uint32_t)Y.bk_max) Y.bk_max = 1024;
     Y.off_mk = take(Y.L_cap * 4);
-    Y.off_succ = take((uint64_t)n_asm_max * Y.nv_cap * 4);
-    Y.off_vgid = take((uint64_t)n_asm_max * Y.nv_cap * 4);
+    Y.off_tab = take((uint64_t)n_asm_max * Y.nv_cap * 8);          // vertex tables, interleaved by assembly (p2p_tab)
     // world > 1: every sighting travels to the owners of its two vertices as a 24-byte record (no remote loads)
     Y.cap2 = world > 1 ? (uint64_t)((double)cap_total / world / world * 2.0 * 1.3) + 8192 : 0;
     Y.off_pred = take(world > 1 ? (uint64_t)n_asm_max * Y.nv_cap * 4 : 0);
     Y.off_cnt2 = take(256);
     Y.off_rec2 = take((uint64_t)world * Y.cap2 * 24);
-    // world > 1: minimizer records arrive per source in one sequential segment (coalesced remote stores, one TLB-friendly
-    // stream per peer) and the OWNER cuts them into buckets with local stores
-    Y.cap1 = world > 1 ? (uint64_t)((double)cap_total / world / world * 1.3) + 8192 : 0;
     Y.off_cnt1 = take(256);
     Y.off_seg1 = take((uint64_t)world * Y.cap1 * 16);
     Y.bytes = at;
@@ -864,10 +978,11 @@ int mxe_p2p_create(mxe_t* e, int rank, int world, uint64_t cap_total, int n_asm_
         cudaFuncAttributes fa;
         const void* kernels[] = {(const void*)p2p_signal_kernel, (const void*)p2p_wait_kernel, (const void*)p2p_scatter_kernel,
                                  (const void*)p2p_push_counts_kernel, (const void*)p2p_scatter_seg_kernel, (const void*)p2p_push_cnt1_kernel,
-                                 (const void*)p2p_partition_kernel, (const void*)p2p_bucket_kernel, (const void*)p2p_vbase_kernel,
+                                 (const void*)p2p_part_count_kernel, (const void*)p2p_part_start_kernel, (const void*)p2p_part_place_kernel,
+                                 (const void*)p2p_bucket_kernel<512>, (const void*)p2p_bucket_kernel<1024>, (const void*)p2p_vbase_kernel,
                                  (const void*)p2p_vertices_kernel, (const void*)p2p_flags_kernel, (const void*)p2p_compact_kernel,
                                  (const void*)p2p_succ_kernel, (const void*)p2p_edge_owner_kernel, (const void*)p2p_first_count_kernel,
-                                 (const void*)p2p_first_start_kernel, (const void*)p2p_clear_tail_kernel, (const void*)p2p_edge_emit_kernel,
+                                 (const void*)p2p_first_start_kernel, (const void*)p2p_edge_emit_kernel,
                                  (const void*)p2p_sight_kernel, (const void*)p2p_push_cnt2_kernel, (const void*)p2p_table_kernel,
                                  (const void*)p2p_rec_owner_kernel, (const void*)p2p_rec_emit_kernel};
         for (const void* k : kernels) cudaFuncGetAttributes(&fa, k);
@@ -939,6 +1054,7 @@ int mxe_p2p_scatter(mxe_p2p_t* X, const void* const* d_hash, const void* const* 
     mxe_engine* e = X->eng;
     MXE_CUDA(cudaSetDevice(e->device));
     cudaStream_t st = e->stream;
+    X->Y.n_asm = n_asm;
     const P2PLayout& Y = X->Y;
     Span whole(e, "filter");
     Span part(e, "p2p_scatter");
@@ -979,11 +1095,14 @@ int mxe_p2p_scatter(mxe_p2p_t* X, const void* const* d_hash, const void* const* 
     // its own tables or writes into a peer's workspace again
     MXE_TRY(p2p_barrier_signal(X, 0));
     MXE_TRY(p2p_barrier_wait(X, 0));
-    MXE_CUDA(cudaMemsetAsync(X->ws + Y.off_succ, 0, (size_t)n_asm * Y.nv_cap * 4, st));
+    // vertex tables: in records mode (world > 1) only the vertices with a successor / predecessor get their entries
+    // written, so the tables start from zero; otherwise p2p_succ_kernel writes every entry of every vertex
+    const bool tables_by_records = Y.world > 1 && X->records;
+    if (tables_by_records) MXE_CUDA(cudaMemsetAsync(X->ws + Y.off_tab, 0, (size_t)n_asm * Y.nv_cap * 8, st));
     // marks of own minimizers: every record that reaches its bucket gets one; a record dropped by an overflowing bucket
     // (the call then fails and falls back) must not leave an unwritten word behind
     if (L) MXE_CUDA(cudaMemsetAsync(X->ws + Y.off_mk, 0, L * 4, st));
-    if (Y.world > 1) MXE_CUDA(cudaMemsetAsync(X->ws + Y.off_pred, 0, (size_t)n_asm * Y.nv_cap * 4, st));
+    if (tables_by_records) MXE_CUDA(cudaMemsetAsync(X->ws + Y.off_pred, 0, (size_t)n_asm * Y.nv_cap * 4, st));
     AsmCounts C;
     C.n_asm = n_asm;
     for (int a = 0; a < n_asm; a++) C.n[a] = n[a];
@@ -991,8 +1110,7 @@ int mxe_p2p_scatter(mxe_p2p_t* X, const void* const* d_hash, const void* const* 
         if (L) { Span k_(e, "k_p2p_scatter_kernel"); MXE_LAUNCH(e, p2p_scatter_kernel, p2p_grid(L), 256, 0, X->H, X->S, L, X->P, Y, X->cursor); }
         { Span k_(e, "k_p2p_push_counts_kernel"); MXE_LAUNCH(e, p2p_push_counts_kernel, p2p_grid(std::max<uint64_t>(Y.n_buckets, (uint64_t)Y.world * n_asm)), 256, 0, X->cursor, C, X->P, Y); }
     } else {
-        // own bucket-count table is filled by the partition pass of stage 2 (local atomics): clear it now
-        MXE_CUDA(cudaMemsetAsync(X->ws + Y.off_rec_cnt, 0, (size_t)Y.nb_own_max * Y.world * 4, st));
+        // (the bucket counts of the owner-side partition of stage 2 are taken in X->cursor, cleared above)
         if (L) { Span k_(e, "k_p2p_scatter_seg_kernel"); MXE_LAUNCH(e, p2p_scatter_seg_kernel, p2p_grid(L), 256, 0, X->H, X->S, L, X->P, Y, X->cur1); }
         { Span k_(e, "k_p2p_push_cnt1_kernel"); MXE_LAUNCH(e, p2p_push_cnt1_kernel, 1, 512, 0, X->cur1, C, X->P, Y); }
     }
@@ -1011,10 +1129,23 @@ int mxe_p2p_buckets(mxe_p2p_t* X)
     Span part(e, "p2p_buckets");
     MXE_TRY(p2p_barrier_wait(X, 1));
     const uint32_t nb = Y.fb[Y.rank + 1] - Y.fb[Y.rank];
-    const size_t bk_smem = (size_t)4 * P2P_BK_MAX * sizeof(uint64_t);
-    MXE_CUDA(cudaFuncSetAttribute(p2p_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bk_smem));
-    if (Y.world > 1) { Span k_(e, "k_p2p_partition_kernel"); MXE_LAUNCH(e, p2p_partition_kernel, p2p_grid((uint64_t)Y.world * Y.cap1), 256, 0, X->P, Y); }
-    if (nb) { Span k_(e, "k_p2p_bucket_kernel"); MXE_LAUNCH(e, p2p_bucket_kernel, nb, P2P_BK_THREADS, bk_smem, X->P, Y, X->n_asm); }
+    const size_t bk_smem = (size_t)4 * Y.bk_max * sizeof(uint64_t);
+    if (Y.world > 1) {
+        const unsigned grid = p2p_grid((uint64_t)Y.world * Y.cap1);
+        { Span k_(e, "k_p2p_partition_kernel"); MXE_LAUNCH(e, p2p_part_count_kernel, grid, 256, 0, X->P, Y, X->cursor); }
+        MXE_LAUNCH(e, p2p_part_start_kernel, 1, 1024, 0, X->P, Y, X->cursor);
+        { Span k_(e, "k_p2p_partition_kernel"); MXE_LAUNCH(e, p2p_part_place_kernel, grid, 256, 0, X->P, Y, X->cursor); }
+    }
+    if (nb) {
+        Span k_(e, "k_p2p_bucket_kernel");
+        if (Y.bk_max == 512) {
+            MXE_CUDA(cudaFuncSetAttribute(p2p_bucket_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bk_smem));
+            MXE_LAUNCH(e, p2p_bucket_kernel<512>, nb, P2P_BK_THREADS, bk_smem, X->P, Y, X->n_asm);
+        } else {
+            MXE_CUDA(cudaFuncSetAttribute(p2p_bucket_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bk_smem));
+            MXE_LAUNCH(e, p2p_bucket_kernel<1024>, nb, P2P_BK_THREADS, bk_smem, X->P, Y, X->n_asm);
+        }
+    }
     MXE_TRY(p2p_barrier_signal(X, 2));
     MXE_CUDA(cudaGetLastError());
     return MXE_OK;
@@ -1092,12 +1223,11 @@ int mxe_p2p_finish(mxe_p2p_t* X, mxe_result_t** out)
     const int n_asm = X->n_asm;
     const bool home = Y.world == 1 || !X->records;       // edges emitted by the rank that sketched the sighting
     if (home) MXE_TRY(p2p_barrier_wait(X, 4));
-    // owned edges: world == 1 in creation order over the survivors (own[] past n_keep is cleared first: the scan runs
+    // owned edges: world == 1 in creation order over the survivors (p2p_edge_owner_kernel clears own[] past n_keep: the scan runs
     // over L entries); world > 1 over the record index space of this owner
     const uint64_t n_scan = home ? L : (uint64_t)Y.world * Y.cap2;
     {
         ArenaScope scope(e);
-        if (home && L) { Span k_(e, "k_p2p_clear_tail_kernel"); MXE_LAUNCH(e, p2p_clear_tail_kernel, p2p_grid(L), 256, 0, X->own, X->kprefix, L); }
         MXE_TRY(exclusive_scan_u32_u64(e, X->own, X->uprefix, n_scan));
     }
     uint64_t sizes[2] = {0, 0};
@@ -1137,16 +1267,17 @@ int mxe_p2p_finish(mxe_p2p_t* X, mxe_result_t** out)
         DBuf<uint64_t> fprefix;
         if (Y.world == 1) {
             MXE_TRY(fcount.alloc(nE, st)); MXE_TRY(fprefix.alloc(nE + 1, st)); MXE_TRY(vst.alloc(nV ? nV : 1, st));
-            { Span k_(e, "k_p2p_first_count_kernel"); MXE_LAUNCH(e, p2p_first_count_kernel, p2p_grid(L), 256, 0, X->cvid, X->cg, X->own, X->uprefix, X->kprefix, L, X->P, Y, n_asm, fcount.p); }
+            uint32_t* smask_j = X->eflag;       // the sighting flags are dead after p2p_edge_owner_kernel: the array now holds the source masks
+            { Span k_(e, "k_p2p_first_count_kernel"); MXE_LAUNCH(e, p2p_first_count_kernel, p2p_grid(L), 256, 0, X->cvid, X->cloc, X->own, X->uprefix, X->kprefix, L, X->S, X->P, Y, n_asm, fcount.p, smask_j); }
             MXE_TRY(exclusive_scan_u32_u64(e, fcount.p, fprefix.p, nE));
-            { Span k_(e, "k_p2p_first_start_kernel"); MXE_LAUNCH(e, p2p_first_start_kernel, p2p_grid(L), 256, 0, X->cvid, X->cg, X->own, X->uprefix, fprefix.p, X->kprefix, L, X->P, Y, n_asm, vst.p); }
+            { Span k_(e, "k_p2p_first_start_kernel"); MXE_LAUNCH(e, p2p_first_start_kernel, p2p_grid(L), 256, 0, X->cvid, X->cloc, X->own, smask_j, X->uprefix, fprefix.p, X->kprefix, L, X->S, vst.p); }
             vstart = vst.p;
-            { Span k_(e, "k_p2p_edge_emit_kernel"); MXE_LAUNCH(e, p2p_edge_emit_kernel, p2p_grid(L), 256, 0, X->cvid, X->cg, X->cloc, X->own, X->emask_j, X->uprefix, X->kprefix, L, X->S, X->H, X->A,
+            { Span k_(e, "k_p2p_edge_emit_kernel"); MXE_LAUNCH(e, p2p_edge_emit_kernel, p2p_grid(L), 256, 0, X->cvid, X->cg, X->cloc, X->own, X->emask_j, smask_j, X->uprefix, fprefix.p, X->kprefix, L, X->S, X->H, X->A,
                        X->P, Y, X->T, vstart, E); }
         } else if (home) {
             MXE_CUDA(cudaMallocAsync((void**)&R->d_ekey, nE * 8, st));
             E.ekey = R->d_ekey;
-            { Span k_(e, "k_p2p_edge_emit_kernel"); MXE_LAUNCH(e, p2p_edge_emit_kernel, p2p_grid(L), 256, 0, X->cvid, X->cg, X->cloc, X->own, X->emask_j, X->uprefix, X->kprefix, L, X->S, X->H, X->A,
+            { Span k_(e, "k_p2p_edge_emit_kernel"); MXE_LAUNCH(e, p2p_edge_emit_kernel, p2p_grid(L), 256, 0, X->cvid, X->cg, X->cloc, X->own, X->emask_j, (const uint32_t*)nullptr, X->uprefix, (const uint64_t*)nullptr, X->kprefix, L, X->S, X->H, X->A,
                        X->P, Y, X->T, vstart, E); }
         } else {
             MXE_CUDA(cudaMallocAsync((void**)&R->d_ekey, nE * 8, st));

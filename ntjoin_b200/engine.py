@@ -56,6 +56,12 @@ class Sketch:
         dt = [np.uint64, np.uint64, np.uint32, np.uint32, np.uint8]
         return tuple(_np_view(x.value, n.value, d) for x, d in zip(p, dt))
 
+    def prefetch_host(self):
+        """Start the device->host copy of the tuples now and return at once (mxe_sketch_prefetch_host): it runs beside the
+        next assembly's host->device copy and sketch; a later fetch() / view only waits for it."""
+        check(self._e._lib, self._e._lib.mxe_sketch_prefetch_host(self._h))
+        return self
+
     out_hash = property(lambda s: s._view()[0])
     min_hash = property(lambda s: s._view()[1])
     pos = property(lambda s: s._view()[2])
@@ -295,15 +301,19 @@ class Engine:
         self._prefetched = getattr(self, "_prefetched", [])[-3:] + [keep]
         return keep
 
-    def sketch_many(self, assemblies, k, w, canonical="sum"):
+    def sketch_many(self, assemblies, k, w, canonical="sum", prefetch_host=False):
         """assemblies: [(seq, offsets[, names])] in assembly order.  Sketches them one after the other with the
-        host->device copy of each assembly overlapping the sketch of the one before."""
+        host->device copy of each assembly overlapping the sketch of the one before.  prefetch_host=True: the caller
+        wants the minimizer tuples in host memory -- every sketch starts its device->host copy as soon as it is done,
+        beside the next assembly's host->device copy (the other PCIe direction) and sketch."""
         bufs = [self._host_ptr(a[0])[1] for a in assemblies]
         out = []
         for i, a in enumerate(assemblies):
             for b in bufs[i:i + 2]:
                 self.prefetch(b)
             out.append(self.sketch_buffers(bufs[i], a[1], k, w, names=a[2] if len(a) > 2 else None, canonical=canonical))
+            if prefetch_host:
+                out[-1].prefetch_host()
         return out
 
     def sketch_buffers(self, seq, offsets, k, w, names=None, canonical="sum"):

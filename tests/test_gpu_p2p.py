@@ -65,20 +65,20 @@ def _fetch(res, world):
     return d
 
 
-@pytest.mark.parametrize("world,n_ref,w", [(1, 1, 100), (2, 1, 100), (3, 2, 250), (5, 1, 50), (8, 3, 100)])
-def test_lockstep_ranks_one_device(oracle, world, n_ref, w):
+def _lockstep(oracle, asms, weights, world, k, w, reps=2):
+    """`world` ranks in this process, stage by stage; the merged shards must equal the oracle's steps 2-3"""
     import ntjoin_b200
-    asms = _case(n_ref, 1_500_000)
-    weights = [2.0] * n_ref + [1.0]
     engines = [ntjoin_b200.Engine(0) for _ in range(world)]          # one engine (own stream, own arena) per simulated rank
     try:
-        per_rank = [_shard_sketches(engines[r], asms, world, 32, w)[r] for r in range(world)]
+        per_rank = [_shard_sketches(engines[r], asms, world, k, w)[r] for r in range(world)]
         total = sum(sk.n for sks in per_rank for sk in sks)
         groups = [engines[r].p2p(r, world, int(total * 1.2) + 1000, n_asm_max=len(asms)) for r in range(world)]
         bases = [g.workspace() for g in groups]
         for g in groups:
             g.connect_pointers(bases)
-        for rep in range(2):                                          # twice: the workspaces are reused across calls
+        full = [oracle.sketch(s, o, k, w) for s, o in asms]
+        want = oracle.filter_and_edges([f["out_hash"] for f in full], [f["contig"] for f in full], weights)
+        for rep in range(reps):                                       # the workspaces are reused across calls
             for r in range(world):
                 groups[r].scatter_sketches(per_rank[r], weights)
             for stage in ("buckets", "adjacency", "edges"):
@@ -86,17 +86,46 @@ def test_lockstep_ranks_one_device(oracle, world, n_ref, w):
                     getattr(groups[r], stage)()
             shards = [groups[r].finish() for r in range(world)]
             merged = merge_shards([_fetch(s, world) for s in shards])
-            full = [oracle.sketch(s, o, 32, w) for s, o in asms]
-            want = oracle.filter_and_edges([f["out_hash"] for f in full], [f["contig"] for f in full], weights)
             _check(merged, want)
-            assert len(merged["vertices"]) > 1000 and len(merged["edge_u"]) > 1000
             for s in shards:
                 s.close()
         for g in groups:
             g.close()
+        return merged
     finally:
         for e in engines:
             e.close()
+
+
+@pytest.mark.parametrize("world,n_ref,w,records", [(1, 1, 100, 1), (2, 1, 100, 1), (3, 2, 250, 1), (5, 1, 50, 1), (8, 3, 100, 1),
+                                                   (1, 3, 100, 1), (2, 1, 100, 0), (4, 2, 100, 0)])
+def test_lockstep_ranks_one_device(oracle, world, n_ref, w, records, monkeypatch):
+    """records = 0: the variant that keeps the successor tables at the vertex owners and reads / writes them with
+    fine-grained peer accesses (MXE_P2P_RECORDS=0, read when the rank object is created)"""
+    monkeypatch.setenv("MXE_P2P_RECORDS", str(records))
+    merged = _lockstep(oracle, _case(n_ref, 1_500_000), [2.0] * n_ref + [1.0], world, 32, w)
+    assert len(merged["vertices"]) > 1000 and len(merged["edge_u"]) > 1000
+
+
+@pytest.mark.parametrize("world,bkmax", [(2, 512), (3, 1024)])
+def test_repeated_sequence_several_ranks(oracle, world, bkmax, monkeypatch):
+    """Half of every record is one 5 kb unit repeated 150 times: ~100 hashes with 900 copies per assembly, each far more
+    than a bucket CTA holds in shared memory.  The owner places buckets at exact offsets and the bucket kernel keeps two
+    copies of every (hash, assembly) pair while loading, so the multi-rank path answers (world = 1 has the sort-based
+    fallback, test_bucket_overflow_falls_back): flags, vertices and edges equal the oracle's."""
+    monkeypatch.setenv("MXE_P2P_BKMAX", str(bkmax))
+    rng = np.random.default_rng(7)
+    unit = synth.random_bases(5000, rng)
+    parts, offs = [], [0]
+    for _c in range(6):
+        parts += [synth.random_bases(400_000, rng)] + [unit] * 150 + [synth.random_bases(350_000, rng)]
+        offs.append(offs[-1] + 750_000 + 150 * 5000)
+    ref = (np.concatenate(parts), np.array(offs, dtype=np.uint64))
+    tgt = synth.derive_target(ref[0], ref[1], min_len=20_000, max_len=400_000)
+    merged = _lockstep(oracle, [ref, (tgt[0], tgt[1])], [2.0, 1.0], world, 32, 100)
+    assert len(merged["vertices"]) > 10_000
+    n_dup = int((~np.asarray(merged["uniq"][0]).astype(bool)).sum())
+    assert n_dup > 50_000                                             # the repeats really are there
 
 
 def test_bucket_overflow_falls_back(engine, oracle):

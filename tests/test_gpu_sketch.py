@@ -272,3 +272,32 @@ def test_concurrent_sketches_two_streams(engine, oracle):
             assert_same(sk, ref)
     finally:
         engine.set_option("bound_scale", 1.0)
+
+
+def test_host_copy_started_early(engine, oracle):
+    """Engine.sketch_many(prefetch_host=True) / Sketch.prefetch_host(): the device->host copy of the tuples is started on
+    the engine's copy stream as soon as a sketch is done (beside the next assembly's host->device copy and steps 2-3);
+    views and copies taken afterwards hold the same tuples, a sketch closed with the copy in flight is released cleanly"""
+    a = synth.make_reference(1_500_000, n_chrom=3, seed=31, dup_frac=0.02, n_frac=0.004)
+    b = synth.derive_target(a[0], a[1], min_len=3_000, max_len=200_000)
+    refs = [oracle.sketch(s, o, 32, 100) for s, o in ((a[0], a[1]), (b[0], b[1]))]
+    for rep in range(3):                                   # the pinned blocks are pooled: reuse them
+        sks = engine.sketch_many([(a[0], a[1]), (b[0], b[1])], 32, 100, prefetch_host=True)
+        res = engine.filter_and_edges(sks, [2.0, 1.0])     # runs on the engine stream while the copies are in flight
+        for sk, ref in zip(sks, refs):
+            views = sk.fetch(copy=False)
+            np.testing.assert_array_equal(views[0], ref["out_hash"])
+            np.testing.assert_array_equal(views[2].astype(np.uint64), ref["pos"])
+            assert_same(sk, ref)
+        want = oracle.filter_and_edges([r["out_hash"] for r in refs], [r["contig"] for r in refs], [2.0, 1.0])
+        np.testing.assert_array_equal(res.edge_u, want["edges"]["u"])
+        res.close()
+        for sk in sks:
+            sk.close()
+    sk = engine.sketch_buffers(a[0], a[1], 32, 100).prefetch_host()
+    sk.prefetch_host()                                     # second call: nothing to do
+    sk.close()                                             # closed with the copy possibly still in flight
+    sk = engine.sketch_buffers(a[0], a[1], 32, 100)
+    assert_same(sk, refs[0])                               # plain lazy path still works
+    sk.prefetch_host()                                     # after the host copy exists: no-op
+    sk.close()

@@ -1,0 +1,21 @@
+O=gpurun_out/r2w; mkdir -p $O
+timeout 400 python -m pytest tests/test_gpu_p2p.py tests/test_gpu_filter.py tests/test_gpu_sketch.py -m gpu -x -q --durations=8 -k "lockstep or repeated or overflow or golden_steps23 or host_copy or multi_assembly or dropin or four_way or config2" > $O/pytest.log 2>&1; echo "pytest rc=$?"; tail -14 $O/pytest.log
+run() { # name, env...
+  name=$1; shift
+  env "$@" timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $O/bench_$name.json 2> $O/bench_$name.err; echo "bench $name rc=$?"; tail -2 $O/bench_$name.err
+}
+run base MXE_NOP=1
+run fine MXE_TIMING_FINE=1
+run bk1024 MXE_P2P_BKMAX=1024
+run avg800 MXE_P2P_BUCKET_AVG=512
+run avg200 MXE_P2P_BUCKET_AVG=200
+python - <<'PY'
+import json
+for nm in ("base","fine","bk1024","avg800","avg200"):
+    try:
+        d=json.load(open(f"gpurun_out/r2w/bench_{nm}.json"))
+    except Exception as e:
+        print(nm, "unreadable", e); continue
+    r=d["roofline"]
+    print(nm, round(d["value"],1), round(d["ms_per_step"],3), "e2e", round(d["e2e"]["value"],2), round(d["e2e"]["ms_per_step"],2), {k:round(v,3) for k,v in r["phase_ms_per_step"].items()})
+PY
