@@ -57,11 +57,11 @@ struct P2PLayout {
     uint32_t fb[P2P_MAX_WORLD + 1];        // first bucket of every rank
     uint32_t nb_own_max;                   // most buckets one rank owns
     uint32_t cap_sub;                      // records per bucket sub-slot (world == 1; world > 1 places buckets at exact offsets)
-    int bk_max;                            // records a bucket CTA holds in shared memory: 512 or 1024
+    int bk_max;                            // records a bucket CTA holds in shared memory: 256, 512 or 1024
     uint64_t L_cap;                        // minimizers of one rank, all assemblies
     uint64_t nv_cap;                       // vertices of one owner
     // byte offsets inside every rank's workspace
-    uint64_t off_flags, off_err, off_counts, off_rec_cnt, off_nkeep, off_rec, off_mk, off_tab, off_pred, off_cnt2, off_rec2, off_cnt1, off_seg1, bytes;
+    uint64_t off_flags, off_err, off_counts, off_rec_cnt, off_nkeep, off_rec, off_mk, off_tab, off_vgid, off_pred, off_cnt2, off_rec2, off_cnt1, off_seg1, bytes;
     uint64_t cap1;                         // minimizer records per (owner, source) segment (world > 1)
     uint64_t cap2;                         // sighting records per (owner, source) segment (world > 1)
 };
@@ -74,13 +74,20 @@ __host__ __device__ __forceinline__ uint32_t p2p_owner(uint32_t b, int world, in
 // support test of a sighting (the successors of v and of x in every assembly) costs two sector reads instead of
 // 2 * n_asm (the per-assembly planes [a][vertex] of the first version made these kernels the most expensive of steps 2-3:
 // ~146 M random 4-byte accesses per step of configs[2]).
-//   tab[(vloc * n_asm + a) * 2]     = 1 + successor vertex of vloc in assembly a (0 = none); bit 31 = "this sighting
-//                                      created an edge" (ownership mark, p2p_edge_owner_kernel)
-//   tab[(vloc * n_asm + a) * 2 + 1] = creation index of the survivor (a, vloc)
-//   pred[vloc * n_asm + a]          = 1 + predecessor vertex (world > 1, records mode)
+//   tab[vloc * n_asm + a]   = 1 + successor vertex of vloc in assembly a (0 = none); bit 31 = "this sighting created
+//                              an edge" (ownership mark, p2p_edge_owner_kernel)
+//   vgid[vloc * n_asm + a]  = creation index of the survivor (a, vloc): order keys of result shards (world > 1 only; on
+//                              one GPU the first edge of a source is the one of the lowest assembly and nothing reads it)
+//   pred[vloc * n_asm + a]  = 1 + predecessor vertex (world > 1, records mode)
+// The successor table is kept on its own: 8 bytes per vertex at n_asm = 2, so the whole table of configs[2] (45 MB) stays
+// in L2 between the kernel that fills it and the kernels that look things up in it.
 __device__ __forceinline__ uint32_t* p2p_tab(const PeerPtrs& P, const P2PLayout& Y, int o, uint64_t vloc)
 {
-    return reinterpret_cast<uint32_t*>(P.base[o] + Y.off_tab) + vloc * (uint64_t)(2 * Y.n_asm);
+    return reinterpret_cast<uint32_t*>(P.base[o] + Y.off_tab) + vloc * (uint64_t)Y.n_asm;
+}
+__device__ __forceinline__ uint32_t* p2p_vgid(const PeerPtrs& P, const P2PLayout& Y, int o, uint64_t vloc)
+{
+    return reinterpret_cast<uint32_t*>(P.base[o] + Y.off_vgid) + vloc * (uint64_t)Y.n_asm;
 }
 __device__ __forceinline__ uint32_t* p2p_pred(const PeerPtrs& P, const P2PLayout& Y, int o, uint64_t vloc)
 {
@@ -98,7 +105,7 @@ __device__ __forceinline__ int p2p_slice_of(const LocalSlices& S, uint64_t l)
 // signal: after everything this rank issued before it (stream order; the stage kernels have completed, their peer
 // stores are performed), store the epoch into slot [bar][rank] of every peer.  wait: spin until all peers' epochs have
 // arrived here.  The spin is bounded (~2 s): a lost peer sets the error flag instead of hanging the GPU.
-__global__ void p2p_signal_kernel(PeerPtrs P, P2PLayout Y, int bar, uint32_t epoch)
+__global__ void p2p_signal_kernel(const __grid_constant__ PeerPtrs P, const __grid_constant__ P2PLayout Y, int bar, uint32_t epoch)
 {
     __threadfence_system();
     if ((int)threadIdx.x < Y.world) {
@@ -108,7 +115,7 @@ __global__ void p2p_signal_kernel(PeerPtrs P, P2PLayout Y, int bar, uint32_t epo
     __threadfence_system();
 }
 
-__global__ void p2p_wait_kernel(PeerPtrs P, P2PLayout Y, int bar, uint32_t epoch)
+__global__ void p2p_wait_kernel(const __grid_constant__ PeerPtrs P, const __grid_constant__ P2PLayout Y, int bar, uint32_t epoch)
 {
     if ((int)threadIdx.x < Y.world) {
         volatile uint32_t* f = reinterpret_cast<volatile uint32_t*>(P.base[Y.rank] + Y.off_flags) + bar * P2P_MAX_WORLD + threadIdx.x;
@@ -122,7 +129,7 @@ __global__ void p2p_wait_kernel(PeerPtrs P, P2PLayout Y, int bar, uint32_t epoch
 }
 
 // ---------------------------------------------------------------- stage 1: scatter to the bucket owners
-__global__ void __launch_bounds__(256) p2p_scatter_kernel(PtrTab H, LocalSlices S, uint64_t L, PeerPtrs P, P2PLayout Y, uint32_t* __restrict__ cursor)
+__global__ void __launch_bounds__(256) p2p_scatter_kernel(PtrTab H, LocalSlices S, uint64_t L, const __grid_constant__ PeerPtrs P, const __grid_constant__ P2PLayout Y, uint32_t* __restrict__ cursor)
 {
     const uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= L) return;
@@ -138,7 +145,7 @@ __global__ void __launch_bounds__(256) p2p_scatter_kernel(PtrTab H, LocalSlices 
 
 // per-(bucket, source) counts to the owners; this rank's minimizer counts to everybody
 struct AsmCounts { uint64_t n[32]; int n_asm; };
-__global__ void __launch_bounds__(256) p2p_push_counts_kernel(const uint32_t* __restrict__ cursor, AsmCounts C, PeerPtrs P, P2PLayout Y)
+__global__ void __launch_bounds__(256) p2p_push_counts_kernel(const uint32_t* __restrict__ cursor, AsmCounts C, const __grid_constant__ PeerPtrs P, const __grid_constant__ P2PLayout Y)
 {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < Y.n_buckets) {
@@ -197,7 +204,7 @@ __device__ __forceinline__ void cta_append(CtaAppendState& sh, uint64_t* stage, 
 }
 
 // stage 1 (world > 1): own minimizers -> segment [this rank] of the owner of their bucket
-__global__ void __launch_bounds__(256) p2p_scatter_seg_kernel(PtrTab H, LocalSlices S, uint64_t L, PeerPtrs P, P2PLayout Y, uint32_t* __restrict__ cur1)
+__global__ void __launch_bounds__(256) p2p_scatter_seg_kernel(PtrTab H, LocalSlices S, uint64_t L, const __grid_constant__ PeerPtrs P, const __grid_constant__ P2PLayout Y, uint32_t* __restrict__ cur1)
 {
     __shared__ CtaAppendState sh;
     __shared__ uint64_t stage[256 * 2];
@@ -215,7 +222,7 @@ __global__ void __launch_bounds__(256) p2p_scatter_seg_kernel(PtrTab H, LocalSli
 }
 
 // segment counts to the owners; this rank's minimizer counts to everybody
-__global__ void p2p_push_cnt1_kernel(const uint32_t* __restrict__ cur1, AsmCounts C, PeerPtrs P, P2PLayout Y)
+__global__ void p2p_push_cnt1_kernel(const uint32_t* __restrict__ cur1, AsmCounts C, const __grid_constant__ PeerPtrs P, const __grid_constant__ P2PLayout Y)
 {
     if ((int)threadIdx.x < Y.world) {
         const uint32_t c = cur1[threadIdx.x] < Y.cap1 ? cur1[threadIdx.x] : (uint32_t)Y.cap1;
@@ -241,7 +248,7 @@ __device__ __forceinline__ bool p2p_seg_record(const PeerPtrs& P, const P2PLayou
     return true;
 }
 
-__global__ void __launch_bounds__(256) p2p_part_count_kernel(PeerPtrs P, P2PLayout Y, uint32_t* __restrict__ bcount)
+__global__ void __launch_bounds__(256) p2p_part_count_kernel(const __grid_constant__ PeerPtrs P, const __grid_constant__ P2PLayout Y, uint32_t* __restrict__ bcount)
 {
     ulonglong2 r;
     if (!p2p_seg_record(P, Y, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, &r)) return;
@@ -250,7 +257,7 @@ __global__ void __launch_bounds__(256) p2p_part_count_kernel(PeerPtrs P, P2PLayo
 
 // one CTA: bstart[bl] = exclusive prefix of the bucket counts (nb + 1 entries, in the workspace: the bucket and vertex
 // kernels read it); the counts are replaced by the same values = placement cursors
-__global__ void __launch_bounds__(1024) p2p_part_start_kernel(PeerPtrs P, P2PLayout Y, uint32_t* __restrict__ bcount)
+__global__ void __launch_bounds__(1024) p2p_part_start_kernel(const __grid_constant__ PeerPtrs P, const __grid_constant__ P2PLayout Y, uint32_t* __restrict__ bcount)
 {
     __shared__ uint32_t sw[32];
     __shared__ uint32_t carry_s;
@@ -278,7 +285,7 @@ __global__ void __launch_bounds__(1024) p2p_part_start_kernel(PeerPtrs P, P2PLay
     if (threadIdx.x == 0) bstart[nb] = carry_s;
 }
 
-__global__ void __launch_bounds__(256) p2p_part_place_kernel(PeerPtrs P, P2PLayout Y, uint32_t* __restrict__ bcursor)
+__global__ void __launch_bounds__(256) p2p_part_place_kernel(const __grid_constant__ PeerPtrs P, const __grid_constant__ P2PLayout Y, uint32_t* __restrict__ bcursor)
 {
     ulonglong2 r;
     if (!p2p_seg_record(P, Y, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, &r)) return;
@@ -307,7 +314,7 @@ __device__ __forceinline__ bool rec_greater(uint64_t ka, uint64_t ta, uint64_t k
 constexpr uint64_t P2P_EMPTY = ~0ULL;      // free slot of the reduction table of an oversized bucket
 
 template <int BKMAX>
-__global__ void __launch_bounds__(P2P_BK_THREADS) p2p_bucket_kernel(PeerPtrs P, P2PLayout Y, int n_asm)
+__global__ void __launch_bounds__(P2P_BK_THREADS) p2p_bucket_kernel(const __grid_constant__ PeerPtrs P, const __grid_constant__ P2PLayout Y, int n_asm)
 {
     extern __shared__ uint64_t bk_smem[];
     uint64_t* skey = bk_smem;                          // sorted records
@@ -492,7 +499,7 @@ struct HomeTabs {
     uint64_t* goff;         // n_asm: global index of this rank's first minimizer of assembly a  (+ [n_asm] = N)
 };
 
-__global__ void __launch_bounds__(1024) p2p_vbase_kernel(PeerPtrs P, P2PLayout Y, int n_asm, HomeTabs T)
+__global__ void __launch_bounds__(1024) p2p_vbase_kernel(const __grid_constant__ PeerPtrs P, const __grid_constant__ P2PLayout Y, int n_asm, HomeTabs T)
 {
     __shared__ uint32_t sw[32];
     __shared__ uint32_t carry_s;
@@ -532,14 +539,16 @@ __global__ void __launch_bounds__(1024) p2p_vbase_kernel(PeerPtrs P, P2PLayout Y
     }
 }
 
-// the owner's vertices (ascending hash): bucket by bucket from the kept lists
-__global__ void __launch_bounds__(128) p2p_vertices_kernel(PeerPtrs P, P2PLayout Y, HomeTabs T, uint64_t* __restrict__ vertices)
+// the owner's vertices (ascending hash): bucket by bucket from the kept lists, one warp per bucket (~90 hashes)
+__global__ void __launch_bounds__(128) p2p_vertices_kernel(const __grid_constant__ PeerPtrs P, const __grid_constant__ P2PLayout Y, HomeTabs T, uint64_t* __restrict__ vertices)
 {
-    const uint32_t bl = blockIdx.x, b = Y.fb[Y.rank] + bl;
+    const uint32_t bl = blockIdx.x * 4u + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
+    if (bl >= Y.fb[Y.rank + 1] - Y.fb[Y.rank]) return;
+    const uint32_t b = Y.fb[Y.rank] + bl;
     const uint32_t v0 = T.vbase[b] - T.vown[Y.rank], nk = T.vbase[b + 1] - T.vbase[b];
     uint32_t n_in;
     const uint64_t* kept = reinterpret_cast<const uint64_t*>(p2p_bucket_range(P, Y, bl, &n_in));
-    for (uint32_t i = threadIdx.x; i < nk; i += 128) vertices[v0 + i] = kept[i];
+    for (uint32_t i = lane; i < nk; i += 32) vertices[v0 + i] = kept[i];
 }
 
 __global__ void __launch_bounds__(256) p2p_flags_kernel(const uint32_t* __restrict__ mk, uint64_t L, uint32_t* __restrict__ kflag,
@@ -556,7 +565,7 @@ __global__ void __launch_bounds__(256) p2p_flags_kernel(const uint32_t* __restri
 
 // ordered survivors: global vertex id, global (creation) index, local index
 __global__ void __launch_bounds__(256) p2p_compact_kernel(const uint32_t* __restrict__ mk, PtrTab H, LocalSlices S, uint64_t L,
-                                                           const uint64_t* __restrict__ kprefix, P2PLayout Y, HomeTabs T,
+                                                           const uint64_t* __restrict__ kprefix, const __grid_constant__ P2PLayout Y, HomeTabs T,
                                                            uint32_t* __restrict__ cvid, uint32_t* __restrict__ cg, uint32_t* __restrict__ cloc)
 {
     const uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -578,13 +587,13 @@ __device__ __forceinline__ int p2p_vowner(const uint32_t* vown, int world, uint3
     return o;
 }
 
-// adjacent survivors of the same record and assembly: sighting flag; the table entry (a, v) -- successor and creation
-// index in ONE 8-byte store -- at the owner of v.  Every vertex has exactly one survivor in every assembly, so every
-// entry of every vertex is written here: the tables need no clearing in this mode.
+// adjacent survivors of the same record and assembly: sighting flag; the table entry (a, v) at the owner of v.  Every
+// vertex has exactly one survivor in every assembly, so every entry of every vertex is written here: the tables need
+// no clearing in this mode.
 __global__ void __launch_bounds__(256) p2p_succ_kernel(const uint32_t* __restrict__ cvid, const uint32_t* __restrict__ cg,
                                                         const uint32_t* __restrict__ cloc,
                                                         const uint64_t* __restrict__ kprefix, uint64_t L, LocalSlices S, PtrTab Ctg,
-                                                        PeerPtrs P, P2PLayout Y, HomeTabs T, uint32_t* __restrict__ eflag)
+                                                        const __grid_constant__ PeerPtrs P, const __grid_constant__ P2PLayout Y, HomeTabs T, uint32_t* __restrict__ eflag)
 {
     const uint64_t n_keep = kprefix[L];
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -602,7 +611,8 @@ __global__ void __launch_bounds__(256) p2p_succ_kernel(const uint32_t* __restric
         }
     }
     const int o = p2p_vowner(T.vown, Y.world, v);
-    *reinterpret_cast<uint2*>(p2p_tab(P, Y, o, v - T.vown[o]) + 2 * a) = make_uint2(f ? x + 1u : 0u, cg[j]);
+    p2p_tab(P, Y, o, v - T.vown[o])[a] = f ? x + 1u : 0u;
+    if (Y.world > 1) p2p_vgid(P, Y, o, v - T.vown[o])[a] = cg[j];
     eflag[j] = f;
 }
 
@@ -612,7 +622,7 @@ __global__ void __launch_bounds__(256) p2p_succ_kernel(const uint32_t* __restric
 __global__ void __launch_bounds__(256) p2p_edge_owner_kernel(const uint32_t* __restrict__ cvid, const uint32_t* __restrict__ cg,
                                                               const uint32_t* __restrict__ cloc, const uint32_t* __restrict__ eflag,
                                                               const uint64_t* __restrict__ kprefix, uint64_t L, LocalSlices S, int n_asm,
-                                                              PeerPtrs P, P2PLayout Y, HomeTabs T, uint32_t* __restrict__ own, uint32_t* __restrict__ mask_out)
+                                                              const __grid_constant__ PeerPtrs P, const __grid_constant__ P2PLayout Y, HomeTabs T, uint32_t* __restrict__ own, uint32_t* __restrict__ mask_out)
 {
     const uint64_t n_keep = kprefix[L];
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -627,12 +637,12 @@ __global__ void __launch_bounds__(256) p2p_edge_owner_kernel(const uint32_t* __r
         const uint32_t* tx = p2p_tab(P, Y, ox, x - T.vown[ox]);
         uint32_t mask = 0;
         for (int b = 0; b < n_asm; b++)       // bit 31 of an entry is its ownership mark (below): compare the low 31 bits
-            if ((tv[2 * b] & 0x7FFFFFFFu) == x + 1u || (tx[2 * b] & 0x7FFFFFFFu) == v + 1u) mask |= 1u << b;
+            if ((tv[b] & 0x7FFFFFFFu) == x + 1u || (tx[b] & 0x7FFFFFFFu) == v + 1u) mask |= 1u << b;
         is_owner = (__ffs(mask) - 1) == a;
         mask_out[j] = mask;
         // "vertex v is the source of an edge created in assembly a": entry (a, v) has this sighting as its only writer,
         // so a plain store marks it (no atomics; readers of the successor ignore the bit)
-        if (is_owner) tv[2 * a] = (x + 1u) | 0x80000000u;
+        if (is_owner) tv[a] = (x + 1u) | 0x80000000u;
     }
     own[j] = is_owner;
 }
@@ -644,14 +654,14 @@ __device__ __forceinline__ uint32_t p2p_source_mask(const PeerPtrs& P, const P2P
 {
     const uint32_t* tv = p2p_tab(P, Y, o, vloc);
     uint32_t smask = 0;
-    for (int b = 0; b < n_asm; b++) smask |= (tv[2 * b] >> 31) << b;
+    for (int b = 0; b < n_asm; b++) smask |= (tv[b] >> 31) << b;
     return smask;
 }
 // ... and the creation index of its first one (the order key of its block of edges)
 __device__ __forceinline__ uint32_t p2p_source_info(const PeerPtrs& P, const P2PLayout& Y, int o, uint32_t vloc, int n_asm, uint32_t* first_gid)
 {
     const uint32_t smask = p2p_source_mask(P, Y, o, vloc, n_asm);
-    *first_gid = smask ? p2p_tab(P, Y, o, vloc)[2 * (__ffs(smask) - 1) + 1] : 0xFFFFFFFFu;
+    *first_gid = smask ? p2p_vgid(P, Y, o, vloc)[__ffs(smask) - 1] : 0xFFFFFFFFu;
     return smask;
 }
 
@@ -664,7 +674,7 @@ __device__ __forceinline__ uint32_t p2p_source_info(const PeerPtrs& P, const P2P
 // p2p_first_start_kernel and p2p_edge_emit_kernel are sequential passes for everything else.
 __global__ void __launch_bounds__(256) p2p_first_count_kernel(const uint32_t* __restrict__ cvid, const uint32_t* __restrict__ cloc,
                                                                const uint32_t* __restrict__ own, const uint64_t* __restrict__ uprefix,
-                                                               const uint64_t* __restrict__ kprefix, uint64_t L, LocalSlices S, PeerPtrs P, P2PLayout Y, int n_asm,
+                                                               const uint64_t* __restrict__ kprefix, uint64_t L, LocalSlices S, const __grid_constant__ PeerPtrs P, const __grid_constant__ P2PLayout Y, int n_asm,
                                                                uint32_t* __restrict__ fcount, uint32_t* __restrict__ smask_j)
 {
     const uint64_t n_keep = kprefix[L];
@@ -696,7 +706,7 @@ __global__ void __launch_bounds__(256) p2p_edge_emit_kernel(const uint32_t* __re
                                                              const uint32_t* __restrict__ mask_in, const uint32_t* __restrict__ smask_j,
                                                              const uint64_t* __restrict__ uprefix, const uint64_t* __restrict__ fprefix,
                                                              const uint64_t* __restrict__ kprefix, uint64_t L, LocalSlices S, PtrTab H, AsmOffsets A,
-                                                             PeerPtrs P, P2PLayout Y, HomeTabs T, const uint32_t* __restrict__ vstart, EdgeOut E)
+                                                             const __grid_constant__ PeerPtrs P, const __grid_constant__ P2PLayout Y, HomeTabs T, const uint32_t* __restrict__ vstart, EdgeOut E)
 {
     const uint64_t n_keep = kprefix[L];
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -736,7 +746,7 @@ __global__ void __launch_bounds__(256) p2p_edge_emit_kernel(const uint32_t* __re
 // atomic per (CTA, destination).
 __global__ void __launch_bounds__(256) p2p_sight_kernel(const uint32_t* __restrict__ cvid, const uint32_t* __restrict__ cg,
                                                          const uint32_t* __restrict__ cloc, const uint64_t* __restrict__ kprefix, uint64_t L,
-                                                         LocalSlices S, PtrTab H, PtrTab Ctg, PeerPtrs P, P2PLayout Y, HomeTabs T,
+                                                         LocalSlices S, PtrTab H, PtrTab Ctg, const __grid_constant__ PeerPtrs P, const __grid_constant__ P2PLayout Y, HomeTabs T,
                                                          uint32_t* __restrict__ cur2)
 {
     __shared__ CtaAppendState sh;
@@ -763,7 +773,7 @@ __global__ void __launch_bounds__(256) p2p_sight_kernel(const uint32_t* __restri
     cta_append<3, 2>(sh, stage, dest, rec, cur2, P, Y.off_rec2, Y.cap2, Y, 3u);
 }
 
-__global__ void p2p_push_cnt2_kernel(const uint32_t* __restrict__ cur2, PeerPtrs P, P2PLayout Y)
+__global__ void p2p_push_cnt2_kernel(const uint32_t* __restrict__ cur2, const __grid_constant__ PeerPtrs P, const __grid_constant__ P2PLayout Y)
 {
     if ((int)threadIdx.x < Y.world) {
         const uint32_t c = cur2[threadIdx.x] < Y.cap2 ? cur2[threadIdx.x] : (uint32_t)Y.cap2;
@@ -781,7 +791,7 @@ __device__ __forceinline__ const uint64_t* p2p_rec2(const PeerPtrs& P, const P2P
 }
 
 // successor (+ creation index) / predecessor of every own vertex in every assembly (entries 1 + vertex id, 0 = none)
-__global__ void __launch_bounds__(256) p2p_table_kernel(PeerPtrs P, P2PLayout Y)
+__global__ void __launch_bounds__(256) p2p_table_kernel(const __grid_constant__ PeerPtrs P, const __grid_constant__ P2PLayout Y)
 {
     const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool ok;
@@ -791,10 +801,10 @@ __global__ void __launch_bounds__(256) p2p_table_kernel(PeerPtrs P, P2PLayout Y)
     const uint64_t a = (w2 >> 1) & 0x7F, vloc = w1 >> 32;
     const uint32_t other = (uint32_t)w1 + 1u;
     if (w2 & 1ULL) p2p_pred(P, Y, Y.rank, vloc)[a] = other;
-    else *reinterpret_cast<uint2*>(p2p_tab(P, Y, Y.rank, vloc) + 2 * a) = make_uint2(other, (uint32_t)(w2 >> 8));
+    else { p2p_tab(P, Y, Y.rank, vloc)[a] = other; p2p_vgid(P, Y, Y.rank, vloc)[a] = (uint32_t)(w2 >> 8); }
 }
 
-__global__ void __launch_bounds__(256) p2p_rec_owner_kernel(PeerPtrs P, P2PLayout Y, int n_asm, uint32_t* __restrict__ own, uint32_t* __restrict__ mask_out)
+__global__ void __launch_bounds__(256) p2p_rec_owner_kernel(const __grid_constant__ PeerPtrs P, const __grid_constant__ P2PLayout Y, int n_asm, uint32_t* __restrict__ own, uint32_t* __restrict__ mask_out)
 {
     const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (uint64_t)Y.world * Y.cap2) return;
@@ -810,15 +820,15 @@ __global__ void __launch_bounds__(256) p2p_rec_owner_kernel(PeerPtrs P, P2PLayou
         const uint32_t* pv = p2p_pred(P, Y, Y.rank, vloc);
         uint32_t mask = 0;
         for (int b = 0; b < n_asm; b++)
-            if ((tv[2 * b] & 0x7FFFFFFFu) == x1 || pv[b] == x1) mask |= 1u << b;
+            if ((tv[b] & 0x7FFFFFFFu) == x1 || pv[b] == x1) mask |= 1u << b;
         is_owner = (__ffs(mask) - 1) == a;
         mask_out[idx] = mask;
-        if (is_owner) tv[2 * a] = x1 | 0x80000000u;      // ownership mark (see p2p_edge_owner_kernel)
+        if (is_owner) tv[a] = x1 | 0x80000000u;      // ownership mark (see p2p_edge_owner_kernel)
     }
     own[idx] = is_owner;
 }
 
-__global__ void __launch_bounds__(256) p2p_rec_emit_kernel(PeerPtrs P, P2PLayout Y, AsmOffsets A, const uint32_t* __restrict__ own,
+__global__ void __launch_bounds__(256) p2p_rec_emit_kernel(const __grid_constant__ PeerPtrs P, const __grid_constant__ P2PLayout Y, AsmOffsets A, const uint32_t* __restrict__ own,
                                                             const uint32_t* __restrict__ mask_in, const uint64_t* __restrict__ uprefix,
                                                             const uint64_t* __restrict__ vertices, EdgeOut E)
 {
@@ -958,11 +968,13 @@ int mxe_p2p_create(mxe_t* e, int rank, int world, uint64_t cap_total, int n_asm_
     Y.off_rec = take(std::max<uint64_t>((uint64_t)Y.nb_own_max * world * Y.cap_sub, (uint64_t)world * Y.cap1) * sizeof(P2PRecord));
     // shared memory of a bucket CTA: 4 x bk_max x 8 bytes.  512 records (16 KB, 14 CTAs per SM) where the average bucket
     // at full capacity leaves room for its fluctuations, else 1024
-    Y.bk_max = (double)(cap_total >> B) * 1.5 + 64.0 <= 512.0 ? 512 : 1024;
-    if (const char* sv = getenv("MXE_P2P_BKMAX")) { const int v = atoi(sv); if (v == 512 || v == 1024) Y.bk_max = v; }
-    if (world == 1 && Y.cap_sub > (uint32_t)Y.bk_max) Y.bk_max = 1024;
+    const double bk_need = (double)(cap_total >> B) * 1.5 + 64.0;
+    Y.bk_max = bk_need <= 256.0 ? 256 : bk_need <= 512.0 ? 512 : 1024;
+    if (const char* sv = getenv("MXE_P2P_BKMAX")) { const int v = atoi(sv); if (v == 256 || v == 512 || v == 1024) Y.bk_max = v; }
+    while (world == 1 && Y.cap_sub > (uint32_t)Y.bk_max && Y.bk_max < 1024) Y.bk_max *= 2;
     Y.off_mk = take(Y.L_cap * 4);
-    Y.off_tab = take((uint64_t)n_asm_max * Y.nv_cap * 8);          // vertex tables, interleaved by assembly (p2p_tab)
+    Y.off_tab = take((uint64_t)n_asm_max * Y.nv_cap * 4);          // vertex tables, interleaved by assembly (p2p_tab, p2p_vgid)
+    Y.off_vgid = take(world > 1 ? (uint64_t)n_asm_max * Y.nv_cap * 4 : 0);
     // world > 1: every sighting travels to the owners of its two vertices as a 24-byte record (no remote loads)
     Y.cap2 = world > 1 ? (uint64_t)((double)cap_total / world / world * 2.0 * 1.3) + 8192 : 0;
     Y.off_pred = take(world > 1 ? (uint64_t)n_asm_max * Y.nv_cap * 4 : 0);
@@ -979,7 +991,7 @@ int mxe_p2p_create(mxe_t* e, int rank, int world, uint64_t cap_total, int n_asm_
         const void* kernels[] = {(const void*)p2p_signal_kernel, (const void*)p2p_wait_kernel, (const void*)p2p_scatter_kernel,
                                  (const void*)p2p_push_counts_kernel, (const void*)p2p_scatter_seg_kernel, (const void*)p2p_push_cnt1_kernel,
                                  (const void*)p2p_part_count_kernel, (const void*)p2p_part_start_kernel, (const void*)p2p_part_place_kernel,
-                                 (const void*)p2p_bucket_kernel<512>, (const void*)p2p_bucket_kernel<1024>, (const void*)p2p_vbase_kernel,
+                                 (const void*)p2p_bucket_kernel<256>, (const void*)p2p_bucket_kernel<512>, (const void*)p2p_bucket_kernel<1024>, (const void*)p2p_vbase_kernel,
                                  (const void*)p2p_vertices_kernel, (const void*)p2p_flags_kernel, (const void*)p2p_compact_kernel,
                                  (const void*)p2p_succ_kernel, (const void*)p2p_edge_owner_kernel, (const void*)p2p_first_count_kernel,
                                  (const void*)p2p_first_start_kernel, (const void*)p2p_edge_emit_kernel,
@@ -1098,7 +1110,7 @@ int mxe_p2p_scatter(mxe_p2p_t* X, const void* const* d_hash, const void* const* 
     // vertex tables: in records mode (world > 1) only the vertices with a successor / predecessor get their entries
     // written, so the tables start from zero; otherwise p2p_succ_kernel writes every entry of every vertex
     const bool tables_by_records = Y.world > 1 && X->records;
-    if (tables_by_records) MXE_CUDA(cudaMemsetAsync(X->ws + Y.off_tab, 0, (size_t)n_asm * Y.nv_cap * 8, st));
+    if (tables_by_records) MXE_CUDA(cudaMemsetAsync(X->ws + Y.off_tab, 0, (size_t)n_asm * Y.nv_cap * 4, st));
     // marks of own minimizers: every record that reaches its bucket gets one; a record dropped by an overflowing bucket
     // (the call then fails and falls back) must not leave an unwritten word behind
     if (L) MXE_CUDA(cudaMemsetAsync(X->ws + Y.off_mk, 0, L * 4, st));
@@ -1138,7 +1150,9 @@ int mxe_p2p_buckets(mxe_p2p_t* X)
     }
     if (nb) {
         Span k_(e, "k_p2p_bucket_kernel");
-        if (Y.bk_max == 512) {
+        if (Y.bk_max == 256) {
+            MXE_LAUNCH(e, p2p_bucket_kernel<256>, nb, P2P_BK_THREADS, bk_smem, X->P, Y, X->n_asm);
+        } else if (Y.bk_max == 512) {
             MXE_CUDA(cudaFuncSetAttribute(p2p_bucket_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bk_smem));
             MXE_LAUNCH(e, p2p_bucket_kernel<512>, nb, P2P_BK_THREADS, bk_smem, X->P, Y, X->n_asm);
         } else {
@@ -1253,7 +1267,7 @@ int mxe_p2p_finish(mxe_p2p_t* X, mxe_result_t** out)
     X->luniq = X->lkeep = nullptr;
     if (nV) {
         MXE_CUDA(cudaMallocAsync((void**)&R->d_vertices, nV * 8, st));
-        { Span k_(e, "k_p2p_vertices_kernel"); MXE_LAUNCH(e, p2p_vertices_kernel, Y.fb[Y.rank + 1] - Y.fb[Y.rank], 128, 0, X->P, Y, X->T, R->d_vertices); }
+        { Span k_(e, "k_p2p_vertices_kernel"); MXE_LAUNCH(e, p2p_vertices_kernel, (Y.fb[Y.rank + 1] - Y.fb[Y.rank] + 3) / 4, 128, 0, X->P, Y, X->T, R->d_vertices); }
     }
     if (nE) {
         EdgeOut E;

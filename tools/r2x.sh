@@ -1,17 +1,17 @@
-O=gpurun_out/r2w; mkdir -p $O
-timeout 400 python -m pytest tests/test_gpu_p2p.py tests/test_gpu_filter.py tests/test_gpu_sketch.py -m gpu -x -q --durations=8 -k "lockstep or repeated or overflow or golden_steps23 or host_copy or multi_assembly or dropin or four_way or config2" > $O/pytest.log 2>&1; echo "pytest rc=$?"; tail -14 $O/pytest.log
+O=gpurun_out/r2x; mkdir -p $O
+timeout 400 python -m pytest tests/test_gpu_p2p.py tests/test_gpu_filter.py tests/test_gpu_sketch.py -m gpu -x -q -k "lockstep or repeated or overflow or golden_steps23 or host_copy or four_way" > $O/pytest.log 2>&1; echo "pytest rc=$?"; tail -4 $O/pytest.log
 run() { # name, env...
   name=$1; shift
   env "$@" timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $O/bench_$name.json 2> $O/bench_$name.err; echo "bench $name rc=$?"; tail -2 $O/bench_$name.err
 }
 run base MXE_NOP=1
-run bk1024 MXE_P2P_BKMAX=1024
-run avg800 MXE_P2P_BUCKET_AVG=512
+run fine MXE_TIMING_FINE=1
+run bk256 MXE_P2P_BKMAX=256 MXE_P2P_BUCKET_AVG=100
 python - <<'PY'
 import json
-for nm in ("base","bk1024","avg800"):
+for nm in ("base","fine","bk256"):
     try:
-        d=json.load(open(f"gpurun_out/r2w/bench_{nm}.json"))
+        d=json.load(open(f"gpurun_out/r2x/bench_{nm}.json"))
     except Exception as e:
         print(nm, "unreadable", e); continue
     r=d["roofline"]
