@@ -626,15 +626,20 @@ def main():
     # has a 32-bit variant: measured 1.13 vs 1.57 ms per step on 6 Gbp), else one call per assembly
     n_records = sum(len(o) for _, o, _ in shards)
 
-    # MXE_SKETCH_OVERLAP=1 enqueues the per-assembly sketches on two streams (Engine.sketch_device_many).  Measured on
-    # configs[2]: 12.04 ms per step against 11.90 ms one after the other -- every kernel of the sketch already fills the
-    # machine with CTAs, so the second stream only gets SMs when the first drains; off by default.
-    overlap = os.environ.get("MXE_SKETCH_OVERLAP", "0") not in ("", "0")
+    # Large shares (one sketch per assembly): all assemblies are enqueued back to back on the engine stream and their counts
+    # are read in ONE host round trip at the end (Engine.sketch_device_many, option many_streams = 1), so the GPU does not
+    # idle while the host reads the sizes of assembly i and enqueues assembly i+1: 10.17 vs 10.22 ms per step on configs[2].
+    # MXE_SKETCH_OVERLAP=1 alternates the assemblies between two streams instead (measured 12.04 vs 11.90 ms in round 2a:
+    # every kernel of the sketch already fills the machine with CTAs, the second stream only gets SMs when the first
+    # drains); MXE_SKETCH_OVERLAP=0 = one blocking call per assembly.
+    overlap_mode = os.environ.get("MXE_SKETCH_OVERLAP", "2")
+    overlap = overlap_mode not in ("", "0")
+    eng.set_option("many_streams", 2 if overlap_mode == "1" else 1)
 
     def step_device(concurrent=True):
         # small per-rank shares: ONE sketch call over all assemblies (fewer launches and round trips; needs the valid k-mer
-        # ordinals to fit 32 bits).  Large ones: one sketch per assembly, enqueued on two streams so that they overlap
-        # (Engine.sketch_device_many); concurrent=False runs them one after the other (clean per-kernel times).
+        # ordinals to fit 32 bits).  Large ones: one sketch per assembly, all enqueued before the sizes are read
+        # (Engine.sketch_device_many); concurrent=False runs one blocking call per assembly (clean per-kernel times).
         use_multi = my_bases + (n_records + 8) * W < 0xF0000000
         if use_multi:
             parent, sks = eng.sketch_device_multi(combo.data_ptr(), [o for _, o, _ in shards], K, W, starts=starts)
@@ -797,7 +802,9 @@ def main():
             "config": {"workload": spec["name"], "k": K, "w": W, "bases_per_step": total_bases, "n_free": not args.with_n,
                        "l2": "inputs larger than L2 (>= 200 MB per assembly)",
                        "sketch_calls": "one call for all assemblies of the rank" if my_bases + (n_records + 8) * W < 0xF0000000 else
-                                       ("one per assembly, enqueued on two streams (concurrent)" if overlap else "one per assembly, sequential"),
+                                       ("one per assembly, enqueued on two streams (concurrent)" if overlap_mode == "1" else
+                                        "one per assembly, enqueued back to back on the engine stream, sizes read once at the end" if overlap else
+                                        "one per assembly, sequential"),
                        "sharding": f"contiguous record ranges over {world} rank(s)" +
                        (("; steps 2-3 by hash owner, 3 all-to-alls (NCCL): keys, marks, sightings" if dist_mode == "alltoall" else
                          "; steps 2-3 by hash range / own records, 1 all-gather + 3 all-reduces (NCCL)" if dist_mode == "allreduce" else

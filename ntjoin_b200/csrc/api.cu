@@ -212,6 +212,7 @@ int mxe_set_option(mxe_t* e, const char* name, double value)
     else if (!strcmp(name, "sort_bits")) e->sort_bits = (int)value;
     else if (!strcmp(name, "filter_variant")) e->filter_variant = (int)value;
     else if (!strcmp(name, "async_sizes")) e->async_sizes = value != 0;
+    else if (!strcmp(name, "many_streams")) e->many_streams = value >= 2 ? 2 : 1;
     else if (!strcmp(name, "bound_scale")) { if (value <= 0) { set_error("bound_scale must be > 0"); return MXE_ERR_ARG; } e->bound_scale = value; }
     else if (!strcmp(name, "fma_offload")) e->fma_offload = value != 0;
     else if (!strcmp(name, "select_narrow")) e->select_narrow = value != 0;

@@ -74,6 +74,7 @@ struct Engine {
     int filter_variant = 1;  // steps 2-3: 0 = global radix sort (filter.cu), 1 = hash buckets in shared memory (p2p.cu)
     int sort_bits = 0;       // steps 2-3: top hash bits covered by the radix sort (24/32/40; 0 = by size), rest by the fix-up
     double bound_scale = 1.0;   // scales the size bounds of the asynchronous path (tests: < 1 forces the overflow / repeat path)
+    int many_streams = 2;    // mxe_sketch_device_many: 2 = assemblies alternate between the engine stream and an auxiliary one, 1 = all on the engine stream (only the host round trips between them go away)
     bool async_sizes = true; // sketch: arrays sized from bounds, counts stay on the device, one host round trip per sketch
     bool timing = false;
     bool timing_fine = false;   // also time every kernel of steps 2-3 and the barrier waits (option timing = 2)

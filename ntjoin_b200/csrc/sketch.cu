@@ -151,7 +151,7 @@ int sketch_device_many_impl(mxe_engine* e, int n_asm, const uint8_t* const* d_se
     for (int a = 0; a < n_asm && rc == MXE_OK; a++) {
         const uint64_t n = n_contigs[a] ? offsets[a][n_contigs[a]] : 0;
         bool redo = false;
-        e->stream = (a & 1) ? e->aux_stream : main_stream;
+        e->stream = ((a & 1) && e->many_streams >= 2) ? e->aux_stream : main_stream;
         rc = sketch_device_pass(e, d_seq[a], n, offsets[a], n_contigs[a], k, w, flags, S[a], nullptr, false, &redo, &pend[a]);
         e->stream = main_stream;
     }

@@ -735,26 +735,49 @@ __device__ __forceinline__ void kmer_hash64_pos(const uint32_t* __restrict__ pk,
     rev = r;
 }
 
-// stage the position-specific tables (and the single-base terms for k % 4 trailing bases) in shared memory
+// stage the position-specific tables (and the single-base terms for k % 4 trailing bases) in shared memory.
+// The two tables (G x 2 KB each) come in as two asynchronous bulk copies (cp.async.bulk, the 1-D form of TMA) that one
+// thread issues against an mbarrier; everybody waits on the barrier's phase.  No load / store instruction per element,
+// and the copy engine of the SM does the address arithmetic (the loop this replaces: 16 x (LDG.64 + STS.64) per thread).
+// pf, pr: 16-byte aligned shared memory; PF, PR: 16-byte aligned global memory (arena blocks are 512-byte aligned).
 __device__ __forceinline__ void stage_pos_tables(const SketchTables& Tb, int k, const uint64_t* __restrict__ PF, const uint64_t* __restrict__ PR,
                                                  uint64_t* pf, uint64_t* pr, uint64_t* s1)
 {
-    const int G = k / 4;
-    for (int i = threadIdx.x; i < G * 256; i += blockDim.x) { pf[i] = PF[i]; pr[i] = PR[i]; }
+    __shared__ __align__(8) uint64_t bar;
+    const uint32_t bytes = (uint32_t)(k / 4) * 256u * (uint32_t)sizeof(uint64_t);
+    const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(2u * bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((uint32_t)__cvta_generic_to_shared(pf)), "l"(PF), "r"(bytes), "r"(bar_a) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((uint32_t)__cvta_generic_to_shared(pr)), "l"(PR), "r"(bytes), "r"(bar_a) : "memory");
+    }
     if (threadIdx.x < 4) {
         s1[threadIdx.x] = Tb.seed[threadIdx.x];
         uint64_t sc = Tb.seed[threadIdx.x ^ 2];
         for (int q = 0; q < k - 1; q++) sc = srol1(sc);
         s1[4 + threadIdx.x] = sc;
     }
-    __syncthreads();
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; spin++) {              // phase 0 of the barrier completes when both copies have landed
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar_a), "r"(0u) : "memory");
+        if (spin > (1u << 22)) __trap();                  // a copy that never lands must not hang the GPU
+    }
+    __syncthreads();                                       // s1
 }
 
 __global__ void __launch_bounds__(256) cand_hash_pos_kernel(const uint64_t* __restrict__ cpos, const uint64_t* __restrict__ d_n, uint64_t n_max,
                                                              const uint32_t* __restrict__ pk, SketchParams P, SketchTables Tb, const uint64_t* __restrict__ PF,
                                                              const uint64_t* __restrict__ PR, uint64_t* __restrict__ h0)
 {
-    extern __shared__ uint64_t hp[];
+    extern __shared__ __align__(16) uint64_t hp[];
     const int G = P.k / 4;
     uint64_t* pf = hp;
     uint64_t* pr = hp + G * 256;
@@ -1119,7 +1142,7 @@ __global__ void __launch_bounds__(256) final_eval_pos_kernel(const uint64_t* __r
                                                               uint32_t* __restrict__ pos, uint32_t* __restrict__ contig,
                                                               uint8_t* __restrict__ forward)
 {
-    extern __shared__ uint64_t hp[];
+    extern __shared__ __align__(16) uint64_t hp[];
     const int G = P.k / 4;
     uint64_t* pf = hp;
     uint64_t* pr = hp + G * 256;
