@@ -296,8 +296,15 @@ void mxe_a2a_free(mxe_a2a_t* x);
  *   mxe_p2p_finish(h, &result)                                   world 1: full result in the reference's order;
  *                                                                world > 1: shard (own flags, owned vertices, own edges
  *                                                                in creation order + mxe_result_edge_keys)
- * A bucket that overflows its capacity (one hash repeated thousands of times) makes mxe_p2p_finish fail with
- * MXE_ERR_INTERNAL; mxe_filter_and_edges then falls back to the sort-based formulation by itself.
+ * Repeated sequence (one hash thousands of times in one bucket): world > 1 places the buckets at exact offsets at the
+ * owner and a bucket larger than a CTA's shared memory is reduced to two copies per (hash, assembly) while it is loaded,
+ * so the call answers; world = 1 uses fixed bucket slots, an overflow there makes mxe_p2p_finish fail with
+ * MXE_ERR_INTERNAL and mxe_filter_and_edges falls back to the sort-based formulation by itself.  What remains an error
+ * (MXE_ERR_INTERNAL from mxe_p2p_finish on the rank that saw it): more than ~500 / 1000 DISTINCT hashes in one bucket, or
+ * a rank that receives more than its segment capacity (cap_total / world^2 * 1.3 + 8192 records per source rank).
+ * Environment (read by mxe_p2p_create): MXE_P2P_RECORDS=0 keeps the successor tables at the vertex owners and accesses
+ * them with fine-grained peer loads / stores; MXE_P2P_BUCKET_AVG / MXE_P2P_BKMAX size the buckets (default 400 records on
+ * average at full capacity; 512 or 1024 records of shared memory per bucket CTA).
  */
 int mxe_p2p_create(mxe_t* e, int rank, int world, uint64_t cap_total, int n_asm_max, mxe_p2p_t** out);
 int mxe_p2p_handle(mxe_p2p_t* h, void* handle64, uint64_t* workspace_bytes);

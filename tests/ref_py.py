@@ -9,27 +9,41 @@ import types
 
 
 class RecordingGraph:
-    """Just enough of igraph.Graph for build_graph: names, edges by name or index, es attributes."""
+    """Just enough of igraph.Graph for build_graph: names, edges by name or index, es attributes.
+    Like the C library it stands in for, it only STORES what add_vertices / add_edges are given (igraph appends to C
+    arrays); names and edge ids are resolved when somebody asks.  (The first version did a dict insert and two name
+    look-ups per edge in Python: 1.4 s for the 375 k edges of bench.py's file-seam measurement, more than the drop-in
+    functions it was standing behind.)"""
 
     def __init__(self):
-        self.vnames, self.edges, self.eattr = [], [], {}
-        self._index, self._eid = {}, {}
+        self.vnames, self.eattr = [], {}
+        self._raw = []                     # edge end points as given: vertex names or vertex indices
+        self._edges = self._eid = None     # resolved views, built on demand
 
     def add_vertices(self, names):
-        for n in names:
-            self._index[n] = len(self.vnames)
-            self.vnames.append(n)
+        self.vnames.extend(names)
+        self._edges = self._eid = None
+
+    def add_edges(self, pairs):
+        self._raw.extend(pairs)
+        self._edges = self._eid = None
+
+    @property
+    def edges(self):
+        """[(source name, target name)] in insertion order"""
+        if self._edges is None:
+            vn = self.vnames
+            self._edges = [(vn[s] if isinstance(s, int) else s, vn[t] if isinstance(t, int) else t) for s, t in self._raw]
+        return self._edges
 
     def _name(self, v):
         return self.vnames[v] if isinstance(v, int) else v
 
-    def add_edges(self, pairs):
-        for s, t in pairs:
-            s, t = self._name(s), self._name(t)
-            self._eid[(s, t)] = self._eid[(t, s)] = len(self.edges)
-            self.edges.append((s, t))
-
     def get_eid(self, s, t):
+        if self._eid is None:
+            self._eid = {}
+            for i, (a, b) in enumerate(self.edges):
+                self._eid[(a, b)] = self._eid[(b, a)] = i
         return self._eid[(self._name(s), self._name(t))]
 
     class _ES:
@@ -46,7 +60,7 @@ class RecordingGraph:
             return iter(())
 
         def __len__(self):
-            return len(self.g.edges)
+            return len(self.g._raw)
 
     @property
     def es(self):
