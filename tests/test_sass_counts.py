@@ -79,3 +79,30 @@ def test_scan_bs2_instruction_mix_per_base():
     assert abs(alu - bench.ALU_OPS_PER_BASE["scan_bs2_kernel"]) <= 0.2, alu
     assert 105 <= lop3 <= 120, lop3            # per step of 32 positions
     assert len(ops) / 512.0 < 4.4              # whole trip
+
+
+@pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump not on PATH")
+def test_steps23_kernels_keep_their_parameters_in_place():
+    """Every kernel of csrc/p2p.cu indexes the table of peer pointers with a run-time rank.  Taking the table by value and
+    passing it on by reference made the compiler copy all 128 bytes into local memory in every thread (16 STL.64 per
+    thread; steps 2-3 took 2.8 instead of 1.7 ms per step); `const __grid_constant__` parameters are read where they are.
+    The shipped SASS of these kernels must not touch local memory at all."""
+    out = subprocess.run(["cuobjdump", "-sass", ntjoin_b200.library_path()], capture_output=True, text=True, check=True).stdout
+    fns = [c for c in out.split("Function : ") if re.match(r"_ZN3mxe\d+p2p_", c)]
+    assert len(fns) >= 20, "the kernels of csrc/p2p.cu were not found in libmxe.so"
+    for fn in fns:
+        name = fn.split()[0]
+        assert not re.search(r"\b(STL|LDL)\b", fn), name + " spills or copies its parameters to local memory"
+
+
+@pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump not on PATH")
+def test_hash_tables_are_staged_by_bulk_copies():
+    """cand_hash_pos_kernel and final_eval_pos_kernel stage their position-specific tables with cp.async.bulk against an
+    mbarrier: UBLKCP + the transaction-count arrive + the phase wait must be in their SASS"""
+    out = subprocess.run(["cuobjdump", "-sass", ntjoin_b200.library_path()], capture_output=True, text=True, check=True).stdout
+    chunks = out.split("Function : ")
+    for mangled in ("_ZN3mxe20cand_hash_pos_kernel", "_ZN3mxe21final_eval_pos_kernel"):
+        fn = [c for c in chunks if c.startswith(mangled)]
+        assert len(fn) == 1, mangled
+        assert fn[0].count("UBLKCP.S.G") == 2, mangled
+        assert "SYNCS.ARRIVE.TRANS64" in fn[0] and "SYNCS.PHASECHK.TRANS64.TRYWAIT" in fn[0], mangled
