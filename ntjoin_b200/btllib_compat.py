@@ -87,9 +87,6 @@ class SeqReader:
         pass
 
     def __iter__(self):
-        if str(self._path).endswith(".gz"):
-            yield from self._iter_python()
-            return
         # the engine's own reader (host only: mxe_fasta_read), the one mxe_sketch_file sketches from
         import ctypes as C
         from ._lib import check, load_library
@@ -107,32 +104,4 @@ class SeqReader:
         finally:
             lib.mxe_fasta_free(h)
 
-    def _iter_python(self):
-        import gzip
-        num, name, comment, parts = 0, None, "", []
-        with gzip.open(self._path, "rt") as fh:
-            first = fh.read(1)
-            fh.seek(0)
-            if first == "@":
-                while True:
-                    h = fh.readline()
-                    if not h:
-                        break
-                    seq = fh.readline().strip()
-                    fh.readline()
-                    qual = fh.readline().strip()
-                    f = h[1:].split(None, 1)
-                    yield SeqRecord(num, f[0] if f else "", f[1].strip() if len(f) > 1 else "", seq.upper(), qual)
-                    num += 1
-                return
-            for line in fh:
-                if line.startswith(">"):
-                    if name is not None:
-                        yield SeqRecord(num, name, comment, "".join(parts).upper(), "")
-                        num += 1
-                    f = line[1:].split(None, 1)
-                    name, comment, parts = (f[0] if f else ""), (f[1].strip() if len(f) > 1 else ""), []
-                else:
-                    parts.append(line.strip())
-            if name is not None:
-                yield SeqRecord(num, name, comment, "".join(parts).upper(), "")
+

@@ -87,6 +87,33 @@ static int parse_fastq(const char* base, size_t size, HostText& seq, std::vector
     return MXE_OK;
 }
 
+static int parse_text(const char* path, const char* base, size_t size, HostText& seq, std::vector<uint64_t>& offsets, std::vector<std::string>& names);
+
+// btllib reads gzip / bzip2 / xz / zstd input through external decompressors (a pipe from `gzip -dc` and friends); so does
+// this reader: the decompressed text is collected in memory and parsed like a mapped file.
+static int read_compressed(const char* path, const char* tool, HostText& seq, std::vector<uint64_t>& offsets, std::vector<std::string>& names)
+{
+    std::string cmd = std::string(tool) + " -dc -- '";
+    for (const char* q = path; *q; q++) { if (*q == '\'') cmd += "'\\''"; else cmd += *q; }      // the path inside single quotes
+    cmd += "' 2>/dev/null";
+    FILE* pipe = popen(cmd.c_str(), "r");
+    if (!pipe) { set_error("cannot start `%s` for %s: %s", tool, path, strerror(errno)); return MXE_ERR_IO; }
+    HostText text;
+    size_t n = 0;
+    for (;;) {
+        if (text.size() < n + (1 << 20)) text.resize(std::max<size_t>(text.size() * 2, (size_t)64 << 20));
+        const size_t r = fread(text.data() + n, 1, text.size() - n, pipe);
+        if (r == 0) break;
+        n += r;
+    }
+    const int status = pclose(pipe);
+    if (status != 0) {
+        set_error("`%s -dc %s` failed (exit status %d): the file is damaged or the tool is not installed", tool, path, status);
+        return MXE_ERR_IO;
+    }
+    return parse_text(path, text.data(), n, seq, offsets, names);
+}
+
 int read_fasta(const char* path, HostText& seq, std::vector<uint64_t>& offsets, std::vector<std::string>& names)
 {
     offsets.clear(); names.clear();
@@ -128,15 +155,21 @@ int read_fasta(const char* path, HostText& seq, std::vector<uint64_t>& offsets, 
     if (base == (const char*)MAP_FAILED) { set_error("cannot map %s: %s", path, strerror(errno)); return MXE_ERR_IO; }
     madvise((void*)base, size, MADV_SEQUENTIAL);
     struct Unmap { const char* p; size_t n; ~Unmap() { munmap((void*)p, n); } } unmap{base, size};
-    // btllib reads gzip / bzip2 / xz / zstd input through external decompressors; this reader takes plain text only and
-    // says so instead of sketching compressed bytes as if they were bases (the make driver stops: non-zero exit)
-    if (size >= 2 && (((unsigned char)base[0] == 0x1f && (unsigned char)base[1] == 0x8b) ||                 // gzip
-                      (base[0] == 'B' && base[1] == 'Z') ||                                                  // bzip2
-                      ((unsigned char)base[0] == 0xfd && base[1] == '7') ||                                  // xz
-                      ((unsigned char)base[0] == 0x28 && (unsigned char)base[1] == 0xb5))) {                 // zstd
-        set_error("%s is compressed: decompress it first (e.g. `gzip -dc`); this reader takes plain FASTA / FASTQ text", path);
-        return MXE_ERR_IO;
+    if (size >= 4) {
+        const unsigned char* m = (const unsigned char*)base;
+        const char* tool = (m[0] == 0x1f && m[1] == 0x8b) ? "gzip"
+                         : (m[0] == 'B' && m[1] == 'Z' && m[2] == 'h') ? "bzip2"
+                         : (m[0] == 0xfd && m[1] == '7' && m[2] == 'z' && m[3] == 'X') ? "xz"
+                         : (m[0] == 0x28 && m[1] == 0xb5 && m[2] == 0x2f && m[3] == 0xfd) ? "zstd" : nullptr;
+        if (tool) return read_compressed(path, tool, seq, offsets, names);
     }
+    return parse_text(path, base, size, seq, offsets, names);
+}
+
+// plain FASTA / FASTQ text in memory (a mapped file or the output of a decompressor)
+static int parse_text(const char* path, const char* base, size_t size, HostText& seq, std::vector<uint64_t>& offsets, std::vector<std::string>& names)
+{
+    if (size == 0) { offsets.push_back(0); seq.resize(64); memset(seq.data(), 0, 64); return MXE_OK; }
     if (base[0] != '>' && base[0] != '@' && base[0] != '\n' && base[0] != '\r' && (base[0] < 0x20 || (unsigned char)base[0] > 0x7e)) {
         set_error("%s does not look like FASTA / FASTQ text (first byte 0x%02x)", path, (unsigned char)base[0]);
         return MXE_ERR_IO;

@@ -95,19 +95,53 @@ def test_reader_edge_files(tmp_path):
         assert _records(p) == want, name
 
 
-def test_compressed_input_is_refused(tmp_path):
-    """btllib reads .gz transparently; this reader takes plain text and must say so (MXE_ERR_IO) rather than sketch
-    compressed bytes as bases and exit 0"""
+def _read_c(path):
     import ctypes as C
-    import gzip
     from ntjoin_b200._lib import load_library
     lib = load_library()
-    p = tmp_path / "x.fa.gz"
-    with gzip.open(p, "wb") as fh:
-        fh.write(b">a\nACGTACGTACGT\n")
     h = C.c_void_p()
-    rc = lib.mxe_fasta_read(str(p).encode(), C.byref(h))
-    assert rc == -2 and b"compressed" in lib.mxe_last_error()
+    rc = lib.mxe_fasta_read(str(path).encode(), C.byref(h))
+    if rc != 0:
+        return rc, lib.mxe_last_error()
+    n, offs, text, nm = C.c_uint32(), C.c_void_p(), C.c_void_p(), C.c_char_p()
+    assert lib.mxe_fasta_view(h, C.byref(n), C.byref(offs), C.byref(text)) == 0
+    o = C.cast(offs, C.POINTER(C.c_uint64))
+    out = []
+    for i in range(n.value):
+        assert lib.mxe_fasta_name(h, i, C.byref(nm)) == 0
+        out.append((nm.value.decode(), C.string_at(text.value + o[i], o[i + 1] - o[i]).decode()))
+    lib.mxe_fasta_free(h)
+    return 0, out
+
+
+def test_compressed_input_is_read_through_the_decompressor(tmp_path):
+    """btllib reads gzip / bzip2 / xz / zstd input through a pipe from the external tool; so does mxe_fasta_read (by the
+    magic bytes, whatever the file is called).  A damaged file is an error (MXE_ERR_IO), never a sketch of compressed bytes."""
+    import bz2
+    import gzip
+    import lzma
+    import shutil
+    text = b">a d\nACGTacgtNN\nGG\n>b\n" + b"ACGT" * 50000 + b"\n"
+    want = [("a", "ACGTACGTNNGG"), ("b", "ACGT" * 50000)]
+    for tool, name, opener in (("gzip", "x.fa.gz", gzip.open), ("bzip2", "y.fa.bz2", bz2.open), ("xz", "z.data", lzma.open)):
+        p = tmp_path / name
+        with opener(p, "wb") as fh:
+            fh.write(text)
+        if shutil.which(tool) is None:
+            continue
+        assert _read_c(p) == (0, want), tool
+    fq = tmp_path / "r.fq.gz"
+    with gzip.open(fq, "wb") as fh:
+        fh.write(b"@r1 d\nACgt\n+\nIIII\n")
+    assert _read_c(fq) == (0, [("r1", "ACGT")])
+    quoted = tmp_path / "it's here.fa.gz"                      # the path goes through a shell command line
+    with gzip.open(quoted, "wb") as fh:
+        fh.write(b">q\nAC\n")
+    assert _read_c(quoted) == (0, [("q", "AC")])
+    bad = tmp_path / "bad.fa.gz"
+    bad.write_bytes((tmp_path / "x.fa.gz").read_bytes()[:40])    # truncated stream
+    rc, msg = _read_c(bad)
+    assert rc == -2 and b"failed" in msg
 
 
 def test_fastq_trailing_blank_line(tmp_path):
