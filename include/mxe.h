@@ -68,7 +68,9 @@ int  mxe_set_option(mxe_t* e, const char* name, double value);
 
 /* ---- step 1: ordered minimizer sketch --------------------------------------------------- */
 
-/* FASTA file (multi-line records, '>' headers; id = header up to first whitespace).
+/* FASTA / FASTQ file (multi-line records, '>' headers; id = header up to first whitespace); gzip, bzip2, xz and zstd
+ * files (recognised by their first bytes) are read through a pipe from `gzip -dc` etc., as btllib does.  Records of
+ * 2^32 bases or more are rejected (MXE_ERR_ARG): positions are 32-bit in the TSV arrays.
  * Replaces: indexlr subprocess, ntJoin:204-205. */
 int mxe_sketch_file(mxe_t* e, const char* fasta_path, int k, int w, int flags, mxe_sketch_t** out);
 
