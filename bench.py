@@ -459,6 +459,8 @@ def run_t3(args, eng, spec, dev):
         baseline["gbases_per_s_t4"] = total / baseline["total_t4_s"] / 1e9
         baseline["kind"] = "port (oracle/mxo_indexlr.c + tests/ref_py.py): the reference's own step 1 is an un-vendored binary, its bin/ is not on this box"
         out["cpu"] = baseline
+        out["graph_note"] = ("python-igraph is not installable here: both arms hand their vertices and edges to tests/ref_py.RecordingGraph, which "
+                             "only stores what it is given (as the C library would) and resolves names / edge ids on demand")
         out["same_edge_count"] = baseline["edges"] == t["edges"]
         out["speedup_vs_t4"] = baseline["total_t4_s"] / t["total_s"]
         out["speedup_vs_all_cores"] = baseline["total_all_s"] / t["total_s"]
