@@ -24,6 +24,8 @@ def ref_utils():
     spec.loader.exec_module(mg)
     saved = sys.modules.get("igraph")
     utils = mg.load_reference_utils()
+    import ntjoin as ntjoin_mod                    # the reference's bin/ntjoin.py (print_graph)
+    utils._mg, utils._ntjoin_mod = mg, ntjoin_mod
     yield utils
     if saved is not None:
         sys.modules["igraph"] = saved
@@ -101,6 +103,35 @@ def test_random_lists_oracle_equals_reference(oracle, ref_utils, tmp_path, n_asm
         assert [[key[f] for f in sup] for sup in graph.eattr["support"]] == \
             [[b for b in range(n_asm) if m >> b & 1] for m in e["support_mask"].tolist()], (seed, rep)     # support lists in assembly order
         assert graph.eattr["weight"] == e["weight"].tolist(), (seed, rep)
+        # the product's .mx.dot writer (host only) from arrays, against the reference's own Ntjoin.print_graph
+        if rep % 4 == 0:
+            from ntjoin_b200.dot import write_mx_dot
+            list_mx_info = {}
+            with ref_utils.HiddenPrints():
+                for tsv in tsvs:
+                    list_mx_info[tsv], _m = ref_utils.read_minimizers(tsv)
+            vnames = [str(int(v)) for v in got["vertices"]]
+            base = {t: os.path.basename(t) for t in tsvs}
+            want_path = str(tmp_path / f"want.{seed}.{rep}.mx.dot")
+            ref_utils._mg.reference_print_graph(ref_utils._ntjoin_mod, ref_utils, vnames, graph.edges,
+                                                [[base[f] for f in sup] for sup in graph.eattr["support"]], graph.eattr["weight"],
+                                                {base[t]: list_mx_info[t] for t in tsvs}, want_path)
+            index = {v: i for i, v in enumerate(vnames)}
+            names, v_ctg, v_pos = [], [], []
+            for t in tsvs:
+                info = list_mx_info[t]
+                nm = sorted({c for c, _p in info.values()})
+                at = {c: i for i, c in enumerate(nm)}
+                names.append(nm)
+                v_ctg.append([at[info[v][0]] for v in vnames])
+                v_pos.append([info[v][1] for v in vnames])
+            pairs = [sorted((index[str(int(u))], index[str(int(v))])) for u, v in zip(e["u"], e["v"])]   # igraph: source = lower id
+            got_path = tmp_path / f"got.{seed}.{rep}.mx.dot"
+            write_mx_dot(got_path, got["vertices"], [base[t] for t in tsvs], names, v_ctg, v_pos,
+                         [p[0] for p in pairs], [p[1] for p in pairs], e["support_mask"], weights_all[:n_asm])
+            want_bytes = open(want_path, "rb").read()
+            assert got_path.read_bytes() == want_bytes, (seed, rep)
+            assert want_bytes.count(b" --") == len(e) and want_bytes.count(b"[label=") == len(vnames), (seed, rep)
         seen["edges"] += len(e)
         seen["multi_support"] += int(sum(bin(m).count("1") > 1 for m in e["support_mask"].tolist()))
         seen["not_unique"] += int(sum((~u).sum() for u in got["uniq"]))
