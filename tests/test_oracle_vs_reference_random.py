@@ -70,7 +70,14 @@ def _write_tsv(path, recs):
 
 @pytest.mark.parametrize("n_asm,universe,n_rec,max_len,seed", [(1, 40, 3, 12, 0), (2, 60, 4, 15, 1), (2, 25, 5, 10, 2), (3, 80, 5, 20, 3),
                                                               (3, 30, 6, 8, 4), (4, 100, 6, 18, 5), (5, 70, 5, 14, 6), (2, 400, 12, 60, 7)])
-def test_random_lists_oracle_equals_reference(oracle, ref_utils, tmp_path, n_asm, universe, n_rec, max_len, seed):
+def test_random_lists_oracle_equals_reference(oracle, ref_utils, tmp_path, monkeypatch, n_asm, universe, n_rec, max_len, seed):
+    import ref_py
+    from ntjoin_b200 import dropin
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "harness"))
+    from fake_engine import FakeEngine
+    monkeypatch.setattr(dropin, "_ENGINE", FakeEngine())
+    monkeypatch.setattr(dropin, "_LAST_FILTER", None)
+    dropin_mod = dropin.install(ref_py.as_module())
     rng = np.random.default_rng(1000 + seed)
     weights_all = [2.0, 1.0, 1.5, 0.1, 3.0]
     seen = {"edges": 0, "multi_support": 0, "not_unique": 0, "dropped_by_intersection": 0, "sources_with_several_edges": 0}
@@ -132,12 +139,30 @@ def test_random_lists_oracle_equals_reference(oracle, ref_utils, tmp_path, n_asm
             want_bytes = open(want_path, "rb").read()
             assert got_path.read_bytes() == want_bytes, (seed, rep)
             assert want_bytes.count(b" --") == len(e) and want_bytes.count(b"[label=") == len(vnames), (seed, rep)
+        # the product's drop-in functions (ntjoin_b200/dropin.py, engine calls served by the oracle-backed stand-in)
+        # against the reference's: same dict (content and insertion order), same lists, same graph
+        if rep % 2 == 1:
+            d_info, d_mxs = {}, {}
+            for tsv in tsvs:
+                d_info[tsv], d_mxs[tsv] = dropin_mod.read_minimizers(tsv)
+            with ref_utils.HiddenPrints():
+                for tsv in tsvs:
+                    r_info, _m = ref_utils.read_minimizers(tsv)
+                    assert d_info[tsv] == r_info and list(d_info[tsv]) == list(r_info), (seed, rep)
+            assert {t: list(v) for t, v in d_mxs.items()} == list_mxs, (seed, rep)
+            d_filt = dropin_mod.filter_minimizers(d_mxs)
+            assert {t: list(v) for t, v in d_filt.items()} == filtered, (seed, rep)
+            d_graph = dropin_mod.build_graph(d_filt, wdict)
+            assert sorted(d_graph.vnames, key=int) == sorted(graph.vnames, key=int), (seed, rep)
+            assert d_graph.edges == graph.edges, (seed, rep)
+            assert d_graph.eattr["support"] == graph.eattr["support"] and d_graph.eattr["weight"] == graph.eattr["weight"], (seed, rep)
         seen["edges"] += len(e)
         seen["multi_support"] += int(sum(bin(m).count("1") > 1 for m in e["support_mask"].tolist()))
         seen["not_unique"] += int(sum((~u).sum() for u in got["uniq"]))
         seen["dropped_by_intersection"] += int(sum((u & ~k).sum() for u, k in zip(got["uniq"], got["keep"])))
         srcs = [s for s, _t in graph.edges]
         seen["sources_with_several_edges"] += len(srcs) - len(set(srcs))
+    monkeypatch.setattr(dropin, "_LAST_FILTER", None)
     # the random cases must really contain what this test is about
     assert seen["edges"] > 20 and seen["not_unique"] > 10, seen
     if n_asm > 1:
