@@ -157,3 +157,28 @@ def test_fastq_trailing_blank_line(tmp_path):
     assert lib.mxe_fasta_view(h, C.byref(n), C.byref(offs), C.byref(text)) == 0
     assert n.value == 2
     lib.mxe_fasta_free(h)
+
+
+def test_compressed_big_messy_file_equals_plain(tmp_path):
+    """the ~28 MB messy file through `gzip -dc` gives the same records as the mapped plain file; a second file whose text
+    is larger than the first block of the pipe buffer (64 MB) exercises the buffer growth"""
+    import shutil
+    if shutil.which("gzip") is None:
+        pytest.skip("gzip not installed")
+    p = tmp_path / "big.fa"
+    want = _big_messy_fasta(p)
+    z = tmp_path / "big.fa.gz"
+    with open(p, "rb") as src, gzip.open(z, "wb", compresslevel=1) as dst:
+        shutil.copyfileobj(src, dst)
+    got = _records(z)
+    assert [g[0] for g in got] == [w[0] for w in want] and all(g[1] == w[1] for g, w in zip(got, want))
+    long_rec = b"ACGTTGCAAC" * 9_000_000                     # 90 MB of sequence in lines of 100
+    z2 = tmp_path / "long.fa.gz"
+    with gzip.open(z2, "wb", compresslevel=1) as dst:
+        dst.write(b">only one\n")
+        for i in range(0, len(long_rec), 9_000_000):
+            block = long_rec[i:i + 9_000_000]
+            dst.write(b"\n".join(block[j:j + 100] for j in range(0, len(block), 100)) + b"\n")
+    rc, recs = _read_c(z2)
+    assert rc == 0 and len(recs) == 1 and recs[0][0] == "only" and len(recs[0][1]) == len(long_rec)
+    assert recs[0][1][:20] == long_rec[:20].decode() and recs[0][1][-20:] == long_rec[-20:].decode()
