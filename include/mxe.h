@@ -89,7 +89,10 @@ int mxe_sketch_buffers(mxe_t* e, const uint8_t* seq, const uint64_t* offsets, ui
 
 /* Optional: start the host->device copy of a buffer that a later mxe_sketch_buffers call (same
  * pointer and length) will sketch.  Returns at once; the copy runs on the engine's copy streams
- * while earlier work is still computing (at most two buffers in flight; further calls are no-ops). */
+ * while earlier work is still computing (at most two buffers in flight; further calls are no-ops).
+ * Like any asynchronous copy: the buffer must stay allocated and UNCHANGED until the sketch call that consumes it has
+ * returned -- the staged copy is recognised by (pointer, length) alone, a buffer rewritten or recycled in between would
+ * be sketched in its old state.  A prefetch that is never consumed is dropped when its slot is needed again. */
 int mxe_prefetch_buffers(mxe_t* e, const uint8_t* seq, uint64_t n);
 
 /* Same, with `d_seq` already resident in device memory of this engine's device (16-byte aligned).
