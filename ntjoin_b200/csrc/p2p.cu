@@ -5,7 +5,7 @@
 // weights (:54-56) -- same results as filter.cu, different machine mapping:
 //
 //   * no global sort.  The 64-bit out_hash is uniformly mixed, so its top B bits cut the minimizers of all assemblies
-//     into 2^B BUCKETS of ~700 records; a bucket is sorted and analysed by one CTA in shared memory (uniqueness per
+//     into 2^B BUCKETS of ~200 records; a bucket is sorted and analysed by one CTA in shared memory (uniqueness per
 //     assembly, found-in-all runs, vertex ranks), the kernels before and after it are single passes.
 //   * one code path for 1..16 GPUs.  Bucket b belongs to rank (b * world) >> B (monotone in the hash, so the ranks'
 //     vertex lists concatenate to the ascending single-GPU order).  Every rank holds the same SYMMETRIC workspace; the
@@ -13,8 +13,10 @@
 //     through CUDA IPC, a few atomics for the first-source tables), and a device-side barrier (one flag store per peer,
 //     one spinning warp) separates the stages.  No collective library, no host round trip between the stages:
 //
-//       scatter    (source)  record {hash, asm | rank | local index} -> bucket sub-slot [bucket][source] at the OWNER
-//       --- barrier 1 (per-(bucket, source) counts and the per-rank minimizer counts ride along)
+//       scatter    (source)  record {hash, asm | rank | local index} -> the OWNER of its bucket (one GPU: straight into
+//                            the bucket's slot; several: appended to the owner's segment of this source, which the owner
+//                            cuts into buckets)
+//       --- barrier 1 (the record counts and the per-rank minimizer counts ride along)
 //       buckets    (owner)   sort + run analysis in shared memory; the mark of every record goes back to its SOURCE,
 //                            the bucket's survivor count to EVERY rank
 //       --- barrier 2
