@@ -63,3 +63,32 @@ def test_prefilter_is_exact_and_threshold_independent(oracle, k, w):
     for tau in (0.5, 3.0, 9.0, 40.0):
         got = minimizers_by_prefilter(oracle, seq, k, w, tau, rng)
         assert got == want, (k, w, tau)
+
+
+@pytest.mark.parametrize("w", [250, 1000, 5000])
+def test_twelve_bit_lane_test_is_a_superset(w):
+    """scan_bs2_kernel decides from the top 12 bits of the two 31-bit lanes alone: with
+    hash0 = fwd + rev (mod 2^64), t = hash0 >> 33 = (f31 + r31 + c) mod 2^31 where c is the carry out of the low 33 bits,
+    and S = (f31 >> 19) + (r31 >> 19) + 1 (mod 2^12) satisfies  t <= T  =>  S <= (T >> 19) + 1: every k-mer below the
+    threshold is flagged, whatever the dropped bits and carries are; the flagged set is only a few per cent larger."""
+    rng = np.random.default_rng(w)
+    n = 2_000_000
+    fwd = rng.integers(0, 2**64, size=n, dtype=np.uint64)
+    rev = rng.integers(0, 2**64, size=n, dtype=np.uint64)
+    # values at the edges of the carry cases
+    fwd[:4] = [0, 2**64 - 1, (1 << 33) - 1, 1 << 33]
+    rev[:4] = [0, 1, 1, (1 << 64) - (1 << 33)]
+    h0 = fwd + rev                                                       # wraps mod 2^64
+    t = (h0 >> np.uint64(33)).astype(np.int64)
+    f31, r31 = (fwd >> np.uint64(33)).astype(np.int64), (rev >> np.uint64(33)).astype(np.int64)
+    c = (((fwd & np.uint64((1 << 33) - 1)).astype(np.int64) + (rev & np.uint64((1 << 33) - 1)).astype(np.int64)) >> 33)
+    assert np.array_equal(t, (f31 + r31 + c) & ((1 << 31) - 1))          # the two rotation groups never mix
+    T = int(9.0 * 2**31 / w)
+    S = ((f31 >> 19) + (r31 >> 19) + 1) & 0xFFF
+    Q = min((T >> 19) + 1, 0xFFF)
+    flagged = S <= Q
+    below = t <= T
+    assert not np.any(below & ~flagged)
+    assert below.sum() > 0 and flagged.sum() >= below.sum()
+    if w >= 1000:
+        assert flagged.sum() < 1.6 * below.sum() + 50
