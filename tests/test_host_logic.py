@@ -93,3 +93,20 @@ def test_mxlists_pickle_as_plain_lists():
         pickle.dumps(lists._sketch.handle)
     back = pickle.loads(pickle.dumps({"asm.tsv": lists}))
     assert type(back["asm.tsv"]) is list and back["asm.tsv"] == [["1", "2"], [], ["3"]]
+
+
+def test_bucket_ownership_formulas_agree_for_every_world_size():
+    """csrc/p2p.cu: the kernels route a record to owner(b) = (b * world) >> B, the host gives rank r the buckets
+    [fb[r], fb[r + 1]) with fb[r] = ceil(r * 2^B / world).  The two must describe the same partition -- monotone in the
+    hash, every bucket owned once, no rank empty -- for every world size up to 16 and every bucket count (the GPU tests
+    run worlds 1, 2, 3, 4, 5 and 8)."""
+    for world in range(1, 17):
+        for B in range(6, 21):
+            n_buckets = 1 << B
+            fb = [((r << B) + world - 1) // world for r in range(world + 1)]
+            assert fb[0] == 0 and fb[world] == n_buckets
+            owner = (np.arange(n_buckets, dtype=np.int64) * world) >> B
+            assert (np.diff(owner) >= 0).all()
+            for r in range(world):
+                seg = owner[fb[r]:fb[r + 1]]
+                assert len(seg) > 0 and (seg == r).all(), (world, B, r)
