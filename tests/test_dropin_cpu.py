@@ -70,3 +70,65 @@ def test_dropin_gc_state_is_restored():
         assert not gc.isenabled()
     finally:
         gc.enable()
+
+
+def _tsvs(g, golden_dir, relative=True):
+    out = []
+    for i, f in enumerate(g["files"]):
+        tsv = f"{i}.{f}.k{g['k']}.w{g['w']}.tsv"
+        subprocess.check_call([oracle_lib.CLI, "--seq", "--long", "--pos", "-k", str(g["k"]), "-w", str(g["w"]),
+                               os.path.join(golden_dir, "inputs", f), "-o", tsv])
+        out.append(tsv)
+    return out
+
+
+def test_dropin_print_graph_and_min_max_with_oracle_engine(golden_dir, tmp_path, monkeypatch):
+    """CPU twins of test_gpu_dropin.py::test_dropin_print_graph_bytes / test_dropin_find_mx_min_max: the array-fed
+    `.mx.dot` writer gives the bytes of the reference's own print_graph, find_mx_min_max from arrays equals the reference's
+    loop (bin/ntjoin_assemble.py:688-702) including the dict order"""
+    import types
+    from fake_engine import FakeEngine
+    from ntjoin_b200 import dropin
+    oracle_lib.build()
+    monkeypatch.setattr(dropin, "_ENGINE", FakeEngine())
+    monkeypatch.setattr(dropin, "_LAST_FILTER", None)
+    mod = dropin.install(ref_py.as_module())
+    calls = []
+
+    class Ntjoin:
+        def print_graph(self, graph, out_prefix=None):
+            calls.append(graph)
+
+    class NtjoinScaffolder:
+        def find_mx_min_max(self, target):
+            vertices = {v["name"] for v in self.graph.vs}
+            out = {}
+            for mx, (ctg, pos) in self.list_mx_info[target].items():
+                if mx in vertices:
+                    out[ctg] = (min(out[ctg][0], pos), max(out[ctg][1], pos)) if ctg in out else (pos, pos)
+            return out
+
+    original = NtjoinScaffolder.find_mx_min_max
+    nt = dropin.install_print_graph(types.SimpleNamespace(Ntjoin=Ntjoin))
+    sc = dropin.install_scaffolder(types.SimpleNamespace(NtjoinScaffolder=NtjoinScaffolder)).NtjoinScaffolder
+    monkeypatch.chdir(tmp_path)
+    for name in ("config1_ff_w500", "three_way_w1000", "misassembled_frrf_w500", "selfdup_w250", "multiple_w500", "overlap_k15_w10"):
+        g = json.load(open(os.path.join(golden_dir, f"steps23_{name}.json")))
+        obj, scaf = nt.Ntjoin(), sc()
+        obj.list_mx_info, list_mxs, weights = {}, {}, {}
+        for i, tsv in enumerate(_tsvs(g, golden_dir)):
+            obj.list_mx_info[tsv], list_mxs[tsv] = mod.read_minimizers(tsv)
+            weights[tsv] = g["weights"][i]
+        gr = mod.build_graph(mod.filter_minimizers(list_mxs), weights)
+        obj.args = types.SimpleNamespace(p=f"out_{name}")
+        obj.print_graph(gr)
+        want = open(os.path.join(golden_dir, "expected", f"print_graph_{name}.mx.dot"), "rb").read()
+        assert open(f"out_{name}.mx.dot", "rb").read() == want, name
+        scaf.list_mx_info, scaf.graph = obj.list_mx_info, gr
+        for target in list_mxs:
+            got, ref = scaf.find_mx_min_max(target), original(scaf, target)
+            assert got == ref and list(got) == list(ref), (name, target)
+    assert not calls
+    obj.print_graph(types.SimpleNamespace(vs=[], es=[]))     # not built by the engine: the original must run
+    assert len(calls) == 1
+    monkeypatch.setattr(dropin, "_LAST_FILTER", None)
