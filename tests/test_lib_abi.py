@@ -48,3 +48,37 @@ def test_product_never_imports_oracle():
                     if re.search(r"oracle_lib|libmxo|mxo_|oracle/", t):
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """the boundary is a C ABI: include/mxe.h compiles as C99 (no C++, no torch types) and a C program links against
+    libmxe.so, reads the version string and -- on a box without a GPU -- gets a clean error from mxe_create"""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not on PATH")
+    src = tmp_path / "use_mxe.c"
+    src.write_text('''
+#include <stdio.h>
+#include <string.h>
+#include "mxe.h"
+int main(void)
+{
+    mxe_t* e = NULL;
+    printf("%s\\n", mxe_version());
+    int rc = mxe_create(0, &e);
+    if (rc != MXE_OK) { printf("create: %d %s\\n", rc, mxe_last_error()); return e == NULL ? 0 : 2; }
+    mxe_destroy(e);
+    printf("create: ok\\n");
+    return 0;
+}
+''')
+    exe = tmp_path / "use_mxe"
+    libdir = os.path.dirname(ntjoin_b200.library_path())
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-l:libmxe.so", "-Wl,-rpath," + libdir], check=True, capture_output=True, text=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = r.stdout.splitlines()
+    assert "sm_100a" in lines[0]
+    assert lines[1] == "create: ok" or ("create:" in lines[1] and "no CPU fallback" in lines[1])
